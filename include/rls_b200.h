@@ -1,0 +1,346 @@
+/*
+ * rls_b200.h -- C ABI of the B200-native rlShaders BSDF hot path.
+ *
+ * This is the drop-in boundary for the per-shading-sample path of shihchinw/rlShaders:
+ * the Arnold BRDF-callback triple
+ *
+ *     static AtVector evalSample(const void *brdfData, float rx, float ry);
+ *     static AtColor  evalBrdf  (const void *brdfData, const AtVector *indir);
+ *     static float    evalPdf   (const void *brdfData, const AtVector *indir);
+ *
+ * (reference src/rlGgx.h:97,110,121 and src/rlDisney.cpp:109,120,139), the sampler
+ * constructors that build `brdfData` from AtShaderGlobals + node parameters
+ * (src/rlGgx.h:130-156, src/rlDisney.cpp:155-192) and the diffusion-profile surface
+ * NDProfile::{setDistance,getRadius,getPdf,evalProfile} (src/rlSss.h:49-55) -- all
+ * restated as BATCHED, structure-of-arrays entry points.  One array element = one
+ * shading sample; the per-shading-point `brdfData` object is replaced by the SoA
+ * shading inputs (`rls_shading_soa`) plus a parameter block whose field names are the
+ * node parameter names of src/rlShaders.mtd / node_parameters verbatim.
+ *
+ * Conventions
+ *   - Plain C: pointers, sizes, PODs.  No torch / CUDA types in any signature
+ *     (the stream is passed as an opaque void* = cudaStream_t).
+ *   - Every array pointer is a DEVICE pointer unless the entry point ends in `_host`,
+ *     in which case every array pointer is a (preferably pinned) HOST pointer and the
+ *     library stages chunks through its own device scratch (H2D, kernel, D2H overlapped).
+ *   - The caller owns all buffers.  Device entry points do not allocate and do not
+ *     synchronise: work is enqueued on the context's stream.
+ *   - Return value: RLS_OK (0) or a negative RLS_ERR_* code; rls_last_error_string()
+ *     gives the detail.  There is no CPU fallback: without a usable sm_100 device
+ *     rls_init fails.
+ *   - Error semantics of the reference are preserved in-band: an invalid sample is the
+ *     zero vector (src/rlDisney.cpp:385-387), a zero `indir` evaluates to black
+ *     (src/rlGgx.h:112-115, src/rlDisney.cpp:124-127) and to pdf 0 in rlDisney
+ *     (src/rlDisney.cpp:141-144) but NOT in rlGgx (src/rlGgx.h:121-127).
+ */
+#ifndef RLS_B200_H
+#define RLS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLS_B200_ABI_VERSION 1
+
+/* ------------------------------------------------------------------ errors */
+#define RLS_OK                    0
+#define RLS_ERR_INVALID_ARGUMENT (-1)
+#define RLS_ERR_CUDA             (-2)
+#define RLS_ERR_NO_DEVICE        (-3)
+#define RLS_ERR_OUT_OF_MEMORY    (-4)
+
+/* Sample type of the rlDisney triple; values mirror AI_RAY_DIFFUSE / AI_RAY_GLOSSY as
+ * passed to DisneySampler::setSampleType (src/rlDisney.cpp:194,242,268,275,281). */
+#define RLS_RAY_DIFFUSE 0x20
+#define RLS_RAY_GLOSSY  0x40
+
+/* ------------------------------------------------- per-sample flags (u32) */
+/* Bit-exact parity target.  For the fused rlDisney op the low half-word describes the
+ * specular (glossy) triple and the high half-word the diffuse triple (same layout,
+ * shifted by RLS_FLAG_DIFFUSE_SHIFT). */
+#define RLS_FLAG_ZERO_L         0x0001u /* sampled direction is the zero vector (invalid sample)     */
+#define RLS_FLAG_BELOW_HORIZON  0x0002u /* dot(L, N) <= 0 for the sampled direction                  */
+#define RLS_FLAG_PDF_ZERO       0x0004u /* evalPdf returned exactly 0                                */
+#define RLS_FLAG_F_BLACK        0x0008u /* evalBrdf returned exactly (0,0,0)                         */
+#define RLS_FLAG_ENTERING       0x0010u /* dot(sg->N, sg->Rd) < 1e-4, src/rlGgx.h:137                */
+#define RLS_FLAG_TIR            0x0020u /* refraction failed, sample reflected, src/rlGgx.h:232-236  */
+#define RLS_FLAG_PDF_FLOORED    0x0040u /* pdf floor 1e-4 was taken, src/rlGgx.h:79, rlDisney.cpp:517 */
+#define RLS_FLAG_LOBE_SHIFT     8       /* bits 8-9: rlDisney 0 = GTR2, 1 = GTR1 (rlDisney.cpp:375); */
+#define RLS_FLAG_LOBE_MASK      0x0300u /*           profile: colour channel 0..2 (rlSss.h:30-42)    */
+#define RLS_FLAG_EXP_LOBE       0x0400u /* profile: second exponential (3d) chosen, rlSss.cpp:57     */
+#define RLS_FLAG_DEGENERATE     0x0800u /* profile: maxRadius or d below 1e-4, rlSss.cpp:38,46       */
+#define RLS_FLAG_PROBE_AXIS_SHIFT 12    /* bits 12-13: probe axis 0 = N, 2 = U, 3 = V (rlSss.h:491-500) */
+#define RLS_FLAG_PROBE_AXIS_MASK  0x3000u
+#define RLS_FLAG_DIFFUSE_SHIFT  16
+
+/* ------------------------------------------------------------ basic types */
+typedef struct rls_context rls_context;
+
+typedef struct rls_cvec3 { const float *x, *y, *z; } rls_cvec3;   /* SoA input vector / colour  */
+typedef struct rls_vec3  { float *x, *y, *z; } rls_vec3;          /* SoA output vector / colour */
+
+/* A node parameter: uniform `value`, or one value per sample when `array` is non-NULL
+ * (Arnold evaluates linked parameters per shading point: AiShaderEvalParam*). */
+typedef struct rls_param1 { float value;    const float *array; } rls_param1;
+typedef struct rls_param3 { float value[3]; rls_cvec3    array; } rls_param3;
+
+/* The AtShaderGlobals fields the path reads, one entry per sample.
+ *   U,V,N : the orthonormal shading frame mBasis / mAxisU,V,N with N = sg->Nf
+ *           (src/rlGgx.h:145-146, src/rlDisney.cpp:173-174).  Supplied explicitly
+ *           because AiBuildLocalFramePolar is proprietary.
+ *   wo    : view direction mViewDir = -sg->Rd (src/rlGgx.h:144, src/rlDisney.cpp:172).
+ *   backfacing : optional (may be NULL = all 0).  1 where sg->N == -sg->Nf, which makes
+ *           the rlGgx constructor swap the IORs (src/rlGgx.h:137-142). */
+typedef struct rls_shading_soa {
+    rls_cvec3      U, V, N;
+    rls_cvec3      wo;
+    const uint8_t *backfacing;
+} rls_shading_soa;
+
+/* rlGgx node parameters (src/rlGgx.cpp:172-186, src/rlShaders.mtd:7-29).  The sampler
+ * path reads KsColor, specularRoughness, ior, anisotropic; the others are accepted so a
+ * parameter block can be filled straight from the node and are ignored here (they scale
+ * results outside the BRDF triple, src/rlGgx.cpp:297-305). */
+typedef struct rls_ggx_params {
+    rls_param3 KsColor;
+    rls_param1 Ks;
+    rls_param1 specularRoughness;
+    rls_param1 ior;
+    rls_param1 anisotropic;
+    rls_param3 KdColor;
+    rls_param1 Kd;
+    rls_param1 diffuseRoughness;
+    rls_param3 KtColor;
+    rls_param1 Kt;
+    rls_param1 opacity;
+    rls_param3 opacity_color;
+} rls_ggx_params;
+
+/* rlDisney node parameters (src/rlDisney.cpp:606-625). */
+typedef struct rls_disney_params {
+    rls_param3 base_color;
+    rls_param1 subsurface;
+    rls_param1 metallic;
+    rls_param1 specular;
+    rls_param1 specular_tint;
+    rls_param1 roughness;
+    rls_param1 anisotropic;
+    rls_param1 sheen;
+    rls_param1 sheen_tint;
+    rls_param1 clearcoat;
+    rls_param1 clearcoat_gloss;
+    rls_param3 opacity;               /* accepted, ignored */
+    rls_param1 indirectDiffuseScale;  /* accepted, ignored */
+    rls_param1 indirectSpecularScale; /* accepted, ignored */
+} rls_disney_params;
+
+/* rlSkin node parameters (src/rlSkin.cpp:109-131, src/rlShaders.mtd:43-64).  The
+ * profile path reads sss_color, sss_dist_multiplier, sss_scatter_dist; the layer-weight
+ * op reads sss_weight, specular_weight, sheen_weight. */
+typedef struct rls_skin_params {
+    rls_param3 sss_color;
+    rls_param1 sss_weight;
+    rls_param1 sss_dist_multiplier;
+    rls_param3 sss_scatter_dist;
+    int32_t    sss_cavity_fadeout;
+    rls_param3 specular_color;
+    rls_param1 specular_weight;
+    rls_param1 specular_roughness;
+    rls_param1 specular_ior;
+    rls_param3 sheen_color;
+    rls_param1 sheen_weight;
+    rls_param1 sheen_roughness;
+    rls_param1 sheen_ior;
+    rls_param1 opacity;
+    rls_param3 opacity_color;
+} rls_skin_params;
+
+/* Result of one fused {construct, evalSample, evalBrdf, evalPdf} unit. */
+typedef struct rls_bsdf_out {
+    rls_vec3  wi;       /* L = evalSample(rx, ry); zero vector = invalid sample             */
+    rls_vec3  f;        /* evalBrdf(L): BRDF x cosine, RGB                                   */
+    float    *pdf;      /* evalPdf(L)                                                        */
+    float    *fresnel;  /* optional (NULL): the fresnel(L, M) term evalSample accumulates
+                           for getAvgReflectWeight, src/rlGgx.h:103,181-184                  */
+    uint32_t *flags;    /* RLS_FLAG_*                                                        */
+} rls_bsdf_out;
+
+/* Result of the rough-dielectric unit (Walter'07): one visible-normal sample m, then
+ * BOTH branches, as in integrateRefract's loop body (src/rlGgx.h:228-243). */
+typedef struct rls_ggx_dielectric_out {
+    float    *fresnel;   /* F = fresnel(wi_r, m), src/rlGgx.h:103,249-270                     */
+    rls_vec3  wi_r;      /* reflectDirection(wo, m), src/rlUtil.h:31-34                       */
+    float    *f_r;       /* reflection(wo, wi_r, N) * dot(wi_r, N)  (evalBrdf with KsColor 1) */
+    float    *pdf_r;     /* evalPdf(wi_r), src/rlGgx.h:121-127                                */
+    rls_vec3  wi_t;      /* getRefractDirection(m, wo), src/rlGgx.h:277-291; on TIR the
+                            reflected direction (src/rlGgx.h:232-236)                         */
+    float    *f_t;       /* refraction(wo, wi_t, N), src/rlGgx.h:316-328; 0 on TIR            */
+    float    *weight_t;  /* getSampleWeight(wo, wi_t, m), src/rlGgx.h:294-301                 */
+    uint32_t *flags;
+} rls_ggx_dielectric_out;
+
+/* Result of the fused rlDisney unit: specular (glossy) triple + diffuse triple. */
+typedef struct rls_disney_out {
+    rls_vec3  wi_s, f_s;  float *pdf_s;
+    rls_vec3  wi_d, f_d;  float *pdf_d;
+    uint32_t *flags;
+} rls_disney_out;
+
+/* NDProfile state produced by setDistance (src/rlSss.cpp:20-34), one per sample. */
+typedef struct rls_ndprofile_soa {
+    rls_vec3 distance;    /* mDistance        */
+    rls_vec3 C1, C2;      /* mC1, mC2         */
+    float   *max_radius;  /* mMaxRadius       */
+} rls_ndprofile_soa;
+
+/* Result of the fused skin-profile unit: setDistance + getRadius + getPdf + evalProfile. */
+typedef struct rls_profile_out {
+    float    *r;      /* getRadius(rx), src/rlSss.cpp:36-66    */
+    float    *pdf;    /* getPdf(r), src/rlSss.cpp:68-84         */
+    rls_vec3  Rd;     /* evalProfile(r), src/rlSss.cpp:86-106   */
+    uint32_t *flags;
+} rls_profile_out;
+
+/* Probe-ray geometry of SssSampler::getProbeRay (src/rlSss.h:487-533). */
+typedef struct rls_probe_out {
+    float    *r;         /* sampled radius                        */
+    rls_vec3  origin;    /* ray.origin - sg->P (offset only)      */
+    rls_vec3  dir;       /* ray.dir                               */
+    float    *maxdist;   /* ray.maxdist = 2 sqrt(rmax^2 - r^2)    */
+    uint32_t *flags;     /* channel, exp lobe, probe axis         */
+} rls_probe_out;
+
+/* ------------------------------------------------------------ life cycle */
+/* Creates a context on CUDA device `device`.  `stream` is an existing cudaStream_t to
+ * enqueue on (NULL = the library creates its own non-blocking stream).  Fails with
+ * RLS_ERR_NO_DEVICE when no sm_100 device is usable -- there is no CPU path.
+ * Replaces the plugin entry NodeLoader (src/_PluginMain.cpp:16-47) + node_initialize. */
+int  rls_init(int device, void *stream, rls_context **out_ctx);
+int  rls_shutdown(rls_context *ctx);                      /* node_finish analogue          */
+int  rls_synchronize(rls_context *ctx);                   /* waits for the context stream  */
+const char *rls_last_error_string(const rls_context *ctx);/* ctx may be NULL: init errors  */
+int  rls_abi_version(void);
+/* Number of kernels this context has launched since creation (bench bookkeeping). */
+uint64_t rls_kernel_launch_count(const rls_context *ctx);
+/* The node names this library stands in for: "rlGgx", "rlDisney", "rlSkin"; NULL past
+ * the end -- same enumeration contract as NodeLoader(i, ...). */
+const char *rls_node_name(int i);
+
+/* -------------------------------------------------------------- rlGgx */
+/* GgxSampler ctor + evalSample (src/rlGgx.h:97-107,130-156; src/rlGgx.cpp:14-99). */
+int rls_ggx_eval_sample(rls_context *ctx, size_t n, const rls_shading_soa *sg,
+                        const rls_ggx_params *params, const float *rx, const float *ry,
+                        rls_vec3 out_wi, float *out_fresnel /* may be NULL */);
+/* GgxSampler ctor + evalBrdf at a caller-supplied indir (src/rlGgx.h:110-119,158-165). */
+int rls_ggx_eval_brdf(rls_context *ctx, size_t n, const rls_shading_soa *sg,
+                      const rls_ggx_params *params, rls_cvec3 wi, rls_vec3 out_f);
+/* GgxSampler ctor + evalPdf at a caller-supplied indir (src/rlGgx.h:121-127,72-80). */
+int rls_ggx_eval_pdf(rls_context *ctx, size_t n, const rls_shading_soa *sg,
+                     const rls_ggx_params *params, rls_cvec3 wi, float *out_pdf);
+/* The fused unit of work: ctor + evalSample + evalBrdf(L) + evalPdf(L). */
+int rls_ggx_sample_eval_pdf(rls_context *ctx, size_t n, const rls_shading_soa *sg,
+                            const rls_ggx_params *params, const float *rx, const float *ry,
+                            const rls_bsdf_out *out);
+/* Rough dielectric: reflection + refraction branches from one visible-normal sample. */
+int rls_ggx_dielectric_sample_eval_pdf(rls_context *ctx, size_t n, const rls_shading_soa *sg,
+                                       const rls_ggx_params *params, const float *rx,
+                                       const float *ry, const rls_ggx_dielectric_out *out);
+
+/* ------------------------------------------------------------ rlDisney */
+/* sample_type: RLS_RAY_DIFFUSE or RLS_RAY_GLOSSY (DisneySampler::setSampleType). */
+int rls_disney_eval_sample(rls_context *ctx, size_t n, const rls_shading_soa *sg,
+                           const rls_disney_params *params, int sample_type,
+                           const float *rx, const float *ry, rls_vec3 out_wi,
+                           uint32_t *out_flags /* may be NULL */);
+int rls_disney_eval_brdf(rls_context *ctx, size_t n, const rls_shading_soa *sg,
+                         const rls_disney_params *params, int sample_type, rls_cvec3 wi,
+                         rls_vec3 out_f);
+int rls_disney_eval_pdf(rls_context *ctx, size_t n, const rls_shading_soa *sg,
+                        const rls_disney_params *params, int sample_type, rls_cvec3 wi,
+                        float *out_pdf);
+/* Fused: ctor + glossy triple on (rx_s, ry_s) + diffuse triple on (rx_d, ry_d). */
+int rls_disney_sample_eval_pdf(rls_context *ctx, size_t n, const rls_shading_soa *sg,
+                               const rls_disney_params *params, const float *rx_s,
+                               const float *ry_s, const float *rx_d, const float *ry_d,
+                               const rls_disney_out *out);
+
+/* ------------------------------------------------- rlSss / rlSkin profile */
+/* `dist` is the already-multiplied scatter distance (src/rlSkin.cpp:236). */
+int rls_ndprofile_set_distance(rls_context *ctx, size_t n, rls_cvec3 dist, rls_cvec3 albedo,
+                               const rls_ndprofile_soa *out_profile);
+int rls_ndprofile_get_radius(rls_context *ctx, size_t n, const rls_ndprofile_soa *profile,
+                             const float *rx, float *out_r, uint32_t *out_flags /* may be NULL */);
+int rls_ndprofile_get_pdf(rls_context *ctx, size_t n, const rls_ndprofile_soa *profile,
+                          const float *r, float *out_pdf);
+int rls_ndprofile_eval_profile(rls_context *ctx, size_t n, const rls_ndprofile_soa *profile,
+                               const float *r, rls_vec3 out_rd);
+/* Fused skin-profile unit: scatterDist = sss_scatter_dist * sss_dist_multiplier,
+ * setDistance(scatterDist, sss_color), r = getRadius(rx), getPdf(r), evalProfile(r). */
+int rls_skin_profile_sample_eval_pdf(rls_context *ctx, size_t n, const rls_skin_params *params,
+                                     const float *rx, const rls_profile_out *out);
+/* rlSkin layer hand-off (src/rlSkin.cpp:204,228,231,238): from the two average Fresnel
+ * weights to the specular scale and the SSS weight. */
+int rls_skin_layer_weights(rls_context *ctx, size_t n, const rls_skin_params *params,
+                           const float *avg_fresnel_sheen, const float *avg_fresnel_specular,
+                           float *out_specular_scale, float *out_sss_weight);
+
+/* -------------------------------------------- host-buffer (end-to-end) forms */
+/* Same contracts as the device forms above but every array pointer is a HOST pointer.
+ * `chunk` = samples per staged chunk (0 = library default).  Synchronous. */
+int rls_ggx_sample_eval_pdf_host(rls_context *ctx, size_t n, const rls_shading_soa *sg,
+                                 const rls_ggx_params *params, const float *rx, const float *ry,
+                                 const rls_bsdf_out *out, size_t chunk);
+int rls_ggx_dielectric_sample_eval_pdf_host(rls_context *ctx, size_t n, const rls_shading_soa *sg,
+                                            const rls_ggx_params *params, const float *rx,
+                                            const float *ry, const rls_ggx_dielectric_out *out,
+                                            size_t chunk);
+int rls_disney_sample_eval_pdf_host(rls_context *ctx, size_t n, const rls_shading_soa *sg,
+                                    const rls_disney_params *params, const float *rx_s,
+                                    const float *ry_s, const float *rx_d, const float *ry_d,
+                                    const rls_disney_out *out, size_t chunk);
+int rls_skin_profile_sample_eval_pdf_host(rls_context *ctx, size_t n, const rls_skin_params *params,
+                                          const float *rx, const rls_profile_out *out, size_t chunk);
+/* Pinned host allocation helpers for the _host forms. */
+int rls_host_alloc(rls_context *ctx, size_t bytes, void **out_ptr);
+int rls_host_free(rls_context *ctx, void *ptr);
+
+/* --------------------------------------- directional-albedo / furnace sweep */
+/* Table cell (i_r, i_c, i_e) has roughness = lerp over [roughness_lo, roughness_hi],
+ * cos(theta_v) = (i_c + 1) / n_cos, ior = lerp over [ior_lo, ior_hi].  For sample k in
+ * [spp_begin, spp_end) of every cell the rlGgx unit is evaluated with KsColor = 1 on the
+ * canonical frame and five sums are accumulated per cell, in FP64:
+ *   [0] sum f_r / pdf_r (valid samples)   [1] sum weight_t (refracted samples)
+ *   [2] sum fresnel                       [3] valid-sample count   [4] TIR count
+ * `table` is a device array of n_rough * n_cos * n_ior * 5 doubles and is OVERWRITTEN.
+ * Sharding spp ranges across GPUs and summing the tables (NCCL all-reduce) gives the
+ * full sweep; sums are order-independent up to FP64 rounding. */
+typedef struct rls_sweep_grid {
+    int32_t n_rough, n_cos, n_ior;
+    float   roughness_lo, roughness_hi;
+    float   ior_lo, ior_hi;
+} rls_sweep_grid;
+#define RLS_SWEEP_VALUES_PER_CELL 5
+int rls_albedo_sweep(rls_context *ctx, const rls_sweep_grid *grid, uint64_t seed,
+                     uint32_t spp_begin, uint32_t spp_end, double *table);
+
+/* ------------------------------------------- synthetic workload generators */
+/* Counter-based integer hash h(seed, stream, index) -> 24-bit uniform in
+ * [2^-24, 1 - 2^-24]; out[i] = lo + (hi - lo) * u(first_index + i).  The integer part is
+ * bit-reproducible on the host (tests restate it in numpy). */
+int rls_synth_uniform(rls_context *ctx, size_t n, uint64_t seed, uint32_t stream,
+                      uint64_t first_index, float lo, float hi, float *out);
+/* Random orthonormal frames (N uniform on the sphere) and view vectors with
+ * cos(theta_v) ~ U[cos_lo, cos_hi], phi ~ U[0, 2pi) about N.  Writes the 12 arrays of
+ * `sg` (cast away const) and, if sg->backfacing != NULL, 1 with probability
+ * `backfacing_fraction`. */
+int rls_synth_shading(rls_context *ctx, size_t n, uint64_t seed, uint64_t first_index,
+                      float cos_lo, float cos_hi, float backfacing_fraction,
+                      const rls_shading_soa *sg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLS_B200_H */

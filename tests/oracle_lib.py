@@ -1,0 +1,347 @@
+"""Test-side loader for the CPU oracles (oracle/oracle_api.h) and numpy workload builders.
+
+TEST INFRASTRUCTURE: the product package never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from rlshaders_b200 import _abi as abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PORT_SO = os.path.join(ROOT, "oracle", "librls_oracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "librls_ref.so")
+REFERENCE_SRC = "/root/reference/src"
+
+f32 = np.float32
+
+
+def build_oracles():
+    """(Re)build what can be built here: always the port; the reference library only
+    where /root/reference exists (the build container)."""
+    target = ["port"]
+    if os.path.exists(os.path.join(REFERENCE_SRC, "rlGgx.h")):
+        target.append("ref")
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")] + target, check=True)
+
+
+# ----------------------------------------------------------------- numpy hash
+_M1 = np.uint64(0x9E3779B97F4A7C15)
+_M2 = np.uint64(0xD1B54A32D192ED03)
+_M3 = np.uint64(0xBF58476D1CE4E5B9)
+_M4 = np.uint64(0x94D049BB133111EB)
+
+
+def hash_uniform(n, seed, stream, first_index=0, lo=0.0, hi=1.0):
+    """numpy restatement of the synthetic generators' integer hash (oracle_common.h,
+    rlshaders_b200/csrc/rls_synth.cuh): bit-identical uniforms on host and device."""
+    with np.errstate(over="ignore"):
+        idx = np.arange(n, dtype=np.uint64) + np.uint64(first_index)
+        z = np.uint64(seed) + _M1 * (idx + np.uint64(1)) + _M2 * np.uint64(stream)
+        z = (z ^ (z >> np.uint64(30))) * _M3
+        z = (z ^ (z >> np.uint64(27))) * _M4
+        z = z ^ (z >> np.uint64(31))
+    k = (z >> np.uint64(40)).astype(np.uint32)
+    k = np.maximum(k, np.uint32(1))
+    u = k.astype(f32) * f32(2.0 ** -24)
+    return (f32(lo) + (f32(hi) - f32(lo)) * u).astype(f32)
+
+
+def make_shading(n, seed, cos_lo=0.02, cos_hi=1.0, backfacing_fraction=0.0):
+    """Random orthonormal frames + view vectors (host construction; the device
+    generator rls_synth_shading follows the same recipe but its sin/cos bits differ, so
+    parity tests always move ONE side's arrays to the other)."""
+    u1 = hash_uniform(n, seed, 10)
+    u2 = hash_uniform(n, seed, 11)
+    u3 = hash_uniform(n, seed, 12)
+    u4 = hash_uniform(n, seed, 13)
+    u5 = hash_uniform(n, seed, 14)
+    u6 = hash_uniform(n, seed, 15)
+    nz = (f32(1.0) - f32(2.0) * u1).astype(f32)
+    rn = np.sqrt(np.maximum(f32(0.0), f32(1.0) - nz * nz)).astype(f32)
+    phn = (f32(2.0 * np.pi) * u2).astype(f32)
+    N = np.stack([rn * np.cos(phn), rn * np.sin(phn), nz]).astype(f32)
+    # tangent: any vector not parallel to N, Gram-Schmidt, then rotate by a random angle
+    a = np.where(np.abs(N[0]) < 0.9, 1.0, 0.0).astype(f32)
+    A = np.stack([a, f32(1.0) - a, np.zeros(n, f32)]).astype(f32)
+    T = A - N * np.sum(A * N, axis=0, dtype=f32)
+    T = (T / np.sqrt(np.sum(T * T, axis=0, dtype=f32))).astype(f32)
+    B = np.cross(N.T, T.T).T.astype(f32)
+    pht = (f32(2.0 * np.pi) * u3).astype(f32)
+    U = (T * np.cos(pht) + B * np.sin(pht)).astype(f32)
+    U = (U / np.sqrt(np.sum(U * U, axis=0, dtype=f32))).astype(f32)
+    V = np.cross(N.T, U.T).T.astype(f32)
+    cz = (f32(cos_lo) + f32(cos_hi - cos_lo) * u4).astype(f32)
+    sr = np.sqrt(np.maximum(f32(0.0), f32(1.0) - cz * cz)).astype(f32)
+    phv = (f32(2.0 * np.pi) * u5).astype(f32)
+    wo = (U * (sr * np.cos(phv)) + V * (sr * np.sin(phv)) + N * cz).astype(f32)
+    wo = (wo / np.sqrt(np.sum(wo * wo, axis=0, dtype=f32))).astype(f32)
+    sg = {}
+    for name, M in (("U", U), ("V", V), ("N", N), ("wo", wo)):
+        for j, c in enumerate("xyz"):
+            sg[name + c] = np.ascontiguousarray(M[j], dtype=f32)
+    sg["backfacing"] = (u6 < f32(backfacing_fraction)).astype(np.uint8) if backfacing_fraction > 0 else None
+    return sg
+
+
+def shading_struct(sg):
+    return abi.shading((sg["Ux"], sg["Uy"], sg["Uz"]), (sg["Vx"], sg["Vy"], sg["Vz"]),
+                       (sg["Nx"], sg["Ny"], sg["Nz"]), (sg["wox"], sg["woy"], sg["woz"]),
+                       sg.get("backfacing"))
+
+
+def _z(n, dtype=f32):
+    return np.zeros(n, dtype=dtype)
+
+
+def _v3(n):
+    return (_z(n), _z(n), _z(n))
+
+
+def _cv3(t):
+    return abi.vec3(tuple(np.ascontiguousarray(a, dtype=f32) for a in t))
+
+
+class Oracle:
+    """ctypes front-end over one oracle library; every method returns numpy arrays."""
+
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.path = path
+        self.lib = C.CDLL(path)
+        self.lib.oracle_kind.restype = C.c_char_p
+        self.lib.oracle_max_threads.restype = C.c_int
+        self.kind = self.lib.oracle_kind().decode()
+
+    def set_threads(self, n):
+        self.lib.oracle_set_threads(C.c_int(n))
+
+    def max_threads(self):
+        return self.lib.oracle_max_threads()
+
+    # ---- rlGgx
+    def ggx_eval_sample(self, sg, params, rx, ry):
+        n = len(rx)
+        wi, F = _v3(n), _z(n)
+        self.lib.oracle_ggx_eval_sample(C.c_size_t(n), C.byref(shading_struct(sg)), C.byref(params),
+                                        C.c_void_p(rx.ctypes.data), C.c_void_p(ry.ctypes.data),
+                                        abi.vec3(wi), C.c_void_p(F.ctypes.data))
+        return dict(wi=np.stack(wi), fresnel=F)
+
+    def ggx_eval_brdf(self, sg, params, wi):
+        n = wi.shape[1]
+        f = _v3(n)
+        keep = [np.ascontiguousarray(wi[j], dtype=f32) for j in range(3)]
+        self.lib.oracle_ggx_eval_brdf(C.c_size_t(n), C.byref(shading_struct(sg)), C.byref(params),
+                                      abi.vec3(keep), abi.vec3(f))
+        return np.stack(f)
+
+    def ggx_eval_pdf(self, sg, params, wi):
+        n = wi.shape[1]
+        pdf = _z(n)
+        keep = [np.ascontiguousarray(wi[j], dtype=f32) for j in range(3)]
+        self.lib.oracle_ggx_eval_pdf(C.c_size_t(n), C.byref(shading_struct(sg)), C.byref(params),
+                                     abi.vec3(keep), C.c_void_p(pdf.ctypes.data))
+        return pdf
+
+    def ggx_sample_eval_pdf(self, sg, params, rx, ry):
+        n = len(rx)
+        wi, f, pdf, F, fl = _v3(n), _v3(n), _z(n), _z(n), _z(n, np.uint32)
+        out = abi.BsdfOut(abi.vec3(wi), abi.vec3(f), pdf.ctypes.data, F.ctypes.data, fl.ctypes.data)
+        self.lib.oracle_ggx_sample_eval_pdf(C.c_size_t(n), C.byref(shading_struct(sg)), C.byref(params),
+                                            C.c_void_p(rx.ctypes.data), C.c_void_p(ry.ctypes.data),
+                                            C.byref(out))
+        return dict(wi=np.stack(wi), f=np.stack(f), pdf=pdf, fresnel=F, flags=fl)
+
+    def ggx_dielectric(self, sg, params, rx, ry):
+        n = len(rx)
+        F, wir, fr, pr, wit, ft, wt, fl = _z(n), _v3(n), _z(n), _z(n), _v3(n), _z(n), _z(n), _z(n, np.uint32)
+        out = abi.GgxDielectricOut(F.ctypes.data, abi.vec3(wir), fr.ctypes.data, pr.ctypes.data,
+                                   abi.vec3(wit), ft.ctypes.data, wt.ctypes.data, fl.ctypes.data)
+        self.lib.oracle_ggx_dielectric_sample_eval_pdf(
+            C.c_size_t(n), C.byref(shading_struct(sg)), C.byref(params),
+            C.c_void_p(rx.ctypes.data), C.c_void_p(ry.ctypes.data), C.byref(out))
+        return dict(fresnel=F, wi_r=np.stack(wir), f_r=fr, pdf_r=pr, wi_t=np.stack(wit), f_t=ft,
+                    weight_t=wt, flags=fl)
+
+    # ---- rlDisney
+    def disney_eval_sample(self, sg, params, sample_type, rx, ry):
+        n = len(rx)
+        wi, fl = _v3(n), _z(n, np.uint32)
+        self.lib.oracle_disney_eval_sample(C.c_size_t(n), C.byref(shading_struct(sg)), C.byref(params),
+                                           C.c_int(sample_type), C.c_void_p(rx.ctypes.data),
+                                           C.c_void_p(ry.ctypes.data), abi.vec3(wi),
+                                           C.c_void_p(fl.ctypes.data))
+        return dict(wi=np.stack(wi), flags=fl)
+
+    def disney_eval_brdf(self, sg, params, sample_type, wi):
+        n = wi.shape[1]
+        f = _v3(n)
+        keep = [np.ascontiguousarray(wi[j], dtype=f32) for j in range(3)]
+        self.lib.oracle_disney_eval_brdf(C.c_size_t(n), C.byref(shading_struct(sg)), C.byref(params),
+                                         C.c_int(sample_type), abi.vec3(keep), abi.vec3(f))
+        return np.stack(f)
+
+    def disney_eval_pdf(self, sg, params, sample_type, wi):
+        n = wi.shape[1]
+        pdf = _z(n)
+        keep = [np.ascontiguousarray(wi[j], dtype=f32) for j in range(3)]
+        self.lib.oracle_disney_eval_pdf(C.c_size_t(n), C.byref(shading_struct(sg)), C.byref(params),
+                                        C.c_int(sample_type), abi.vec3(keep), C.c_void_p(pdf.ctypes.data))
+        return pdf
+
+    def disney_sample_eval_pdf(self, sg, params, rx_s, ry_s, rx_d, ry_d):
+        n = len(rx_s)
+        wis, fs, ps, wid, fd, pd, fl = _v3(n), _v3(n), _z(n), _v3(n), _v3(n), _z(n), _z(n, np.uint32)
+        out = abi.DisneyOut(abi.vec3(wis), abi.vec3(fs), ps.ctypes.data, abi.vec3(wid), abi.vec3(fd),
+                            pd.ctypes.data, fl.ctypes.data)
+        self.lib.oracle_disney_sample_eval_pdf(
+            C.c_size_t(n), C.byref(shading_struct(sg)), C.byref(params),
+            C.c_void_p(rx_s.ctypes.data), C.c_void_p(ry_s.ctypes.data),
+            C.c_void_p(rx_d.ctypes.data), C.c_void_p(ry_d.ctypes.data), C.byref(out))
+        return dict(wi_s=np.stack(wis), f_s=np.stack(fs), pdf_s=ps, wi_d=np.stack(wid),
+                    f_d=np.stack(fd), pdf_d=pd, flags=fl)
+
+    # ---- NDProfile / rlSkin
+    @staticmethod
+    def _profile_struct(prof):
+        return abi.NdProfileSoA(_cv3(prof["distance"]), _cv3(prof["C1"]), _cv3(prof["C2"]),
+                                prof["max_radius"].ctypes.data)
+
+    def ndprofile_set_distance(self, dist, albedo):
+        n = dist.shape[1]
+        d, c1, c2, R = _v3(n), _v3(n), _v3(n), _z(n)
+        out = abi.NdProfileSoA(abi.vec3(d), abi.vec3(c1), abi.vec3(c2), R.ctypes.data)
+        kd = [np.ascontiguousarray(dist[j], dtype=f32) for j in range(3)]
+        ka = [np.ascontiguousarray(albedo[j], dtype=f32) for j in range(3)]
+        self.lib.oracle_ndprofile_set_distance(C.c_size_t(n), abi.vec3(kd), abi.vec3(ka), C.byref(out))
+        return dict(distance=np.stack(d), C1=np.stack(c1), C2=np.stack(c2), max_radius=R)
+
+    def ndprofile_get_radius(self, prof, rx):
+        n = len(rx)
+        r, fl = _z(n), _z(n, np.uint32)
+        keep = {k: (np.ascontiguousarray(v) if v.ndim == 1 else [np.ascontiguousarray(v[j]) for j in range(3)])
+                for k, v in prof.items()}
+        s = abi.NdProfileSoA(abi.vec3(keep["distance"]), abi.vec3(keep["C1"]), abi.vec3(keep["C2"]),
+                             keep["max_radius"].ctypes.data)
+        self.lib.oracle_ndprofile_get_radius(C.c_size_t(n), C.byref(s), C.c_void_p(rx.ctypes.data),
+                                             C.c_void_p(r.ctypes.data), C.c_void_p(fl.ctypes.data))
+        return dict(r=r, flags=fl)
+
+    def ndprofile_get_pdf(self, prof, r):
+        n = len(r)
+        pdf = _z(n)
+        keep = {k: (np.ascontiguousarray(v) if v.ndim == 1 else [np.ascontiguousarray(v[j]) for j in range(3)])
+                for k, v in prof.items()}
+        s = abi.NdProfileSoA(abi.vec3(keep["distance"]), abi.vec3(keep["C1"]), abi.vec3(keep["C2"]),
+                             keep["max_radius"].ctypes.data)
+        self.lib.oracle_ndprofile_get_pdf(C.c_size_t(n), C.byref(s), C.c_void_p(r.ctypes.data),
+                                          C.c_void_p(pdf.ctypes.data))
+        return pdf
+
+    def ndprofile_eval_profile(self, prof, r):
+        n = len(r)
+        rd = _v3(n)
+        keep = {k: (np.ascontiguousarray(v) if v.ndim == 1 else [np.ascontiguousarray(v[j]) for j in range(3)])
+                for k, v in prof.items()}
+        s = abi.NdProfileSoA(abi.vec3(keep["distance"]), abi.vec3(keep["C1"]), abi.vec3(keep["C2"]),
+                             keep["max_radius"].ctypes.data)
+        self.lib.oracle_ndprofile_eval_profile(C.c_size_t(n), C.byref(s), C.c_void_p(r.ctypes.data),
+                                               abi.vec3(rd))
+        return np.stack(rd)
+
+    def skin_profile(self, params, rx):
+        n = len(rx)
+        r, pdf, rd, fl = _z(n), _z(n), _v3(n), _z(n, np.uint32)
+        out = abi.ProfileOut(r.ctypes.data, pdf.ctypes.data, abi.vec3(rd), fl.ctypes.data)
+        self.lib.oracle_skin_profile_sample_eval_pdf(C.c_size_t(n), C.byref(params),
+                                                     C.c_void_p(rx.ctypes.data), C.byref(out))
+        return dict(r=r, pdf=pdf, Rd=np.stack(rd), flags=fl)
+
+    def skin_layer_weights(self, params, avg_f_sheen, avg_f_spec):
+        n = len(avg_f_sheen)
+        a, b = _z(n), _z(n)
+        self.lib.oracle_skin_layer_weights(C.c_size_t(n), C.byref(params),
+                                           C.c_void_p(avg_f_sheen.ctypes.data),
+                                           C.c_void_p(avg_f_spec.ctypes.data),
+                                           C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data))
+        return dict(specular_scale=a, sss_weight=b)
+
+    def skin_probe_ray(self, sg, params, rx, ry):
+        n = len(rx)
+        r, o, d, md, fl = _z(n), _v3(n), _v3(n), _z(n), _z(n, np.uint32)
+        out = abi.ProbeOut(r.ctypes.data, abi.vec3(o), abi.vec3(d), md.ctypes.data, fl.ctypes.data)
+        self.lib.oracle_skin_probe_ray(C.c_size_t(n), C.byref(shading_struct(sg)), C.byref(params),
+                                       C.c_void_p(rx.ctypes.data), C.c_void_p(ry.ctypes.data),
+                                       C.byref(out))
+        return dict(r=r, origin=np.stack(o), dir=np.stack(d), maxdist=md, flags=fl)
+
+    def albedo_sweep(self, grid, seed, spp_begin, spp_end):
+        cells = grid.n_rough * grid.n_cos * grid.n_ior
+        table = np.zeros((cells, abi.SWEEP_VALUES_PER_CELL), dtype=np.float64)
+        self.lib.oracle_albedo_sweep(C.byref(grid), C.c_uint64(seed), C.c_uint32(spp_begin),
+                                     C.c_uint32(spp_end), C.c_void_p(table.ctypes.data))
+        return table
+
+    def synth_uniform(self, n, seed, stream, first_index=0, lo=0.0, hi=1.0):
+        out = _z(n)
+        self.lib.oracle_synth_uniform(C.c_size_t(n), C.c_uint64(seed), C.c_uint32(stream),
+                                      C.c_uint64(first_index), C.c_float(lo), C.c_float(hi),
+                                      C.c_void_p(out.ctypes.data))
+        return out
+
+
+def load_port():
+    if not os.path.exists(PORT_SO):
+        build_oracles()
+    return Oracle(PORT_SO)
+
+
+def load_ref():
+    """The reference library, or None when it has not been built (no /root/reference
+    and no prebuilt .so shipped)."""
+    if not os.path.exists(REF_SO) and os.path.exists(os.path.join(REFERENCE_SRC, "rlGgx.h")):
+        build_oracles()
+    return Oracle(REF_SO) if os.path.exists(REF_SO) else None
+
+
+# ------------------------------------------------ BASELINE.json workload recipes
+def workload_ggx_conductor(n, seed=0x5EED0001):
+    """Config 1: gold fixture (testsuite/mtoa/0002/data/ggx_gold.ass:17-21)."""
+    sg = make_shading(n, seed)
+    rx, ry = hash_uniform(n, seed, 0), hash_uniform(n, seed, 1)
+    return sg, abi.ggx_params(KsColor=(1.0, 1.0, 1.0), specularRoughness=0.3, ior=0.47, anisotropic=0.0), rx, ry
+
+
+def workload_ggx_dielectric(n, seed=0x5EED0002, aniso=False):
+    """Config 2: per-sample roughness ~U[0.05,1], ior ~U[1.05,2.5], 25% back-facing."""
+    sg = make_shading(n, seed, backfacing_fraction=0.25)
+    rx, ry = hash_uniform(n, seed, 0), hash_uniform(n, seed, 1)
+    rough = hash_uniform(n, seed, 2, lo=0.05, hi=1.0)
+    ior = hash_uniform(n, seed, 3, lo=1.05, hi=2.5)
+    kw = dict(specularRoughness=rough, ior=ior)
+    if aniso:
+        kw["anisotropic"] = hash_uniform(n, seed, 4)
+    return sg, abi.ggx_params(**kw), rx, ry
+
+
+def workload_disney(n, seed=0x5EED0003):
+    """Config 3: every parameter spatially varying in [0,1]."""
+    sg = make_shading(n, seed)
+    u = [hash_uniform(n, seed, s) for s in range(4)]
+    names = ["subsurface", "metallic", "specular", "specular_tint", "roughness", "anisotropic",
+             "sheen", "sheen_tint", "clearcoat", "clearcoat_gloss"]
+    kw = {nm: hash_uniform(n, seed, 20 + j) for j, nm in enumerate(names)}
+    kw["base_color"] = tuple(hash_uniform(n, seed, 30 + j) for j in range(3))
+    return sg, abi.disney_params(**kw), u
+
+
+def workload_skin(n, seed=0x5EED0004):
+    """Config 4: sss_color ~U[0.05,1]^3, sss_scatter_dist ~U[0.05,2]^3, multiplier 1."""
+    rx = hash_uniform(n, seed, 0)
+    color = tuple(hash_uniform(n, seed, 40 + j, lo=0.05, hi=1.0) for j in range(3))
+    dist = tuple(hash_uniform(n, seed, 50 + j, lo=0.05, hi=2.0) for j in range(3))
+    return abi.skin_params(sss_color=color, sss_scatter_dist=dist, sss_dist_multiplier=1.0), rx
