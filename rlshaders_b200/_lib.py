@@ -1,0 +1,95 @@
+"""Loads rlshaders_b200/librls_b200.so (the hand-written CUDA library behind
+include/rls_b200.h) and declares its C ABI for ctypes.
+
+There is no fallback: a missing library raises ImportError from `load()`, and
+`rls_init` itself fails when no sm_100 device is present.
+"""
+import ctypes as C
+import os
+
+from . import _abi as abi
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "librls_b200.so")
+
+# Every extern "C" symbol include/rls_b200.h declares (tests check the export list).
+SYMBOLS = [
+    "rls_init", "rls_shutdown", "rls_synchronize", "rls_last_error_string", "rls_abi_version",
+    "rls_kernel_launch_count", "rls_node_name",
+    "rls_ggx_eval_sample", "rls_ggx_eval_brdf", "rls_ggx_eval_pdf", "rls_ggx_sample_eval_pdf",
+    "rls_ggx_dielectric_sample_eval_pdf",
+    "rls_disney_eval_sample", "rls_disney_eval_brdf", "rls_disney_eval_pdf",
+    "rls_disney_sample_eval_pdf",
+    "rls_ndprofile_set_distance", "rls_ndprofile_get_radius", "rls_ndprofile_get_pdf",
+    "rls_ndprofile_eval_profile", "rls_skin_profile_sample_eval_pdf", "rls_skin_layer_weights",
+    "rls_ggx_sample_eval_pdf_host", "rls_ggx_dielectric_sample_eval_pdf_host",
+    "rls_disney_sample_eval_pdf_host", "rls_skin_profile_sample_eval_pdf_host",
+    "rls_host_alloc", "rls_host_free",
+    "rls_albedo_sweep", "rls_synth_uniform", "rls_synth_shading",
+]
+
+_lib = None
+
+
+def load():
+    """Return the ctypes handle, loading it on first use.  Raises ImportError (never
+    falls back) when the CUDA library has not been built -- run __graft_entry__.build()."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension is not built "
+            "(python -c 'import __graft_entry__ as g; g.build()'). rlshaders_b200 has no CPU path.")
+    lib = C.CDLL(LIB_PATH)
+    vp, sz, u64, u32, i32, f = C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int, C.c_float
+    P = C.POINTER
+    sig = {
+        "rls_init": [i32, vp, P(vp)],
+        "rls_shutdown": [vp],
+        "rls_synchronize": [vp],
+        "rls_ggx_eval_sample": [vp, sz, P(abi.ShadingSoA), P(abi.GgxParams), vp, vp, abi.Vec3, vp],
+        "rls_ggx_eval_brdf": [vp, sz, P(abi.ShadingSoA), P(abi.GgxParams), abi.CVec3, abi.Vec3],
+        "rls_ggx_eval_pdf": [vp, sz, P(abi.ShadingSoA), P(abi.GgxParams), abi.CVec3, vp],
+        "rls_ggx_sample_eval_pdf": [vp, sz, P(abi.ShadingSoA), P(abi.GgxParams), vp, vp, P(abi.BsdfOut)],
+        "rls_ggx_dielectric_sample_eval_pdf": [vp, sz, P(abi.ShadingSoA), P(abi.GgxParams), vp, vp,
+                                               P(abi.GgxDielectricOut)],
+        "rls_disney_eval_sample": [vp, sz, P(abi.ShadingSoA), P(abi.DisneyParams), i32, vp, vp, abi.Vec3, vp],
+        "rls_disney_eval_brdf": [vp, sz, P(abi.ShadingSoA), P(abi.DisneyParams), i32, abi.CVec3, abi.Vec3],
+        "rls_disney_eval_pdf": [vp, sz, P(abi.ShadingSoA), P(abi.DisneyParams), i32, abi.CVec3, vp],
+        "rls_disney_sample_eval_pdf": [vp, sz, P(abi.ShadingSoA), P(abi.DisneyParams), vp, vp, vp, vp,
+                                       P(abi.DisneyOut)],
+        "rls_ndprofile_set_distance": [vp, sz, abi.CVec3, abi.CVec3, P(abi.NdProfileSoA)],
+        "rls_ndprofile_get_radius": [vp, sz, P(abi.NdProfileSoA), vp, vp, vp],
+        "rls_ndprofile_get_pdf": [vp, sz, P(abi.NdProfileSoA), vp, vp],
+        "rls_ndprofile_eval_profile": [vp, sz, P(abi.NdProfileSoA), vp, abi.Vec3],
+        "rls_skin_profile_sample_eval_pdf": [vp, sz, P(abi.SkinParams), vp, P(abi.ProfileOut)],
+        "rls_skin_layer_weights": [vp, sz, P(abi.SkinParams), vp, vp, vp, vp],
+        "rls_ggx_sample_eval_pdf_host": [vp, sz, P(abi.ShadingSoA), P(abi.GgxParams), vp, vp,
+                                         P(abi.BsdfOut), sz],
+        "rls_ggx_dielectric_sample_eval_pdf_host": [vp, sz, P(abi.ShadingSoA), P(abi.GgxParams), vp, vp,
+                                                    P(abi.GgxDielectricOut), sz],
+        "rls_disney_sample_eval_pdf_host": [vp, sz, P(abi.ShadingSoA), P(abi.DisneyParams), vp, vp, vp, vp,
+                                            P(abi.DisneyOut), sz],
+        "rls_skin_profile_sample_eval_pdf_host": [vp, sz, P(abi.SkinParams), vp, P(abi.ProfileOut), sz],
+        "rls_host_alloc": [vp, sz, P(vp)],
+        "rls_host_free": [vp, vp],
+        "rls_albedo_sweep": [vp, P(abi.SweepGrid), u64, u32, u32, vp],
+        "rls_synth_uniform": [vp, sz, u64, u32, u64, f, f, vp],
+        "rls_synth_shading": [vp, sz, u64, u64, f, f, f, P(abi.ShadingSoA)],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.rls_last_error_string.argtypes = [vp]
+    lib.rls_last_error_string.restype = C.c_char_p
+    lib.rls_abi_version.argtypes = []
+    lib.rls_abi_version.restype = C.c_int
+    lib.rls_kernel_launch_count.argtypes = [vp]
+    lib.rls_kernel_launch_count.restype = C.c_uint64
+    lib.rls_node_name.argtypes = [i32]
+    lib.rls_node_name.restype = C.c_char_p
+    if lib.rls_abi_version() != abi.ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.rls_abi_version()} != {abi.ABI_VERSION}")
+    _lib = lib
+    return lib

@@ -1,0 +1,367 @@
+"""Host-side mirror of the reference's sampler interface over the C ABI.
+
+The reference hands Arnold three callbacks per sampler object -- evalSample(rx, ry),
+evalBrdf(indir), evalPdf(indir) (src/rlGgx.h:97-127, src/rlDisney.cpp:109-152) -- on a
+sampler constructed per shading point from AtShaderGlobals + node parameters.  Here the
+same names operate on BATCHES: a sampler object is constructed from a `ShadingBatch`
+(one shading frame + view vector per sample) and node parameters that are either
+uniform scalars or per-sample arrays, and every call processes the whole batch on the
+GPU through librls_b200.so.
+
+torch is used for device memory and streams only.  Tensors on a CUDA device go to the
+device entry points (asynchronous on the context's stream); pinned CPU tensors go to the
+`*_host` entry points (chunked H2D -> kernel -> D2H pipeline, synchronous).
+"""
+import ctypes as C
+
+import torch
+
+from . import _abi as abi
+from ._lib import load
+
+
+class RlsError(RuntimeError):
+    pass
+
+
+def _check(ctx_handle, rc, lib):
+    if rc != abi.RLS_OK:
+        msg = lib.rls_last_error_string(ctx_handle)
+        raise RlsError(f"rls error {rc}: {msg.decode() if msg else ''}")
+
+
+class Context:
+    """Owns one rls_context bound to a CUDA device and a stream (default: torch's current
+    stream on that device, so torch.cuda.Event timing sees the kernels)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load()
+        self.index = int(device if not isinstance(device, torch.device) else (device.index or 0))
+        handle = C.c_void_p()
+        if stream is None and torch.cuda.is_available():
+            stream = torch.cuda.current_stream(self.index)
+        self.stream = stream
+        raw = C.c_void_p(stream.cuda_stream) if stream is not None else None
+        rc = self.lib.rls_init(self.index, raw, C.byref(handle))
+        if rc != abi.RLS_OK:
+            msg = self.lib.rls_last_error_string(None)
+            raise RlsError(f"rls_init failed ({rc}): {msg.decode() if msg else ''}")
+        self.handle = handle
+        self.device = torch.device("cuda", self.index)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.rls_shutdown(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        _check(self.handle, self.lib.rls_synchronize(self.handle), self.lib)
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.rls_kernel_launch_count(self.handle))
+
+    # ---- allocation helpers -------------------------------------------------
+    def empty(self, *shape, dtype=torch.float32, like=None):
+        if like is not None and like.device.type == "cpu":
+            return torch.empty(*shape, dtype=dtype, pin_memory=True)
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    # ---- synthetic workload generators --------------------------------------
+    def synth_uniform(self, n, seed, stream, first_index=0, lo=0.0, hi=1.0, out=None):
+        out = self.empty(n) if out is None else out
+        _check(self.handle, self.lib.rls_synth_uniform(self.handle, n, seed, stream, first_index,
+                                                       lo, hi, out.data_ptr()), self.lib)
+        return out
+
+    def synth_shading(self, n, seed, first_index=0, cos_lo=0.02, cos_hi=1.0, backfacing_fraction=0.0):
+        sg = ShadingBatch(self.empty(3, n), self.empty(3, n), self.empty(3, n), self.empty(3, n),
+                          self.empty(n, dtype=torch.uint8) if backfacing_fraction > 0 else None)
+        _check(self.handle, self.lib.rls_synth_shading(self.handle, n, seed, first_index, cos_lo, cos_hi,
+                                                       backfacing_fraction, C.byref(sg.struct)), self.lib)
+        return sg
+
+    # ---- albedo sweep ----------------------------------------------------------
+    def albedo_sweep(self, grid, seed, spp_begin, spp_end, out=None):
+        cells = grid.n_rough * grid.n_cos * grid.n_ior
+        if out is None:
+            out = torch.empty(cells, abi.SWEEP_VALUES_PER_CELL, dtype=torch.float64, device=self.device)
+        _check(self.handle, self.lib.rls_albedo_sweep(self.handle, C.byref(grid), seed, spp_begin, spp_end,
+                                                      out.data_ptr()), self.lib)
+        return out
+
+
+def _f32rows(t, name):
+    if t.dtype != torch.float32 or t.dim() != 2 or t.shape[0] != 3 or not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous float32 tensor of shape [3, n]")
+    return (t[0], t[1], t[2])
+
+
+def _f32(t, name, n=None):
+    if t.dtype != torch.float32 or t.dim() != 1 or not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous float32 tensor of shape [n]")
+    if n is not None and t.shape[0] != n:
+        raise ValueError(f"{name}: expected {n} samples, got {t.shape[0]}")
+    return t
+
+
+class ShadingBatch:
+    """The AtShaderGlobals fields the path reads, one per sample: frame (U, V, N = sg->Nf),
+    view direction wo = -sg->Rd, optional `backfacing` (sg->N == -sg->Nf).  [3, n] tensors."""
+
+    def __init__(self, U, V, N, wo, backfacing=None):
+        self.U, self.V, self.N, self.wo, self.backfacing = U, V, N, wo, backfacing
+        self.n = U.shape[1]
+        self.on_host = U.device.type == "cpu"
+        self.struct = abi.shading(_f32rows(U, "U"), _f32rows(V, "V"), _f32rows(N, "N"),
+                                  _f32rows(wo, "wo"), backfacing)
+
+    @classmethod
+    def from_numpy(cls, sg, device=None, pin=False):
+        """From the dict-of-arrays form used by the tests (keys Ux..woz, backfacing)."""
+        import numpy as np
+
+        def mk(prefix):
+            t = torch.from_numpy(np.stack([sg[prefix + c] for c in "xyz"]))
+            if device is not None:
+                return t.to(device)
+            return t.pin_memory() if pin else t
+        bf = sg.get("backfacing")
+        if bf is not None:
+            bf = torch.from_numpy(bf)
+            bf = bf.to(device) if device is not None else (bf.pin_memory() if pin else bf)
+        return cls(mk("U"), mk("V"), mk("N"), mk("wo"), bf)
+
+
+def _param(v):
+    """Node-parameter value -> what _abi.param1/param3 accept (scalars stay uniform)."""
+    return v
+
+
+class GgxSampler:
+    """Batched rls::GgxSampler (src/rlGgx.h:92-375).  Constructor arguments follow the
+    reference ctor (sg, specColor, ior, roughness, anisotropic) under their node-parameter
+    names (src/rlGgx.cpp:172-186); each is a scalar or a per-sample tensor."""
+
+    def __init__(self, ctx, sg, KsColor=(1.0, 1.0, 1.0), ior=1.0, specularRoughness=0.0, anisotropic=0.0,
+                 **ignored_node_params):
+        self.ctx, self.sg = ctx, sg
+        self.params = abi.ggx_params(KsColor=KsColor, ior=ior, specularRoughness=specularRoughness,
+                                     anisotropic=anisotropic, **ignored_node_params)
+
+    def evalSample(self, rx, ry, want_fresnel=True):
+        n, c = self.sg.n, self.ctx
+        wi = c.empty(3, n, like=rx)
+        F = c.empty(n, like=rx) if want_fresnel else None
+        _check(c.handle, c.lib.rls_ggx_eval_sample(
+            c.handle, n, C.byref(self.sg.struct), C.byref(self.params), _f32(rx, "rx", n).data_ptr(),
+            _f32(ry, "ry", n).data_ptr(), abi.vec3(_f32rows(wi, "wi")), F.data_ptr() if F is not None else None), c.lib)
+        return wi, F
+
+    def evalBrdf(self, wi):
+        n, c = self.sg.n, self.ctx
+        f = c.empty(3, n, like=wi)
+        _check(c.handle, c.lib.rls_ggx_eval_brdf(c.handle, n, C.byref(self.sg.struct), C.byref(self.params),
+                                                 abi.vec3(_f32rows(wi, "wi")), abi.vec3(_f32rows(f, "f"))), c.lib)
+        return f
+
+    def evalPdf(self, wi):
+        n, c = self.sg.n, self.ctx
+        pdf = c.empty(n, like=wi)
+        _check(c.handle, c.lib.rls_ggx_eval_pdf(c.handle, n, C.byref(self.sg.struct), C.byref(self.params),
+                                                abi.vec3(_f32rows(wi, "wi")), pdf.data_ptr()), c.lib)
+        return pdf
+
+    def alloc_out(self, like, want_fresnel=True):
+        n, c = self.sg.n, self.ctx
+        return dict(wi=c.empty(3, n, like=like), f=c.empty(3, n, like=like), pdf=c.empty(n, like=like),
+                    fresnel=c.empty(n, like=like) if want_fresnel else None,
+                    flags=c.empty(n, dtype=torch.int32, like=like))
+
+    def sampleEvalPdf(self, rx, ry, out=None, want_fresnel=True, chunk=0):
+        """The fused unit of work: ctor + evalSample + evalBrdf(L) + evalPdf(L)."""
+        n, c = self.sg.n, self.ctx
+        out = self.alloc_out(rx, want_fresnel) if out is None else out
+        o = abi.BsdfOut(abi.vec3(_f32rows(out["wi"], "wi")), abi.vec3(_f32rows(out["f"], "f")),
+                        out["pdf"].data_ptr(), out["fresnel"].data_ptr() if out.get("fresnel") is not None else None,
+                        out["flags"].data_ptr())
+        args = (c.handle, n, C.byref(self.sg.struct), C.byref(self.params), _f32(rx, "rx", n).data_ptr(),
+                _f32(ry, "ry", n).data_ptr(), C.byref(o))
+        if self.sg.on_host:
+            _check(c.handle, c.lib.rls_ggx_sample_eval_pdf_host(*args, chunk), c.lib)
+        else:
+            _check(c.handle, c.lib.rls_ggx_sample_eval_pdf(*args), c.lib)
+        return out
+
+    def alloc_dielectric_out(self, like):
+        n, c = self.sg.n, self.ctx
+        e = lambda *s, **k: c.empty(*s, like=like, **k)   # noqa: E731
+        return dict(fresnel=e(n), wi_r=e(3, n), f_r=e(n), pdf_r=e(n), wi_t=e(3, n), f_t=e(n), weight_t=e(n),
+                    flags=e(n, dtype=torch.int32))
+
+    def dielectricSampleEvalPdf(self, rx, ry, out=None, chunk=0):
+        """Rough dielectric (Walter'07): one visible-normal sample, reflection AND
+        refraction branches (src/rlGgx.h:228-243, 277-328)."""
+        n, c = self.sg.n, self.ctx
+        out = self.alloc_dielectric_out(rx) if out is None else out
+        o = abi.GgxDielectricOut(out["fresnel"].data_ptr(), abi.vec3(_f32rows(out["wi_r"], "wi_r")),
+                                 out["f_r"].data_ptr(), out["pdf_r"].data_ptr(),
+                                 abi.vec3(_f32rows(out["wi_t"], "wi_t")), out["f_t"].data_ptr(),
+                                 out["weight_t"].data_ptr(), out["flags"].data_ptr())
+        args = (c.handle, n, C.byref(self.sg.struct), C.byref(self.params), _f32(rx, "rx", n).data_ptr(),
+                _f32(ry, "ry", n).data_ptr(), C.byref(o))
+        if self.sg.on_host:
+            _check(c.handle, c.lib.rls_ggx_dielectric_sample_eval_pdf_host(*args, chunk), c.lib)
+        else:
+            _check(c.handle, c.lib.rls_ggx_dielectric_sample_eval_pdf(*args), c.lib)
+        return out
+
+
+class DisneySampler:
+    """Batched DisneySampler (src/rlDisney.cpp:105-602).  Node parameters by name
+    (src/rlDisney.cpp:606-610); setSampleType mirrors :194."""
+
+    def __init__(self, ctx, sg, **node_params):
+        self.ctx, self.sg = ctx, sg
+        self.params = abi.disney_params(**node_params)
+        self.sample_type = abi.RLS_RAY_GLOSSY
+
+    def setSampleType(self, sample_type):
+        if sample_type not in (abi.RLS_RAY_DIFFUSE, abi.RLS_RAY_GLOSSY):
+            raise ValueError("sample type must be RLS_RAY_DIFFUSE or RLS_RAY_GLOSSY")
+        self.sample_type = sample_type
+
+    def evalSample(self, rx, ry):
+        n, c = self.sg.n, self.ctx
+        wi = c.empty(3, n, like=rx)
+        flags = c.empty(n, dtype=torch.int32, like=rx)
+        _check(c.handle, c.lib.rls_disney_eval_sample(
+            c.handle, n, C.byref(self.sg.struct), C.byref(self.params), self.sample_type,
+            _f32(rx, "rx", n).data_ptr(), _f32(ry, "ry", n).data_ptr(), abi.vec3(_f32rows(wi, "wi")),
+            flags.data_ptr()), c.lib)
+        return wi, flags
+
+    def evalBrdf(self, wi):
+        n, c = self.sg.n, self.ctx
+        f = c.empty(3, n, like=wi)
+        _check(c.handle, c.lib.rls_disney_eval_brdf(c.handle, n, C.byref(self.sg.struct), C.byref(self.params),
+                                                    self.sample_type, abi.vec3(_f32rows(wi, "wi")),
+                                                    abi.vec3(_f32rows(f, "f"))), c.lib)
+        return f
+
+    def evalPdf(self, wi):
+        n, c = self.sg.n, self.ctx
+        pdf = c.empty(n, like=wi)
+        _check(c.handle, c.lib.rls_disney_eval_pdf(c.handle, n, C.byref(self.sg.struct), C.byref(self.params),
+                                                   self.sample_type, abi.vec3(_f32rows(wi, "wi")),
+                                                   pdf.data_ptr()), c.lib)
+        return pdf
+
+    def alloc_out(self, like):
+        n, c = self.sg.n, self.ctx
+        e = lambda *s, **k: c.empty(*s, like=like, **k)   # noqa: E731
+        return dict(wi_s=e(3, n), f_s=e(3, n), pdf_s=e(n), wi_d=e(3, n), f_d=e(3, n), pdf_d=e(n),
+                    flags=e(n, dtype=torch.int32))
+
+    def sampleEvalPdf(self, rx_s, ry_s, rx_d, ry_d, out=None, chunk=0):
+        """Fused: ctor + glossy triple on (rx_s, ry_s) + diffuse triple on (rx_d, ry_d)."""
+        n, c = self.sg.n, self.ctx
+        out = self.alloc_out(rx_s) if out is None else out
+        o = abi.DisneyOut(abi.vec3(_f32rows(out["wi_s"], "wi_s")), abi.vec3(_f32rows(out["f_s"], "f_s")),
+                          out["pdf_s"].data_ptr(), abi.vec3(_f32rows(out["wi_d"], "wi_d")),
+                          abi.vec3(_f32rows(out["f_d"], "f_d")), out["pdf_d"].data_ptr(), out["flags"].data_ptr())
+        args = (c.handle, n, C.byref(self.sg.struct), C.byref(self.params), _f32(rx_s, "rx_s", n).data_ptr(),
+                _f32(ry_s, "ry_s", n).data_ptr(), _f32(rx_d, "rx_d", n).data_ptr(),
+                _f32(ry_d, "ry_d", n).data_ptr(), C.byref(o))
+        if self.sg.on_host:
+            _check(c.handle, c.lib.rls_disney_sample_eval_pdf_host(*args, chunk), c.lib)
+        else:
+            _check(c.handle, c.lib.rls_disney_sample_eval_pdf(*args), c.lib)
+        return out
+
+
+class NDProfile:
+    """Batched rls::NDProfile (src/rlSss.h:27-61, src/rlSss.cpp:20-106)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.state = None
+
+    def setDistance(self, dist, albedo):
+        n, c = dist.shape[1], self.ctx
+        self.n = n
+        self.state = dict(distance=c.empty(3, n), C1=c.empty(3, n), C2=c.empty(3, n), max_radius=c.empty(n))
+        self._struct = abi.NdProfileSoA(abi.vec3(_f32rows(self.state["distance"], "distance")),
+                                        abi.vec3(_f32rows(self.state["C1"], "C1")),
+                                        abi.vec3(_f32rows(self.state["C2"], "C2")),
+                                        self.state["max_radius"].data_ptr())
+        _check(c.handle, c.lib.rls_ndprofile_set_distance(c.handle, n, abi.vec3(_f32rows(dist, "dist")),
+                                                          abi.vec3(_f32rows(albedo, "albedo")),
+                                                          C.byref(self._struct)), c.lib)
+        return self.state
+
+    def maxRadius(self):
+        return self.state["max_radius"]
+
+    def getRadius(self, rx):
+        c = self.ctx
+        r, fl = c.empty(self.n), c.empty(self.n, dtype=torch.int32)
+        _check(c.handle, c.lib.rls_ndprofile_get_radius(c.handle, self.n, C.byref(self._struct),
+                                                        _f32(rx, "rx", self.n).data_ptr(), r.data_ptr(),
+                                                        fl.data_ptr()), c.lib)
+        return r, fl
+
+    def getPdf(self, r):
+        c = self.ctx
+        pdf = c.empty(self.n)
+        _check(c.handle, c.lib.rls_ndprofile_get_pdf(c.handle, self.n, C.byref(self._struct),
+                                                     _f32(r, "r", self.n).data_ptr(), pdf.data_ptr()), c.lib)
+        return pdf
+
+    def evalProfile(self, r):
+        c = self.ctx
+        rd = c.empty(3, self.n)
+        _check(c.handle, c.lib.rls_ndprofile_eval_profile(c.handle, self.n, C.byref(self._struct),
+                                                          _f32(r, "r", self.n).data_ptr(),
+                                                          abi.vec3(_f32rows(rd, "rd"))), c.lib)
+        return rd
+
+
+class SkinProfile:
+    """The rlSkin diffusion-profile unit (src/rlSkin.cpp:234-241 + NDProfile): node
+    parameters by name (src/rlSkin.cpp:109-131)."""
+
+    def __init__(self, ctx, n, **node_params):
+        self.ctx, self.n = ctx, n
+        self.params = abi.skin_params(**node_params)
+
+    def alloc_out(self, like):
+        c, n = self.ctx, self.n
+        return dict(r=c.empty(n, like=like), pdf=c.empty(n, like=like), Rd=c.empty(3, n, like=like),
+                    flags=c.empty(n, dtype=torch.int32, like=like))
+
+    def sampleEvalPdf(self, rx, out=None, chunk=0):
+        c, n = self.ctx, self.n
+        out = self.alloc_out(rx) if out is None else out
+        o = abi.ProfileOut(out["r"].data_ptr(), out["pdf"].data_ptr(), abi.vec3(_f32rows(out["Rd"], "Rd")),
+                           out["flags"].data_ptr())
+        args = (c.handle, n, C.byref(self.params), _f32(rx, "rx", n).data_ptr(), C.byref(o))
+        if rx.device.type == "cpu":
+            _check(c.handle, c.lib.rls_skin_profile_sample_eval_pdf_host(*args, chunk), c.lib)
+        else:
+            _check(c.handle, c.lib.rls_skin_profile_sample_eval_pdf(*args), c.lib)
+        return out
+
+    def layerWeights(self, avg_fresnel_sheen, avg_fresnel_specular):
+        c, n = self.ctx, self.n
+        a, b = c.empty(n), c.empty(n)
+        _check(c.handle, c.lib.rls_skin_layer_weights(c.handle, n, C.byref(self.params),
+                                                      avg_fresnel_sheen.data_ptr(), avg_fresnel_specular.data_ptr(),
+                                                      a.data_ptr(), b.data_ptr()), c.lib)
+        return a, b

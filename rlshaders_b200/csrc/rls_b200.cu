@@ -1,0 +1,978 @@
+// rls_b200.cu -- kernels and C ABI (include/rls_b200.h) of the B200-native rlShaders BSDF path.
+//
+// Build (see __graft_entry__.build):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+//        -Xcompiler -fPIC -shared -o rlshaders_b200/librls_b200.so rls_b200.cu
+//
+// Layout: one thread = one shading sample; all per-sample state lives in registers; inputs
+// and outputs are structure-of-arrays so that a warp's 32 loads/stores of one component are
+// one fully coalesced 128-byte line.  There is no CPU path in this library.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <new>
+
+#include "../../include/rls_b200.h"
+#include "rls_math.cuh"
+#include "rls_libm.cuh"
+#include "rls_ggx.cuh"
+#include "rls_disney.cuh"
+#include "rls_profile.cuh"
+
+using namespace rls;
+
+// ============================================================== context
+static constexpr int kStages = 3;          // host-staging pipeline depth
+static constexpr int kBlock = 256;
+
+struct rls_context {
+    int          device = 0;
+    cudaStream_t stream = nullptr;
+    bool         own_stream = false;
+    std::string  err;
+    uint64_t     launches = 0;
+    // host-staging resources (lazily created by the *_host entry points)
+    cudaStream_t stage_stream[kStages] = { nullptr, nullptr, nullptr };
+    cudaEvent_t  stage_done[kStages] = { nullptr, nullptr, nullptr };
+    void        *stage_buf[kStages] = { nullptr, nullptr, nullptr };
+    size_t       stage_bytes = 0;
+};
+
+static thread_local std::string g_init_error;
+
+static int fail(rls_context *ctx, int code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg; else g_init_error = msg;
+    return code;
+}
+static int cuda_fail(rls_context *ctx, cudaError_t e, const char *what)
+{
+    return fail(ctx, e == cudaErrorMemoryAllocation ? RLS_ERR_OUT_OF_MEMORY : RLS_ERR_CUDA,
+                std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define RLS_CUDA(ctx, call)                                            \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+extern "C" int rls_abi_version(void) { return RLS_B200_ABI_VERSION; }
+
+extern "C" const char *rls_node_name(int i)
+{
+    static const char *names[] = { "rlGgx", "rlDisney", "rlSkin" };   // src/_PluginMain.cpp:8-13
+    return (i >= 0 && i < 3) ? names[i] : nullptr;
+}
+
+extern "C" int rls_init(int device, void *stream, rls_context **out_ctx)
+{
+    if (!out_ctx) return fail(nullptr, RLS_ERR_INVALID_ARGUMENT, "rls_init: out_ctx is NULL");
+    *out_ctx = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, RLS_ERR_NO_DEVICE, std::string("rls_init: no CUDA device (") +
+                    cudaGetErrorString(e) + "); this library has no CPU path");
+    if (device < 0 || device >= count)
+        return fail(nullptr, RLS_ERR_INVALID_ARGUMENT, "rls_init: device index out of range");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return fail(nullptr, RLS_ERR_NO_DEVICE, std::string("rls_init: device '") + prop.name +
+                    "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                    "; kernels are built for sm_100a only");
+    rls_context *ctx = new (std::nothrow) rls_context();
+    if (!ctx) return fail(nullptr, RLS_ERR_OUT_OF_MEMORY, "rls_init: host allocation failed");
+    ctx->device = device;
+    DeviceGuard guard(device);
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaStreamCreateWithFlags"); }
+        ctx->own_stream = true;
+    }
+    *out_ctx = ctx;
+    return RLS_OK;
+}
+
+extern "C" int rls_shutdown(rls_context *ctx)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int b = 0; b < kStages; b++) {
+        if (ctx->stage_stream[b]) { cudaStreamSynchronize(ctx->stage_stream[b]); cudaStreamDestroy(ctx->stage_stream[b]); }
+        if (ctx->stage_done[b]) cudaEventDestroy(ctx->stage_done[b]);
+        if (ctx->stage_buf[b]) cudaFree(ctx->stage_buf[b]);
+    }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return RLS_OK;
+}
+
+extern "C" int rls_synchronize(rls_context *ctx)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    RLS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RLS_OK;
+}
+
+extern "C" const char *rls_last_error_string(const rls_context *ctx)
+{
+    return ctx ? ctx->err.c_str() : g_init_error.c_str();
+}
+
+extern "C" uint64_t rls_kernel_launch_count(const rls_context *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int rls_host_alloc(rls_context *ctx, size_t bytes, void **out_ptr)
+{
+    if (!ctx || !out_ptr) return RLS_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    RLS_CUDA(ctx, cudaHostAlloc(out_ptr, bytes, cudaHostAllocDefault));
+    return RLS_OK;
+}
+extern "C" int rls_host_free(rls_context *ctx, void *ptr)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    RLS_CUDA(ctx, cudaFreeHost(ptr));
+    return RLS_OK;
+}
+
+// ==================================================== ABI struct -> device struct
+static inline CV3 cv(const rls_cvec3 &v) { CV3 o; o.x = v.x; o.y = v.y; o.z = v.z; return o; }
+static inline V3  mv(const rls_vec3 &v) { V3 o; o.x = v.x; o.y = v.y; o.z = v.z; return o; }
+static inline P1  p1(const rls_param1 &p) { P1 o; o.value = p.value; o.array = p.array; return o; }
+static inline P3  p3(const rls_param3 &p)
+{
+    P3 o; o.value[0] = p.value[0]; o.value[1] = p.value[1]; o.value[2] = p.value[2];
+    o.x = p.array.x; o.y = p.array.y; o.z = p.array.z; return o;
+}
+static inline ShadingSoA sh(const rls_shading_soa &s)
+{
+    ShadingSoA o; o.U = cv(s.U); o.V = cv(s.V); o.N = cv(s.N); o.wo = cv(s.wo); o.backfacing = s.backfacing; return o;
+}
+static inline bool has3(const rls_cvec3 &v) { return v.x && v.y && v.z; }
+static inline bool has3(const rls_vec3 &v) { return v.x && v.y && v.z; }
+static inline bool ok_shading(const rls_shading_soa *s) { return s && has3(s->U) && has3(s->V) && has3(s->N) && has3(s->wo); }
+static inline bool ok_p3(const rls_param3 &p) { return (!p.array.x && !p.array.y && !p.array.z) || has3(p.array); }
+
+struct GgxParamsDev { P3 ks; P1 rough, ior, aniso; };
+static inline GgxParamsDev dev(const rls_ggx_params &p)
+{
+    GgxParamsDev o; o.ks = p3(p.KsColor); o.rough = p1(p.specularRoughness); o.ior = p1(p.ior); o.aniso = p1(p.anisotropic); return o;
+}
+static inline DisneyParamsDev dev(const rls_disney_params &p)
+{
+    DisneyParamsDev o;
+    o.base_color = p3(p.base_color); o.subsurface = p1(p.subsurface); o.metallic = p1(p.metallic);
+    o.specular = p1(p.specular); o.specular_tint = p1(p.specular_tint); o.roughness = p1(p.roughness);
+    o.anisotropic = p1(p.anisotropic); o.sheen = p1(p.sheen); o.sheen_tint = p1(p.sheen_tint);
+    o.clearcoat = p1(p.clearcoat); o.clearcoat_gloss = p1(p.clearcoat_gloss);
+    return o;
+}
+static inline SkinParamsDev dev(const rls_skin_params &p)
+{
+    SkinParamsDev o;
+    o.sss_color = p3(p.sss_color); o.sss_scatter_dist = p3(p.sss_scatter_dist);
+    o.sss_weight = p1(p.sss_weight); o.sss_dist_multiplier = p1(p.sss_dist_multiplier);
+    o.specular_weight = p1(p.specular_weight); o.sheen_weight = p1(p.sheen_weight);
+    return o;
+}
+
+static inline unsigned grid_for(size_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+#define RLS_INDEX()                                                            \
+    size_t i = (size_t)blockIdx.x * (size_t)blockDim.x + threadIdx.x;          \
+    if (i >= n) return;
+
+// ================================================================ rlGgx kernels
+RLS_DEV Ggx ggx_make(const ShadingSoA &sg, const GgxParamsDev &p, size_t i)
+{
+    Shading s = load_shading(sg, i);
+    Ggx g;
+    ggx_init(g, s, fetch(p.ks, i), fetch(p.ior, i), fetch(p.rough, i), fetch(p.aniso, i));
+    return g;
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_ggx_eval_sample(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, V3 wi, float *fresnel)
+{
+    RLS_INDEX();
+    Ggx g = ggx_make(sg, p, i);
+    f3 M = sample_visible_normal(g.wo, g.U, g.V, g.N, g.ax, g.ay, __ldg(rx + i), __ldg(ry + i));
+    f3 L = reflect_direction(g.wo, M);                 // src/rlGgx.h:100-101
+    store3(wi, i, L);
+    if (fresnel) fresnel[i] = ggx_fresnel(g, L, M);    // :103-104,181-184 with one sample
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_ggx_eval_brdf(size_t n, ShadingSoA sg, GgxParamsDev p, CV3 wi, V3 f)
+{
+    RLS_INDEX();
+    Ggx g = ggx_make(sg, p, i);
+    store3(f, i, ggx_eval_brdf(g, load3(wi, i)));
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_ggx_eval_pdf(size_t n, ShadingSoA sg, GgxParamsDev p, CV3 wi, float *pdf)
+{
+    RLS_INDEX();
+    Ggx g = ggx_make(sg, p, i);
+    pdf[i] = ggx_eval_pdf(g, load3(wi, i));
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_ggx_sample_eval_pdf(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry,
+                      V3 wi, V3 f, float *pdf, float *fresnel, uint32_t *flags)
+{
+    RLS_INDEX();
+    Ggx g = ggx_make(sg, p, i);
+    f3 M = sample_visible_normal(g.wo, g.U, g.V, g.N, g.ax, g.ay, __ldg(rx + i), __ldg(ry + i));
+    f3 L = reflect_direction(g.wo, M);
+    f3 fv = ggx_eval_brdf(g, L);
+    float pd = ggx_eval_pdf(g, L);
+    store3(wi, i, L);
+    store3(f, i, fv);
+    pdf[i] = pd;
+    if (fresnel) fresnel[i] = ggx_fresnel(g, L, M);
+    uint32_t fl = bsdf_flags(L, g.N, fv, pd);
+    if (g.entering) fl |= RLS_FLAG_ENTERING;
+    flags[i] = fl;
+}
+
+struct Dielectric { float F, f_r, pdf_r, f_t, w_t; f3 wi_r, wi_t; uint32_t flags; };
+
+// The rough-dielectric unit: src/rlGgx.h:228-243 loop body, with the in-tree
+// getRefractDirection standing in for Arnold's AiRefractRay.
+RLS_DEV Dielectric dielectric_unit(const Shading &s, float ior, float rough, float aniso, float rx, float ry)
+{
+    Dielectric r;
+    Ggx g;
+    ggx_init(g, s, mk3(1.0f, 1.0f, 1.0f), ior, rough, aniso);
+    f3 m = sample_visible_normal(g.wo, g.U, g.V, g.N, g.ax, g.ay, rx, ry);
+    r.wi_r = reflect_direction(g.wo, m);
+    r.F = ggx_fresnel(g, r.wi_r, m);
+    f3 fr = ggx_eval_brdf(g, r.wi_r);
+    r.f_r = fr.x;
+    r.pdf_r = ggx_eval_pdf(g, r.wi_r);
+    r.flags = bsdf_flags(r.wi_r, g.N, fr, r.pdf_r);
+    if (g.entering) r.flags |= RLS_FLAG_ENTERING;
+    f3 t;
+    if (ggx_refract_direction(g, m, g.wo, t)) {
+        r.wi_t = t;
+        r.f_t = ggx_refraction(g, g.wo, t, g.N);
+    } else {
+        r.wi_t = reflect_direction(g.wo, m);
+        r.f_t = 0.0f;
+        r.flags |= RLS_FLAG_TIR;
+    }
+    r.w_t = ggx_sample_weight(g, g.wo, r.wi_t, m);
+    return r;
+}
+
+struct DielectricOutDev { float *fresnel; V3 wi_r; float *f_r, *pdf_r; V3 wi_t; float *f_t, *weight_t; uint32_t *flags; };
+
+__global__ void __launch_bounds__(kBlock)
+k_ggx_dielectric(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, DielectricOutDev o)
+{
+    RLS_INDEX();
+    Shading s = load_shading(sg, i);
+    Dielectric r = dielectric_unit(s, fetch(p.ior, i), fetch(p.rough, i), fetch(p.aniso, i), __ldg(rx + i), __ldg(ry + i));
+    o.fresnel[i] = r.F;
+    store3(o.wi_r, i, r.wi_r);
+    o.f_r[i] = r.f_r;
+    o.pdf_r[i] = r.pdf_r;
+    store3(o.wi_t, i, r.wi_t);
+    o.f_t[i] = r.f_t;
+    o.weight_t[i] = r.w_t;
+    o.flags[i] = r.flags;
+}
+
+// ============================================================= rlDisney kernels
+__global__ void __launch_bounds__(kBlock)
+k_disney_eval_sample(size_t n, ShadingSoA sg, DisneyParamsDev p, int type, const float *rx, const float *ry, V3 wi, uint32_t *flags)
+{
+    RLS_INDEX();
+    Disney d; disney_init(d, load_shading(sg, i), p, i);
+    uint32_t lobe = 0;
+    f3 L = (type == kRayDiffuse) ? disney_sample_diffuse(d, __ldg(rx + i), __ldg(ry + i))
+                                 : disney_sample_specular(d, __ldg(rx + i), __ldg(ry + i), lobe);
+    store3(wi, i, L);
+    if (flags) {
+        uint32_t fl = lobe << RLS_FLAG_LOBE_SHIFT;
+        if (is_zero(L)) fl |= RLS_FLAG_ZERO_L;
+        if (dot(L, d.N) <= 0.0f) fl |= RLS_FLAG_BELOW_HORIZON;
+        flags[i] = fl;
+    }
+}
+__global__ void __launch_bounds__(kBlock)
+k_disney_eval_brdf(size_t n, ShadingSoA sg, DisneyParamsDev p, int type, CV3 wi, V3 f)
+{
+    RLS_INDEX();
+    Disney d; disney_init(d, load_shading(sg, i), p, i);
+    store3(f, i, disney_eval_brdf(d, type, load3(wi, i)));
+}
+__global__ void __launch_bounds__(kBlock)
+k_disney_eval_pdf(size_t n, ShadingSoA sg, DisneyParamsDev p, int type, CV3 wi, float *pdf)
+{
+    RLS_INDEX();
+    Disney d; disney_init(d, load_shading(sg, i), p, i);
+    pdf[i] = disney_eval_pdf(d, type, load3(wi, i));
+}
+
+struct DisneyOutDev { V3 wi_s, f_s; float *pdf_s; V3 wi_d, f_d; float *pdf_d; uint32_t *flags; };
+
+__global__ void __launch_bounds__(kBlock)
+k_disney_sample_eval_pdf(size_t n, ShadingSoA sg, DisneyParamsDev p, const float *rx_s, const float *ry_s,
+                         const float *rx_d, const float *ry_d, DisneyOutDev o)
+{
+    RLS_INDEX();
+    Disney d; disney_init(d, load_shading(sg, i), p, i);
+    uint32_t lobe = 0;
+    f3 Ls = disney_sample_specular(d, __ldg(rx_s + i), __ldg(ry_s + i), lobe);
+    f3 fs = disney_eval_brdf(d, kRayGlossy, Ls);
+    float ps = disney_eval_pdf(d, kRayGlossy, Ls);
+    f3 Ld = disney_sample_diffuse(d, __ldg(rx_d + i), __ldg(ry_d + i));
+    f3 fd = disney_eval_brdf(d, kRayDiffuse, Ld);
+    float pd = disney_eval_pdf(d, kRayDiffuse, Ld);
+    store3(o.wi_s, i, Ls); store3(o.f_s, i, fs); o.pdf_s[i] = ps;
+    store3(o.wi_d, i, Ld); store3(o.f_d, i, fd); o.pdf_d[i] = pd;
+    uint32_t fls = (bsdf_flags(Ls, d.N, fs, ps) & ~RLS_FLAG_PDF_FLOORED) | (lobe << RLS_FLAG_LOBE_SHIFT);
+    uint32_t fld = bsdf_flags(Ld, d.N, fd, pd);
+    o.flags[i] = fls | (fld << RLS_FLAG_DIFFUSE_SHIFT);
+}
+
+// ================================================================ profile kernels
+struct NdProfileSoADev { V3 distance, C1, C2; float *max_radius; };
+RLS_DEV NdProfile nd_load(const NdProfileSoADev &s, size_t i)
+{
+    NdProfile p;
+    p.d[0] = s.distance.x[i]; p.d[1] = s.distance.y[i]; p.d[2] = s.distance.z[i];
+    p.C1[0] = s.C1.x[i]; p.C1[1] = s.C1.y[i]; p.C1[2] = s.C1.z[i];
+    p.C2[0] = s.C2.x[i]; p.C2[1] = s.C2.y[i]; p.C2[2] = s.C2.z[i];
+    p.R = s.max_radius[i];
+    return p;
+}
+__global__ void __launch_bounds__(kBlock)
+k_nd_set_distance(size_t n, CV3 dist, NdProfileSoADev o)
+{
+    RLS_INDEX();
+    NdProfile p; nd_set_distance(p, load3(dist, i));
+    store3(o.distance, i, mk3(p.d[0], p.d[1], p.d[2]));
+    store3(o.C1, i, mk3(p.C1[0], p.C1[1], p.C1[2]));
+    store3(o.C2, i, mk3(p.C2[0], p.C2[1], p.C2[2]));
+    o.max_radius[i] = p.R;
+}
+__global__ void __launch_bounds__(kBlock)
+k_nd_get_radius(size_t n, NdProfileSoADev s, const float *rx, float *r, uint32_t *flags)
+{
+    RLS_INDEX();
+    NdProfile p = nd_load(s, i);
+    uint32_t fl;
+    r[i] = nd_get_radius(p, __ldg(rx + i), fl);
+    if (flags) flags[i] = fl;
+}
+__global__ void __launch_bounds__(kBlock)
+k_nd_get_pdf(size_t n, NdProfileSoADev s, const float *r, float *pdf)
+{
+    RLS_INDEX();
+    NdProfile p = nd_load(s, i);
+    pdf[i] = nd_get_pdf(p, __ldg(r + i));
+}
+__global__ void __launch_bounds__(kBlock)
+k_nd_eval_profile(size_t n, NdProfileSoADev s, const float *r, V3 rd)
+{
+    RLS_INDEX();
+    NdProfile p = nd_load(s, i);
+    store3(rd, i, nd_eval_profile(p, __ldg(r + i)));
+}
+struct ProfileOutDev { float *r, *pdf; V3 Rd; uint32_t *flags; };
+__global__ void __launch_bounds__(kBlock)
+k_skin_profile(size_t n, SkinParamsDev sp, const float *rx, ProfileOutDev o)
+{
+    RLS_INDEX();
+    NdProfile p; nd_set_distance(p, skin_scatter_dist(sp, i));
+    uint32_t fl;
+    float r = nd_get_radius(p, __ldg(rx + i), fl);
+    o.r[i] = r;
+    o.pdf[i] = nd_get_pdf(p, r);
+    store3(o.Rd, i, nd_eval_profile(p, r));
+    o.flags[i] = fl;
+}
+// src/rlSkin.cpp:191,204,214,228,231,238
+__global__ void __launch_bounds__(kBlock)
+k_skin_layer_weights(size_t n, SkinParamsDev sp, const float *avgSheen, const float *avgSpec, float *specScale, float *sssWeight)
+{
+    RLS_INDEX();
+    float sheenWeight = fetch(sp.sheen_weight, i);
+    float specularWeight = fetch(sp.specular_weight, i);
+    float w = fetch(sp.sss_weight, i);
+    float sheenFresnel = 0.0f, specularFresnel = 0.0f;
+    if (sheenWeight > kEps) sheenFresnel = __ldg(avgSheen + i) * sheenWeight;
+    if (specularWeight > kEps) specularFresnel = __ldg(avgSpec + i) * specularWeight;
+    specScale[i] = specularWeight * (1.0f - sheenFresnel);
+    w *= 1.0f - specularFresnel * (1.0f - sheenFresnel);
+    sssWeight[i] = w;
+}
+
+// ============================================================ synthetic generators
+RLS_DEV uint64_t hash64(uint64_t seed, uint32_t stream, uint64_t index)
+{
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (index + 1ull) + 0xD1B54A32D192ED03ull * (uint64_t)stream;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+RLS_DEV float uniform24(uint64_t seed, uint32_t stream, uint64_t index)
+{
+    uint32_t k = (uint32_t)(hash64(seed, stream, index) >> 40);
+    if (k == 0u) k = 1u;
+    return (float)k * 5.9604644775390625e-8f;
+}
+__global__ void __launch_bounds__(kBlock)
+k_synth_uniform(size_t n, uint64_t seed, uint32_t stream, uint64_t first, float lo, float hi, float *out)
+{
+    RLS_INDEX();
+    out[i] = lo + (hi - lo) * uniform24(seed, stream, first + i);
+}
+__global__ void __launch_bounds__(kBlock)
+k_synth_shading(size_t n, uint64_t seed, uint64_t first, float cos_lo, float cos_hi, float back_frac,
+                V3 U, V3 V, V3 N, V3 wo, uint8_t *backfacing)
+{
+    RLS_INDEX();
+    uint64_t idx = first + i;
+    float u1 = uniform24(seed, 10, idx), u2 = uniform24(seed, 11, idx), u3 = uniform24(seed, 12, idx);
+    float u4 = uniform24(seed, 13, idx), u5 = uniform24(seed, 14, idx), u6 = uniform24(seed, 15, idx);
+    float nz = 1.0f - 2.0f * u1;
+    float rn = sqrtf(fmaxf(0.0f, 1.0f - nz * nz));
+    float sn, cn; sincosf(kTwoPi * u2, &sn, &cn);
+    f3 Nn = normalize(mk3(rn * cn, rn * sn, nz));
+    f3 A = fabsf(Nn.x) < 0.9f ? mk3(1.0f, 0.0f, 0.0f) : mk3(0.0f, 1.0f, 0.0f);
+    f3 T = normalize(A - Nn * dot(A, Nn));
+    f3 B = mk3(Nn.y * T.z - Nn.z * T.y, Nn.z * T.x - Nn.x * T.z, Nn.x * T.y - Nn.y * T.x);
+    float st, ct; sincosf(kTwoPi * u3, &st, &ct);
+    f3 Uu = normalize(T * ct + B * st);
+    f3 Vv = mk3(Nn.y * Uu.z - Nn.z * Uu.y, Nn.z * Uu.x - Nn.x * Uu.z, Nn.x * Uu.y - Nn.y * Uu.x);
+    float cz = cos_lo + (cos_hi - cos_lo) * u4;
+    float sr = sqrtf(fmaxf(0.0f, 1.0f - cz * cz));
+    float sv, cvv; sincosf(kTwoPi * u5, &sv, &cvv);
+    f3 w = normalize(Uu * (sr * cvv) + Vv * (sr * sv) + Nn * cz);
+    store3(U, i, Uu); store3(V, i, Vv); store3(N, i, Nn); store3(wo, i, w);
+    if (backfacing) backfacing[i] = (u6 < back_frac) ? 1 : 0;
+}
+
+// ================================================================= albedo sweep
+struct SweepGridDev { int n_rough, n_cos, n_ior; float rlo, rhi, ilo, ihi; };
+
+__global__ void __launch_bounds__(kBlock)
+k_albedo_sweep(SweepGridDev g, uint64_t seed, uint32_t k0, uint32_t k1, double *table)
+{
+    const uint32_t cell = blockIdx.x;
+    uint32_t ie = cell % (uint32_t)g.n_ior;
+    uint32_t ic = (cell / (uint32_t)g.n_ior) % (uint32_t)g.n_cos;
+    uint32_t ir = cell / (uint32_t)(g.n_ior * g.n_cos);
+    float tr = g.n_rough > 1 ? (float)ir / (float)(g.n_rough - 1) : 0.0f;
+    float te = g.n_ior > 1 ? (float)ie / (float)(g.n_ior - 1) : 0.0f;
+    float rough = g.rlo + (g.rhi - g.rlo) * tr;
+    float ior = g.ilo + (g.ihi - g.ilo) * te;
+    float cosv = (float)(ic + 1u) / (float)g.n_cos;
+
+    Shading s;
+    s.U = mk3(1.0f, 0.0f, 0.0f); s.V = mk3(0.0f, 1.0f, 0.0f); s.N = mk3(0.0f, 0.0f, 1.0f);
+    s.wo = mk3(sqrtf(1.0f - cosv * cosv), 0.0f, cosv);
+    s.backfacing = false;
+
+    double acc[RLS_SWEEP_VALUES_PER_CELL] = { 0.0, 0.0, 0.0, 0.0, 0.0 };
+    for (uint32_t k = k0 + threadIdx.x; k < k1; k += kBlock) {
+        uint64_t idx = ((uint64_t)cell << 32) | (uint64_t)k;
+        float rx = uniform24(seed, 0u, idx);
+        float ry = uniform24(seed, 1u, idx);
+        Dielectric r = dielectric_unit(s, ior, rough, 0.0f, rx, ry);
+        bool valid = !(r.flags & (RLS_FLAG_ZERO_L | RLS_FLAG_BELOW_HORIZON));
+        if (valid) { acc[0] += (double)(r.f_r / r.pdf_r); acc[3] += 1.0; }
+        if (r.flags & RLS_FLAG_TIR) acc[4] += 1.0; else acc[1] += (double)r.w_t;
+        acc[2] += (double)r.F;
+    }
+    __shared__ double red[RLS_SWEEP_VALUES_PER_CELL][kBlock / 32];
+#pragma unroll
+    for (int j = 0; j < RLS_SWEEP_VALUES_PER_CELL; j++) {
+        double v = acc[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[j][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < RLS_SWEEP_VALUES_PER_CELL) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kBlock / 32; w++) v += red[threadIdx.x][w];
+        table[(size_t)cell * RLS_SWEEP_VALUES_PER_CELL + threadIdx.x] = v;
+    }
+}
+
+// ====================================================== launch helpers (one stream)
+#define RLS_LAUNCH_CHECK(ctx)                                                    \
+    do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return cuda_fail(ctx, e_, "kernel launch"); \
+         (ctx)->launches++; } while (0)
+#define RLS_REQUIRE(ctx, cond, msg)                                              \
+    do { if (!(cond)) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, msg); } while (0)
+
+static int launch_ggx_sample_eval_pdf(rls_context *ctx, cudaStream_t st, size_t n, const rls_shading_soa *sg,
+                                      const rls_ggx_params *p, const float *rx, const float *ry, const rls_bsdf_out *o)
+{
+    k_ggx_sample_eval_pdf<<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), dev(*p), rx, ry, mv(o->wi), mv(o->f), o->pdf, o->fresnel, o->flags);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+static int launch_ggx_dielectric(rls_context *ctx, cudaStream_t st, size_t n, const rls_shading_soa *sg,
+                                 const rls_ggx_params *p, const float *rx, const float *ry, const rls_ggx_dielectric_out *o)
+{
+    DielectricOutDev d; d.fresnel = o->fresnel; d.wi_r = mv(o->wi_r); d.f_r = o->f_r; d.pdf_r = o->pdf_r;
+    d.wi_t = mv(o->wi_t); d.f_t = o->f_t; d.weight_t = o->weight_t; d.flags = o->flags;
+    k_ggx_dielectric<<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), dev(*p), rx, ry, d);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+static int launch_disney_sample_eval_pdf(rls_context *ctx, cudaStream_t st, size_t n, const rls_shading_soa *sg,
+                                         const rls_disney_params *p, const float *rx_s, const float *ry_s,
+                                         const float *rx_d, const float *ry_d, const rls_disney_out *o)
+{
+    DisneyOutDev d; d.wi_s = mv(o->wi_s); d.f_s = mv(o->f_s); d.pdf_s = o->pdf_s;
+    d.wi_d = mv(o->wi_d); d.f_d = mv(o->f_d); d.pdf_d = o->pdf_d; d.flags = o->flags;
+    k_disney_sample_eval_pdf<<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), dev(*p), rx_s, ry_s, rx_d, ry_d, d);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+static int launch_skin_profile(rls_context *ctx, cudaStream_t st, size_t n, const rls_skin_params *p,
+                               const float *rx, const rls_profile_out *o)
+{
+    ProfileOutDev d; d.r = o->r; d.pdf = o->pdf; d.Rd = mv(o->Rd); d.flags = o->flags;
+    k_skin_profile<<<grid_for(n), kBlock, 0, st>>>(n, dev(*p), rx, d);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+
+static bool ok_ggx_params(const rls_ggx_params *p) { return p && ok_p3(p->KsColor); }
+static bool ok_bsdf_out(const rls_bsdf_out *o) { return o && has3(o->wi) && has3(o->f) && o->pdf && o->flags; }
+static bool ok_dielectric_out(const rls_ggx_dielectric_out *o)
+{
+    return o && o->fresnel && has3(o->wi_r) && o->f_r && o->pdf_r && has3(o->wi_t) && o->f_t && o->weight_t && o->flags;
+}
+static bool ok_disney_out(const rls_disney_out *o)
+{
+    return o && has3(o->wi_s) && has3(o->f_s) && o->pdf_s && has3(o->wi_d) && has3(o->f_d) && o->pdf_d && o->flags;
+}
+static bool ok_profile_out(const rls_profile_out *o) { return o && o->r && o->pdf && has3(o->Rd) && o->flags; }
+static bool ok_sample_type(int t) { return t == RLS_RAY_DIFFUSE || t == RLS_RAY_GLOSSY; }
+
+// =================================================================== C ABI: rlGgx
+extern "C" int rls_ggx_eval_sample(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
+                                   const float *rx, const float *ry, rls_vec3 out_wi, float *out_fresnel)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && rx && ry && has3(out_wi), "rls_ggx_eval_sample: NULL argument");
+    if (n == 0) return RLS_OK;
+    DeviceGuard guard(ctx->device);
+    k_ggx_eval_sample<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), rx, ry, mv(out_wi), out_fresnel);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+extern "C" int rls_ggx_eval_brdf(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
+                                 rls_cvec3 wi, rls_vec3 out_f)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && has3(wi) && has3(out_f), "rls_ggx_eval_brdf: NULL argument");
+    if (n == 0) return RLS_OK;
+    DeviceGuard guard(ctx->device);
+    k_ggx_eval_brdf<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), cv(wi), mv(out_f));
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+extern "C" int rls_ggx_eval_pdf(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
+                                rls_cvec3 wi, float *out_pdf)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && has3(wi) && out_pdf, "rls_ggx_eval_pdf: NULL argument");
+    if (n == 0) return RLS_OK;
+    DeviceGuard guard(ctx->device);
+    k_ggx_eval_pdf<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), cv(wi), out_pdf);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+extern "C" int rls_ggx_sample_eval_pdf(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
+                                       const float *rx, const float *ry, const rls_bsdf_out *out)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && rx && ry && ok_bsdf_out(out), "rls_ggx_sample_eval_pdf: NULL argument");
+    if (n == 0) return RLS_OK;
+    DeviceGuard guard(ctx->device);
+    return launch_ggx_sample_eval_pdf(ctx, ctx->stream, n, sg, p, rx, ry, out);
+}
+extern "C" int rls_ggx_dielectric_sample_eval_pdf(rls_context *ctx, size_t n, const rls_shading_soa *sg,
+                                                  const rls_ggx_params *p, const float *rx, const float *ry,
+                                                  const rls_ggx_dielectric_out *out)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && rx && ry && ok_dielectric_out(out),
+                "rls_ggx_dielectric_sample_eval_pdf: NULL argument");
+    if (n == 0) return RLS_OK;
+    DeviceGuard guard(ctx->device);
+    return launch_ggx_dielectric(ctx, ctx->stream, n, sg, p, rx, ry, out);
+}
+
+// ================================================================ C ABI: rlDisney
+static bool ok_disney_params(const rls_disney_params *p) { return p && ok_p3(p->base_color); }
+
+extern "C" int rls_disney_eval_sample(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_disney_params *p,
+                                      int sample_type, const float *rx, const float *ry, rls_vec3 out_wi, uint32_t *out_flags)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_disney_params(p) && rx && ry && has3(out_wi), "rls_disney_eval_sample: NULL argument");
+    RLS_REQUIRE(ctx, ok_sample_type(sample_type), "rls_disney_eval_sample: sample_type must be RLS_RAY_DIFFUSE or RLS_RAY_GLOSSY");
+    if (n == 0) return RLS_OK;
+    DeviceGuard guard(ctx->device);
+    k_disney_eval_sample<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), sample_type, rx, ry, mv(out_wi), out_flags);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+extern "C" int rls_disney_eval_brdf(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_disney_params *p,
+                                    int sample_type, rls_cvec3 wi, rls_vec3 out_f)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_disney_params(p) && has3(wi) && has3(out_f), "rls_disney_eval_brdf: NULL argument");
+    RLS_REQUIRE(ctx, ok_sample_type(sample_type), "rls_disney_eval_brdf: sample_type must be RLS_RAY_DIFFUSE or RLS_RAY_GLOSSY");
+    if (n == 0) return RLS_OK;
+    DeviceGuard guard(ctx->device);
+    k_disney_eval_brdf<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), sample_type, cv(wi), mv(out_f));
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+extern "C" int rls_disney_eval_pdf(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_disney_params *p,
+                                   int sample_type, rls_cvec3 wi, float *out_pdf)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_disney_params(p) && has3(wi) && out_pdf, "rls_disney_eval_pdf: NULL argument");
+    RLS_REQUIRE(ctx, ok_sample_type(sample_type), "rls_disney_eval_pdf: sample_type must be RLS_RAY_DIFFUSE or RLS_RAY_GLOSSY");
+    if (n == 0) return RLS_OK;
+    DeviceGuard guard(ctx->device);
+    k_disney_eval_pdf<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), sample_type, cv(wi), out_pdf);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+extern "C" int rls_disney_sample_eval_pdf(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_disney_params *p,
+                                          const float *rx_s, const float *ry_s, const float *rx_d, const float *ry_d,
+                                          const rls_disney_out *out)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_disney_params(p) && rx_s && ry_s && rx_d && ry_d && ok_disney_out(out),
+                "rls_disney_sample_eval_pdf: NULL argument");
+    if (n == 0) return RLS_OK;
+    DeviceGuard guard(ctx->device);
+    return launch_disney_sample_eval_pdf(ctx, ctx->stream, n, sg, p, rx_s, ry_s, rx_d, ry_d, out);
+}
+
+// ========================================================== C ABI: rlSss / rlSkin
+static bool ok_profile(const rls_ndprofile_soa *s) { return s && has3(s->distance) && has3(s->C1) && has3(s->C2) && s->max_radius; }
+static NdProfileSoADev dev(const rls_ndprofile_soa &s)
+{
+    NdProfileSoADev o; o.distance = mv(s.distance); o.C1 = mv(s.C1); o.C2 = mv(s.C2); o.max_radius = s.max_radius; return o;
+}
+static bool ok_skin_params(const rls_skin_params *p) { return p && ok_p3(p->sss_color) && ok_p3(p->sss_scatter_dist); }
+
+extern "C" int rls_ndprofile_set_distance(rls_context *ctx, size_t n, rls_cvec3 dist, rls_cvec3 albedo, const rls_ndprofile_soa *out)
+{
+    (void)albedo;   // only feeds the dead `s` of src/rlSss.cpp:22-23
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, has3(dist) && ok_profile(out), "rls_ndprofile_set_distance: NULL argument");
+    if (n == 0) return RLS_OK;
+    DeviceGuard guard(ctx->device);
+    k_nd_set_distance<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, cv(dist), dev(*out));
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+extern "C" int rls_ndprofile_get_radius(rls_context *ctx, size_t n, const rls_ndprofile_soa *profile, const float *rx,
+                                        float *out_r, uint32_t *out_flags)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, ok_profile(profile) && rx && out_r, "rls_ndprofile_get_radius: NULL argument");
+    if (n == 0) return RLS_OK;
+    DeviceGuard guard(ctx->device);
+    k_nd_get_radius<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, dev(*profile), rx, out_r, out_flags);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+extern "C" int rls_ndprofile_get_pdf(rls_context *ctx, size_t n, const rls_ndprofile_soa *profile, const float *r, float *out_pdf)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, ok_profile(profile) && r && out_pdf, "rls_ndprofile_get_pdf: NULL argument");
+    if (n == 0) return RLS_OK;
+    DeviceGuard guard(ctx->device);
+    k_nd_get_pdf<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, dev(*profile), r, out_pdf);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+extern "C" int rls_ndprofile_eval_profile(rls_context *ctx, size_t n, const rls_ndprofile_soa *profile, const float *r, rls_vec3 out_rd)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, ok_profile(profile) && r && has3(out_rd), "rls_ndprofile_eval_profile: NULL argument");
+    if (n == 0) return RLS_OK;
+    DeviceGuard guard(ctx->device);
+    k_nd_eval_profile<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, dev(*profile), r, mv(out_rd));
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+extern "C" int rls_skin_profile_sample_eval_pdf(rls_context *ctx, size_t n, const rls_skin_params *p, const float *rx,
+                                                const rls_profile_out *out)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, ok_skin_params(p) && rx && ok_profile_out(out), "rls_skin_profile_sample_eval_pdf: NULL argument");
+    if (n == 0) return RLS_OK;
+    DeviceGuard guard(ctx->device);
+    return launch_skin_profile(ctx, ctx->stream, n, p, rx, out);
+}
+extern "C" int rls_skin_layer_weights(rls_context *ctx, size_t n, const rls_skin_params *p, const float *avg_sheen,
+                                      const float *avg_spec, float *out_spec_scale, float *out_sss_weight)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, p && avg_sheen && avg_spec && out_spec_scale && out_sss_weight, "rls_skin_layer_weights: NULL argument");
+    if (n == 0) return RLS_OK;
+    DeviceGuard guard(ctx->device);
+    k_skin_layer_weights<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, dev(*p), avg_sheen, avg_spec, out_spec_scale, out_sss_weight);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+
+// ================================================================= C ABI: sweep
+extern "C" int rls_albedo_sweep(rls_context *ctx, const rls_sweep_grid *grid, uint64_t seed, uint32_t spp_begin,
+                                uint32_t spp_end, double *table)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, grid && table, "rls_albedo_sweep: NULL argument");
+    RLS_REQUIRE(ctx, grid->n_rough > 0 && grid->n_cos > 0 && grid->n_ior > 0 && spp_end >= spp_begin, "rls_albedo_sweep: bad grid");
+    SweepGridDev g; g.n_rough = grid->n_rough; g.n_cos = grid->n_cos; g.n_ior = grid->n_ior;
+    g.rlo = grid->roughness_lo; g.rhi = grid->roughness_hi; g.ilo = grid->ior_lo; g.ihi = grid->ior_hi;
+    unsigned cells = (unsigned)(grid->n_rough * grid->n_cos * grid->n_ior);
+    DeviceGuard guard(ctx->device);
+    k_albedo_sweep<<<cells, kBlock, 0, ctx->stream>>>(g, seed, spp_begin, spp_end, table);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+
+// ================================================================= C ABI: synth
+extern "C" int rls_synth_uniform(rls_context *ctx, size_t n, uint64_t seed, uint32_t stream, uint64_t first_index,
+                                 float lo, float hi, float *out)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, out, "rls_synth_uniform: NULL argument");
+    if (n == 0) return RLS_OK;
+    DeviceGuard guard(ctx->device);
+    k_synth_uniform<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, seed, stream, first_index, lo, hi, out);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+extern "C" int rls_synth_shading(rls_context *ctx, size_t n, uint64_t seed, uint64_t first_index, float cos_lo, float cos_hi,
+                                 float backfacing_fraction, const rls_shading_soa *sg)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, ok_shading(sg), "rls_synth_shading: NULL argument");
+    if (n == 0) return RLS_OK;
+    DeviceGuard guard(ctx->device);
+    V3 U = { (float *)sg->U.x, (float *)sg->U.y, (float *)sg->U.z };
+    V3 V = { (float *)sg->V.x, (float *)sg->V.y, (float *)sg->V.z };
+    V3 N = { (float *)sg->N.x, (float *)sg->N.y, (float *)sg->N.z };
+    V3 W = { (float *)sg->wo.x, (float *)sg->wo.y, (float *)sg->wo.z };
+    k_synth_shading<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, seed, first_index, cos_lo, cos_hi, backfacing_fraction,
+                                                            U, V, N, W, (uint8_t *)sg->backfacing);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+
+// ===================================================== host-buffer (end-to-end) forms
+// A chunk of samples is staged through one of kStages device buffers: H2D of every input
+// slice, the kernel, D2H of every output slice, all on that stage's stream, so that chunk
+// k+1's upload and chunk k-1's download overlap chunk k's kernel (PCIe is full duplex).
+namespace {
+
+struct Stager {
+    rls_context *ctx;
+    size_t chunk;        // samples per chunk (capacity)
+    size_t first = 0;    // first sample of the current chunk
+    size_t count = 0;    // samples in the current chunk
+    int    stage = 0;
+    size_t offset = 0;   // bump pointer into the stage buffer
+    cudaError_t err = cudaSuccess;
+    struct Pending { void *host; const void *dev; size_t bytes; };
+    std::vector<Pending> downloads;
+
+    static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+    void *slot(size_t elem)
+    {
+        void *p = (char *)ctx->stage_buf[stage] + offset;
+        offset += align256(chunk * elem);
+        return p;
+    }
+    template <typename T> const T *in(const T *host)
+    {
+        if (!host) return nullptr;
+        T *d = (T *)slot(sizeof(T));
+        cudaError_t e = cudaMemcpyAsync(d, host + first, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stage_stream[stage]);
+        if (e != cudaSuccess && err == cudaSuccess) err = e;
+        return d;
+    }
+    template <typename T> T *out(T *host)
+    {
+        if (!host) return nullptr;
+        T *d = (T *)slot(sizeof(T));
+        downloads.push_back({ (void *)(host + first), d, count * sizeof(T) });
+        return d;
+    }
+    rls_cvec3 in3(const rls_cvec3 &v) { rls_cvec3 o; o.x = in(v.x); o.y = in(v.y); o.z = in(v.z); return o; }
+    rls_vec3 out3(const rls_vec3 &v) { rls_vec3 o; o.x = out(v.x); o.y = out(v.y); o.z = out(v.z); return o; }
+    rls_param1 in1(const rls_param1 &p) { rls_param1 o = p; o.array = in(p.array); return o; }
+    rls_param3 inp3(const rls_param3 &p) { rls_param3 o = p; o.array = in3(p.array); return o; }
+    rls_shading_soa shading(const rls_shading_soa &s)
+    {
+        rls_shading_soa o; o.U = in3(s.U); o.V = in3(s.V); o.N = in3(s.N); o.wo = in3(s.wo); o.backfacing = in(s.backfacing); return o;
+    }
+    void finish()
+    {
+        for (const Pending &d : downloads) {
+            cudaError_t e = cudaMemcpyAsync(d.host, d.dev, d.bytes, cudaMemcpyDeviceToHost, ctx->stage_stream[stage]);
+            if (e != cudaSuccess && err == cudaSuccess) err = e;
+        }
+        downloads.clear();
+        cudaError_t e = cudaEventRecord(ctx->stage_done[stage], ctx->stage_stream[stage]);
+        if (e != cudaSuccess && err == cudaSuccess) err = e;
+    }
+};
+
+int stage_prepare(rls_context *ctx, size_t bytes_per_stage)
+{
+    for (int b = 0; b < kStages; b++) {
+        if (!ctx->stage_stream[b]) RLS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stage_stream[b], cudaStreamNonBlocking));
+        if (!ctx->stage_done[b]) RLS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_done[b], cudaEventDisableTiming));
+    }
+    if (bytes_per_stage > ctx->stage_bytes) {
+        for (int b = 0; b < kStages; b++) {
+            if (ctx->stage_buf[b]) { RLS_CUDA(ctx, cudaFree(ctx->stage_buf[b])); ctx->stage_buf[b] = nullptr; }
+        }
+        ctx->stage_bytes = 0;
+        for (int b = 0; b < kStages; b++) RLS_CUDA(ctx, cudaMalloc(&ctx->stage_buf[b], bytes_per_stage));
+        ctx->stage_bytes = bytes_per_stage;
+    }
+    return RLS_OK;
+}
+
+// Runs `body(stager)` once per chunk; `arrays_bytes_per_sample` bounds the stage size.
+template <typename Body>
+int run_staged(rls_context *ctx, size_t n, size_t chunk, size_t slots, Body body)
+{
+    if (chunk == 0) chunk = (size_t)1 << 20;
+    if (chunk > n) chunk = n;
+    chunk = (chunk + 63) & ~(size_t)63;
+    DeviceGuard guard(ctx->device);
+    int rc = stage_prepare(ctx, slots * Stager::align256(chunk * sizeof(float)));
+    if (rc != RLS_OK) return rc;
+    Stager st{ ctx, chunk };
+    size_t c = 0;
+    for (size_t first = 0; first < n; first += chunk, c++) {
+        st.stage = (int)(c % kStages);
+        st.first = first;
+        st.count = (n - first < chunk) ? (n - first) : chunk;
+        st.offset = 0;
+        if (c >= (size_t)kStages) RLS_CUDA(ctx, cudaEventSynchronize(ctx->stage_done[st.stage]));
+        rc = body(st);
+        if (rc != RLS_OK) return rc;
+        st.finish();
+        if (st.err != cudaSuccess) return cuda_fail(ctx, st.err, "host staging copy");
+    }
+    for (int b = 0; b < kStages; b++) RLS_CUDA(ctx, cudaStreamSynchronize(ctx->stage_stream[b]));
+    return RLS_OK;
+}
+
+} // namespace
+
+extern "C" int rls_ggx_sample_eval_pdf_host(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
+                                            const float *rx, const float *ry, const rls_bsdf_out *out, size_t chunk)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && rx && ry && ok_bsdf_out(out), "rls_ggx_sample_eval_pdf_host: NULL argument");
+    if (n == 0) return RLS_OK;
+    return run_staged(ctx, n, chunk, 32, [&](Stager &st) {
+        rls_shading_soa s = st.shading(*sg);
+        rls_ggx_params q = *p;
+        q.KsColor = st.inp3(p->KsColor); q.specularRoughness = st.in1(p->specularRoughness);
+        q.ior = st.in1(p->ior); q.anisotropic = st.in1(p->anisotropic);
+        const float *drx = st.in(rx), *dry = st.in(ry);
+        rls_bsdf_out o; o.wi = st.out3(out->wi); o.f = st.out3(out->f); o.pdf = st.out(out->pdf);
+        o.fresnel = st.out(out->fresnel); o.flags = st.out(out->flags);
+        return launch_ggx_sample_eval_pdf(ctx, ctx->stage_stream[st.stage], st.count, &s, &q, drx, dry, &o);
+    });
+}
+extern "C" int rls_ggx_dielectric_sample_eval_pdf_host(rls_context *ctx, size_t n, const rls_shading_soa *sg,
+                                                       const rls_ggx_params *p, const float *rx, const float *ry,
+                                                       const rls_ggx_dielectric_out *out, size_t chunk)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && rx && ry && ok_dielectric_out(out),
+                "rls_ggx_dielectric_sample_eval_pdf_host: NULL argument");
+    if (n == 0) return RLS_OK;
+    return run_staged(ctx, n, chunk, 36, [&](Stager &st) {
+        rls_shading_soa s = st.shading(*sg);
+        rls_ggx_params q = *p;
+        q.KsColor = st.inp3(p->KsColor); q.specularRoughness = st.in1(p->specularRoughness);
+        q.ior = st.in1(p->ior); q.anisotropic = st.in1(p->anisotropic);
+        const float *drx = st.in(rx), *dry = st.in(ry);
+        rls_ggx_dielectric_out o;
+        o.fresnel = st.out(out->fresnel); o.wi_r = st.out3(out->wi_r); o.f_r = st.out(out->f_r); o.pdf_r = st.out(out->pdf_r);
+        o.wi_t = st.out3(out->wi_t); o.f_t = st.out(out->f_t); o.weight_t = st.out(out->weight_t); o.flags = st.out(out->flags);
+        return launch_ggx_dielectric(ctx, ctx->stage_stream[st.stage], st.count, &s, &q, drx, dry, &o);
+    });
+}
+extern "C" int rls_disney_sample_eval_pdf_host(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_disney_params *p,
+                                               const float *rx_s, const float *ry_s, const float *rx_d, const float *ry_d,
+                                               const rls_disney_out *out, size_t chunk)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_disney_params(p) && rx_s && ry_s && rx_d && ry_d && ok_disney_out(out),
+                "rls_disney_sample_eval_pdf_host: NULL argument");
+    if (n == 0) return RLS_OK;
+    return run_staged(ctx, n, chunk, 48, [&](Stager &st) {
+        rls_shading_soa s = st.shading(*sg);
+        rls_disney_params q = *p;
+        q.base_color = st.inp3(p->base_color); q.subsurface = st.in1(p->subsurface); q.metallic = st.in1(p->metallic);
+        q.specular = st.in1(p->specular); q.specular_tint = st.in1(p->specular_tint); q.roughness = st.in1(p->roughness);
+        q.anisotropic = st.in1(p->anisotropic); q.sheen = st.in1(p->sheen); q.sheen_tint = st.in1(p->sheen_tint);
+        q.clearcoat = st.in1(p->clearcoat); q.clearcoat_gloss = st.in1(p->clearcoat_gloss);
+        const float *a = st.in(rx_s), *b = st.in(ry_s), *c = st.in(rx_d), *d = st.in(ry_d);
+        rls_disney_out o;
+        o.wi_s = st.out3(out->wi_s); o.f_s = st.out3(out->f_s); o.pdf_s = st.out(out->pdf_s);
+        o.wi_d = st.out3(out->wi_d); o.f_d = st.out3(out->f_d); o.pdf_d = st.out(out->pdf_d); o.flags = st.out(out->flags);
+        return launch_disney_sample_eval_pdf(ctx, ctx->stage_stream[st.stage], st.count, &s, &q, a, b, c, d, &o);
+    });
+}
+extern "C" int rls_skin_profile_sample_eval_pdf_host(rls_context *ctx, size_t n, const rls_skin_params *p, const float *rx,
+                                                     const rls_profile_out *out, size_t chunk)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, ok_skin_params(p) && rx && ok_profile_out(out), "rls_skin_profile_sample_eval_pdf_host: NULL argument");
+    if (n == 0) return RLS_OK;
+    return run_staged(ctx, n, chunk, 16, [&](Stager &st) {
+        rls_skin_params q = *p;
+        q.sss_color = st.inp3(p->sss_color); q.sss_scatter_dist = st.inp3(p->sss_scatter_dist);
+        q.sss_dist_multiplier = st.in1(p->sss_dist_multiplier);
+        const float *drx = st.in(rx);
+        rls_profile_out o; o.r = st.out(out->r); o.pdf = st.out(out->pdf); o.Rd = st.out3(out->Rd); o.flags = st.out(out->flags);
+        return launch_skin_profile(ctx, ctx->stage_stream[st.stage], st.count, &q, drx, &o);
+    });
+}

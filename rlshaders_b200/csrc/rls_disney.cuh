@@ -1,0 +1,183 @@
+// rls_disney.cuh -- device restatement of DisneySampler (reference src/rlDisney.cpp:105-602).
+#pragma once
+#include "rls_ggx.cuh"
+
+namespace rls {
+
+constexpr int kRayDiffuse = 0x20;   // AI_RAY_DIFFUSE
+constexpr int kRayGlossy  = 0x40;   // AI_RAY_GLOSSY
+
+struct DisneyParamsDev {
+    P3 base_color;
+    P1 subsurface, metallic, specular, specular_tint, roughness, anisotropic, sheen, sheen_tint,
+       clearcoat, clearcoat_gloss;
+};
+
+struct Disney {
+    f3 U, V, N, wo;
+    f3 base, F0, sheenColor;
+    float roughness, subsurface, metallic, clearcoat, clearcoatGloss;
+    float specRough, ax, ay;
+};
+
+// src/rlDisney.cpp:155-192
+RLS_DEV void disney_init(Disney &d, const Shading &sh, const DisneyParamsDev &p, size_t i)
+{
+    d.U = sh.U; d.V = sh.V; d.N = sh.N; d.wo = sh.wo;
+    d.base = fetch(p.base_color, i);
+    d.roughness = fetch(p.roughness, i);
+    d.subsurface = fetch(p.subsurface, i);
+    float specular = fetch(p.specular, i) * 0.08f;            // :163
+    float specularTint = fetch(p.specular_tint, i);
+    d.metallic = fetch(p.metallic, i);
+    float sheen = fetch(p.sheen, i);
+    float sheenTint = fetch(p.sheen_tint, i);
+    float anisotropic = fetch(p.anisotropic, i);
+    d.clearcoat = fetch(p.clearcoat, i) * 0.25f;              // :169
+    d.clearcoatGloss = fetch(p.clearcoat_gloss, i);
+
+    float aspect = sqrtf(1.0f - anisotropic * 0.9f);          // :177
+    d.ax = max_m(1e-2f, sqr(d.roughness) / aspect);           // :178 (floor 1e-2, not 1e-4)
+    d.ay = max_m(1e-2f, sqr(d.roughness) * aspect);
+    d.specRough = sqr(d.roughness);                           // :181
+
+    float luminance = color_to_luminance(d.base);             // :185
+    f3 white = mk3(1.0f, 1.0f, 1.0f);
+    f3 tint = luminance > 0.0f ? mk3(d.base.x / luminance, d.base.y / luminance, d.base.z / luminance) : white;
+    f3 metallicColor = lerp_m(specularTint, white, tint) * specular;   // :187
+    d.F0 = lerp_m(d.metallic, metallicColor, d.base);                  // :188
+    d.sheenColor = lerp_m(sheenTint, white, tint) * sheen;             // :190
+}
+// src/rlDisney.cpp:570-577
+RLS_DEV float smithG_GGX(float NdotV, float alphaG)
+{
+    float a = alphaG * alphaG;
+    float b = NdotV * NdotV;
+    return 1.0f / (NdotV + sqrtf(a + b - a * b));
+}
+// src/rlDisney.cpp:545-551
+RLS_DEV float D_GTR1(const Disney &d, float MdotN2)
+{
+    float alpha = lerp_m(d.clearcoatGloss, 0.1f, 0.001f);
+    float a2 = sqr(alpha);
+    float denominator = rlm::logf_(a2) * (1.0f + (a2 - 1.0f) * MdotN2);
+    return (a2 - 1.0f) * kInvPi / denominator;
+}
+// src/rlDisney.cpp:561-568
+RLS_DEV float D_GTR2Aniso(const Disney &d, f3 m, float MdotN2)
+{
+    float HdotU = dot(m, d.U);
+    float HdotV = dot(m, d.V);
+    float denominator = d.ax * d.ay * sqr(sqr(HdotU / d.ax) + sqr(HdotV / d.ay) + MdotN2);
+    return kInvPi / denominator;
+}
+// src/rlDisney.cpp:199-236
+RLS_DEV f3 disney_eval_diffuse(const Disney &d, f3 L)
+{
+    float LdotN = dot(L, d.N);
+    float VdotN = dot(d.wo, d.N);
+    if (LdotN < kEps || VdotN < kEps) return mk3(0.0f, 0.0f, 0.0f);
+    f3 H = normalize(L + d.wo);
+    float LdotH = dot(L, H);
+    float NdotH = dot(d.wo, H);   // sic: V.H (:210)
+    if (NdotH < kEps || LdotH < kEps) return mk3(0.0f, 0.0f, 0.0f);
+    float LdotH2 = sqr(LdotH);
+    float FL = rlm::pow5f_(clamp_m(1.0f - LdotN, 0.0f, 1.0f));
+    float FV = rlm::pow5f_(clamp_m(1.0f - VdotN, 0.0f, 1.0f));
+    float F90 = 0.5f + 2.0f * d.roughness * LdotH2;
+    float diffuseFactor = lerp_m(FL, 1.0f, F90) * lerp_m(FV, 1.0f, F90);
+    float Fss90 = d.roughness * LdotH2;
+    float Fss = lerp_m(FL, 1.0f, Fss90) * lerp_m(FV, 1.0f, Fss90);
+    float ssFactor = 1.25f * (Fss * (1.0f / (LdotN + VdotN) - 0.5f) + 0.5f);
+    f3 diffuse = d.base * kInvPi * lerp_m(d.subsurface, diffuseFactor, ssFactor);
+    return diffuse * (1.0f - d.metallic);
+}
+// src/rlDisney.cpp:318-356
+RLS_DEV f3 disney_eval_specular(const Disney &d, f3 L)
+{
+    float LdotN = dot(L, d.N);
+    float VdotN = dot(d.wo, d.N);
+    if (LdotN < kEps || VdotN < kEps) return mk3(0.0f, 0.0f, 0.0f);
+    f3 M = normalize(L + d.wo);
+    float LdotM = dot(L, M);
+    float NdotM = dot(d.N, M);
+    if (NdotM < kEps || LdotM < kEps) return mk3(0.0f, 0.0f, 0.0f);
+    float NdotM2 = sqr(NdotM);
+    float Ds = D_GTR2Aniso(d, M, NdotM2);
+    float FH = rlm::pow5f_(clamp_m(1.0f - LdotM, 0.0f, 1.0f));
+    f3 Fs = lerp_m(FH, d.F0, mk3(1.0f, 1.0f, 1.0f));
+    float Gs = smithG_GGX(LdotN, d.specRough) * smithG_GGX(VdotN, d.specRough);
+    float Dr = D_GTR1(d, NdotM2);
+    float Fr = lerp_m(FH, 0.04f, 1.0f);
+    float Gr = smithG_GGX(LdotN, 0.25f) * smithG_GGX(VdotN, 0.25f);
+    f3 Fsheen = d.sheenColor * FH * (1.0f - d.metallic);
+    f3 spec = Fs * Ds * Gs;
+    float coat = d.clearcoat * Dr * Fr * Gr;
+    return mk3(spec.x + coat, spec.y + coat, spec.z + coat) + Fsheen;
+}
+// src/rlDisney.cpp:120-137
+RLS_DEV f3 disney_eval_brdf(const Disney &d, int type, f3 L)
+{
+    if (is_zero(L)) return mk3(0.0f, 0.0f, 0.0f);
+    float NdotL = dot(d.N, L);
+    f3 f = (type == kRayDiffuse) ? disney_eval_diffuse(d, L) : disney_eval_specular(d, L);
+    return f * NdotL;
+}
+// src/rlDisney.cpp:359-365
+RLS_DEV f3 disney_sample_diffuse(const Disney &d, float rx, float ry)
+{
+    f2 k = concentric_disk_sample(rx, ry);
+    f3 omega = mk3(k.x, k.y, sqrtf(max_m(0.0f, 1.0f - sqr(k.x) - sqr(k.y))));
+    return rotate_to_frame(omega, d.U, d.V, d.N);
+}
+// src/rlDisney.cpp:393-404 (a2 = roughness^2, NOT the clearcoat-gloss alpha of D_GTR1)
+RLS_DEV f3 disney_sample_gtr1(const Disney &d, float rx, float ry)
+{
+    float phiH = kTwoPi * rx;
+    float a2 = sqr(d.roughness);
+    float cosThetaH = (a2 == 1.0f) ? sqrtf(1.0f - ry)
+                                   : sqrtf((1.0f - rlm::powf_(a2, 1.0f - ry)) / (1.0f - a2));
+    f3 omega = spherical_direction(cosThetaH, phiH);
+    return normalize(rotate_to_frame(omega, d.U, d.V, d.N));
+}
+// src/rlDisney.cpp:367-390; lobe: 0 = GTR2 (visible normals), 1 = GTR1 (clearcoat)
+RLS_DEV f3 disney_sample_specular(const Disney &d, float rx, float ry, uint32_t &lobe)
+{
+    f3 M;
+    float gtr2Weight = 1.0f / (d.clearcoat + 1.0f);
+    if (rx < gtr2Weight) {
+        rx /= gtr2Weight;
+        M = sample_visible_normal(d.wo, d.U, d.V, d.N, d.ax, d.ay, rx, ry);
+        lobe = 0;
+    } else {
+        rx = (rx - gtr2Weight) / (1.0f - gtr2Weight);
+        M = disney_sample_gtr1(d, rx, ry);
+        lobe = 1;
+    }
+    if (dot(d.N, M) < 0.0f) return mk3(0.0f, 0.0f, 0.0f);
+    return reflect_direction(d.wo, M);
+}
+// src/rlDisney.cpp:515-518
+RLS_DEV float disney_diffuse_pdf(const Disney &d, f3 i) { return max_m(1e-4f, dot(i, d.N) * kInvPi); }
+// src/rlDisney.cpp:520-543 (mSampleFromVisibleNormal == true)
+RLS_DEV float disney_specular_pdf(const Disney &d, f3 i)
+{
+    f3 m = normalize(i + d.wo);
+    float IdotM = abs_m(dot(i, m));
+    float MdotN = dot(m, d.N);
+    if (MdotN < 0.0f) return 0.0f;
+    float MdotN2 = sqr(MdotN);
+    float clearcoatWeight = d.clearcoat / (d.clearcoat + 1.0f);
+    float VdotN = max_m(1e-4f, dot(d.wo, d.N));
+    float Dw = smithG_GGX(IdotM, d.specRough) * D_GTR2Aniso(d, m, MdotN2) * 2.0f * IdotM / VdotN;
+    float D = lerp_m(clearcoatWeight, Dw, D_GTR1(d, MdotN2) * abs_m(MdotN) / IdotM);
+    return D * 0.25f;
+}
+// src/rlDisney.cpp:139-152
+RLS_DEV float disney_eval_pdf(const Disney &d, int type, f3 L)
+{
+    if (is_zero(L)) return 0.0f;
+    return (type == kRayDiffuse) ? disney_diffuse_pdf(d, L) : disney_specular_pdf(d, L);
+}
+
+} // namespace rls

@@ -6,6 +6,14 @@ import ctypes as C
 import os
 import subprocess
 
+import os as _os
+import sys as _sys
+
+_ROOT = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+for _p in (_ROOT, _os.path.join(_ROOT, "tests")):
+    if _p not in _sys.path:
+        _sys.path.insert(0, _p)
+
 import numpy as np
 
 from rlshaders_b200 import _abi as abi
