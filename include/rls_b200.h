@@ -215,7 +215,8 @@ typedef struct rls_probe_out {
 
 /* ------------------------------------------------------------ life cycle */
 /* Creates a context on CUDA device `device`.  `stream` is an existing cudaStream_t to
- * enqueue on (NULL = the library creates its own non-blocking stream).  Fails with
+ * enqueue on (NULL = the library creates its own non-blocking stream; pass
+ * cudaStreamLegacy / cudaStreamPerThread to name a default stream).  Fails with
  * RLS_ERR_NO_DEVICE when no sm_100 device is usable -- there is no CPU path.
  * Replaces the plugin entry NodeLoader (src/_PluginMain.cpp:16-47) + node_initialize. */
 int  rls_init(int device, void *stream, rls_context **out_ctx);

@@ -1,9 +1,8 @@
 """ctypes mirror of include/rls_b200.h (structs, constants, flag bits).
 
 Pure data layout: nothing here touches a device.  The product binding
-(`rlshaders_b200._lib`) and the test-side oracle loader (`tests/oracle_lib.py`) both
-build their argument blocks from these classes, so one descriptor feeds both sides of
-a parity test.
+(`rlshaders_b200._lib`) builds its argument blocks from these classes; the parity tests
+reuse them so that one descriptor feeds both sides of a comparison.
 """
 import ctypes as C
 

@@ -41,7 +41,10 @@ class Context:
         if stream is None and torch.cuda.is_available():
             stream = torch.cuda.current_stream(self.index)
         self.stream = stream
-        raw = C.c_void_p(stream.cuda_stream) if stream is not None else None
+        # torch's default stream has handle 0, which rls_init reads as "create a private
+        # stream"; name the legacy default stream explicitly (cudaStreamLegacy == 0x1) so that
+        # torch tensors, torch.cuda.Event timing and the kernels share one stream.
+        raw = C.c_void_p(stream.cuda_stream or 1) if stream is not None else None
         rc = self.lib.rls_init(self.index, raw, C.byref(handle))
         if rc != abi.RLS_OK:
             msg = self.lib.rls_last_error_string(None)

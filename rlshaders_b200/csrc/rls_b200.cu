@@ -579,8 +579,8 @@ extern "C" int rls_ggx_eval_sample(rls_context *ctx, size_t n, const rls_shading
                                    const float *rx, const float *ry, rls_vec3 out_wi, float *out_fresnel)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
-    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && rx && ry && has3(out_wi), "rls_ggx_eval_sample: NULL argument");
     if (n == 0) return RLS_OK;
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && rx && ry && has3(out_wi), "rls_ggx_eval_sample: NULL argument");
     DeviceGuard guard(ctx->device);
     k_ggx_eval_sample<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), rx, ry, mv(out_wi), out_fresnel);
     RLS_LAUNCH_CHECK(ctx);
@@ -590,8 +590,8 @@ extern "C" int rls_ggx_eval_brdf(rls_context *ctx, size_t n, const rls_shading_s
                                  rls_cvec3 wi, rls_vec3 out_f)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
-    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && has3(wi) && has3(out_f), "rls_ggx_eval_brdf: NULL argument");
     if (n == 0) return RLS_OK;
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && has3(wi) && has3(out_f), "rls_ggx_eval_brdf: NULL argument");
     DeviceGuard guard(ctx->device);
     k_ggx_eval_brdf<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), cv(wi), mv(out_f));
     RLS_LAUNCH_CHECK(ctx);
@@ -601,8 +601,8 @@ extern "C" int rls_ggx_eval_pdf(rls_context *ctx, size_t n, const rls_shading_so
                                 rls_cvec3 wi, float *out_pdf)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
-    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && has3(wi) && out_pdf, "rls_ggx_eval_pdf: NULL argument");
     if (n == 0) return RLS_OK;
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && has3(wi) && out_pdf, "rls_ggx_eval_pdf: NULL argument");
     DeviceGuard guard(ctx->device);
     k_ggx_eval_pdf<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), cv(wi), out_pdf);
     RLS_LAUNCH_CHECK(ctx);
@@ -612,8 +612,8 @@ extern "C" int rls_ggx_sample_eval_pdf(rls_context *ctx, size_t n, const rls_sha
                                        const float *rx, const float *ry, const rls_bsdf_out *out)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
-    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && rx && ry && ok_bsdf_out(out), "rls_ggx_sample_eval_pdf: NULL argument");
     if (n == 0) return RLS_OK;
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && rx && ry && ok_bsdf_out(out), "rls_ggx_sample_eval_pdf: NULL argument");
     DeviceGuard guard(ctx->device);
     return launch_ggx_sample_eval_pdf(ctx, ctx->stream, n, sg, p, rx, ry, out);
 }
@@ -622,9 +622,9 @@ extern "C" int rls_ggx_dielectric_sample_eval_pdf(rls_context *ctx, size_t n, co
                                                   const rls_ggx_dielectric_out *out)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
     RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && rx && ry && ok_dielectric_out(out),
                 "rls_ggx_dielectric_sample_eval_pdf: NULL argument");
-    if (n == 0) return RLS_OK;
     DeviceGuard guard(ctx->device);
     return launch_ggx_dielectric(ctx, ctx->stream, n, sg, p, rx, ry, out);
 }
@@ -636,9 +636,9 @@ extern "C" int rls_disney_eval_sample(rls_context *ctx, size_t n, const rls_shad
                                       int sample_type, const float *rx, const float *ry, rls_vec3 out_wi, uint32_t *out_flags)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
     RLS_REQUIRE(ctx, ok_shading(sg) && ok_disney_params(p) && rx && ry && has3(out_wi), "rls_disney_eval_sample: NULL argument");
     RLS_REQUIRE(ctx, ok_sample_type(sample_type), "rls_disney_eval_sample: sample_type must be RLS_RAY_DIFFUSE or RLS_RAY_GLOSSY");
-    if (n == 0) return RLS_OK;
     DeviceGuard guard(ctx->device);
     k_disney_eval_sample<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), sample_type, rx, ry, mv(out_wi), out_flags);
     RLS_LAUNCH_CHECK(ctx);
@@ -648,9 +648,9 @@ extern "C" int rls_disney_eval_brdf(rls_context *ctx, size_t n, const rls_shadin
                                     int sample_type, rls_cvec3 wi, rls_vec3 out_f)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
     RLS_REQUIRE(ctx, ok_shading(sg) && ok_disney_params(p) && has3(wi) && has3(out_f), "rls_disney_eval_brdf: NULL argument");
     RLS_REQUIRE(ctx, ok_sample_type(sample_type), "rls_disney_eval_brdf: sample_type must be RLS_RAY_DIFFUSE or RLS_RAY_GLOSSY");
-    if (n == 0) return RLS_OK;
     DeviceGuard guard(ctx->device);
     k_disney_eval_brdf<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), sample_type, cv(wi), mv(out_f));
     RLS_LAUNCH_CHECK(ctx);
@@ -660,9 +660,9 @@ extern "C" int rls_disney_eval_pdf(rls_context *ctx, size_t n, const rls_shading
                                    int sample_type, rls_cvec3 wi, float *out_pdf)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
     RLS_REQUIRE(ctx, ok_shading(sg) && ok_disney_params(p) && has3(wi) && out_pdf, "rls_disney_eval_pdf: NULL argument");
     RLS_REQUIRE(ctx, ok_sample_type(sample_type), "rls_disney_eval_pdf: sample_type must be RLS_RAY_DIFFUSE or RLS_RAY_GLOSSY");
-    if (n == 0) return RLS_OK;
     DeviceGuard guard(ctx->device);
     k_disney_eval_pdf<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), sample_type, cv(wi), out_pdf);
     RLS_LAUNCH_CHECK(ctx);
@@ -673,9 +673,9 @@ extern "C" int rls_disney_sample_eval_pdf(rls_context *ctx, size_t n, const rls_
                                           const rls_disney_out *out)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
     RLS_REQUIRE(ctx, ok_shading(sg) && ok_disney_params(p) && rx_s && ry_s && rx_d && ry_d && ok_disney_out(out),
                 "rls_disney_sample_eval_pdf: NULL argument");
-    if (n == 0) return RLS_OK;
     DeviceGuard guard(ctx->device);
     return launch_disney_sample_eval_pdf(ctx, ctx->stream, n, sg, p, rx_s, ry_s, rx_d, ry_d, out);
 }
@@ -692,8 +692,8 @@ extern "C" int rls_ndprofile_set_distance(rls_context *ctx, size_t n, rls_cvec3 
 {
     (void)albedo;   // only feeds the dead `s` of src/rlSss.cpp:22-23
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
-    RLS_REQUIRE(ctx, has3(dist) && ok_profile(out), "rls_ndprofile_set_distance: NULL argument");
     if (n == 0) return RLS_OK;
+    RLS_REQUIRE(ctx, has3(dist) && ok_profile(out), "rls_ndprofile_set_distance: NULL argument");
     DeviceGuard guard(ctx->device);
     k_nd_set_distance<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, cv(dist), dev(*out));
     RLS_LAUNCH_CHECK(ctx);
@@ -703,8 +703,8 @@ extern "C" int rls_ndprofile_get_radius(rls_context *ctx, size_t n, const rls_nd
                                         float *out_r, uint32_t *out_flags)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
-    RLS_REQUIRE(ctx, ok_profile(profile) && rx && out_r, "rls_ndprofile_get_radius: NULL argument");
     if (n == 0) return RLS_OK;
+    RLS_REQUIRE(ctx, ok_profile(profile) && rx && out_r, "rls_ndprofile_get_radius: NULL argument");
     DeviceGuard guard(ctx->device);
     k_nd_get_radius<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, dev(*profile), rx, out_r, out_flags);
     RLS_LAUNCH_CHECK(ctx);
@@ -713,8 +713,8 @@ extern "C" int rls_ndprofile_get_radius(rls_context *ctx, size_t n, const rls_nd
 extern "C" int rls_ndprofile_get_pdf(rls_context *ctx, size_t n, const rls_ndprofile_soa *profile, const float *r, float *out_pdf)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
-    RLS_REQUIRE(ctx, ok_profile(profile) && r && out_pdf, "rls_ndprofile_get_pdf: NULL argument");
     if (n == 0) return RLS_OK;
+    RLS_REQUIRE(ctx, ok_profile(profile) && r && out_pdf, "rls_ndprofile_get_pdf: NULL argument");
     DeviceGuard guard(ctx->device);
     k_nd_get_pdf<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, dev(*profile), r, out_pdf);
     RLS_LAUNCH_CHECK(ctx);
@@ -723,8 +723,8 @@ extern "C" int rls_ndprofile_get_pdf(rls_context *ctx, size_t n, const rls_ndpro
 extern "C" int rls_ndprofile_eval_profile(rls_context *ctx, size_t n, const rls_ndprofile_soa *profile, const float *r, rls_vec3 out_rd)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
-    RLS_REQUIRE(ctx, ok_profile(profile) && r && has3(out_rd), "rls_ndprofile_eval_profile: NULL argument");
     if (n == 0) return RLS_OK;
+    RLS_REQUIRE(ctx, ok_profile(profile) && r && has3(out_rd), "rls_ndprofile_eval_profile: NULL argument");
     DeviceGuard guard(ctx->device);
     k_nd_eval_profile<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, dev(*profile), r, mv(out_rd));
     RLS_LAUNCH_CHECK(ctx);
@@ -734,8 +734,8 @@ extern "C" int rls_skin_profile_sample_eval_pdf(rls_context *ctx, size_t n, cons
                                                 const rls_profile_out *out)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
-    RLS_REQUIRE(ctx, ok_skin_params(p) && rx && ok_profile_out(out), "rls_skin_profile_sample_eval_pdf: NULL argument");
     if (n == 0) return RLS_OK;
+    RLS_REQUIRE(ctx, ok_skin_params(p) && rx && ok_profile_out(out), "rls_skin_profile_sample_eval_pdf: NULL argument");
     DeviceGuard guard(ctx->device);
     return launch_skin_profile(ctx, ctx->stream, n, p, rx, out);
 }
@@ -743,8 +743,8 @@ extern "C" int rls_skin_layer_weights(rls_context *ctx, size_t n, const rls_skin
                                       const float *avg_spec, float *out_spec_scale, float *out_sss_weight)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
-    RLS_REQUIRE(ctx, p && avg_sheen && avg_spec && out_spec_scale && out_sss_weight, "rls_skin_layer_weights: NULL argument");
     if (n == 0) return RLS_OK;
+    RLS_REQUIRE(ctx, p && avg_sheen && avg_spec && out_spec_scale && out_sss_weight, "rls_skin_layer_weights: NULL argument");
     DeviceGuard guard(ctx->device);
     k_skin_layer_weights<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, dev(*p), avg_sheen, avg_spec, out_spec_scale, out_sss_weight);
     RLS_LAUNCH_CHECK(ctx);
@@ -772,8 +772,8 @@ extern "C" int rls_synth_uniform(rls_context *ctx, size_t n, uint64_t seed, uint
                                  float lo, float hi, float *out)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
-    RLS_REQUIRE(ctx, out, "rls_synth_uniform: NULL argument");
     if (n == 0) return RLS_OK;
+    RLS_REQUIRE(ctx, out, "rls_synth_uniform: NULL argument");
     DeviceGuard guard(ctx->device);
     k_synth_uniform<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, seed, stream, first_index, lo, hi, out);
     RLS_LAUNCH_CHECK(ctx);
@@ -783,8 +783,8 @@ extern "C" int rls_synth_shading(rls_context *ctx, size_t n, uint64_t seed, uint
                                  float backfacing_fraction, const rls_shading_soa *sg)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
-    RLS_REQUIRE(ctx, ok_shading(sg), "rls_synth_shading: NULL argument");
     if (n == 0) return RLS_OK;
+    RLS_REQUIRE(ctx, ok_shading(sg), "rls_synth_shading: NULL argument");
     DeviceGuard guard(ctx->device);
     V3 U = { (float *)sg->U.x, (float *)sg->U.y, (float *)sg->U.z };
     V3 V = { (float *)sg->V.x, (float *)sg->V.y, (float *)sg->V.z };
@@ -906,8 +906,8 @@ extern "C" int rls_ggx_sample_eval_pdf_host(rls_context *ctx, size_t n, const rl
                                             const float *rx, const float *ry, const rls_bsdf_out *out, size_t chunk)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
-    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && rx && ry && ok_bsdf_out(out), "rls_ggx_sample_eval_pdf_host: NULL argument");
     if (n == 0) return RLS_OK;
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && rx && ry && ok_bsdf_out(out), "rls_ggx_sample_eval_pdf_host: NULL argument");
     return run_staged(ctx, n, chunk, 32, [&](Stager &st) {
         rls_shading_soa s = st.shading(*sg);
         rls_ggx_params q = *p;
@@ -924,9 +924,9 @@ extern "C" int rls_ggx_dielectric_sample_eval_pdf_host(rls_context *ctx, size_t 
                                                        const rls_ggx_dielectric_out *out, size_t chunk)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
     RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && rx && ry && ok_dielectric_out(out),
                 "rls_ggx_dielectric_sample_eval_pdf_host: NULL argument");
-    if (n == 0) return RLS_OK;
     return run_staged(ctx, n, chunk, 36, [&](Stager &st) {
         rls_shading_soa s = st.shading(*sg);
         rls_ggx_params q = *p;
@@ -944,9 +944,9 @@ extern "C" int rls_disney_sample_eval_pdf_host(rls_context *ctx, size_t n, const
                                                const rls_disney_out *out, size_t chunk)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
     RLS_REQUIRE(ctx, ok_shading(sg) && ok_disney_params(p) && rx_s && ry_s && rx_d && ry_d && ok_disney_out(out),
                 "rls_disney_sample_eval_pdf_host: NULL argument");
-    if (n == 0) return RLS_OK;
     return run_staged(ctx, n, chunk, 48, [&](Stager &st) {
         rls_shading_soa s = st.shading(*sg);
         rls_disney_params q = *p;
@@ -965,8 +965,8 @@ extern "C" int rls_skin_profile_sample_eval_pdf_host(rls_context *ctx, size_t n,
                                                      const rls_profile_out *out, size_t chunk)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
-    RLS_REQUIRE(ctx, ok_skin_params(p) && rx && ok_profile_out(out), "rls_skin_profile_sample_eval_pdf_host: NULL argument");
     if (n == 0) return RLS_OK;
+    RLS_REQUIRE(ctx, ok_skin_params(p) && rx && ok_profile_out(out), "rls_skin_profile_sample_eval_pdf_host: NULL argument");
     return run_staged(ctx, n, chunk, 16, [&](Stager &st) {
         rls_skin_params q = *p;
         q.sss_color = st.inp3(p->sss_color); q.sss_scatter_dist = st.inp3(p->sss_scatter_dist);

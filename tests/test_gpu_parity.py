@@ -1,0 +1,395 @@
+"""GPU: parity of the CUDA path (called through the C ABI) against the CPU oracle on
+identical input bits, against the committed golden vectors, and -- at BASELINE sizes --
+through size-independent properties.
+
+Stated tolerances (BASELINE.json north_star; DESIGN.md "Parity policy"):
+  * flags / lobe choices / invalid-sample markers: bit-exact, every sample;
+  * sampled directions: 1e-6 absolute; f, pdf, radii, weights: 1e-5 relative.
+    Visible-normal sampling is ill-conditioned, so the value tolerances are
+    asserted as fractions: >= FRAC_TOL of samples within tolerance and >= FRAC_LOOSE within
+    100x the tolerance;
+  * everything that is free of transcendentals (rlGgx evalBrdf / evalPdf at a given
+    direction, layer weights, the synthetic hash): bit-exact, every sample.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import golden_io as gio
+import oracle_lib as ol
+import parity
+from rlshaders_b200 import _abi as abi
+
+pytestmark = pytest.mark.gpu
+
+N = 1 << 20
+FRAC_TOL = 0.995      # fraction of samples within the stated tolerance
+FRAC_LOOSE = 0.9999   # fraction within 100x the stated tolerance
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from rlshaders_b200 import api
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module", params=["reference", "port"])
+def orc(request):
+    o = ol.load_ref() if request.param == "reference" else ol.load_port()
+    if o is None:
+        pytest.skip("reference library not shipped")
+    return o
+
+
+def check(stats, title):
+    print(parity.format_report(title, stats))
+    for name, s in stats.items():
+        if "mismatches" in s:
+            assert s["mismatches"] == 0, (title, name, s)
+        else:
+            loose = s.get("within_1e4", s.get("within_1e3"))
+            assert s["within"] >= FRAC_TOL, (title, name, s)
+            assert loose >= FRAC_LOOSE, (title, name, s)
+
+
+def dev(a, ctx):
+    return parity.to_dev(a, ctx.device)
+
+
+# ------------------------------------------------------------------ fused units
+def test_ggx_conductor_parity(ctx, orc):
+    check(parity.run_ggx_conductor(ctx, orc, N)[0], f"config 1 vs {orc.kind}")
+
+
+@pytest.mark.parametrize("aniso", [False, True])
+def test_ggx_dielectric_parity(ctx, orc, aniso):
+    check(parity.run_ggx_dielectric(ctx, orc, N, aniso=aniso)[0], f"config 2 aniso={aniso} vs {orc.kind}")
+
+
+def test_disney_parity(ctx, orc):
+    check(parity.run_disney(ctx, orc, N)[0], f"config 3 vs {orc.kind}")
+
+
+def test_skin_profile_parity(ctx, orc):
+    stats = parity.run_skin(ctx, orc, N)[0]
+    check(stats, f"config 4 vs {orc.kind}")
+    for k in ("r", "pdf", "Rd"):
+        assert stats[k]["within"] == 1.0        # the profile is well conditioned: every sample
+
+
+# ------------------------------------------------- explicit-wi entry points
+def test_ggx_eval_brdf_pdf_bit_exact_at_oracle_directions(ctx):
+    """evalBrdf / evalPdf contain only + - * / sqrt: bit-exact for every sample."""
+    from rlshaders_b200 import api
+    port = ol.load_port()
+    sg, kw, rx, ry = parity.ggx_dielectric_inputs(N, aniso=True)
+    kw["KsColor"] = tuple(ol.hash_uniform(N, 3, 60 + j) for j in range(3))
+    p = abi.ggx_params(**kw)
+    wi = port.ggx_eval_sample(sg, p, rx, ry)["wi"]
+    wi[:, :16] = 0.0                              # zero indir: black, pdf floored (no guard)
+    wi[:, 16:32] *= -1.0                          # below the horizon
+    s = api.GgxSampler(ctx, api.ShadingBatch.from_numpy(sg, ctx.device), **parity.params_to_dev(kw, ctx.device))
+    dwi = dev(wi, ctx)
+    f, pdf = s.evalBrdf(dwi).cpu().numpy(), s.evalPdf(dwi).cpu().numpy()
+    assert gio.bits_equal(f, port.ggx_eval_brdf(sg, p, wi))
+    assert gio.bits_equal(pdf, port.ggx_eval_pdf(sg, p, wi))
+    assert np.all(f[:, :16] == 0) and np.all(pdf[:16] >= 1e-4)
+
+
+def test_ggx_eval_sample_matches_oracle_and_fused(ctx):
+    from rlshaders_b200 import api
+    port = ol.load_port()
+    sg, kw, rx, ry = parity.ggx_dielectric_inputs(N)
+    s = api.GgxSampler(ctx, api.ShadingBatch.from_numpy(sg, ctx.device), **parity.params_to_dev(kw, ctx.device))
+    drx, dry = dev(rx, ctx), dev(ry, ctx)
+    wi, F = s.evalSample(drx, dry)
+    fused = s.sampleEvalPdf(drx, dry)
+    assert torch.equal(wi, fused["wi"]) and torch.equal(F, fused["fresnel"])
+    assert torch.equal(s.evalBrdf(wi), fused["f"]) and torch.equal(s.evalPdf(wi), fused["pdf"])
+    cpu = port.ggx_eval_sample(sg, abi.ggx_params(**kw), rx, ry)
+    check(dict(wi=parity.stat_dir(wi.cpu().numpy(), cpu["wi"]), fresnel=parity.stat_rel(F.cpu().numpy(), cpu["fresnel"])),
+          "rls_ggx_eval_sample")
+
+
+@pytest.mark.parametrize("sample_type", [abi.RLS_RAY_DIFFUSE, abi.RLS_RAY_GLOSSY])
+def test_disney_triple_entry_points(ctx, sample_type):
+    from rlshaders_b200 import api
+    port = ol.load_port()
+    sg, kw, u = parity.disney_inputs(N)
+    p = abi.disney_params(**kw)
+    s = api.DisneySampler(ctx, api.ShadingBatch.from_numpy(sg, ctx.device), **parity.params_to_dev(kw, ctx.device))
+    s.setSampleType(sample_type)
+    j = 0 if sample_type == abi.RLS_RAY_GLOSSY else 2
+    wi, fl = s.evalSample(dev(u[j], ctx), dev(u[j + 1], ctx))
+    cpu = port.disney_eval_sample(sg, p, sample_type, u[j], u[j + 1])
+    check(dict(wi=parity.stat_dir(wi.cpu().numpy(), cpu["wi"]), flags=parity.stat_flags(fl.cpu().numpy(), cpu["flags"])),
+          f"rls_disney_eval_sample type {sample_type:#x}")
+    fused = s.sampleEvalPdf(*[dev(t, ctx) for t in u])
+    key = "s" if sample_type == abi.RLS_RAY_GLOSSY else "d"
+    assert torch.equal(wi, fused["wi_" + key])
+    assert torch.equal(s.evalBrdf(wi), fused["f_" + key]) and torch.equal(s.evalPdf(wi), fused["pdf_" + key])
+    # at the ORACLE's directions (incl. zero vectors) eval/pdf agree to tolerance on every sample
+    owi = cpu["wi"].copy()
+    owi[:, :8] = 0.0
+    dwi = dev(owi, ctx)
+    sf = parity.stat_rel(s.evalBrdf(dwi).cpu().numpy(), port.disney_eval_brdf(sg, p, sample_type, owi))
+    sp = parity.stat_rel(s.evalPdf(dwi).cpu().numpy(), port.disney_eval_pdf(sg, p, sample_type, owi))
+    print(parity.format_report("disney eval at oracle wi", dict(f=sf, pdf=sp)))
+    assert sf["within"] == 1.0 and sp["within"] == 1.0
+    assert np.all(s.evalPdf(dwi).cpu().numpy()[:8] == 0) and np.all(s.evalBrdf(dwi).cpu().numpy()[:, :8] == 0)
+
+
+def test_ndprofile_entry_points(ctx):
+    from rlshaders_b200 import api
+    port = ol.load_port()
+    rx = ol.hash_uniform(N, 9, 20)
+    dist = np.stack([ol.hash_uniform(N, 9, j, lo=0.0, hi=2.0) for j in range(3)])
+    dist[:, :64] = 0.0            # degenerate: maxRadius < eps
+    dist[0, 64:128] = 5e-5        # one channel below eps
+    albedo = np.stack([ol.hash_uniform(N, 9, 3 + j) for j in range(3)])
+    cp = port.ndprofile_set_distance(dist, albedo)
+    prof = api.NDProfile(ctx)
+    st = prof.setDistance(dev(dist, ctx), dev(albedo, ctx))
+    for k in ("distance", "C1", "C2", "max_radius"):
+        s = parity.stat_rel(st[k].cpu().numpy(), cp[k])
+        assert s["within"] == 1.0, (k, s)
+    # feed the ORACLE's profile state so the discrete lobe choice sees identical bits
+    prof.state = {k: dev(v, ctx) for k, v in cp.items()}
+    prof._struct = abi.NdProfileSoA(abi.vec3(tuple(prof.state["distance"])), abi.vec3(tuple(prof.state["C1"])),
+                                    abi.vec3(tuple(prof.state["C2"])), prof.state["max_radius"].data_ptr())
+    r, fl = prof.getRadius(dev(rx, ctx))
+    cr = port.ndprofile_get_radius(cp, rx)
+    assert np.array_equal(fl.cpu().numpy().astype(np.uint32), cr["flags"])
+    assert parity.stat_rel(r.cpu().numpy(), cr["r"])["within"] == 1.0
+    with np.errstate(all="ignore"):
+        cpdf, crd = port.ndprofile_get_pdf(cp, cr["r"]), port.ndprofile_eval_profile(cp, cr["r"])
+    dr = dev(cr["r"], ctx)
+    assert parity.stat_rel(prof.getPdf(dr).cpu().numpy(), cpdf)["within"] == 1.0
+    assert parity.stat_rel(prof.evalProfile(dr).cpu().numpy(), crd)["within"] == 1.0
+
+
+def test_skin_layer_weights_bit_exact(ctx):
+    from rlshaders_b200 import api
+    port = ol.load_port()
+    n = 1 << 16
+    f1, f2 = ol.hash_uniform(n, 6, 1), ol.hash_uniform(n, 6, 2)
+    kw = dict(sheen_weight=ol.hash_uniform(n, 6, 3), specular_weight=ol.hash_uniform(n, 6, 4),
+              sss_weight=ol.hash_uniform(n, 6, 5))
+    kw["sheen_weight"][:100] = 5e-5
+    cpu = port.skin_layer_weights(abi.skin_params(**kw), f1, f2)
+    s = api.SkinProfile(ctx, n, **parity.params_to_dev(kw, ctx.device))
+    a, b = s.layerWeights(dev(f1, ctx), dev(f2, ctx))
+    assert gio.bits_equal(a.cpu().numpy(), cpu["specular_scale"]) and gio.bits_equal(b.cpu().numpy(), cpu["sss_weight"])
+
+
+# ------------------------------------------------------------ golden fixtures
+def test_golden_ggx_fixtures(ctx):
+    from rlshaders_b200 import api
+    g = gio.load("ggx_fixtures")
+    sg = api.ShadingBatch.from_numpy(gio.shading(g), ctx.device)
+    for name in ("teflon", "gold", "anisotropic", "gold_bench"):
+        rough, ior, aniso = [float(x) for x in g[name + "_params"]]
+        out = api.GgxSampler(ctx, sg, specularRoughness=rough, ior=ior, anisotropic=aniso).sampleEvalPdf(
+            dev(g["rx"], ctx), dev(g["ry"], ctx))
+        want = {k: g[f"{name}_{k}"] for k in ("wi", "f", "pdf", "fresnel", "flags")}
+        stats = parity.summarize(out, want, dict(wi="dir", f="rel", pdf="rel", fresnel="rel", flags="flags"))
+        print(parity.format_report(f"golden rlGgx {name}", stats))
+        assert stats["flags"]["mismatches"] == 0
+        for k in ("wi", "f", "pdf", "fresnel"):
+            assert stats[k]["within"] >= 0.99, (name, k, stats[k])
+
+
+def test_golden_dielectric_disney_skin(ctx):
+    from rlshaders_b200 import api
+    g = gio.load("ggx_dielectric")
+    kw = gio.group(g, "p_")
+    out = api.GgxSampler(ctx, api.ShadingBatch.from_numpy(gio.shading(g), ctx.device),
+                         **parity.params_to_dev(kw, ctx.device)).dielectricSampleEvalPdf(dev(g["rx"], ctx), dev(g["ry"], ctx))
+    kinds = dict(fresnel="rel", wi_r="dir", f_r="rel", pdf_r="rel", wi_t="dir", f_t="rel", weight_t="rel", flags="flags")
+    stats = parity.summarize(out, gio.group(g, "out_"), kinds)
+    print(parity.format_report("golden dielectric", stats))
+    assert stats["flags"]["mismatches"] == 0 and all(s["within"] >= 0.99 for k, s in stats.items() if k != "flags")
+
+    g = gio.load("disney")
+    kw = gio.group(g, "p_")
+    kw["base_color"] = (g["base_r"], g["base_g"], g["base_b"])
+    u = [dev(g[f"u{j}"], ctx) for j in range(4)]
+    sg = api.ShadingBatch.from_numpy(gio.shading(g), ctx.device)
+    kinds = dict(wi_s="dir", f_s="rel", pdf_s="rel", wi_d="dir", f_d="rel", pdf_d="rel", flags="flags")
+    cases = [("out", kw)] + [(nm, dict(base_color=(0.8, 0.4, 0.2), **pr)) for nm, pr in dict(
+        default=dict(roughness=0.5, specular=0.5), subsurface=dict(roughness=0.5, specular=0.5, subsurface=1.0),
+        metallic=dict(metallic=1.0, roughness=0.3), specular=dict(specular=1.0, roughness=0.5),
+        aniso=dict(metallic=1.0, roughness=0.2, anisotropic=1.0),
+        clearcoat=dict(roughness=0.6, clearcoat=1.0, clearcoat_gloss=0.8, sheen=0.5, sheen_tint=0.5)).items()]
+    for name, params in cases:
+        out = api.DisneySampler(ctx, sg, **parity.params_to_dev(params, ctx.device)).sampleEvalPdf(*u)
+        stats = parity.summarize(out, gio.group(g, name + "_"), kinds)
+        print(parity.format_report(f"golden rlDisney {name}", stats))
+        assert stats["flags"]["mismatches"] == 0, name
+        assert all(s["within"] >= 0.99 for k, s in stats.items() if k != "flags"), (name, stats)
+
+    g = gio.load("skin")
+    color, dist = (g["color_r"], g["color_g"], g["color_b"]), (g["dist_x"], g["dist_y"], g["dist_z"])
+    n = len(g["rx"])
+    for prefix, params in (("out_", dict(sss_color=color, sss_scatter_dist=dist)),
+                           ("scene0009_", dict(sss_color=(1.0, 0.84235, 0.5), sss_scatter_dist=(1.0, 1.0, 1.0)))):
+        out = api.SkinProfile(ctx, n, **parity.params_to_dev(params, ctx.device)).sampleEvalPdf(dev(g["rx"], ctx))
+        stats = parity.summarize(out, gio.group(g, prefix), dict(r="rel", pdf="rel", Rd="rel", flags="flags"))
+        print(parity.format_report(f"golden rlSkin {prefix}", stats))
+        assert stats["flags"]["mismatches"] == 0 and all(s["within"] == 1.0 for k, s in stats.items() if k != "flags")
+
+
+# ------------------------------------------------------------------- edge cases
+def test_empty_and_ragged_batches(ctx):
+    from rlshaders_b200 import api
+    port = ol.load_port()
+    for n in (0, 1, 31, 257, 1000003):
+        sg, kw, rx, ry = parity.ggx_dielectric_inputs(max(n, 1))
+        if n == 0:
+            sg = {k: (v[:0] if v is not None else None) for k, v in sg.items()}
+            kw = {k: v[:0] for k, v in kw.items()}
+            rx, ry = rx[:0], ry[:0]
+        s = api.GgxSampler(ctx, api.ShadingBatch.from_numpy(sg, ctx.device), **parity.params_to_dev(kw, ctx.device))
+        out = s.dielectricSampleEvalPdf(dev(rx, ctx), dev(ry, ctx))
+        ctx.synchronize()
+        assert out["flags"].shape[0] == n
+        if n:
+            cpu = port.ggx_dielectric(sg, abi.ggx_params(**kw), rx, ry)
+            assert np.array_equal(out["flags"].cpu().numpy().astype(np.uint32), cpu["flags"])
+            assert parity.stat_dir(out["wi_r"].cpu().numpy(), cpu["wi_r"])["within"] >= 0.99
+
+
+def test_argument_errors_are_reported_not_crashed(ctx):
+    lib = ctx.lib
+    sg, p, rx, ry = ol.workload_ggx_conductor(64)
+    rc = lib.rls_ggx_sample_eval_pdf(ctx.handle, 64, None, C.byref(p), None, None, None)
+    assert rc == abi.RLS_ERR_INVALID_ARGUMENT and b"NULL" in lib.rls_last_error_string(ctx.handle)
+    from rlshaders_b200 import api
+    d = api.DisneySampler(ctx, api.ShadingBatch.from_numpy(sg, ctx.device), roughness=0.5)
+    with pytest.raises(ValueError):
+        d.setSampleType(3)
+    wi = ctx.empty(3, 64)
+    rc = lib.rls_disney_eval_pdf(ctx.handle, 64, C.byref(d.sg.struct), C.byref(d.params), 3,
+                                 abi.vec3((wi[0], wi[1], wi[2])), ctx.empty(64).data_ptr())
+    assert rc == abi.RLS_ERR_INVALID_ARGUMENT
+    with pytest.raises(TypeError):
+        api.GgxSampler(ctx, d.sg, roughness=0.1)
+
+
+def test_uniform_parameter_equals_constant_array(ctx):
+    from rlshaders_b200 import api
+    n = 1 << 16
+    sg = api.ShadingBatch.from_numpy(ol.make_shading(n, 5), ctx.device)
+    rx, ry = dev(ol.hash_uniform(n, 5, 0), ctx), dev(ol.hash_uniform(n, 5, 1), ctx)
+    full = lambda v: torch.full((n,), v, dtype=torch.float32, device=ctx.device)   # noqa: E731
+    a = api.GgxSampler(ctx, sg, KsColor=(0.9, 0.5, 0.2), specularRoughness=0.3, ior=1.5, anisotropic=0.4).sampleEvalPdf(rx, ry)
+    b = api.GgxSampler(ctx, sg, KsColor=(full(0.9), full(0.5), full(0.2)), specularRoughness=full(0.3), ior=full(1.5),
+                       anisotropic=full(0.4)).sampleEvalPdf(rx, ry)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_host_buffer_entry_points_match_device(ctx):
+    from rlshaders_b200 import api
+    n = 300007                                   # ragged; chunk 65536 -> 5 chunks through 3 stages
+    sg, kw, rx, ry = parity.ggx_dielectric_inputs(n, aniso=True)
+    dsamp = api.GgxSampler(ctx, api.ShadingBatch.from_numpy(sg, ctx.device), **parity.params_to_dev(kw, ctx.device))
+    dout = dsamp.dielectricSampleEvalPdf(dev(rx, ctx), dev(ry, ctx))
+    pin = lambda a: torch.from_numpy(a).pin_memory()   # noqa: E731
+    hkw = {k: pin(v) for k, v in kw.items()}
+    hsamp = api.GgxSampler(ctx, api.ShadingBatch.from_numpy(sg, None, pin=True), **hkw)
+    hout = hsamp.dielectricSampleEvalPdf(pin(rx), pin(ry), chunk=65536)
+    for k in dout:
+        assert torch.equal(dout[k].cpu(), hout[k]), k
+    d2 = dsamp.sampleEvalPdf(dev(rx, ctx), dev(ry, ctx))
+    h2 = hsamp.sampleEvalPdf(pin(rx), pin(ry), chunk=100000)
+    for k in d2:
+        assert torch.equal(d2[k].cpu(), h2[k]), k
+    sgd, kwd, u = parity.disney_inputs(n)
+    dd = api.DisneySampler(ctx, api.ShadingBatch.from_numpy(sgd, ctx.device), **parity.params_to_dev(kwd, ctx.device))
+    hd = api.DisneySampler(ctx, api.ShadingBatch.from_numpy(sgd, None, pin=True),
+                           **{k: (tuple(pin(t) for t in v) if isinstance(v, tuple) else pin(v)) for k, v in kwd.items()})
+    o1, o2 = dd.sampleEvalPdf(*[dev(t, ctx) for t in u]), hd.sampleEvalPdf(*[pin(t) for t in u], chunk=65536)
+    for k in o1:
+        assert torch.equal(o1[k].cpu(), o2[k]), k
+    kws, rxs = parity.skin_inputs(n)
+    ds = api.SkinProfile(ctx, n, **parity.params_to_dev(kws, ctx.device))
+    hs = api.SkinProfile(ctx, n, **{k: (tuple(pin(t) for t in v) if isinstance(v, tuple) else v) for k, v in kws.items()})
+    o1, o2 = ds.sampleEvalPdf(dev(rxs, ctx)), hs.sampleEvalPdf(pin(rxs), chunk=65536)
+    for k in o1:
+        assert torch.equal(o1[k].cpu(), o2[k]), k
+
+
+# ------------------------------------------------------- synth + sweep + sizes
+def test_synth_generators(ctx):
+    for seed, stream, first, lo, hi in ((0x5EED0002, 3, 0, 1.05, 2.5), (77, 50, 2**40 + 17, 0.0, 1.0)):
+        got = ctx.synth_uniform(1 << 18, seed, stream, first, lo, hi).cpu().numpy()
+        assert gio.bits_equal(got, ol.hash_uniform(1 << 18, seed, stream, first, lo, hi))
+    sg = ctx.synth_shading(1 << 18, 9, 0, 0.02, 1.0, 0.25)
+    U, V, Nn, wo = (t.double() for t in (sg.U, sg.V, sg.N, sg.wo))
+    for a in (U, V, Nn, wo):
+        assert torch.allclose((a * a).sum(0), torch.ones_like(a[0]), atol=1e-5)
+    for a, b in ((U, V), (U, Nn), (V, Nn)):
+        assert (a * b).sum(0).abs().max() < 1e-5
+    c = (wo * Nn).sum(0)
+    assert c.min() > 0.019 and c.max() <= 1.0 + 1e-6
+    assert 0.24 < sg.backfacing.float().mean().item() < 0.26
+
+
+def test_albedo_sweep_vs_oracle_and_partition_invariance(ctx, orc):
+    grid = abi.SweepGrid(6, 5, 3, 0.05, 1.0, 1.0, 2.5)
+    want = orc.albedo_sweep(grid, 0x5EED0005, 0, 1024)
+    got = ctx.albedo_sweep(grid, 0x5EED0005, 0, 1024).cpu().numpy()
+    assert np.array_equal(got[:, 3:], want[:, 3:])               # valid / TIR counts: exact
+    assert np.allclose(got[:, :3], want[:, :3], rtol=2e-4, atol=1e-6)
+    parts = sum(ctx.albedo_sweep(grid, 0x5EED0005, b, e).cpu().numpy() for b, e in ((0, 256), (256, 700), (700, 1024)))
+    assert np.array_equal(parts[:, 3:], got[:, 3:]) and np.allclose(parts, got, rtol=1e-12)
+    g = gio.load("sweep")
+    n, r = [int(x) for x in g["grid"]], [float(x) for x in g["ranges"]]
+    gg = ctx.albedo_sweep(abi.SweepGrid(n[0], n[1], n[2], r[0], r[1], r[2], r[3]), int(g["seed"]), 0, int(g["spp"])).cpu().numpy()
+    assert np.array_equal(gg[:, 3:], g["table"][:, 3:]) and np.allclose(gg, g["table"], rtol=2e-4, atol=1e-6)
+
+
+def test_full_size_properties_config2(ctx):
+    """BASELINE configs[1] at full size (2^26): determinism, shard invariance (two halves ==
+    whole, bit for bit), finite outputs, and oracle parity on a strided subsample."""
+    from rlshaders_b200 import api
+    n = 1 << 26
+    sg = ctx.synth_shading(n, 0x5EED0002, 0, 0.02, 1.0, 0.25)
+    rough, ior = ctx.synth_uniform(n, 0x5EED0002, 2, 0, 0.05, 1.0), ctx.synth_uniform(n, 0x5EED0002, 3, 0, 1.05, 2.5)
+    rx, ry = ctx.synth_uniform(n, 0x5EED0002, 0), ctx.synth_uniform(n, 0x5EED0002, 1)
+    s = api.GgxSampler(ctx, sg, specularRoughness=rough, ior=ior)
+    a = s.dielectricSampleEvalPdf(rx, ry)
+    b = s.dielectricSampleEvalPdf(rx, ry)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k                          # idempotent / deterministic
+    del b
+    h = n // 2
+    for lo, hi in ((0, h), (h, n)):
+        cut = lambda t: t[..., lo:hi].contiguous()                 # noqa: E731
+        part = api.GgxSampler(ctx, api.ShadingBatch(cut(sg.U), cut(sg.V), cut(sg.N), cut(sg.wo), cut(sg.backfacing)),
+                              specularRoughness=cut(rough), ior=cut(ior)).dielectricSampleEvalPdf(cut(rx), cut(ry))
+        for k in a:
+            assert torch.equal(part[k], a[k][..., lo:hi]), k       # shard invariance
+        del part
+    assert torch.isfinite(a["wi_r"]).all() and torch.isfinite(a["pdf_r"]).all() and (a["pdf_r"] >= 1e-4).all()
+    assert ((a["fresnel"] >= 0) & (a["fresnel"] <= 1)).all()
+    tir = (a["flags"] & abi.FLAG_TIR) != 0
+    assert (a["f_t"][tir] == 0).all()
+    entering = (a["flags"] & abi.FLAG_ENTERING) != 0
+    assert torch.equal(entering, sg.backfacing == 0)
+    # oracle on every 64th sample (2^20 samples) of the same device-generated bits
+    idx = torch.arange(0, n, 64, device=ctx.device)
+    hs = {}
+    for name, t in (("U", sg.U), ("V", sg.V), ("N", sg.N), ("wo", sg.wo)):
+        for j, c in enumerate("xyz"):
+            hs[name + c] = t[j, idx].cpu().numpy()
+    hs["backfacing"] = sg.backfacing[idx].cpu().numpy()
+    p = abi.ggx_params(specularRoughness=rough[idx].cpu().numpy(), ior=ior[idx].cpu().numpy())
+    cpu = ol.load_port().ggx_dielectric(hs, p, rx[idx].cpu().numpy(), ry[idx].cpu().numpy())
+    kinds = dict(fresnel="rel", wi_r="dir", f_r="rel", pdf_r="rel", wi_t="dir", f_t="rel", weight_t="rel", flags="flags")
+    check(parity.summarize({k: v[..., idx] for k, v in a.items()}, cpu, kinds), "config 2 full size, strided subsample")

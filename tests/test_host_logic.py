@@ -1,0 +1,97 @@
+"""CPU: host-side logic -- the synthetic generators' integer hash, index-range sharding,
+and the N > 1 sweep reduction over a world_size-2 gloo group (the oracle stands in for the
+kernel so the partition + all-reduce plumbing is what is under test)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle_lib as ol
+from rlshaders_b200 import _abi as abi
+from rlshaders_b200 import shard
+
+
+def test_hash_uniform_numpy_matches_c():
+    orc = ol.load_port()
+    for seed, stream, first, lo, hi in ((0x5EED0001, 0, 0, 0.0, 1.0), (7, 3, 123456789012, 0.05, 2.5),
+                                        (2**63 + 5, 50, 2**40, -1.0, 1.0)):
+        a = orc.synth_uniform(4096, seed, stream, first, lo, hi)
+        b = ol.hash_uniform(4096, seed, stream, first, lo, hi)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    u = ol.hash_uniform(1 << 20, 1, 0)
+    assert u.min() >= 2.0 ** -24 and u.max() <= 1 - 2.0 ** -24     # never 0 or 1
+    assert abs(u.mean() - 0.5) < 2e-3
+
+
+def test_hash_is_index_addressed():
+    """Slices are reproducible independent of how the range is partitioned."""
+    full = ol.hash_uniform(10000, 42, 5)
+    for world in (2, 4, 8):
+        parts = [ol.hash_uniform(e - b, 42, 5, first_index=b) for b, e in
+                 (shard.shard_range(10000, r, world) for r in range(world))]
+        assert np.array_equal(np.concatenate(parts), full)
+
+
+def test_shard_range_partitions_exactly():
+    for total in (0, 1, 7, 4096, 2**26 + 3):
+        for world in (1, 2, 3, 4, 8):
+            ranges = [shard.shard_range(total, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == total
+            assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in ranges]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard.shard_range(10, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _sweep_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    orc = ol.load_port()
+    orc.set_threads(1)
+    grid = abi.SweepGrid(3, 4, 2, 0.05, 1.0, 1.0, 2.0)
+    k0, k1 = shard.spp_range(96, rank, world)
+    table = torch.from_numpy(orc.albedo_sweep(grid, 99, k0, k1))
+    shard.reduce_table(table, dist)
+    if rank == 0:
+        ret.put(table.numpy().copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sweep_shards_sum_to_the_full_table_gloo_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sweep_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    reduced = ret.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    orc = ol.load_port()
+    grid = abi.SweepGrid(3, 4, 2, 0.05, 1.0, 1.0, 2.0)
+    full = orc.albedo_sweep(grid, 99, 0, 96)
+    # counts are exact; FP64 sums agree to rounding regardless of the partition
+    assert np.array_equal(reduced[:, 3:], full[:, 3:])
+    assert np.allclose(reduced, full, rtol=1e-12, atol=0)
+
+
+def test_reduce_table_is_identity_without_a_group():
+    t = torch.arange(10, dtype=torch.float64)
+    assert torch.equal(shard.reduce_table(t.clone(), None), t)
+    assert torch.equal(shard.reduce_table(t.clone(), dist), t)

@@ -1,0 +1,137 @@
+"""CPU: pins the C port of the oracle (oracle/rls_oracle.c) against
+  (1) the golden vectors generated from the reference's own sources (tests/golden/), and
+  (2) the reference library itself, bit for bit, where it is built (oracle/_ref/).
+"""
+import numpy as np
+import pytest
+
+import golden_io as gio
+import oracle_lib as ol
+from rlshaders_b200 import _abi as abi
+
+
+@pytest.fixture(scope="module")
+def port():
+    return ol.load_port()
+
+
+@pytest.fixture(scope="module")
+def ref():
+    r = ol.load_ref()
+    if r is None:
+        pytest.skip("reference library not built (no /root/reference here)")
+    return r
+
+
+def assert_same(a, b, what):
+    for k in a:
+        assert gio.bits_equal(a[k], b[k]), f"{what}: {k} differs"
+
+
+def test_port_vs_golden_ggx_fixtures(port):
+    g = gio.load("ggx_fixtures")
+    sg = gio.shading(g)
+    for name in ("teflon", "gold", "anisotropic", "gold_bench"):
+        rough, ior, aniso = [float(x) for x in g[name + "_params"]]
+        got = port.ggx_sample_eval_pdf(sg, abi.ggx_params(specularRoughness=rough, ior=ior, anisotropic=aniso),
+                                       g["rx"], g["ry"])
+        want = {k: g[f"{name}_{k}"] for k in got}
+        assert_same(want, got, name)
+
+
+def test_port_vs_golden_dielectric(port):
+    g = gio.load("ggx_dielectric")
+    kw = gio.group(g, "p_")
+    got = port.ggx_dielectric(gio.shading(g), abi.ggx_params(**kw), g["rx"], g["ry"])
+    assert_same(gio.group(g, "out_"), got, "dielectric")
+
+
+def test_port_vs_golden_disney(port):
+    g = gio.load("disney")
+    sg = gio.shading(g)
+    u = [g[f"u{j}"] for j in range(4)]
+    kw = gio.group(g, "p_")
+    kw["base_color"] = (g["base_r"], g["base_g"], g["base_b"])
+    assert_same(gio.group(g, "out_"), port.disney_sample_eval_pdf(sg, abi.disney_params(**kw), *u), "disney")
+    scenes = dict(default=dict(roughness=0.5, specular=0.5), subsurface=dict(roughness=0.5, specular=0.5, subsurface=1.0),
+                  metallic=dict(metallic=1.0, roughness=0.3), specular=dict(specular=1.0, roughness=0.5),
+                  aniso=dict(metallic=1.0, roughness=0.2, anisotropic=1.0),
+                  clearcoat=dict(roughness=0.6, clearcoat=1.0, clearcoat_gloss=0.8, sheen=0.5, sheen_tint=0.5))
+    for name, params in scenes.items():
+        got = port.disney_sample_eval_pdf(sg, abi.disney_params(base_color=(0.8, 0.4, 0.2), **params), *u)
+        assert_same(gio.group(g, name + "_"), got, name)
+
+
+def test_port_vs_golden_skin(port):
+    g = gio.load("skin")
+    color = (g["color_r"], g["color_g"], g["color_b"])
+    dist = (g["dist_x"], g["dist_y"], g["dist_z"])
+    assert_same(gio.group(g, "out_"), port.skin_profile(abi.skin_params(sss_color=color, sss_scatter_dist=dist), g["rx"]), "skin")
+    got = port.skin_profile(abi.skin_params(sss_color=(1.0, 0.84235, 0.5), sss_scatter_dist=(1.0, 1.0, 1.0)), g["rx"])
+    assert_same(gio.group(g, "scene0009_"), got, "scene 0009")
+    sgp = gio.shading(g, "probe_sg_")
+    got = port.skin_probe_ray(sgp, abi.skin_params(sss_color=color, sss_scatter_dist=dist), g["rx"], g["probe_ry"])
+    want = {k: g["probe_" + k] for k in ("r", "origin", "dir", "maxdist", "flags")}
+    assert_same(want, got, "probe ray")
+
+
+def test_port_vs_golden_sweep(port):
+    g = gio.load("sweep")
+    n = [int(x) for x in g["grid"]]
+    r = [float(x) for x in g["ranges"]]
+    grid = abi.SweepGrid(n[0], n[1], n[2], r[0], r[1], r[2], r[3])
+    got = port.albedo_sweep(grid, int(g["seed"]), 0, int(g["spp"]))
+    assert np.array_equal(got, g["table"])
+
+
+N = 1 << 16
+
+
+def test_port_vs_reference_ggx(port, ref):
+    sg, p, rx, ry = ol.workload_ggx_conductor(N)
+    a = ref.ggx_sample_eval_pdf(sg, p, rx, ry)
+    assert_same(a, port.ggx_sample_eval_pdf(sg, p, rx, ry), "ggx fused")
+    sg, p, rx, ry = ol.workload_ggx_dielectric(N, aniso=True)
+    d = ref.ggx_dielectric(sg, p, rx, ry)
+    assert_same(d, port.ggx_dielectric(sg, p, rx, ry), "ggx dielectric")
+    assert_same(ref.ggx_eval_sample(sg, p, rx, ry), port.ggx_eval_sample(sg, p, rx, ry), "ggx evalSample")
+    assert gio.bits_equal(ref.ggx_eval_brdf(sg, p, d["wi_r"]), port.ggx_eval_brdf(sg, p, d["wi_r"]))
+    assert gio.bits_equal(ref.ggx_eval_pdf(sg, p, d["wi_t"]), port.ggx_eval_pdf(sg, p, d["wi_t"]))
+
+
+def test_port_vs_reference_disney(port, ref):
+    sg, p, u = ol.workload_disney(N)
+    a = ref.disney_sample_eval_pdf(sg, p, *u)
+    assert_same(a, port.disney_sample_eval_pdf(sg, p, *u), "disney fused")
+    for t in (abi.RLS_RAY_DIFFUSE, abi.RLS_RAY_GLOSSY):
+        assert_same(ref.disney_eval_sample(sg, p, t, u[0], u[1]), port.disney_eval_sample(sg, p, t, u[0], u[1]), "evalSample")
+        assert gio.bits_equal(ref.disney_eval_brdf(sg, p, t, a["wi_s"]), port.disney_eval_brdf(sg, p, t, a["wi_s"]))
+        assert gio.bits_equal(ref.disney_eval_pdf(sg, p, t, a["wi_d"]), port.disney_eval_pdf(sg, p, t, a["wi_d"]))
+
+
+def test_port_vs_reference_profile(port, ref):
+    p, rx = ol.workload_skin(N)
+    assert_same(ref.skin_profile(p, rx), port.skin_profile(p, rx), "skin fused")
+    dist = np.stack([ol.hash_uniform(N, 9, j, lo=0.0, hi=2.0) for j in range(3)])
+    dist[:, :64] = 0.0            # degenerate profiles: maxRadius < eps
+    dist[0, 64:128] = 5e-5        # one channel below eps
+    albedo = np.stack([ol.hash_uniform(N, 9, 3 + j) for j in range(3)])
+    pa, pb = ref.ndprofile_set_distance(dist, albedo), port.ndprofile_set_distance(dist, albedo)
+    assert_same(pa, pb, "setDistance")
+    ra, rb = ref.ndprofile_get_radius(pa, rx), port.ndprofile_get_radius(pb, rx)
+    assert_same(ra, rb, "getRadius")
+    with np.errstate(all="ignore"):
+        assert gio.bits_equal(ref.ndprofile_get_pdf(pa, ra["r"]), port.ndprofile_get_pdf(pb, rb["r"]))
+        assert gio.bits_equal(ref.ndprofile_eval_profile(pa, ra["r"]), port.ndprofile_eval_profile(pb, rb["r"]))
+    sg = ol.make_shading(N, 77)
+    ry = ol.hash_uniform(N, 5, 9)
+    assert_same(ref.skin_probe_ray(sg, p, rx, ry), port.skin_probe_ray(sg, p, rx, ry), "probe ray")
+    f1, f2 = ol.hash_uniform(N, 6, 1), ol.hash_uniform(N, 6, 2)
+    sp = abi.skin_params(sheen_weight=ol.hash_uniform(N, 6, 3), specular_weight=ol.hash_uniform(N, 6, 4),
+                         sss_weight=ol.hash_uniform(N, 6, 5))
+    assert_same(ref.skin_layer_weights(sp, f1, f2), port.skin_layer_weights(sp, f1, f2), "layer weights")
+
+
+def test_port_vs_reference_sweep(port, ref):
+    g = abi.SweepGrid(3, 5, 2, 0.02, 1.0, 1.0, 2.5)
+    assert np.array_equal(ref.albedo_sweep(g, 123, 0, 128), port.albedo_sweep(g, 123, 0, 128))
