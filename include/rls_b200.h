@@ -341,6 +341,15 @@ int rls_synth_shading(rls_context *ctx, size_t n, uint64_t seed, uint64_t first_
                       float cos_lo, float cos_hi, float backfacing_fraction,
                       const rls_shading_soa *sg);
 
+/* ------------------------------------------------------------ diagnostics */
+/* Evaluates one of the library's own binary32 transcendentals (the device restatement of the
+ * host libm the reference links against, rlshaders_b200/csrc/rls_libm.cuh) element-wise, so a
+ * test can compare the DEVICE results with the host C library bit for bit.
+ * fn: 0 sincosf(a) -> out0 = sin, out1 = cos;  1 tanf(a);  2 atanf(a);  3 acosf(a);  4 expf(a);
+ *     5 logf(a);  6 atan2f(a, b);  7 powf(a, b).  `b` / `out1` may be NULL when unused. */
+int rls_debug_libm(rls_context *ctx, int fn, size_t n, const float *a, const float *b,
+                   float *out0, float *out1);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,7 @@ SYMBOLS = [
     "rls_ggx_sample_eval_pdf_host", "rls_ggx_dielectric_sample_eval_pdf_host",
     "rls_disney_sample_eval_pdf_host", "rls_skin_profile_sample_eval_pdf_host",
     "rls_host_alloc", "rls_host_free",
-    "rls_albedo_sweep", "rls_synth_uniform", "rls_synth_shading",
+    "rls_albedo_sweep", "rls_synth_uniform", "rls_synth_shading", "rls_debug_libm",
 ]
 
 _lib = None
@@ -76,6 +76,7 @@ def load():
         "rls_albedo_sweep": [vp, P(abi.SweepGrid), u64, u32, u32, vp],
         "rls_synth_uniform": [vp, sz, u64, u32, u64, f, f, vp],
         "rls_synth_shading": [vp, sz, u64, u64, f, f, f, P(abi.ShadingSoA)],
+        "rls_debug_libm": [vp, i32, sz, vp, vp, vp, vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)

@@ -90,6 +90,19 @@ class Context:
                                                        backfacing_fraction, C.byref(sg.struct)), self.lib)
         return sg
 
+    # ---- diagnostics ------------------------------------------------------------
+    LIBM_FUNCTIONS = dict(sincosf=0, tanf=1, atanf=2, acosf=3, expf=4, logf=5, atan2f=6, powf=7)
+
+    def debug_libm(self, name, a, b=None):
+        """Element-wise evaluation of the library's own device libm (for parity tests)."""
+        fn = self.LIBM_FUNCTIONS[name]
+        out0 = torch.empty_like(a)
+        out1 = torch.empty_like(a) if fn == 0 else None
+        _check(self.handle, self.lib.rls_debug_libm(self.handle, fn, a.numel(), a.data_ptr(),
+                                                    b.data_ptr() if b is not None else None, out0.data_ptr(),
+                                                    out1.data_ptr() if out1 is not None else None), self.lib)
+        return (out0, out1) if fn == 0 else out0
+
     # ---- albedo sweep ----------------------------------------------------------
     def albedo_sweep(self, grid, seed, spp_begin, spp_end, out=None):
         cells = grid.n_rough * grid.n_cos * grid.n_ior

@@ -796,6 +796,36 @@ extern "C" int rls_synth_shading(rls_context *ctx, size_t n, uint64_t seed, uint
     return RLS_OK;
 }
 
+// ================================================================= C ABI: diagnostics
+__global__ void __launch_bounds__(kBlock)
+k_debug_libm(int fn, size_t n, const float *a, const float *b, float *out0, float *out1)
+{
+    RLS_INDEX();
+    float x = a[i], y = b ? b[i] : 0.0f, r0 = 0.0f, r1 = 0.0f;
+    switch (fn) {
+    case 0: rlm::sincosf_(x, &r0, &r1); break;
+    case 1: r0 = rlm::tanf_(x); break;
+    case 2: r0 = rlm::atanf_(x); break;
+    case 3: r0 = rlm::acosf_(x); break;
+    case 4: r0 = rlm::expf_(x); break;
+    case 5: r0 = rlm::logf_(x); break;
+    case 6: r0 = rlm::atan2f_(x, y); break;
+    default: r0 = rlm::powf_(x, y); break;
+    }
+    out0[i] = r0;
+    if (out1) out1[i] = r1;
+}
+extern "C" int rls_debug_libm(rls_context *ctx, int fn, size_t n, const float *a, const float *b, float *out0, float *out1)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
+    RLS_REQUIRE(ctx, fn >= 0 && fn <= 7 && a && out0 && (fn < 6 || b), "rls_debug_libm: bad argument");
+    DeviceGuard guard(ctx->device);
+    k_debug_libm<<<grid_for(n), kBlock, 0, ctx->stream>>>(fn, n, a, b, out0, out1);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+
 // ===================================================== host-buffer (end-to-end) forms
 // A chunk of samples is staged through one of kStages device buffers: H2D of every input
 // slice, the kernel, D2H of every output slice, all on that stage's stream, so that chunk
