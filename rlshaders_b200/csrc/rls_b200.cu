@@ -21,6 +21,7 @@
 #include "rls_ggx.cuh"
 #include "rls_disney.cuh"
 #include "rls_profile.cuh"
+#include "rls_fused.cuh"
 
 using namespace rls;
 
@@ -236,47 +237,12 @@ k_ggx_sample_eval_pdf(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, 
 {
     RLS_INDEX();
     Ggx g = ggx_make(sg, p, i);
-    f3 M = sample_visible_normal(g.wo, g.U, g.V, g.N, g.ax, g.ay, __ldg(rx + i), __ldg(ry + i));
-    f3 L = reflect_direction(g.wo, M);
-    f3 fv = ggx_eval_brdf(g, L);
-    float pd = ggx_eval_pdf(g, L);
-    store3(wi, i, L);
-    store3(f, i, fv);
-    pdf[i] = pd;
-    if (fresnel) fresnel[i] = ggx_fresnel(g, L, M);
-    uint32_t fl = bsdf_flags(L, g.N, fv, pd);
-    if (g.entering) fl |= RLS_FLAG_ENTERING;
-    flags[i] = fl;
-}
-
-struct Dielectric { float F, f_r, pdf_r, f_t, w_t; f3 wi_r, wi_t; uint32_t flags; };
-
-// The rough-dielectric unit: src/rlGgx.h:228-243 loop body, with the in-tree
-// getRefractDirection standing in for Arnold's AiRefractRay.
-RLS_DEV Dielectric dielectric_unit(const Shading &s, float ior, float rough, float aniso, float rx, float ry)
-{
-    Dielectric r;
-    Ggx g;
-    ggx_init(g, s, mk3(1.0f, 1.0f, 1.0f), ior, rough, aniso);
-    f3 m = sample_visible_normal(g.wo, g.U, g.V, g.N, g.ax, g.ay, rx, ry);
-    r.wi_r = reflect_direction(g.wo, m);
-    r.F = ggx_fresnel(g, r.wi_r, m);
-    f3 fr = ggx_eval_brdf(g, r.wi_r);
-    r.f_r = fr.x;
-    r.pdf_r = ggx_eval_pdf(g, r.wi_r);
-    r.flags = bsdf_flags(r.wi_r, g.N, fr, r.pdf_r);
-    if (g.entering) r.flags |= RLS_FLAG_ENTERING;
-    f3 t;
-    if (ggx_refract_direction(g, m, g.wo, t)) {
-        r.wi_t = t;
-        r.f_t = ggx_refraction(g, g.wo, t, g.N);
-    } else {
-        r.wi_t = reflect_direction(g.wo, m);
-        r.f_t = 0.0f;
-        r.flags |= RLS_FLAG_TIR;
-    }
-    r.w_t = ggx_sample_weight(g, g.wo, r.wi_t, m);
-    return r;
+    GgxBsdf o = ggx_unit(g, __ldg(rx + i), __ldg(ry + i));
+    store3(wi, i, o.L);
+    store3(f, i, o.f);
+    pdf[i] = o.pdf;
+    if (fresnel) fresnel[i] = o.fresnel;
+    flags[i] = o.flags;
 }
 
 struct DielectricOutDev { float *fresnel; V3 wi_r; float *f_r, *pdf_r; V3 wi_t; float *f_t, *weight_t; uint32_t *flags; };

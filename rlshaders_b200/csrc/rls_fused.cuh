@@ -1,0 +1,164 @@
+// rls_fused.cuh -- the fused units of work (construct + sample + eval + pdf) with every
+// sub-expression that the reference evaluates more than once computed ONCE.
+//
+// The reference's callbacks re-derive the half vector, D, the view-side masking term and the
+// IOR ratio on every call (src/rlGgx.h:304-357 is entered through evalBrdf, evalPdf,
+// getSampleWeight and refraction separately).  In a fused kernel all of them see the same
+// operand bits, so sharing is bit-exact as long as the shared value is produced by the same
+// IEEE operations in the same order -- the identities used are noted inline:
+//   * a + b == b + a, a * b == b * a bitwise (IEEE commutativity);
+//   * dot(v, s*h) == s*dot(v, h) and (s*x)^2 == x^2 bitwise for s = +-1 (negation is exact and
+//     round-to-nearest is sign-symmetric);
+//   * 2/d == 2*(1/d) bitwise while neither side over/underflows (power-of-two scaling is exact).
+// tests/test_gpu_parity.py asserts fused == separate entry points == oracle, bit for bit.
+#pragma once
+#include "rls_ggx.cuh"
+#include "rls_disney.cuh"
+
+namespace rls {
+
+struct Dielectric { float F, f_r, pdf_r, f_t, w_t; f3 wi_r, wi_t; uint32_t flags; };
+
+// G1's value part with the final 2/d as 2*(1/d): d = 1 + sqrt(..) lies in [2, 2^64] or is inf/NaN.
+RLS_DEV float ggx_G1_value2(const Ggx &g, float VdotN)
+{
+    float cosSqr = sqr(VdotN);
+    float tanSqr = 1.0f / cosSqr - 1.0f;
+    float denominator = 1.0f + sqrtf(1.0f + sqr(g.rough) * tanSqr);
+    return 2.0f * (1.0f / denominator);
+}
+// Fresnel with the IOR ratio squared passed in (src/rlGgx.h:258: SQR(mIorOut / mIorIn)).
+RLS_DEV float ggx_fresnel_c(float ratio2, float c)
+{
+    float gSqr = ratio2 - 1.0f + c * c;
+    if (gSqr < 0.0f) return 1.0f;
+    float gg = sqrtf(gSqr);
+    float gmc = gg - c;
+    float gpc = gg + c;
+    return 0.5f * sqr(gmc / gpc) * (1.0f + sqr((c * gpc - 1.0f) / (c * gmc + 1.0f)));
+}
+
+// One GGX reflection evaluation + pdf at direction L, sharing the half vector, D and the
+// view-side G1 between evalBrdf (src/rlGgx.h:304-313) and evalPdf (:121-127, :72-80).
+struct GgxShared {
+    float VdotN, absVdotN, sgnV, G1v, ratio2;
+};
+RLS_DEV GgxShared ggx_shared(const Ggx &g)
+{
+    GgxShared s;
+    s.VdotN = dot(g.wo, g.N);
+    s.absVdotN = abs_m(s.VdotN);
+    s.sgnV = sgn_m(s.VdotN);
+    s.G1v = ggx_G1_value2(g, s.VdotN);
+    s.ratio2 = sqr(g.iorOut / g.iorIn);
+    return s;
+}
+// Returns reflection(V, L, N) * dot(L, N) (KsColor applied by the caller) and the pdf.
+RLS_DEV void ggx_reflect_eval_pdf(const Ggx &g, const GgxShared &s, f3 L, float LdotN, float G1l,
+                                  float &refl_cos, float &pdf)
+{
+    f3 H = normalize(L + g.wo);                       // o + i (brdf)  ==  V + L (pdf), bitwise
+    float VH = dot(g.wo, H);
+    float LH = dot(L, H);
+    // D(H): also D(hr) for hr = +-H
+    float D_H = ggx_D(g, H);
+    // pdf: G1(V, H, N)
+    float G1_pdf = (VH * s.VdotN < 0.0f) ? 0.0f : s.G1v;
+    pdf = max_m(D_H * G1_pdf / s.absVdotN * 0.25f, kEps);
+    // brdf: hr = sgn(V.N) * H
+    float VHr = VH * s.sgnV, LHr = LH * s.sgnV;
+    float F = ggx_fresnel_c(s.ratio2, abs_m(VHr));
+    float G1i = (VHr * s.VdotN < 0.0f) ? 0.0f : s.G1v;
+    float G1o = (LHr * LdotN < 0.0f) ? 0.0f : G1l;
+    float D_hr = (s.sgnV != 0.0f) ? D_H : __int_as_float(0x7f800000);   // D(0 vector) = 1/0
+    float refl = F * (G1i * G1o) * D_hr * 0.25f / (abs_m(LdotN) * s.absVdotN);
+    refl_cos = refl;
+}
+
+// The rough-dielectric unit: src/rlGgx.h:228-243 loop body with the in-tree
+// getRefractDirection standing in for Arnold's AiRefractRay (same composition as the oracle).
+RLS_DEV Dielectric dielectric_unit(const Shading &sh, float ior, float rough, float aniso, float rx, float ry)
+{
+    Dielectric r;
+    Ggx g;
+    ggx_init(g, sh, mk3(1.0f, 1.0f, 1.0f), ior, rough, aniso);
+    const GgxShared s = ggx_shared(g);
+    f3 m = sample_visible_normal(g.wo, g.U, g.V, g.N, g.ax, g.ay, rx, ry);
+    float Vm = dot(g.wo, m);
+    // reflectDirection(V, m) = 2|V.m| m - V
+    r.wi_r = m * (2.0f * abs_m(Vm)) - g.wo;
+    r.F = ggx_fresnel_c(s.ratio2, abs_m(dot(r.wi_r, m)));
+
+    // evalBrdf(wi_r) with white KsColor, evalPdf(wi_r)
+    const f3 L = r.wi_r;
+    const float LdotN = dot(L, g.N);
+    const float G1l = ggx_G1_value2(g, LdotN);
+    float refl;
+    ggx_reflect_eval_pdf(g, s, L, LdotN, G1l, refl, r.pdf_r);
+    const bool zeroL = is_zero(L);
+    r.f_r = zeroL ? 0.0f : refl * LdotN;              // (1 * refl) * dot(L, N)
+    uint32_t fl = 0;
+    if (zeroL) fl |= 0x0001u;
+    if (LdotN <= 0.0f) fl |= 0x0002u;
+    if (r.pdf_r == 0.0f) fl |= 0x0004u;
+    if (r.f_r == 0.0f) fl |= 0x0008u;
+    if (r.pdf_r == kEps) fl |= 0x0040u;
+    if (g.entering) fl |= 0x0010u;
+
+    // getRefractDirection(m, V): src/rlGgx.h:277-291
+    const float eta = g.iorIn / g.iorOut;
+    const float cosThetaTSqr = 1.0f + eta * (sqr(Vm) - 1.0f);
+    const float mN = dot(m, g.N);
+    float TdotN, G1t;
+    if (cosThetaTSqr < 0.0f) {                        // total internal reflection: reflect about m
+        fl |= 0x0020u;
+        r.wi_t = r.wi_r;
+        r.f_t = 0.0f;
+        TdotN = LdotN;
+        G1t = G1l;
+    } else {
+        float sc = eta * Vm - s.sgnV * sqrtf(cosThetaTSqr);
+        f3 T = m * sc - g.wo * eta;
+        r.wi_t = T;
+        TdotN = dot(T, g.N);
+        G1t = ggx_G1_value2(g, TdotN);
+        // refraction(V, T, N): src/rlGgx.h:316-328
+        f3 ht = -normalize(g.wo * g.iorIn + T * g.iorOut);
+        float IdotH = dot(g.wo, ht);
+        float OdotH = dot(T, ht);
+        float refractWeight = 1.0f - ggx_fresnel_c(s.ratio2, abs_m(IdotH));
+        float denominator = abs_m(TdotN) * s.absVdotN * sqr(g.iorIn * IdotH + g.iorOut * OdotH);
+        float G1i = (IdotH * s.VdotN < 0.0f) ? 0.0f : s.G1v;
+        float G1o = (OdotH * TdotN < 0.0f) ? 0.0f : G1t;
+        r.f_t = abs_m(OdotH * IdotH) * sqr(g.iorOut) * refractWeight * (G1i * G1o) * ggx_D(g, ht) / denominator;
+    }
+    // getSampleWeight(V, wi_t, m): src/rlGgx.h:294-301
+    {
+        float G1i = (Vm * s.VdotN < 0.0f) ? 0.0f : s.G1v;
+        float G1o = (dot(r.wi_t, m) * TdotN < 0.0f) ? 0.0f : G1t;
+        r.w_t = (G1i * G1o) * abs_m(Vm / (s.absVdotN * abs_m(mN)));
+    }
+    r.flags = fl;
+    return r;
+}
+
+// Fused rlGgx unit with a KsColor: ctor + evalSample + evalBrdf + evalPdf (+ the Fresnel term).
+struct GgxBsdf { f3 L, f; float pdf, fresnel; uint32_t flags; };
+RLS_DEV GgxBsdf ggx_unit(const Ggx &g, float rx, float ry)
+{
+    GgxBsdf o;
+    const GgxShared s = ggx_shared(g);
+    f3 m = sample_visible_normal(g.wo, g.U, g.V, g.N, g.ax, g.ay, rx, ry);
+    o.L = m * (2.0f * abs_m(dot(g.wo, m))) - g.wo;
+    o.fresnel = ggx_fresnel_c(s.ratio2, abs_m(dot(o.L, m)));
+    const float LdotN = dot(o.L, g.N);
+    float refl;
+    ggx_reflect_eval_pdf(g, s, o.L, LdotN, ggx_G1_value2(g, LdotN), refl, o.pdf);
+    const bool black = is_zero(o.L) || (abs_m(g.ks.x) < kEps && abs_m(g.ks.y) < kEps && abs_m(g.ks.z) < kEps);
+    o.f = black ? mk3(0.0f, 0.0f, 0.0f) : g.ks * refl * LdotN;
+    o.flags = bsdf_flags(o.L, g.N, o.f, o.pdf);
+    if (g.entering) o.flags |= 0x0010u;
+    return o;
+}
+
+} // namespace rls

@@ -65,7 +65,7 @@ RLS_DEV f2 sample_slope(float theta, float rx, float ry)
 
     float B = rlm::tanf_(theta);
     float B2 = sqr(B);
-    float G1 = 2.0f / (1.0f + sqrtf(1.0f + B2));
+    float G1 = 2.0f * (1.0f / (1.0f + sqrtf(1.0f + B2)));   // == 2/(..) bitwise: the divisor is in [2, 2^64]
 
     float A = 2.0f * rx / G1 - 1.0f;
     float A2 = sqr(A);

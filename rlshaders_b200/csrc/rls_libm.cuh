@@ -199,27 +199,25 @@ RLM_HD void sincosf_(float y, float *sinp, float *cosp)
 {
     double x = (double)y;
     uint32_t top = abstop12(y);
-    if (top < 0x3f4u) {                        // |y| < pi/4
-        double x2 = x * x;
-        if (top < 0x398u) {                    // |y| < 2^-12
-            *sinp = y;
-            *cosp = 1.0f;
-            return;
-        }
-        sincosf_poly(x, x2, false, 0, sinp, cosp);
-    } else if (top < 0x42fu) {                 // |y| < 120: reduce_fast
+    if (top < 0x42fu) {                        // |y| < 120
+        // For |y| < pi/4 the host takes a shortcut that is bit-identical to reduce_fast with
+        // n = 0 (x - 0*hpi == x, sign 1), so one uniform path serves both -- no divergence.
         double r = x * 0x1.45F306DC9C883p+23;  // 2/pi * 2^24
         int n = ((int32_t)r + 0x800000) >> 24;
         x = fma_(-(double)n, 0x1.921FB54442D18p0, x);
-        double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;   // sign[n & 3]
-        sincosf_poly(x * s, x * x, (n & 2) != 0, n, sinp, cosp);
+        double s = ((n + 1) & 2) ? -1.0 : 1.0; // sign[n & 3] = {1, -1, -1, 1}
+        float sv, cv;
+        sincosf_poly(x * s, x * x, (n & 2) != 0, n, &sv, &cv);
+        const bool tiny = top < 0x398u;        // |y| < 2^-12: sin = y, cos = 1
+        *sinp = tiny ? y : sv;
+        *cosp = tiny ? 1.0f : cv;
     } else if (top < 0x7f8u) {
         int n;
         uint32_t xi = f2u(y);
         int sign = (int)(xi >> 31);
         x = sincosf_reduce_large(xi, &n);
         int q = n + sign;
-        double s = (((q & 3) == 1 || (q & 3) == 2) ? -1.0 : 1.0);
+        double s = ((q + 1) & 2) ? -1.0 : 1.0;
         sincosf_poly(x * s, x * x, (q & 2) != 0, n, sinp, cosp);
     } else {
         *sinp = *cosp = y - y;
@@ -227,7 +225,9 @@ RLM_HD void sincosf_(float y, float *sinp, float *cosp)
 }
 
 // ===================================================================== tanf
-// fdlibm k_tanf.c (binary32)
+// fdlibm k_tanf.c (binary32), written with selects instead of branches: every lane runs the
+// same instruction stream (one polynomial, one division) whichever of the routine's three
+// regimes it is in.  Each regime's arithmetic is operation-for-operation the original.
 RLM_HD float kernel_tanf(float x, float y, int iy)
 {
     const float pio4 = 7.8539812565e-01f, pio4lo = 3.7748947079e-08f;
@@ -236,51 +236,55 @@ RLM_HD float kernel_tanf(float x, float y, int iy)
                 T6 = 1.4562094584e-03f, T7 = 5.8804126456e-04f, T8 = 2.4646313977e-04f,
                 T9 = 7.8179444245e-05f, T10 = 7.1407252108e-05f, T11 = -1.8558637748e-05f,
                 T12 = 2.5907305826e-05f;
-    float z, r, v, w, s;
-    int32_t hx = (int32_t)f2u(x);
-    int32_t ix = hx & 0x7fffffff;
-    if (ix < 0x39000000) {                     // |x| < 2^-13
-        if ((int)x == 0) {
-            if ((ix | (iy + 1)) == 0) return 1.0f / fabsf_(x);
-            else if (iy == 1) return x;
-            else return -1.0f / x;
-        }
-    }
-    if (ix >= 0x3f2ca140) {                    // |x| >= 0.6744
-        if (hx < 0) { x = -x; y = -y; }
-        z = pio4 - x;
-        w = pio4lo - y;
-        x = z + w;
+    const float x_in = x;
+    const int32_t hx = (int32_t)f2u(x);
+    const int32_t ix = hx & 0x7fffffff;
+    const bool big = ix >= 0x3f2ca140;         // |x| >= 0.6744
+    const float sgn_big = (float)(1 - ((hx >> 30) & 2));
+    const float fiy = (float)iy;
+    bool big_tiny = false;
+    if (big) {
+        float xa = (hx < 0) ? -x : x, ya = (hx < 0) ? -y : y;
+        float z0 = pio4 - xa;
+        float w0 = pio4lo - ya;
+        x = z0 + w0;
         y = 0.0f;
-        if (fabsf_(x) < 0x1p-13f) return (float)((1 - ((hx >> 30) & 2)) * iy) * (1.0f - (float)(2 * iy) * x);
+        big_tiny = fabsf_(x) < 0x1p-13f;
     }
-    z = x * x;
-    w = z * z;
-    r = T1 + w * (T3 + w * (T5 + w * (T7 + w * (T9 + w * T11))));
-    v = z * (T2 + w * (T4 + w * (T6 + w * (T8 + w * (T10 + w * T12)))));
-    s = z * x;
+    float z = x * x;
+    float w = z * z;
+    float r = T1 + w * (T3 + w * (T5 + w * (T7 + w * (T9 + w * T11))));
+    float v = z * (T2 + w * (T4 + w * (T6 + w * (T8 + w * (T10 + w * T12)))));
+    float s = z * x;
     r = y + z * (s * (r + v) + y);
     r += T0 * s;
     w = x + r;
-    if (ix >= 0x3f2ca140) {
-        v = (float)iy;
-        return (float)(1 - ((hx >> 30) & 2)) * (v - 2.0f * (x - (w * w / (w + v) - r)));
-    }
-    if (iy == 1) return w;
+    // the one division: w*w/(w+iy) (big) or -1/w (small, iy == -1)
+    float q = (big ? w * w : -1.0f) / (big ? w + fiy : w);
+    float res_big = sgn_big * (fiy - 2.0f * (x - (q - r)));
     // -1/(x+r), accurately
-    float a, t;
-    z = u2f(f2u(w) & 0xfffff000u);
-    v = r - (z - x);
-    t = a = -1.0f / w;
-    t = u2f(f2u(t) & 0xfffff000u);
-    s = 1.0f + t * z;
-    return t + a * (s + t * v);
+    float zt = u2f(f2u(w) & 0xfffff000u);
+    float vt = r - (zt - x);
+    float t = u2f(f2u(q) & 0xfffff000u);
+    float st = 1.0f + t * zt;
+    float res_inv = t + q * (st + t * vt);
+    float res = big ? res_big : ((iy == 1) ? w : res_inv);
+    if (big_tiny) res = (float)((1 - ((hx >> 30) & 2)) * iy) * (1.0f - (float)(2 * iy) * x);
+    if (ix < 0x39000000) {                     // |x| < 2^-13
+        if ((int)x_in == 0) {
+            if ((ix | (iy + 1)) == 0) res = 1.0f / fabsf_(x_in);
+            else if (iy == 1) res = x_in;
+            else res = -1.0f / x_in;
+        }
+    }
+    return res;
 }
-// glibc 2.39 s_tanf.c with the binary64 reduce_fast of e_rem_pio2f.c
+// glibc 2.39 s_tanf.c with the binary64 reduce_fast of e_rem_pio2f.c.  For |x| <= pi/4 the host
+// skips the reduction; reducing anyway gives n = 0, y0 = x, y1 = 0 -- the same kernel call -- so
+// one path serves both.
 RLM_HD float tanf_(float x)
 {
     uint32_t ix = f2u(x) & 0x7fffffffu;
-    if (ix <= 0x3f490fdau) return kernel_tanf(x, 0.0f, 1);   // |x| <= pi/4
     if (ix >= 0x7f800000u) return x - x;
     double dx = (double)x;
     int n;
@@ -299,52 +303,39 @@ RLM_HD float tanf_(float x)
 }
 
 // ==================================================================== atanf
-// fdlibm s_atanf.c (binary32)
+// fdlibm s_atanf.c (binary32) with the five argument-reduction branches folded into selects:
+// one division (x/1 == x in the unreduced range), one polynomial.
 RLM_HD float atanf_(float x)
 {
     const float aT0 = 3.3333334327e-01f, aT1 = -2.0000000298e-01f, aT2 = 1.4285714924e-01f,
                 aT3 = -1.1111110449e-01f, aT4 = 9.0908870101e-02f, aT5 = -7.6918758452e-02f,
                 aT6 = 6.6610731184e-02f, aT7 = -5.8335702866e-02f, aT8 = 4.9768779427e-02f,
                 aT9 = -3.6531571299e-02f, aT10 = 1.6285819933e-02f;
-    float w, s1, s2, z, hi = 0.0f, lo = 0.0f;
-    int32_t hx = (int32_t)f2u(x);
-    int32_t ix = hx & 0x7fffffff;
-    int id;
+    const int32_t hx = (int32_t)f2u(x);
+    const int32_t ix = hx & 0x7fffffff;
     if (ix >= 0x4c000000) {                    // |x| >= 2^25
         if (ix > 0x7f800000) return x + x;
         if (hx > 0) return 1.5707962513e+00f + 7.5497894159e-08f;
         else return -1.5707962513e+00f - 7.5497894159e-08f;
     }
-    if (ix < 0x3ee00000) {                     // |x| < 0.4375
-        if (ix < 0x31000000) return x;         // |x| < 2^-29
-        id = -1;
-    } else {
-        x = fabsf_(x);
-        if (ix < 0x3f980000) {                 // |x| < 1.1875
-            if (ix < 0x3f300000) {             // 7/16 <= |x| < 11/16
-                id = 0; x = (2.0f * x - 1.0f) / (2.0f + x);
-                hi = 4.6364760399e-01f; lo = 5.0121582440e-09f;
-            } else {                           // 11/16 <= |x| < 19/16
-                id = 1; x = (x - 1.0f) / (x + 1.0f);
-                hi = 7.8539812565e-01f; lo = 3.7748947079e-08f;
-            }
-        } else {
-            if (ix < 0x401c0000) {             // |x| < 2.4375
-                id = 2; x = (x - 1.5f) / (1.0f + 1.5f * x);
-                hi = 9.8279368877e-01f; lo = 3.4473217170e-08f;
-            } else {
-                id = 3; x = -1.0f / x;
-                hi = 1.5707962513e+00f; lo = 7.5497894159e-08f;
-            }
-        }
-    }
-    z = x * x;
-    w = z * z;
-    s1 = z * (aT0 + w * (aT2 + w * (aT4 + w * (aT6 + w * (aT8 + w * aT10)))));
-    s2 = w * (aT1 + w * (aT3 + w * (aT5 + w * (aT7 + w * aT9))));
-    if (id < 0) return x - x * (s1 + s2);
-    z = hi - ((x * (s1 + s2) - lo) - x);
-    return (hx < 0) ? -z : z;
+    const float ax = fabsf_(x);
+    const bool r0 = ix < 0x3ee00000;           // |x| < 0.4375: no reduction
+    const bool r1 = ix < 0x3f300000;           // < 11/16
+    const bool r2 = ix < 0x3f980000;           // < 19/16
+    const bool r3 = ix < 0x401c0000;           // < 2.4375
+    float num = r0 ? x : (r1 ? 2.0f * ax - 1.0f : (r2 ? ax - 1.0f : (r3 ? ax - 1.5f : -1.0f)));
+    float den = r0 ? 1.0f : (r1 ? 2.0f + ax : (r2 ? ax + 1.0f : (r3 ? 1.0f + 1.5f * ax : ax)));
+    float hi = r1 ? 4.6364760399e-01f : (r2 ? 7.8539812565e-01f : (r3 ? 9.8279368877e-01f : 1.5707962513e+00f));
+    float lo = r1 ? 5.0121582440e-09f : (r2 ? 3.7748947079e-08f : (r3 ? 3.4473217170e-08f : 7.5497894159e-08f));
+    float t = num / den;
+    float z = t * t;
+    float w = z * z;
+    float s1 = z * (aT0 + w * (aT2 + w * (aT4 + w * (aT6 + w * (aT8 + w * aT10)))));
+    float s2 = w * (aT1 + w * (aT3 + w * (aT5 + w * (aT7 + w * aT9))));
+    float ts = t * (s1 + s2);
+    if (r0) return (ix < 0x31000000) ? x : t - ts;   // |x| < 2^-29 returns x
+    float zz = hi - ((ts - lo) - t);
+    return (hx < 0) ? -zz : zz;
 }
 
 // =================================================================== atan2f
@@ -398,7 +389,9 @@ RLM_HD float atan2f_(float y, float x)
 }
 
 // ==================================================================== acosf
-// fdlibm e_acosf.c (binary32) as shipped by glibc 2.39 (six-term P, four-term Q)
+// fdlibm e_acosf.c (binary32) as shipped by glibc 2.39 (six-term P, four-term Q), with the
+// three ranges sharing one P/Q evaluation: z = x*x for |x| < 0.5, else (1 - |x|)/2
+// ((1 + x)*0.5 for x < -0.5 is the same IEEE operation as (1 - |x|)*0.5).
 RLM_HD float acosf_(float x)
 {
     const float pi = 3.1415925026e+00f, pio2_hi = 1.5707962513e+00f, pio2_lo = 7.5497894159e-08f;
@@ -406,41 +399,30 @@ RLM_HD float acosf_(float x)
                 pS3 = -4.0055535734e-02f, pS4 = 7.9153501429e-04f, pS5 = 3.4793309169e-05f,
                 qS1 = -2.4033949375e+00f, qS2 = 2.0209457874e+00f, qS3 = -6.8828397989e-01f,
                 qS4 = 7.7038154006e-02f;
-    float z, p, q, r, w, s, c, df;
-    int32_t hx = (int32_t)f2u(x);
-    int32_t ix = hx & 0x7fffffff;
-    if (ix == 0x3f800000) {
-        if (hx > 0) return 0.0f;
-        return pi + 2.0f * pio2_lo;
-    } else if (ix > 0x3f800000) {
-        return (x - x) / (x - x);
+    const int32_t hx = (int32_t)f2u(x);
+    const int32_t ix = hx & 0x7fffffff;
+    if (ix >= 0x3f800000) {
+        if (ix > 0x3f800000) return (x - x) / (x - x);
+        return (hx > 0) ? 0.0f : pi + 2.0f * pio2_lo;
     }
-    if (ix < 0x3f000000) {                     // |x| < 0.5
+    const bool small = ix < 0x3f000000;        // |x| < 0.5
+    const float z = small ? x * x : (1.0f - fabsf_(x)) * 0.5f;
+    const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    const float q = 1.0f + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    const float r = p / q;
+    if (small) {
         if (ix <= 0x32800000) return pio2_hi + pio2_lo;
-        z = x * x;
-        p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
-        q = 1.0f + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
-        r = p / q;
         return pio2_hi - (x - (pio2_lo - x * r));
-    } else if (hx < 0) {                       // x < -0.5
-        z = (1.0f + x) * 0.5f;
-        p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
-        q = 1.0f + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
-        s = sqrtf_(z);
-        r = p / q;
-        w = r * s - pio2_lo;
-        return pi - 2.0f * (s + w);
-    } else {                                   // x > 0.5
-        z = (1.0f - x) * 0.5f;
-        s = sqrtf_(z);
-        df = u2f(f2u(s) & 0xfffff000u);
-        c = (z - df * df) / (s + df);
-        p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
-        q = 1.0f + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
-        r = p / q;
-        w = r * s + c;
-        return 2.0f * (df + w);
     }
+    const float s = sqrtf_(z);
+    if (hx < 0) {                              // x < -0.5
+        float w = r * s - pio2_lo;
+        return pi - 2.0f * (s + w);
+    }
+    const float df = u2f(f2u(s) & 0xfffff000u);
+    const float c = (z - df * df) / (s + df);
+    const float w = r * s + c;
+    return 2.0f * (df + w);
 }
 
 // ===================================================================== expf
