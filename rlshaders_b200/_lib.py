@@ -9,7 +9,10 @@ import os
 
 from . import _abi as abi
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "librls_b200.so")
+# RLS_B200_LIB lets a developer point at an experimental build of the SAME library (tuning
+# sweeps); there is still exactly one implementation and no fallback.
+LIB_PATH = os.environ.get("RLS_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                          "librls_b200.so")
 
 # Every extern "C" symbol include/rls_b200.h declares (tests check the export list).
 SYMBOLS = [

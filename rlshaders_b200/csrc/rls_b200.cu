@@ -27,7 +27,16 @@ using namespace rls;
 
 // ============================================================== context
 static constexpr int kStages = 3;          // host-staging pipeline depth
-static constexpr int kBlock = 256;
+// Launch shape: 512 threads x >= 2 resident CTAs per SM (<= 64 registers/thread).  Chosen from a
+// sweep on B200 (tools/sweep_variants.sh; profiles/r01_launch_sweep.txt): the kernels are
+// instruction-issue bound, so occupancy beyond ~50 % does not help and tighter register caps spill.
+#ifndef RLS_BLOCK
+#define RLS_BLOCK 512
+#endif
+#ifndef RLS_MIN_BLOCKS
+#define RLS_MIN_BLOCKS 2
+#endif
+static constexpr int kBlock = RLS_BLOCK;
 
 struct rls_context {
     int          device = 0;
@@ -191,12 +200,14 @@ static inline SkinParamsDev dev(const rls_skin_params &p)
 }
 
 static inline unsigned grid_for(size_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+// 32-bit sample index: one IMAD.WIDE per array address instead of a 64-bit add pair; the entry
+// points reject n >= 2^32 (that many samples would not fit in HBM anyway).
 #define RLS_INDEX()                                                            \
-    size_t i = (size_t)blockIdx.x * (size_t)blockDim.x + threadIdx.x;          \
-    if (i >= n) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;                  \
+    if (i >= (uint32_t)n) return;
 
 // ================================================================ rlGgx kernels
-RLS_DEV Ggx ggx_make(const ShadingSoA &sg, const GgxParamsDev &p, size_t i)
+RLS_DEV Ggx ggx_make(const ShadingSoA &sg, const GgxParamsDev &p, uint32_t i)
 {
     Shading s = load_shading(sg, i);
     Ggx g;
@@ -204,7 +215,7 @@ RLS_DEV Ggx ggx_make(const ShadingSoA &sg, const GgxParamsDev &p, size_t i)
     return g;
 }
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_ggx_eval_sample(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, V3 wi, float *fresnel)
 {
     RLS_INDEX();
@@ -215,7 +226,7 @@ k_ggx_eval_sample(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, cons
     if (fresnel) fresnel[i] = ggx_fresnel(g, L, M);    // :103-104,181-184 with one sample
 }
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_ggx_eval_brdf(size_t n, ShadingSoA sg, GgxParamsDev p, CV3 wi, V3 f)
 {
     RLS_INDEX();
@@ -223,7 +234,7 @@ k_ggx_eval_brdf(size_t n, ShadingSoA sg, GgxParamsDev p, CV3 wi, V3 f)
     store3(f, i, ggx_eval_brdf(g, load3(wi, i)));
 }
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_ggx_eval_pdf(size_t n, ShadingSoA sg, GgxParamsDev p, CV3 wi, float *pdf)
 {
     RLS_INDEX();
@@ -231,7 +242,7 @@ k_ggx_eval_pdf(size_t n, ShadingSoA sg, GgxParamsDev p, CV3 wi, float *pdf)
     pdf[i] = ggx_eval_pdf(g, load3(wi, i));
 }
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_ggx_sample_eval_pdf(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry,
                       V3 wi, V3 f, float *pdf, float *fresnel, uint32_t *flags)
 {
@@ -247,7 +258,7 @@ k_ggx_sample_eval_pdf(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, 
 
 struct DielectricOutDev { float *fresnel; V3 wi_r; float *f_r, *pdf_r; V3 wi_t; float *f_t, *weight_t; uint32_t *flags; };
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_ggx_dielectric(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, DielectricOutDev o)
 {
     RLS_INDEX();
@@ -264,7 +275,7 @@ k_ggx_dielectric(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const
 }
 
 // ============================================================= rlDisney kernels
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_disney_eval_sample(size_t n, ShadingSoA sg, DisneyParamsDev p, int type, const float *rx, const float *ry, V3 wi, uint32_t *flags)
 {
     RLS_INDEX();
@@ -280,14 +291,14 @@ k_disney_eval_sample(size_t n, ShadingSoA sg, DisneyParamsDev p, int type, const
         flags[i] = fl;
     }
 }
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_disney_eval_brdf(size_t n, ShadingSoA sg, DisneyParamsDev p, int type, CV3 wi, V3 f)
 {
     RLS_INDEX();
     Disney d; disney_init(d, load_shading(sg, i), p, i);
     store3(f, i, disney_eval_brdf(d, type, load3(wi, i)));
 }
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_disney_eval_pdf(size_t n, ShadingSoA sg, DisneyParamsDev p, int type, CV3 wi, float *pdf)
 {
     RLS_INDEX();
@@ -297,7 +308,7 @@ k_disney_eval_pdf(size_t n, ShadingSoA sg, DisneyParamsDev p, int type, CV3 wi, 
 
 struct DisneyOutDev { V3 wi_s, f_s; float *pdf_s; V3 wi_d, f_d; float *pdf_d; uint32_t *flags; };
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_disney_sample_eval_pdf(size_t n, ShadingSoA sg, DisneyParamsDev p, const float *rx_s, const float *ry_s,
                          const float *rx_d, const float *ry_d, DisneyOutDev o)
 {
@@ -319,7 +330,7 @@ k_disney_sample_eval_pdf(size_t n, ShadingSoA sg, DisneyParamsDev p, const float
 
 // ================================================================ profile kernels
 struct NdProfileSoADev { V3 distance, C1, C2; float *max_radius; };
-RLS_DEV NdProfile nd_load(const NdProfileSoADev &s, size_t i)
+RLS_DEV NdProfile nd_load(const NdProfileSoADev &s, uint32_t i)
 {
     NdProfile p;
     p.d[0] = s.distance.x[i]; p.d[1] = s.distance.y[i]; p.d[2] = s.distance.z[i];
@@ -328,7 +339,7 @@ RLS_DEV NdProfile nd_load(const NdProfileSoADev &s, size_t i)
     p.R = s.max_radius[i];
     return p;
 }
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_nd_set_distance(size_t n, CV3 dist, NdProfileSoADev o)
 {
     RLS_INDEX();
@@ -338,7 +349,7 @@ k_nd_set_distance(size_t n, CV3 dist, NdProfileSoADev o)
     store3(o.C2, i, mk3(p.C2[0], p.C2[1], p.C2[2]));
     o.max_radius[i] = p.R;
 }
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_nd_get_radius(size_t n, NdProfileSoADev s, const float *rx, float *r, uint32_t *flags)
 {
     RLS_INDEX();
@@ -347,14 +358,14 @@ k_nd_get_radius(size_t n, NdProfileSoADev s, const float *rx, float *r, uint32_t
     r[i] = nd_get_radius(p, __ldg(rx + i), fl);
     if (flags) flags[i] = fl;
 }
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_nd_get_pdf(size_t n, NdProfileSoADev s, const float *r, float *pdf)
 {
     RLS_INDEX();
     NdProfile p = nd_load(s, i);
     pdf[i] = nd_get_pdf(p, __ldg(r + i));
 }
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_nd_eval_profile(size_t n, NdProfileSoADev s, const float *r, V3 rd)
 {
     RLS_INDEX();
@@ -362,7 +373,7 @@ k_nd_eval_profile(size_t n, NdProfileSoADev s, const float *r, V3 rd)
     store3(rd, i, nd_eval_profile(p, __ldg(r + i)));
 }
 struct ProfileOutDev { float *r, *pdf; V3 Rd; uint32_t *flags; };
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_skin_profile(size_t n, SkinParamsDev sp, const float *rx, ProfileOutDev o)
 {
     RLS_INDEX();
@@ -375,7 +386,7 @@ k_skin_profile(size_t n, SkinParamsDev sp, const float *rx, ProfileOutDev o)
     o.flags[i] = fl;
 }
 // src/rlSkin.cpp:191,204,214,228,231,238
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_skin_layer_weights(size_t n, SkinParamsDev sp, const float *avgSheen, const float *avgSpec, float *specScale, float *sssWeight)
 {
     RLS_INDEX();
@@ -404,13 +415,13 @@ RLS_DEV float uniform24(uint64_t seed, uint32_t stream, uint64_t index)
     if (k == 0u) k = 1u;
     return (float)k * 5.9604644775390625e-8f;
 }
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_synth_uniform(size_t n, uint64_t seed, uint32_t stream, uint64_t first, float lo, float hi, float *out)
 {
     RLS_INDEX();
     out[i] = lo + (hi - lo) * uniform24(seed, stream, first + i);
 }
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_synth_shading(size_t n, uint64_t seed, uint64_t first, float cos_lo, float cos_hi, float back_frac,
                 V3 U, V3 V, V3 N, V3 wo, uint8_t *backfacing)
 {
@@ -439,7 +450,7 @@ k_synth_shading(size_t n, uint64_t seed, uint64_t first, float cos_lo, float cos
 // ================================================================= albedo sweep
 struct SweepGridDev { int n_rough, n_cos, n_ior; float rlo, rhi, ilo, ihi; };
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_albedo_sweep(SweepGridDev g, uint64_t seed, uint32_t k0, uint32_t k1, double *table)
 {
     const uint32_t cell = blockIdx.x;
@@ -546,6 +557,7 @@ extern "C" int rls_ggx_eval_sample(rls_context *ctx, size_t n, const rls_shading
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && rx && ry && has3(out_wi), "rls_ggx_eval_sample: NULL argument");
     DeviceGuard guard(ctx->device);
     k_ggx_eval_sample<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), rx, ry, mv(out_wi), out_fresnel);
@@ -557,6 +569,7 @@ extern "C" int rls_ggx_eval_brdf(rls_context *ctx, size_t n, const rls_shading_s
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && has3(wi) && has3(out_f), "rls_ggx_eval_brdf: NULL argument");
     DeviceGuard guard(ctx->device);
     k_ggx_eval_brdf<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), cv(wi), mv(out_f));
@@ -568,6 +581,7 @@ extern "C" int rls_ggx_eval_pdf(rls_context *ctx, size_t n, const rls_shading_so
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && has3(wi) && out_pdf, "rls_ggx_eval_pdf: NULL argument");
     DeviceGuard guard(ctx->device);
     k_ggx_eval_pdf<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), cv(wi), out_pdf);
@@ -579,6 +593,7 @@ extern "C" int rls_ggx_sample_eval_pdf(rls_context *ctx, size_t n, const rls_sha
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && rx && ry && ok_bsdf_out(out), "rls_ggx_sample_eval_pdf: NULL argument");
     DeviceGuard guard(ctx->device);
     return launch_ggx_sample_eval_pdf(ctx, ctx->stream, n, sg, p, rx, ry, out);
@@ -589,6 +604,7 @@ extern "C" int rls_ggx_dielectric_sample_eval_pdf(rls_context *ctx, size_t n, co
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && rx && ry && ok_dielectric_out(out),
                 "rls_ggx_dielectric_sample_eval_pdf: NULL argument");
     DeviceGuard guard(ctx->device);
@@ -603,6 +619,7 @@ extern "C" int rls_disney_eval_sample(rls_context *ctx, size_t n, const rls_shad
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, ok_shading(sg) && ok_disney_params(p) && rx && ry && has3(out_wi), "rls_disney_eval_sample: NULL argument");
     RLS_REQUIRE(ctx, ok_sample_type(sample_type), "rls_disney_eval_sample: sample_type must be RLS_RAY_DIFFUSE or RLS_RAY_GLOSSY");
     DeviceGuard guard(ctx->device);
@@ -615,6 +632,7 @@ extern "C" int rls_disney_eval_brdf(rls_context *ctx, size_t n, const rls_shadin
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, ok_shading(sg) && ok_disney_params(p) && has3(wi) && has3(out_f), "rls_disney_eval_brdf: NULL argument");
     RLS_REQUIRE(ctx, ok_sample_type(sample_type), "rls_disney_eval_brdf: sample_type must be RLS_RAY_DIFFUSE or RLS_RAY_GLOSSY");
     DeviceGuard guard(ctx->device);
@@ -627,6 +645,7 @@ extern "C" int rls_disney_eval_pdf(rls_context *ctx, size_t n, const rls_shading
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, ok_shading(sg) && ok_disney_params(p) && has3(wi) && out_pdf, "rls_disney_eval_pdf: NULL argument");
     RLS_REQUIRE(ctx, ok_sample_type(sample_type), "rls_disney_eval_pdf: sample_type must be RLS_RAY_DIFFUSE or RLS_RAY_GLOSSY");
     DeviceGuard guard(ctx->device);
@@ -640,6 +659,7 @@ extern "C" int rls_disney_sample_eval_pdf(rls_context *ctx, size_t n, const rls_
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, ok_shading(sg) && ok_disney_params(p) && rx_s && ry_s && rx_d && ry_d && ok_disney_out(out),
                 "rls_disney_sample_eval_pdf: NULL argument");
     DeviceGuard guard(ctx->device);
@@ -659,6 +679,7 @@ extern "C" int rls_ndprofile_set_distance(rls_context *ctx, size_t n, rls_cvec3 
     (void)albedo;   // only feeds the dead `s` of src/rlSss.cpp:22-23
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, has3(dist) && ok_profile(out), "rls_ndprofile_set_distance: NULL argument");
     DeviceGuard guard(ctx->device);
     k_nd_set_distance<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, cv(dist), dev(*out));
@@ -670,6 +691,7 @@ extern "C" int rls_ndprofile_get_radius(rls_context *ctx, size_t n, const rls_nd
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, ok_profile(profile) && rx && out_r, "rls_ndprofile_get_radius: NULL argument");
     DeviceGuard guard(ctx->device);
     k_nd_get_radius<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, dev(*profile), rx, out_r, out_flags);
@@ -680,6 +702,7 @@ extern "C" int rls_ndprofile_get_pdf(rls_context *ctx, size_t n, const rls_ndpro
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, ok_profile(profile) && r && out_pdf, "rls_ndprofile_get_pdf: NULL argument");
     DeviceGuard guard(ctx->device);
     k_nd_get_pdf<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, dev(*profile), r, out_pdf);
@@ -690,6 +713,7 @@ extern "C" int rls_ndprofile_eval_profile(rls_context *ctx, size_t n, const rls_
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, ok_profile(profile) && r && has3(out_rd), "rls_ndprofile_eval_profile: NULL argument");
     DeviceGuard guard(ctx->device);
     k_nd_eval_profile<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, dev(*profile), r, mv(out_rd));
@@ -701,6 +725,7 @@ extern "C" int rls_skin_profile_sample_eval_pdf(rls_context *ctx, size_t n, cons
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, ok_skin_params(p) && rx && ok_profile_out(out), "rls_skin_profile_sample_eval_pdf: NULL argument");
     DeviceGuard guard(ctx->device);
     return launch_skin_profile(ctx, ctx->stream, n, p, rx, out);
@@ -710,6 +735,7 @@ extern "C" int rls_skin_layer_weights(rls_context *ctx, size_t n, const rls_skin
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, p && avg_sheen && avg_spec && out_spec_scale && out_sss_weight, "rls_skin_layer_weights: NULL argument");
     DeviceGuard guard(ctx->device);
     k_skin_layer_weights<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, dev(*p), avg_sheen, avg_spec, out_spec_scale, out_sss_weight);
@@ -739,6 +765,7 @@ extern "C" int rls_synth_uniform(rls_context *ctx, size_t n, uint64_t seed, uint
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, out, "rls_synth_uniform: NULL argument");
     DeviceGuard guard(ctx->device);
     k_synth_uniform<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, seed, stream, first_index, lo, hi, out);
@@ -750,6 +777,7 @@ extern "C" int rls_synth_shading(rls_context *ctx, size_t n, uint64_t seed, uint
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, ok_shading(sg), "rls_synth_shading: NULL argument");
     DeviceGuard guard(ctx->device);
     V3 U = { (float *)sg->U.x, (float *)sg->U.y, (float *)sg->U.z };
@@ -763,7 +791,7 @@ extern "C" int rls_synth_shading(rls_context *ctx, size_t n, uint64_t seed, uint
 }
 
 // ================================================================= C ABI: diagnostics
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_debug_libm(int fn, size_t n, const float *a, const float *b, float *out0, float *out1)
 {
     RLS_INDEX();
@@ -785,6 +813,7 @@ extern "C" int rls_debug_libm(rls_context *ctx, int fn, size_t n, const float *a
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, fn >= 0 && fn <= 7 && a && out0 && (fn < 6 || b), "rls_debug_libm: bad argument");
     DeviceGuard guard(ctx->device);
     k_debug_libm<<<grid_for(n), kBlock, 0, ctx->stream>>>(fn, n, a, b, out0, out1);
@@ -903,6 +932,7 @@ extern "C" int rls_ggx_sample_eval_pdf_host(rls_context *ctx, size_t n, const rl
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && rx && ry && ok_bsdf_out(out), "rls_ggx_sample_eval_pdf_host: NULL argument");
     return run_staged(ctx, n, chunk, 32, [&](Stager &st) {
         rls_shading_soa s = st.shading(*sg);
@@ -921,6 +951,7 @@ extern "C" int rls_ggx_dielectric_sample_eval_pdf_host(rls_context *ctx, size_t 
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && rx && ry && ok_dielectric_out(out),
                 "rls_ggx_dielectric_sample_eval_pdf_host: NULL argument");
     return run_staged(ctx, n, chunk, 36, [&](Stager &st) {
@@ -941,6 +972,7 @@ extern "C" int rls_disney_sample_eval_pdf_host(rls_context *ctx, size_t n, const
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, ok_shading(sg) && ok_disney_params(p) && rx_s && ry_s && rx_d && ry_d && ok_disney_out(out),
                 "rls_disney_sample_eval_pdf_host: NULL argument");
     return run_staged(ctx, n, chunk, 48, [&](Stager &st) {
@@ -962,6 +994,7 @@ extern "C" int rls_skin_profile_sample_eval_pdf_host(rls_context *ctx, size_t n,
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
     if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, ok_skin_params(p) && rx && ok_profile_out(out), "rls_skin_profile_sample_eval_pdf_host: NULL argument");
     return run_staged(ctx, n, chunk, 16, [&](Stager &st) {
         rls_skin_params q = *p;

@@ -21,7 +21,7 @@ struct Disney {
 };
 
 // src/rlDisney.cpp:155-192
-RLS_DEV void disney_init(Disney &d, const Shading &sh, const DisneyParamsDev &p, size_t i)
+RLS_DEV void disney_init(Disney &d, const Shading &sh, const DisneyParamsDev &p, uint32_t i)
 {
     d.U = sh.U; d.V = sh.V; d.N = sh.N; d.wo = sh.wo;
     d.base = fetch(p.base_color, i);

@@ -66,21 +66,21 @@ RLS_DEV f3 rotate_to_frame(f3 a, f3 u, f3 v, f3 w)
 // ---- parameter fetch: uniform value or per-sample array (include/rls_b200.h rls_param1/3)
 struct P1 { float value; const float *array; };
 struct P3 { float value[3]; const float *x, *y, *z; };
-RLS_DEV float fetch(const P1 &p, size_t i) { return p.array ? __ldg(p.array + i) : p.value; }
-RLS_DEV f3 fetch(const P3 &p, size_t i)
+RLS_DEV float fetch(const P1 &p, uint32_t i) { return p.array ? __ldg(p.array + i) : p.value; }
+RLS_DEV f3 fetch(const P3 &p, uint32_t i)
 {
     return mk3(p.x ? __ldg(p.x + i) : p.value[0], p.y ? __ldg(p.y + i) : p.value[1],
                p.z ? __ldg(p.z + i) : p.value[2]);
 }
 struct CV3 { const float *x, *y, *z; };
 struct V3  { float *x, *y, *z; };
-RLS_DEV f3 load3(const CV3 &v, size_t i) { return mk3(__ldg(v.x + i), __ldg(v.y + i), __ldg(v.z + i)); }
-RLS_DEV void store3(const V3 &v, size_t i, f3 a) { v.x[i] = a.x; v.y[i] = a.y; v.z[i] = a.z; }
+RLS_DEV f3 load3(const CV3 &v, uint32_t i) { return mk3(__ldg(v.x + i), __ldg(v.y + i), __ldg(v.z + i)); }
+RLS_DEV void store3(const V3 &v, uint32_t i, f3 a) { v.x[i] = a.x; v.y[i] = a.y; v.z[i] = a.z; }
 
 // Shading inputs of one sample (include/rls_b200.h rls_shading_soa).
 struct ShadingSoA { CV3 U, V, N, wo; const uint8_t *backfacing; };
 struct Shading { f3 U, V, N, wo; bool backfacing; };
-RLS_DEV Shading load_shading(const ShadingSoA &s, size_t i)
+RLS_DEV Shading load_shading(const ShadingSoA &s, uint32_t i)
 {
     Shading o;
     o.U = load3(s.U, i); o.V = load3(s.V, i); o.N = load3(s.N, i); o.wo = load3(s.wo, i);
