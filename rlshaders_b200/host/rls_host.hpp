@@ -1,0 +1,151 @@
+// rls_host.hpp -- C++ host-side mirror of the reference's sampler interface over the C ABI.
+//
+// The reference gives Arnold, per shading point, a sampler object plus the static callback
+// triple evalSample / evalBrdf / evalPdf (src/rlGgx.h:97-127, src/rlDisney.cpp:109-152) and
+// Arnold loops over samples.  Here the loop is the batch: a sampler is constructed over a
+// whole batch of shading points (SoA, host memory) and each call evaluates every sample on the
+// GPU through include/rls_b200.h.  Names, argument meaning and in-band error behaviour (zero
+// vector = invalid sample, black / pdf 0 on a zero direction) follow the reference.
+//
+// Header-only; link with librls_b200.so.  No CUDA headers are needed by the client.
+#pragma once
+#include <cstdint>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/rls_b200.h"
+
+namespace rls {
+namespace host {
+
+struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
+
+// Owns an rls_context (one per host thread / device, like one Arnold render thread).
+class Context {
+public:
+    explicit Context(int device = 0)
+    {
+        if (rls_init(device, nullptr, &mCtx) != RLS_OK)
+            throw Error(std::string("rls_init: ") + rls_last_error_string(nullptr));
+    }
+    ~Context() { if (mCtx) rls_shutdown(mCtx); }
+    Context(const Context &) = delete;
+    Context &operator=(const Context &) = delete;
+    rls_context *get() const { return mCtx; }
+    void check(int rc) const { if (rc != RLS_OK) throw Error(rls_last_error_string(mCtx)); }
+    // Pinned host arrays: the *_host entry points overlap H2D / kernel / D2H on them.
+    template <typename T> T *alloc(size_t n) const
+    {
+        void *p = nullptr;
+        check(rls_host_alloc(mCtx, n * sizeof(T), &p));
+        return static_cast<T *>(p);
+    }
+    void free(void *p) const { rls_host_free(mCtx, p); }
+private:
+    rls_context *mCtx = nullptr;
+};
+
+// A batch of pinned SoA float arrays with one owner.
+class Arena {
+public:
+    explicit Arena(const Context &ctx) : mCtx(ctx) {}
+    ~Arena() { for (void *p : mBlocks) mCtx.free(p); }
+    float *floats(size_t n) { float *p = mCtx.alloc<float>(n); mBlocks.push_back(p); return p; }
+    uint32_t *words(size_t n) { uint32_t *p = mCtx.alloc<uint32_t>(n); mBlocks.push_back(p); return p; }
+    uint8_t *bytes(size_t n) { uint8_t *p = mCtx.alloc<uint8_t>(n); mBlocks.push_back(p); return p; }
+    rls_vec3 vec3(size_t n) { rls_vec3 v = { floats(n), floats(n), floats(n) }; return v; }
+private:
+    const Context &mCtx;
+    std::vector<void *> mBlocks;
+};
+
+inline rls_cvec3 as_const(const rls_vec3 &v) { rls_cvec3 c = { v.x, v.y, v.z }; return c; }
+inline rls_param1 uniform(float v) { rls_param1 p = { v, nullptr }; return p; }
+inline rls_param3 uniform(float r, float g, float b) { rls_param3 p = { { r, g, b }, { nullptr, nullptr, nullptr } }; return p; }
+inline rls_param1 varying(const float *a) { rls_param1 p = { 0.0f, a }; return p; }
+
+// Node-parameter defaults of the reference (src/rlGgx.cpp:172-186, rlDisney.cpp:606-628,
+// rlSkin.cpp:109-131).
+inline rls_ggx_params ggx_defaults()
+{
+    rls_ggx_params p = {};
+    p.KsColor = uniform(1, 1, 1); p.Ks = uniform(0.5f); p.specularRoughness = uniform(0.0f);
+    p.ior = uniform(1.0f); p.anisotropic = uniform(0.0f);
+    p.KdColor = uniform(1, 1, 1); p.Kd = uniform(0.5f); p.diffuseRoughness = uniform(0.0f);
+    p.KtColor = uniform(1, 1, 1); p.Kt = uniform(0.0f); p.opacity = uniform(1.0f); p.opacity_color = uniform(1, 1, 1);
+    return p;
+}
+inline rls_disney_params disney_defaults()
+{
+    rls_disney_params p = {};
+    p.base_color = uniform(1, 1, 1); p.opacity = uniform(1, 1, 1);
+    p.indirectDiffuseScale = uniform(1.0f); p.indirectSpecularScale = uniform(1.0f);
+    return p;   // the ten scalar parameters default to 0
+}
+inline rls_skin_params skin_defaults()
+{
+    rls_skin_params p = {};
+    p.sss_color = uniform(1, 1, 1); p.sss_weight = uniform(1.0f); p.sss_dist_multiplier = uniform(1.0f);
+    p.sss_scatter_dist = uniform(1, 1, 1); p.sss_cavity_fadeout = 1;
+    p.specular_color = uniform(1, 1, 1); p.specular_weight = uniform(0.6f); p.specular_roughness = uniform(0.5f);
+    p.specular_ior = uniform(1.44f); p.sheen_color = uniform(1, 1, 1); p.sheen_weight = uniform(0.0f);
+    p.sheen_roughness = uniform(0.35f); p.sheen_ior = uniform(1.44f); p.opacity = uniform(1.0f);
+    p.opacity_color = uniform(1, 1, 1);
+    return p;
+}
+
+// Batched rls::GgxSampler.  `sg` and every array are pinned host memory of n entries.
+class GgxSampler {
+public:
+    GgxSampler(const Context &ctx, size_t n, const rls_shading_soa &sg, const rls_ggx_params &params)
+        : mCtx(ctx), mN(n), mSg(sg), mParams(params) {}
+    // evalSample + evalBrdf + evalPdf for every sample (the fused unit of work).
+    void sampleEvalPdf(const float *rx, const float *ry, const rls_bsdf_out &out, size_t chunk = 0) const
+    {
+        mCtx.check(rls_ggx_sample_eval_pdf_host(mCtx.get(), mN, &mSg, &mParams, rx, ry, &out, chunk));
+    }
+    // Rough dielectric: reflection and refraction branches (src/rlGgx.h:228-243).
+    void dielectricSampleEvalPdf(const float *rx, const float *ry, const rls_ggx_dielectric_out &out, size_t chunk = 0) const
+    {
+        mCtx.check(rls_ggx_dielectric_sample_eval_pdf_host(mCtx.get(), mN, &mSg, &mParams, rx, ry, &out, chunk));
+    }
+private:
+    const Context &mCtx;
+    size_t mN;
+    rls_shading_soa mSg;
+    rls_ggx_params mParams;
+};
+
+class DisneySampler {
+public:
+    DisneySampler(const Context &ctx, size_t n, const rls_shading_soa &sg, const rls_disney_params &params)
+        : mCtx(ctx), mN(n), mSg(sg), mParams(params) {}
+    void sampleEvalPdf(const float *rx_s, const float *ry_s, const float *rx_d, const float *ry_d,
+                       const rls_disney_out &out, size_t chunk = 0) const
+    {
+        mCtx.check(rls_disney_sample_eval_pdf_host(mCtx.get(), mN, &mSg, &mParams, rx_s, ry_s, rx_d, ry_d, &out, chunk));
+    }
+private:
+    const Context &mCtx;
+    size_t mN;
+    rls_shading_soa mSg;
+    rls_disney_params mParams;
+};
+
+class SkinProfile {
+public:
+    SkinProfile(const Context &ctx, size_t n, const rls_skin_params &params) : mCtx(ctx), mN(n), mParams(params) {}
+    void sampleEvalPdf(const float *rx, const rls_profile_out &out, size_t chunk = 0) const
+    {
+        mCtx.check(rls_skin_profile_sample_eval_pdf_host(mCtx.get(), mN, &mParams, rx, &out, chunk));
+    }
+private:
+    const Context &mCtx;
+    size_t mN;
+    rls_skin_params mParams;
+};
+
+} // namespace host
+} // namespace rls
