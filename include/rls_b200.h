@@ -117,7 +117,13 @@ typedef struct rls_ggx_params {
     rls_param1 Kt;
     rls_param1 opacity;
     rls_param3 opacity_color;
+    /* Not a node parameter: which microfacet-normal sampler the GgxSamplerT template is
+     * instantiated with.  0 = VNDFKernel (the shipped `using GgxSampler`, src/rlGgx.h:375),
+     * 1 = NDFKernel (src/rlGgx.h:24-56: Burley Eq.14 sampling, pdf D|m.n|/(4|i.m|), no floor). */
+    int32_t    normal_sampler;
 } rls_ggx_params;
+#define RLS_GGX_SAMPLER_VNDF 0
+#define RLS_GGX_SAMPLER_NDF  1
 
 /* rlDisney node parameters (src/rlDisney.cpp:606-625). */
 typedef struct rls_disney_params {
@@ -135,6 +141,9 @@ typedef struct rls_disney_params {
     rls_param3 opacity;               /* accepted, ignored */
     rls_param1 indirectDiffuseScale;  /* accepted, ignored */
     rls_param1 indirectSpecularScale; /* accepted, ignored */
+    /* Not a node parameter: DisneySampler::mSampleFromVisibleNormal (src/rlDisney.cpp:191 sets it
+     * true).  0 selects sampleGTR2AnisoDirection (:406-414) and the pdf branch of :541-542. */
+    int32_t    sample_from_visible_normal;
 } rls_disney_params;
 
 /* rlSkin node parameters (src/rlSkin.cpp:109-131, src/rlShaders.mtd:43-64).  The
@@ -287,6 +296,17 @@ int rls_skin_profile_sample_eval_pdf(rls_context *ctx, size_t n, const rls_skin_
 int rls_skin_layer_weights(rls_context *ctx, size_t n, const rls_skin_params *params,
                            const float *avg_fresnel_sheen, const float *avg_fresnel_specular,
                            float *out_specular_scale, float *out_sss_weight);
+
+/* Probe-ray geometry of SssSampler::getProbeRay (src/rlSss.h:487-533) for one (rx, ry) pair per
+ * sample: axis pick 50/25/25 % N/U/V, r = getRadius(rx'), disc offset, chord length.  `sg`
+ * supplies the probe frame (N = sg->Ns, U/V explicit); origins are relative to sg->P. */
+int rls_skin_probe_ray(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_skin_params *params,
+                       const float *rx, const float *ry, const rls_probe_out *out);
+/* The 3-axis MIS pdf of one probe hit (src/rlSss.h:252-263): `disp` = hit position - sg->P,
+ * `hit_normal` = the hit's shading normal;
+ * pdf = 1/4 p(r_U)|U.n| + 1/4 p(r_V)|V.n| + 1/2 p(r_N)|N.n| with p = NDProfile::getPdf. */
+int rls_skin_probe_mis_pdf(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_skin_params *params,
+                           rls_cvec3 disp, rls_cvec3 hit_normal, float *out_pdf);
 
 /* -------------------------------------------- host-buffer (end-to-end) forms */
 /* Same contracts as the device forms above but every array pointer is a HOST pointer.

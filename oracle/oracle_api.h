@@ -69,6 +69,9 @@ void oracle_skin_layer_weights(size_t n, const rls_skin_params *p, const float *
 void oracle_skin_probe_ray(size_t n, const rls_shading_soa *sg, const rls_skin_params *p,
                            const float *rx, const float *ry, const rls_probe_out *out);
 
+void oracle_skin_probe_mis_pdf(size_t n, const rls_shading_soa *sg, const rls_skin_params *p,
+                               rls_cvec3 disp, rls_cvec3 hit_normal, float *out_pdf);
+
 void oracle_albedo_sweep(const rls_sweep_grid *grid, uint64_t seed, uint32_t spp_begin,
                          uint32_t spp_end, double *table);
 

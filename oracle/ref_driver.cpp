@@ -96,18 +96,19 @@ struct DielectricResult {
     AtVector wi_r, wi_t;
     uint32_t flags;
 };
-inline DielectricResult dielectricUnit(Shading &sh, float ior, float rough, float aniso, float rx, float ry)
+template <typename Sampler>
+inline DielectricResult dielectricUnitT(Shading &sh, float ior, float rough, float aniso, float rx, float ry)
 {
     DielectricResult r;
-    rls::GgxSampler s(&sh.sg, AI_RGB_WHITE, ior, rough, aniso);
+    Sampler s(&sh.sg, AI_RGB_WHITE, ior, rough, aniso);
     const AtVector V = s.mViewDir;
     const AtVector N = s.mAxisN;
     AtVector m = s.mNormalSampler->evalSample(rx, ry);
     r.wi_r = rls::reflectDirection(V, m);
     r.F = s.fresnel(r.wi_r, m);
-    AtColor fr = rls::GgxSampler::evalBrdf(&s, &r.wi_r);
+    AtColor fr = Sampler::evalBrdf(&s, &r.wi_r);
     r.f_r = fr.r;
-    r.pdf_r = rls::GgxSampler::evalPdf(&s, &r.wi_r);
+    r.pdf_r = Sampler::evalPdf(&s, &r.wi_r);
     r.flags = bsdfFlags(r.wi_r, N, fr, r.pdf_r);
     if (AiV3Dot(sh.sg.N, sh.sg.Rd) < AI_EPSILON) r.flags |= RLS_FLAG_ENTERING;
     AtVector t;
@@ -121,6 +122,13 @@ inline DielectricResult dielectricUnit(Shading &sh, float ior, float rough, floa
     }
     r.w_t = s.getSampleWeight(V, r.wi_t, m);
     return r;
+}
+
+typedef rls::GgxSamplerT<rls::NDFKernel> GgxNdfSampler;   /* src/rlGgx.h:24-56 as the template argument */
+inline DielectricResult dielectricUnit(Shading &sh, float ior, float rough, float aniso, float rx, float ry, int kernel = 0)
+{
+    return kernel == RLS_GGX_SAMPLER_NDF ? dielectricUnitT<GgxNdfSampler>(sh, ior, rough, aniso, rx, ry)
+                                         : dielectricUnitT<rls::GgxSampler>(sh, ior, rough, aniso, rx, ry);
 }
 
 inline void disneyTable(const rls_disney_params *p, size_t i, float *t /* [64*3] */)
@@ -174,6 +182,69 @@ inline uint32_t profileFlags(const rls::NDProfile &p, float rx)
 
 } // namespace
 
+template <typename Sampler>
+void ggxEvalSampleT(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p, const float *rx, const float *ry,
+                    rls_vec3 out_wi, float *out_fresnel)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        Shading sh; loadShading(sg, i, sh);
+        GgxArgs a = ggxArgs(p, i);
+        Sampler s(&sh.sg, a.ks, a.ior, a.rough, a.aniso);
+        AtVector L = Sampler::evalSample(&s, rx[i], ry[i]);
+        store3(out_wi, i, L.x, L.y, L.z);
+        if (out_fresnel) out_fresnel[i] = s.getAvgReflectWeight();
+    }
+}
+template <typename Sampler>
+void ggxEvalBrdfT(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p, rls_cvec3 wi, rls_vec3 out_f)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        Shading sh; loadShading(sg, i, sh);
+        GgxArgs a = ggxArgs(p, i);
+        Sampler s(&sh.sg, a.ks, a.ior, a.rough, a.aniso);
+        AtVector L; AiV3Create(L, wi.x[i], wi.y[i], wi.z[i]);
+        AtColor f = Sampler::evalBrdf(&s, &L);
+        store3(out_f, i, f.r, f.g, f.b);
+    }
+}
+template <typename Sampler>
+void ggxEvalPdfT(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p, rls_cvec3 wi, float *out_pdf)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        Shading sh; loadShading(sg, i, sh);
+        GgxArgs a = ggxArgs(p, i);
+        Sampler s(&sh.sg, a.ks, a.ior, a.rough, a.aniso);
+        AtVector L; AiV3Create(L, wi.x[i], wi.y[i], wi.z[i]);
+        out_pdf[i] = Sampler::evalPdf(&s, &L);
+    }
+}
+template <typename Sampler>
+void ggxSampleEvalPdfT(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p, const float *rx, const float *ry,
+                       const rls_bsdf_out *out)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        Shading sh; loadShading(sg, i, sh);
+        GgxArgs a = ggxArgs(p, i);
+        Sampler s(&sh.sg, a.ks, a.ior, a.rough, a.aniso);
+        AtVector L = Sampler::evalSample(&s, rx[i], ry[i]);
+        AtColor f = Sampler::evalBrdf(&s, &L);
+        float pdf = Sampler::evalPdf(&s, &L);
+        store3(out->wi, i, L.x, L.y, L.z);
+        store3(out->f, i, f.r, f.g, f.b);
+        out->pdf[i] = pdf;
+        if (out->fresnel) out->fresnel[i] = s.getAvgReflectWeight();
+        uint32_t fl = bsdfFlags(L, sh.sg.Nf, f, pdf);
+        if (AiV3Dot(sh.sg.N, sh.sg.Rd) < AI_EPSILON) fl |= RLS_FLAG_ENTERING;
+        out->flags[i] = fl;
+    }
+}
+#define GGX_DISPATCH(p, fn, ...) \
+    do { if ((p)->normal_sampler == RLS_GGX_SAMPLER_NDF) fn<GgxNdfSampler>(__VA_ARGS__); else fn<rls::GgxSampler>(__VA_ARGS__); } while (0)
+
 extern "C" {
 
 const char *oracle_kind(void) { return "reference"; }
@@ -197,63 +268,25 @@ void oracle_set_threads(int n)
 void oracle_ggx_eval_sample(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
                             const float *rx, const float *ry, rls_vec3 out_wi, float *out_fresnel)
 {
-#pragma omp parallel for schedule(static)
-    for (size_t i = 0; i < n; i++) {
-        Shading sh; loadShading(sg, i, sh);
-        GgxArgs a = ggxArgs(p, i);
-        rls::GgxSampler s(&sh.sg, a.ks, a.ior, a.rough, a.aniso);
-        AtVector L = rls::GgxSampler::evalSample(&s, rx[i], ry[i]);
-        store3(out_wi, i, L.x, L.y, L.z);
-        if (out_fresnel) out_fresnel[i] = s.getAvgReflectWeight();
-    }
+    GGX_DISPATCH(p, ggxEvalSampleT, n, sg, p, rx, ry, out_wi, out_fresnel);
 }
 
 void oracle_ggx_eval_brdf(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
                           rls_cvec3 wi, rls_vec3 out_f)
 {
-#pragma omp parallel for schedule(static)
-    for (size_t i = 0; i < n; i++) {
-        Shading sh; loadShading(sg, i, sh);
-        GgxArgs a = ggxArgs(p, i);
-        rls::GgxSampler s(&sh.sg, a.ks, a.ior, a.rough, a.aniso);
-        AtVector L; AiV3Create(L, wi.x[i], wi.y[i], wi.z[i]);
-        AtColor f = rls::GgxSampler::evalBrdf(&s, &L);
-        store3(out_f, i, f.r, f.g, f.b);
-    }
+    GGX_DISPATCH(p, ggxEvalBrdfT, n, sg, p, wi, out_f);
 }
 
 void oracle_ggx_eval_pdf(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
                          rls_cvec3 wi, float *out_pdf)
 {
-#pragma omp parallel for schedule(static)
-    for (size_t i = 0; i < n; i++) {
-        Shading sh; loadShading(sg, i, sh);
-        GgxArgs a = ggxArgs(p, i);
-        rls::GgxSampler s(&sh.sg, a.ks, a.ior, a.rough, a.aniso);
-        AtVector L; AiV3Create(L, wi.x[i], wi.y[i], wi.z[i]);
-        out_pdf[i] = rls::GgxSampler::evalPdf(&s, &L);
-    }
+    GGX_DISPATCH(p, ggxEvalPdfT, n, sg, p, wi, out_pdf);
 }
 
 void oracle_ggx_sample_eval_pdf(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
                                 const float *rx, const float *ry, const rls_bsdf_out *out)
 {
-#pragma omp parallel for schedule(static)
-    for (size_t i = 0; i < n; i++) {
-        Shading sh; loadShading(sg, i, sh);
-        GgxArgs a = ggxArgs(p, i);
-        rls::GgxSampler s(&sh.sg, a.ks, a.ior, a.rough, a.aniso);
-        AtVector L = rls::GgxSampler::evalSample(&s, rx[i], ry[i]);
-        AtColor f = rls::GgxSampler::evalBrdf(&s, &L);
-        float pdf = rls::GgxSampler::evalPdf(&s, &L);
-        store3(out->wi, i, L.x, L.y, L.z);
-        store3(out->f, i, f.r, f.g, f.b);
-        out->pdf[i] = pdf;
-        if (out->fresnel) out->fresnel[i] = s.getAvgReflectWeight();
-        uint32_t fl = bsdfFlags(L, sh.sg.Nf, f, pdf);
-        if (AiV3Dot(sh.sg.N, sh.sg.Rd) < AI_EPSILON) fl |= RLS_FLAG_ENTERING;
-        out->flags[i] = fl;
-    }
+    GGX_DISPATCH(p, ggxSampleEvalPdfT, n, sg, p, rx, ry, out);
 }
 
 void oracle_ggx_dielectric_sample_eval_pdf(size_t n, const rls_shading_soa *sg,
@@ -264,7 +297,7 @@ void oracle_ggx_dielectric_sample_eval_pdf(size_t n, const rls_shading_soa *sg,
     for (size_t i = 0; i < n; i++) {
         Shading sh; loadShading(sg, i, sh);
         GgxArgs a = ggxArgs(p, i);
-        DielectricResult r = dielectricUnit(sh, a.ior, a.rough, a.aniso, rx[i], ry[i]);
+        DielectricResult r = dielectricUnit(sh, a.ior, a.rough, a.aniso, rx[i], ry[i], p->normal_sampler);
         out->fresnel[i] = r.F;
         store3(out->wi_r, i, r.wi_r.x, r.wi_r.y, r.wi_r.z);
         out->f_r[i] = r.f_r;
@@ -287,6 +320,7 @@ void oracle_disney_eval_sample(size_t n, const rls_shading_soa *sg, const rls_di
         disneyTable(p, i, table);
         rls_shim_set_param_table(table);
         DisneySampler s(nullptr, &sh.sg);
+        s.mSampleFromVisibleNormal = p->sample_from_visible_normal != 0;   /* src/rlDisney.cpp:191 */
         s.setSampleType((AtUInt16)sample_type);
         AtVector L = DisneySampler::evalSample(&s, rx[i], ry[i]);
         store3(out_wi, i, L.x, L.y, L.z);
@@ -310,6 +344,7 @@ void oracle_disney_eval_brdf(size_t n, const rls_shading_soa *sg, const rls_disn
         disneyTable(p, i, table);
         rls_shim_set_param_table(table);
         DisneySampler s(nullptr, &sh.sg);
+        s.mSampleFromVisibleNormal = p->sample_from_visible_normal != 0;   /* src/rlDisney.cpp:191 */
         s.setSampleType((AtUInt16)sample_type);
         AtVector L; AiV3Create(L, wi.x[i], wi.y[i], wi.z[i]);
         AtColor f = DisneySampler::evalBrdf(&s, &L);
@@ -327,6 +362,7 @@ void oracle_disney_eval_pdf(size_t n, const rls_shading_soa *sg, const rls_disne
         disneyTable(p, i, table);
         rls_shim_set_param_table(table);
         DisneySampler s(nullptr, &sh.sg);
+        s.mSampleFromVisibleNormal = p->sample_from_visible_normal != 0;   /* src/rlDisney.cpp:191 */
         s.setSampleType((AtUInt16)sample_type);
         AtVector L; AiV3Create(L, wi.x[i], wi.y[i], wi.z[i]);
         out_pdf[i] = DisneySampler::evalPdf(&s, &L);
@@ -345,6 +381,7 @@ void oracle_disney_sample_eval_pdf(size_t n, const rls_shading_soa *sg,
         disneyTable(p, i, table);
         rls_shim_set_param_table(table);
         DisneySampler s(nullptr, &sh.sg);
+        s.mSampleFromVisibleNormal = p->sample_from_visible_normal != 0;   /* src/rlDisney.cpp:191 */
 
         s.setSampleType(AI_RAY_GLOSSY);
         AtVector Ls = DisneySampler::evalSample(&s, rx_s[i], ry_s[i]);
@@ -483,6 +520,36 @@ void oracle_skin_probe_ray(size_t n, const rls_shading_soa *sg, const rls_skin_p
         else if (x < 0.75f) { axis = 2; x = LINEARSTEP(0.5f, 0.75f, x); }
         else { axis = 3; x = LINEARSTEP(0.75f, 1.0f, x); }
         out->flags[i] = profileFlags(s.mProfile, x) | (axis << RLS_FLAG_PROBE_AXIS_SHIFT);
+    }
+}
+
+void oracle_skin_probe_mis_pdf(size_t n, const rls_shading_soa *sg, const rls_skin_params *sp,
+                               rls_cvec3 disp, rls_cvec3 hit_normal, float *out_pdf)
+{
+    /* src/rlSss.h:246-266 sits inside integrateScatter (needs Arnold's probe tracer), so the
+     * combine is restated around the reference's own NDProfile::getPdf and the shim's
+     * AiM4Frame / AiM4VectorByMatrixMult. */
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        Shading sh; loadShading(sg, i, sh);
+        float c[3], d[3];
+        orc_p3(&sp->sss_color, i, c);
+        orc_p3(&sp->sss_scatter_dist, i, d);
+        float scale = orc_p1(&sp->sss_dist_multiplier, i);
+        AtVector dist = rls_shim_v3(d[0], d[1], d[2]) * scale;
+        rls::SssSampler<rls::NDProfile> s(&sh.sg, rls_shim_rgb(c[0], c[1], c[2]), dist);
+        AtVector dp; AiV3Create(dp, disp.x[i], disp.y[i], disp.z[i]);
+        AtVector hn; AiV3Create(hn, hit_normal.x[i], hit_normal.y[i], hit_normal.z[i]);
+        AtVector offset;
+        AiM4VectorByMatrixMult(&offset, s.mWorldToLocalMat, &dp);
+        offset *= offset;
+        float rr[3];
+        rr[0] = sqrt(offset[1] + offset[2]);
+        rr[1] = sqrt(offset[0] + offset[2]);
+        rr[2] = sqrt(offset[0] + offset[1]);
+        out_pdf[i] = s.mProfile.getPdf(rr[0]) * ABS(AiV3Dot(s.mAxisU, hn)) * 0.25f
+                   + s.mProfile.getPdf(rr[1]) * ABS(AiV3Dot(s.mAxisV, hn)) * 0.25f
+                   + s.mProfile.getPdf(rr[2]) * ABS(AiV3Dot(s.mAxisN, hn)) * 0.5f;
     }
 }
 

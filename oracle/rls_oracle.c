@@ -190,6 +190,7 @@ typedef struct {
     v3 U, V, N, wo, ks;
     float iorIn, iorOut, rough, ax, ay;
     int entering;
+    int kernel;      /* RLS_GGX_SAMPLER_VNDF (shipped, src/rlGgx.h:375) or RLS_GGX_SAMPLER_NDF */
 } ggx_t;
 
 static inline void load_shading(const rls_shading_soa *s, size_t i, v3 *U, v3 *V, v3 *N, v3 *wo, int *back)
@@ -217,6 +218,21 @@ static void ggx_init(ggx_t *g, v3 U, v3 V, v3 Nf, v3 wo, int backfacing, v3 ks, 
     g->ay = MAXF(1e-4f, SQRF(roughness) * aspect);
     g->rough = MAXF(1e-5f, SQRF(roughness));   /* :155 */
     g->ks = ks;
+    g->kernel = RLS_GGX_SAMPLER_VNDF;
+}
+/* src/rlGgx.h:33-41 (NDFKernel::evalSample, [2] Eq.14) */
+static v3 sample_ndf_normal(v3 U, v3 Vax, v3 N, float ax, float ay, float rx, float ry)
+{
+    float g = sqrtf(rx / (1.0f - rx));
+    float phi = TWO_PI_F * ry;
+    v3 omega = mk3(g * ax * cosf(phi), g * ay * sinf(phi), 1.0f);
+    omega = rotate_to_frame(omega, U, Vax, N);
+    return normalize3(omega);
+}
+static v3 ggx_sample_normal(const ggx_t *g, float rx, float ry)
+{
+    if (g->kernel == RLS_GGX_SAMPLER_NDF) return sample_ndf_normal(g->U, g->V, g->N, g->ax, g->ay, rx, ry);
+    return sample_visible_normal(g->wo, g->U, g->V, g->N, g->ax, g->ay, rx, ry);
 }
 /* src/rlGgx.h:249-270 */
 static float ggx_fresnel(const ggx_t *g, v3 i, v3 m)
@@ -314,13 +330,20 @@ static float ggx_eval_pdf(const ggx_t *g, v3 L)
     v3 H = normalize3(add3(V, L));
     float din = dot3(V, g->N);
     float IdotN = ABSF(din);
+    if (g->kernel == RLS_GGX_SAMPLER_NDF) {
+        /* NDFKernel::evalPdf src/rlGgx.h:45-50: [1] Eq.38, no floor */
+        float dim = dot3(V, H), dmn = dot3(H, g->N);
+        float IdotM = ABSF(dim);
+        float MdotN = ABSF(dmn);
+        return ggx_D(g, H) * MdotN * 0.25f / IdotM;
+    }
     float pdf = ggx_D(g, H) * ggx_G1(g, V, H, g->N) / IdotN * 0.25f;
     return MAXF(pdf, EPS);
 }
 /* src/rlGgx.h:97-107 */
 static v3 ggx_eval_sample(const ggx_t *g, float rx, float ry, float *fresnel)
 {
-    v3 M = sample_visible_normal(g->wo, g->U, g->V, g->N, g->ax, g->ay, rx, ry);
+    v3 M = ggx_sample_normal(g, rx, ry);
     v3 L = reflect_direction(g->wo, M);
     if (fresnel) *fresnel = (0.0f + ggx_fresnel(g, L, M)) / 1.0f;   /* :103-104,181-184 */
     return L;
@@ -345,18 +368,20 @@ static inline void ggx_from_params(ggx_t *g, const rls_shading_soa *sg, const rl
     orc_p3(&p->KsColor, i, c);
     ggx_init(g, U, V, N, wo, back, mk3(c[0], c[1], c[2]), orc_p1(&p->ior, i),
              orc_p1(&p->specularRoughness, i), orc_p1(&p->anisotropic, i));
+    g->kernel = p->normal_sampler;
 }
 
 typedef struct { float F, f_r, pdf_r, f_t, w_t; v3 wi_r, wi_t; uint32_t flags; } dielectric_t;
 
 /* The rough-dielectric unit: src/rlGgx.h:228-243 loop body with the in-tree refraction
  * restatement (getRefractDirection) standing in for Arnold's AiRefractRay. */
-static dielectric_t dielectric_unit(v3 U, v3 V, v3 N, v3 wo, int back, float ior, float rough, float aniso, float rx, float ry)
+static dielectric_t dielectric_unit(v3 U, v3 V, v3 N, v3 wo, int back, float ior, float rough, float aniso, float rx, float ry, int kernel)
 {
     dielectric_t r;
     ggx_t g;
     ggx_init(&g, U, V, N, wo, back, mk3(1.0f, 1.0f, 1.0f), ior, rough, aniso);
-    v3 m = sample_visible_normal(g.wo, g.U, g.V, g.N, g.ax, g.ay, rx, ry);
+    g.kernel = kernel;
+    v3 m = ggx_sample_normal(&g, rx, ry);
     r.wi_r = reflect_direction(g.wo, m);
     r.F = ggx_fresnel(&g, r.wi_r, m);
     v3 fr = ggx_eval_brdf(&g, r.wi_r);
@@ -383,6 +408,7 @@ typedef struct {
     v3 base, F0, sheenColor;
     float roughness, subsurface, metallic, clearcoat, clearcoatGloss;
     float specRough, ax, ay;
+    int visibleNormal;   /* mSampleFromVisibleNormal, src/rlDisney.cpp:191 */
 } disney_t;
 
 /* src/rlDisney.cpp:155-192 */
@@ -416,6 +442,16 @@ static void disney_init(disney_t *d, const rls_shading_soa *sg, const rls_disney
     v3 metallicColor = scale3(lerp3(specularTint, white, tint), specular);   /* :187 */
     d->F0 = lerp3(d->metallic, metallicColor, d->base);                      /* :188 */
     d->sheenColor = scale3(lerp3(sheenTint, white, tint), sheen);            /* :190 */
+    d->visibleNormal = p->sample_from_visible_normal != 0;
+}
+/* src/rlDisney.cpp:406-414 */
+static v3 disney_sample_gtr2_aniso(const disney_t *d, float rx, float ry)
+{
+    float g = sqrtf(ry / (1.0f - ry));
+    float phi = TWO_PI_F * rx;
+    v3 omega = mk3(g * d->ax * cosf(phi), g * d->ay * sinf(phi), 1.0f);
+    omega = rotate_to_frame(omega, d->U, d->V, d->N);
+    return normalize3(omega);
 }
 /* src/rlDisney.cpp:570-577 */
 static inline float smithG_GGX(float NdotV, float alphaG)
@@ -520,7 +556,8 @@ static v3 disney_sample_specular(const disney_t *d, float rx, float ry, uint32_t
     float gtr2Weight = 1.0f / (d->clearcoat + 1.0f);
     if (rx < gtr2Weight) {
         rx /= gtr2Weight;
-        M = sample_visible_normal(d->wo, d->U, d->V, d->N, d->ax, d->ay, rx, ry);
+        M = d->visibleNormal ? sample_visible_normal(d->wo, d->U, d->V, d->N, d->ax, d->ay, rx, ry)
+                             : disney_sample_gtr2_aniso(d, rx, ry);
         *lobe = 0;
     } else {
         rx = (rx - gtr2Weight) / (1.0f - gtr2Weight);
@@ -542,6 +579,10 @@ static float disney_specular_pdf(const disney_t *d, v3 i)
     if (MdotN < 0.0f) return 0.0f;
     float MdotN2 = SQRF(MdotN);
     float clearcoatWeight = d->clearcoat / (d->clearcoat + 1.0f);
+    if (!d->visibleNormal) {                      /* :541-542 */
+        float D0 = lerpf(clearcoatWeight, D_GTR2Aniso(d, m, MdotN2), D_GTR1(d, MdotN2));
+        return D0 * ABSF(MdotN) * 0.25f / IdotM;
+    }
     float dvn = dot3(d->wo, d->N);
     float VdotN = MAXF(1e-4f, dvn);
     float Dw = smithG_GGX(IdotM, d->specRough) * D_GTR2Aniso(d, m, MdotN2) * 2.0f * IdotM / VdotN;
@@ -734,7 +775,7 @@ void oracle_ggx_dielectric_sample_eval_pdf(size_t n, const rls_shading_soa *sg,
         load_shading(sg, i, &U, &V, &N, &wo, &back);
         dielectric_t r = dielectric_unit(U, V, N, wo, back, orc_p1(&p->ior, i),
                                          orc_p1(&p->specularRoughness, i), orc_p1(&p->anisotropic, i),
-                                         rx[i], ry[i]);
+                                         rx[i], ry[i], p->normal_sampler);
         out->fresnel[i] = r.F;
         st3(out->wi_r, i, r.wi_r);
         out->f_r[i] = r.f_r;
@@ -921,6 +962,30 @@ void oracle_skin_probe_ray(size_t n, const rls_shading_soa *sg, const rls_skin_p
     }
 }
 
+/* src/rlSss.h:246-266: world->local offset (shim AiM4Frame), three projected radii, MIS pdf */
+void oracle_skin_probe_mis_pdf(size_t n, const rls_shading_soa *sg, const rls_skin_params *sp,
+                               rls_cvec3 disp, rls_cvec3 hit_normal, float *out_pdf)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        v3 U, V, N, wo; int back;
+        load_shading(sg, i, &U, &V, &N, &wo, &back);
+        ndprofile_t p;
+        nd_set_distance(&p, skin_scatter_dist(sp, i));
+        v3 dp = mk3(disp.x[i], disp.y[i], disp.z[i]);
+        v3 hn = mk3(hit_normal.x[i], hit_normal.y[i], hit_normal.z[i]);
+        v3 offset = mk3(dot3(dp, U), dot3(dp, V), dot3(dp, N));
+        offset = mul3(offset, offset);
+        float rr0 = sqrtf(offset.y + offset.z);
+        float rr1 = sqrtf(offset.x + offset.z);
+        float rr2 = sqrtf(offset.x + offset.y);
+        float du = dot3(U, hn), dv = dot3(V, hn), dn = dot3(N, hn);
+        out_pdf[i] = nd_get_pdf(&p, rr0) * ABSF(du) * 0.25f
+                   + nd_get_pdf(&p, rr1) * ABSF(dv) * 0.25f
+                   + nd_get_pdf(&p, rr2) * ABSF(dn) * 0.5f;
+    }
+}
+
 void oracle_albedo_sweep(const rls_sweep_grid *g, uint64_t seed, uint32_t spp_begin,
                          uint32_t spp_end, double *table)
 {
@@ -936,7 +1001,7 @@ void oracle_albedo_sweep(const rls_sweep_grid *g, uint64_t seed, uint32_t spp_be
             uint64_t idx = ((uint64_t)cell << 32) | (uint64_t)k;
             float rx = orc_uniform(seed, 0u, idx);
             float ry = orc_uniform(seed, 1u, idx);
-            dielectric_t r = dielectric_unit(U, V, N, wo, 0, ior, rough, 0.0f, rx, ry);
+            dielectric_t r = dielectric_unit(U, V, N, wo, 0, ior, rough, 0.0f, rx, ry, RLS_GGX_SAMPLER_VNDF);
             int valid = !(r.flags & (RLS_FLAG_ZERO_L | RLS_FLAG_BELOW_HORIZON));
             if (valid) { acc[0] += (double)(r.f_r / r.pdf_r); acc[3] += 1.0; }
             if (r.flags & RLS_FLAG_TIR) acc[4] += 1.0; else acc[1] += (double)r.w_t;

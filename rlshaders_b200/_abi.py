@@ -17,6 +17,8 @@ RLS_ERR_OUT_OF_MEMORY = -4
 # DisneySampler::setSampleType values (AI_RAY_DIFFUSE / AI_RAY_GLOSSY), rlDisney.cpp:194
 RLS_RAY_DIFFUSE = 0x20
 RLS_RAY_GLOSSY = 0x40
+GGX_SAMPLER_VNDF = 0
+GGX_SAMPLER_NDF = 1
 
 FLAG_ZERO_L = 0x0001
 FLAG_BELOW_HORIZON = 0x0002
@@ -64,7 +66,7 @@ class GgxParams(C.Structure):
                 ("ior", Param1), ("anisotropic", Param1),
                 ("KdColor", Param3), ("Kd", Param1), ("diffuseRoughness", Param1),
                 ("KtColor", Param3), ("Kt", Param1), ("opacity", Param1),
-                ("opacity_color", Param3)]
+                ("opacity_color", Param3), ("normal_sampler", C.c_int32)]
 
 
 class DisneyParams(C.Structure):
@@ -74,7 +76,7 @@ class DisneyParams(C.Structure):
                 ("anisotropic", Param1), ("sheen", Param1), ("sheen_tint", Param1),
                 ("clearcoat", Param1), ("clearcoat_gloss", Param1),
                 ("opacity", Param3), ("indirectDiffuseScale", Param1),
-                ("indirectSpecularScale", Param1)]
+                ("indirectSpecularScale", Param1), ("sample_from_visible_normal", C.c_int32)]
 
 
 class SkinParams(C.Structure):
@@ -128,12 +130,12 @@ class SweepGrid(C.Structure):
 GGX_DEFAULTS = dict(KsColor=(1.0, 1.0, 1.0), Ks=0.5, specularRoughness=0.0, ior=1.0,
                     anisotropic=0.0, KdColor=(1.0, 1.0, 1.0), Kd=0.5, diffuseRoughness=0.0,
                     KtColor=(1.0, 1.0, 1.0), Kt=0.0, opacity=1.0,
-                    opacity_color=(1.0, 1.0, 1.0))                      # rlGgx.cpp:172-186
+                    opacity_color=(1.0, 1.0, 1.0), normal_sampler=0)    # rlGgx.cpp:172-186
 DISNEY_DEFAULTS = dict(base_color=(1.0, 1.0, 1.0), subsurface=0.0, metallic=0.0, specular=0.0,
                        specular_tint=0.0, roughness=0.0, anisotropic=0.0, sheen=0.0,
                        sheen_tint=0.0, clearcoat=0.0, clearcoat_gloss=0.0,
                        opacity=(1.0, 1.0, 1.0), indirectDiffuseScale=1.0,
-                       indirectSpecularScale=1.0)                        # rlDisney.cpp:606-628
+                       indirectSpecularScale=1.0, sample_from_visible_normal=1)  # rlDisney.cpp:606-628
 SKIN_DEFAULTS = dict(sss_color=(1.0, 1.0, 1.0), sss_weight=1.0, sss_dist_multiplier=1.0,
                      sss_scatter_dist=(1.0, 1.0, 1.0), sss_cavity_fadeout=1,
                      specular_color=(1.0, 1.0, 1.0), specular_weight=0.6,

@@ -166,10 +166,11 @@ class GgxSampler:
     names (src/rlGgx.cpp:172-186); each is a scalar or a per-sample tensor."""
 
     def __init__(self, ctx, sg, KsColor=(1.0, 1.0, 1.0), ior=1.0, specularRoughness=0.0, anisotropic=0.0,
-                 **ignored_node_params):
+                 normal_sampler=abi.GGX_SAMPLER_VNDF, **ignored_node_params):
         self.ctx, self.sg = ctx, sg
         self.params = abi.ggx_params(KsColor=KsColor, ior=ior, specularRoughness=specularRoughness,
-                                     anisotropic=anisotropic, **ignored_node_params)
+                                     anisotropic=anisotropic, normal_sampler=normal_sampler,
+                                     **ignored_node_params)
 
     def evalSample(self, rx, ry, want_fresnel=True):
         n, c = self.sg.n, self.ctx
@@ -373,6 +374,29 @@ class SkinProfile:
         else:
             _check(c.handle, c.lib.rls_skin_profile_sample_eval_pdf(*args), c.lib)
         return out
+
+    def getProbeRay(self, sg, rx, ry):
+        """SssSampler::getProbeRay (src/rlSss.h:487-533) for one (rx, ry) per sample; origins are
+        relative to the shading point."""
+        c, n = self.ctx, self.n
+        out = dict(r=c.empty(n), origin=c.empty(3, n), dir=c.empty(3, n), maxdist=c.empty(n),
+                   flags=c.empty(n, dtype=torch.int32))
+        o = abi.ProbeOut(out["r"].data_ptr(), abi.vec3(_f32rows(out["origin"], "origin")),
+                         abi.vec3(_f32rows(out["dir"], "dir")), out["maxdist"].data_ptr(), out["flags"].data_ptr())
+        _check(c.handle, c.lib.rls_skin_probe_ray(c.handle, n, C.byref(sg.struct), C.byref(self.params),
+                                                  _f32(rx, "rx", n).data_ptr(), _f32(ry, "ry", n).data_ptr(),
+                                                  C.byref(o)), c.lib)
+        return out
+
+    def probeMisPdf(self, sg, disp, hit_normal):
+        """The 3-axis MIS pdf of a probe hit (src/rlSss.h:252-263)."""
+        c, n = self.ctx, self.n
+        pdf = c.empty(n)
+        _check(c.handle, c.lib.rls_skin_probe_mis_pdf(c.handle, n, C.byref(sg.struct), C.byref(self.params),
+                                                      abi.vec3(_f32rows(disp, "disp")),
+                                                      abi.vec3(_f32rows(hit_normal, "hit_normal")),
+                                                      pdf.data_ptr()), c.lib)
+        return pdf
 
     def layerWeights(self, avg_fresnel_sheen, avg_fresnel_specular):
         c, n = self.ctx, self.n

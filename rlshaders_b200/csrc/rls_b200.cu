@@ -176,10 +176,11 @@ static inline bool has3(const rls_vec3 &v) { return v.x && v.y && v.z; }
 static inline bool ok_shading(const rls_shading_soa *s) { return s && has3(s->U) && has3(s->V) && has3(s->N) && has3(s->wo); }
 static inline bool ok_p3(const rls_param3 &p) { return (!p.array.x && !p.array.y && !p.array.z) || has3(p.array); }
 
-struct GgxParamsDev { P3 ks; P1 rough, ior, aniso; };
+struct GgxParamsDev { P3 ks; P1 rough, ior, aniso; int ndf; };
 static inline GgxParamsDev dev(const rls_ggx_params &p)
 {
-    GgxParamsDev o; o.ks = p3(p.KsColor); o.rough = p1(p.specularRoughness); o.ior = p1(p.ior); o.aniso = p1(p.anisotropic); return o;
+    GgxParamsDev o; o.ks = p3(p.KsColor); o.rough = p1(p.specularRoughness); o.ior = p1(p.ior); o.aniso = p1(p.anisotropic);
+    o.ndf = p.normal_sampler == RLS_GGX_SAMPLER_NDF; return o;
 }
 static inline DisneyParamsDev dev(const rls_disney_params &p)
 {
@@ -188,6 +189,7 @@ static inline DisneyParamsDev dev(const rls_disney_params &p)
     o.specular = p1(p.specular); o.specular_tint = p1(p.specular_tint); o.roughness = p1(p.roughness);
     o.anisotropic = p1(p.anisotropic); o.sheen = p1(p.sheen); o.sheen_tint = p1(p.sheen_tint);
     o.clearcoat = p1(p.clearcoat); o.clearcoat_gloss = p1(p.clearcoat_gloss);
+    o.sample_from_visible_normal = p.sample_from_visible_normal;
     return o;
 }
 static inline SkinParamsDev dev(const rls_skin_params &p)
@@ -212,6 +214,7 @@ RLS_DEV Ggx ggx_make(const ShadingSoA &sg, const GgxParamsDev &p, uint32_t i)
     Shading s = load_shading(sg, i);
     Ggx g;
     ggx_init(g, s, fetch(p.ks, i), fetch(p.ior, i), fetch(p.rough, i), fetch(p.aniso, i));
+    g.ndf = p.ndf != 0;
     return g;
 }
 
@@ -220,7 +223,7 @@ k_ggx_eval_sample(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, cons
 {
     RLS_INDEX();
     Ggx g = ggx_make(sg, p, i);
-    f3 M = sample_visible_normal(g.wo, g.U, g.V, g.N, g.ax, g.ay, __ldg(rx + i), __ldg(ry + i));
+    f3 M = ggx_sample_normal(g, __ldg(rx + i), __ldg(ry + i));
     f3 L = reflect_direction(g.wo, M);                 // src/rlGgx.h:100-101
     store3(wi, i, L);
     if (fresnel) fresnel[i] = ggx_fresnel(g, L, M);    // :103-104,181-184 with one sample
@@ -263,7 +266,8 @@ k_ggx_dielectric(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const
 {
     RLS_INDEX();
     Shading s = load_shading(sg, i);
-    Dielectric r = dielectric_unit(s, fetch(p.ior, i), fetch(p.rough, i), fetch(p.aniso, i), __ldg(rx + i), __ldg(ry + i));
+    Dielectric r = dielectric_unit(s, fetch(p.ior, i), fetch(p.rough, i), fetch(p.aniso, i), __ldg(rx + i), __ldg(ry + i),
+                                   p.ndf != 0);
     o.fresnel[i] = r.F;
     store3(o.wi_r, i, r.wi_r);
     o.f_r[i] = r.f_r;
@@ -399,6 +403,53 @@ k_skin_layer_weights(size_t n, SkinParamsDev sp, const float *avgSheen, const fl
     specScale[i] = specularWeight * (1.0f - sheenFresnel);
     w *= 1.0f - specularFresnel * (1.0f - sheenFresnel);
     sssWeight[i] = w;
+}
+
+// src/rlSss.h:487-533 (getProbeRay) with origin = 0
+struct ProbeOutDev { float *r; V3 origin, dir; float *maxdist; uint32_t *flags; };
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+k_skin_probe_ray(size_t n, ShadingSoA sg, SkinParamsDev sp, const float *rx_in, const float *ry_in, ProbeOutDev o)
+{
+    RLS_INDEX();
+    Shading s = load_shading(sg, i);
+    NdProfile p; nd_set_distance(p, skin_scatter_dist(sp, i));
+    float rx = __ldg(rx_in + i), ry = __ldg(ry_in + i);
+    int idx;
+    if (rx < 0.5f) { idx = 0; rx = linearstep_m(0.0f, 0.5f, rx); }
+    else if (rx < 0.75f) { idx = 2; rx = linearstep_m(0.5f, 0.75f, rx); }
+    else { idx = 3; rx = linearstep_m(0.75f, 1.0f, rx); }
+    uint32_t fl;
+    float r = nd_get_radius(p, rx, fl);
+    float rmax = p.R;
+    float phi = kTwoPi * ry;
+    float sn, cs;
+    rlm::sincosf_(phi, &sn, &cs);
+    f3 offset = mk3(cs * r, sqrtf(rmax * rmax - r * r), sn * r);
+    float maxdist = offset.y * 2.0f;
+    f3 dir;
+    if (idx < 2) { dir = -s.N; offset = rotate_to_frame(offset, s.U, -dir, s.V); }
+    else if (idx == 2) { dir = s.U; offset = rotate_to_frame(offset, s.V, -dir, s.N); }
+    else { dir = s.V; offset = rotate_to_frame(offset, s.N, -dir, s.U); }
+    o.r[i] = r;
+    store3(o.origin, i, mk3(0.0f + offset.x, 0.0f + offset.y, 0.0f + offset.z));
+    store3(o.dir, i, dir);
+    o.maxdist[i] = maxdist;
+    o.flags[i] = fl | ((uint32_t)idx << RLS_FLAG_PROBE_AXIS_SHIFT);
+}
+// src/rlSss.h:252-263: 3-axis MIS pdf of one probe hit
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+k_skin_probe_mis_pdf(size_t n, ShadingSoA sg, SkinParamsDev sp, CV3 disp, CV3 hitN, float *pdf)
+{
+    RLS_INDEX();
+    Shading s = load_shading(sg, i);
+    NdProfile p; nd_set_distance(p, skin_scatter_dist(sp, i));
+    f3 dp = load3(disp, i), hn = load3(hitN, i);
+    f3 off = mk3(dot(dp, s.U), dot(dp, s.V), dot(dp, s.N));     // world -> local (AiM4VectorByMatrixMult)
+    off = mk3(off.x * off.x, off.y * off.y, off.z * off.z);
+    float rr0 = sqrtf(off.y + off.z), rr1 = sqrtf(off.x + off.z), rr2 = sqrtf(off.x + off.y);
+    pdf[i] = nd_get_pdf(p, rr0) * abs_m(dot(s.U, hn)) * 0.25f
+           + nd_get_pdf(p, rr1) * abs_m(dot(s.V, hn)) * 0.25f
+           + nd_get_pdf(p, rr2) * abs_m(dot(s.N, hn)) * 0.5f;
 }
 
 // ============================================================ synthetic generators
@@ -739,6 +790,34 @@ extern "C" int rls_skin_layer_weights(rls_context *ctx, size_t n, const rls_skin
     RLS_REQUIRE(ctx, p && avg_sheen && avg_spec && out_spec_scale && out_sss_weight, "rls_skin_layer_weights: NULL argument");
     DeviceGuard guard(ctx->device);
     k_skin_layer_weights<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, dev(*p), avg_sheen, avg_spec, out_spec_scale, out_sss_weight);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+
+extern "C" int rls_skin_probe_ray(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_skin_params *p,
+                                  const float *rx, const float *ry, const rls_probe_out *out)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_skin_params(p) && rx && ry && out && out->r && has3(out->origin) && has3(out->dir) &&
+                out->maxdist && out->flags, "rls_skin_probe_ray: NULL argument");
+    DeviceGuard guard(ctx->device);
+    ProbeOutDev d; d.r = out->r; d.origin = mv(out->origin); d.dir = mv(out->dir); d.maxdist = out->maxdist; d.flags = out->flags;
+    k_skin_probe_ray<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), rx, ry, d);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+extern "C" int rls_skin_probe_mis_pdf(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_skin_params *p,
+                                      rls_cvec3 disp, rls_cvec3 hit_normal, float *out_pdf)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_skin_params(p) && has3(disp) && has3(hit_normal) && out_pdf,
+                "rls_skin_probe_mis_pdf: NULL argument");
+    DeviceGuard guard(ctx->device);
+    k_skin_probe_mis_pdf<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), cv(disp), cv(hit_normal), out_pdf);
     RLS_LAUNCH_CHECK(ctx);
     return RLS_OK;
 }

@@ -11,6 +11,7 @@ struct DisneyParamsDev {
     P3 base_color;
     P1 subsurface, metallic, specular, specular_tint, roughness, anisotropic, sheen, sheen_tint,
        clearcoat, clearcoat_gloss;
+    int sample_from_visible_normal;
 };
 
 struct Disney {
@@ -18,6 +19,7 @@ struct Disney {
     f3 base, F0, sheenColor;
     float roughness, subsurface, metallic, clearcoat, clearcoatGloss;
     float specRough, ax, ay;
+    bool visibleNormal;   // mSampleFromVisibleNormal (src/rlDisney.cpp:191)
 };
 
 // src/rlDisney.cpp:155-192
@@ -47,6 +49,7 @@ RLS_DEV void disney_init(Disney &d, const Shading &sh, const DisneyParamsDev &p,
     f3 metallicColor = lerp_m(specularTint, white, tint) * specular;   // :187
     d.F0 = lerp_m(d.metallic, metallicColor, d.base);                  // :188
     d.sheenColor = lerp_m(sheenTint, white, tint) * sheen;             // :190
+    d.visibleNormal = p.sample_from_visible_normal != 0;
 }
 // src/rlDisney.cpp:570-577
 RLS_DEV float smithG_GGX(float NdotV, float alphaG)
@@ -147,7 +150,9 @@ RLS_DEV f3 disney_sample_specular(const Disney &d, float rx, float ry, uint32_t 
     float gtr2Weight = 1.0f / (d.clearcoat + 1.0f);
     if (rx < gtr2Weight) {
         rx /= gtr2Weight;
-        M = sample_visible_normal(d.wo, d.U, d.V, d.N, d.ax, d.ay, rx, ry);
+        // :377-379; sampleGTR2AnisoDirection (:406-414) is NDF sampling with (ry, rx)
+        M = d.visibleNormal ? sample_visible_normal(d.wo, d.U, d.V, d.N, d.ax, d.ay, rx, ry)
+                            : sample_ndf_normal(d.U, d.V, d.N, d.ax, d.ay, ry, rx);
         lobe = 0;
     } else {
         rx = (rx - gtr2Weight) / (1.0f - gtr2Weight);
@@ -168,6 +173,10 @@ RLS_DEV float disney_specular_pdf(const Disney &d, f3 i)
     if (MdotN < 0.0f) return 0.0f;
     float MdotN2 = sqr(MdotN);
     float clearcoatWeight = d.clearcoat / (d.clearcoat + 1.0f);
+    if (!d.visibleNormal) {                                   // :541-542
+        float D0 = lerp_m(clearcoatWeight, D_GTR2Aniso(d, m, MdotN2), D_GTR1(d, MdotN2));
+        return D0 * abs_m(MdotN) * 0.25f / IdotM;
+    }
     float VdotN = max_m(1e-4f, dot(d.wo, d.N));
     float Dw = smithG_GGX(IdotM, d.specRough) * D_GTR2Aniso(d, m, MdotN2) * 2.0f * IdotM / VdotN;
     float D = lerp_m(clearcoatWeight, Dw, D_GTR1(d, MdotN2) * abs_m(MdotN) / IdotM);

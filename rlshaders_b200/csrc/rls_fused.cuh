@@ -62,9 +62,12 @@ RLS_DEV void ggx_reflect_eval_pdf(const Ggx &g, const GgxShared &s, f3 L, float 
     float LH = dot(L, H);
     // D(H): also D(hr) for hr = +-H
     float D_H = ggx_D(g, H);
-    // pdf: G1(V, H, N)
-    float G1_pdf = (VH * s.VdotN < 0.0f) ? 0.0f : s.G1v;
-    pdf = max_m(D_H * G1_pdf / s.absVdotN * 0.25f, kEps);
+    if (g.ndf) {                                      // NDFKernel::evalPdf (src/rlGgx.h:45-50)
+        pdf = D_H * abs_m(dot(H, g.N)) * 0.25f / abs_m(VH);
+    } else {                                          // VNDFKernel::evalPdf: G1(V, H, N), floored
+        float G1_pdf = (VH * s.VdotN < 0.0f) ? 0.0f : s.G1v;
+        pdf = max_m(D_H * G1_pdf / s.absVdotN * 0.25f, kEps);
+    }
     // brdf: hr = sgn(V.N) * H
     float VHr = VH * s.sgnV, LHr = LH * s.sgnV;
     float F = ggx_fresnel_c(s.ratio2, abs_m(VHr));
@@ -77,13 +80,15 @@ RLS_DEV void ggx_reflect_eval_pdf(const Ggx &g, const GgxShared &s, f3 L, float 
 
 // The rough-dielectric unit: src/rlGgx.h:228-243 loop body with the in-tree
 // getRefractDirection standing in for Arnold's AiRefractRay (same composition as the oracle).
-RLS_DEV Dielectric dielectric_unit(const Shading &sh, float ior, float rough, float aniso, float rx, float ry)
+RLS_DEV Dielectric dielectric_unit(const Shading &sh, float ior, float rough, float aniso, float rx, float ry,
+                                   bool ndf = false)
 {
     Dielectric r;
     Ggx g;
     ggx_init(g, sh, mk3(1.0f, 1.0f, 1.0f), ior, rough, aniso);
+    g.ndf = ndf;
     const GgxShared s = ggx_shared(g);
-    f3 m = sample_visible_normal(g.wo, g.U, g.V, g.N, g.ax, g.ay, rx, ry);
+    f3 m = ggx_sample_normal(g, rx, ry);
     float Vm = dot(g.wo, m);
     // reflectDirection(V, m) = 2|V.m| m - V
     r.wi_r = m * (2.0f * abs_m(Vm)) - g.wo;
@@ -148,7 +153,7 @@ RLS_DEV GgxBsdf ggx_unit(const Ggx &g, float rx, float ry)
 {
     GgxBsdf o;
     const GgxShared s = ggx_shared(g);
-    f3 m = sample_visible_normal(g.wo, g.U, g.V, g.N, g.ax, g.ay, rx, ry);
+    f3 m = ggx_sample_normal(g, rx, ry);
     o.L = m * (2.0f * abs_m(dot(g.wo, m))) - g.wo;
     o.fresnel = ggx_fresnel_c(s.ratio2, abs_m(dot(o.L, m)));
     const float LdotN = dot(o.L, g.N);

@@ -117,12 +117,30 @@ RLS_DEV f3 sample_visible_normal(f3 view, f3 U, f3 Vax, f3 N, float ax, float ay
     return normalize(rotate_to_frame(omega, U, Vax, N));
 }
 
+// src/rlGgx.h:33-41 (NDFKernel::evalSample, Burley Eq.14): plain NDF sampling; also
+// DisneySampler::sampleGTR2AnisoDirection (src/rlDisney.cpp:406-414) with (rx, ry) swapped.
+RLS_DEV f3 sample_ndf_normal(f3 U, f3 Vax, f3 N, float ax, float ay, float rx, float ry)
+{
+    float g = sqrtf(rx / (1.0f - rx));
+    float phi = kTwoPi * ry;
+    float s, c;
+    rlm::sincosf_(phi, &s, &c);
+    f3 omega = mk3(g * ax * c, g * ay * s, 1.0f);
+    return normalize(rotate_to_frame(omega, U, Vax, N));
+}
+
 // ------------------------------------------------------------------------ rlGgx
 struct Ggx {
     f3 U, V, N, wo, ks;
     float iorIn, iorOut, rough, ax, ay;
     bool entering;
+    bool ndf;        // GgxSamplerT<NDFKernel> instead of the shipped GgxSamplerT<VNDFKernel>
 };
+RLS_DEV f3 ggx_sample_normal(const Ggx &g, float rx, float ry)
+{
+    if (g.ndf) return sample_ndf_normal(g.U, g.V, g.N, g.ax, g.ay, rx, ry);
+    return sample_visible_normal(g.wo, g.U, g.V, g.N, g.ax, g.ay, rx, ry);
+}
 
 // src/rlGgx.h:130-156 (GgxSamplerT ctor)
 RLS_DEV void ggx_init(Ggx &g, const Shading &sh, f3 ks, float ior, float roughness, float aniso)
@@ -140,6 +158,7 @@ RLS_DEV void ggx_init(Ggx &g, const Shading &sh, f3 ks, float ior, float roughne
     g.ay = max_m(1e-4f, sqr(roughness) * aspect);
     g.rough = max_m(1e-5f, sqr(roughness));      // :155
     g.ks = ks;
+    g.ndf = false;
 }
 // src/rlGgx.h:249-270
 RLS_DEV float ggx_fresnel(const Ggx &g, f3 i, f3 m)
@@ -233,6 +252,11 @@ RLS_DEV f3 ggx_eval_brdf(const Ggx &g, f3 L)
 RLS_DEV float ggx_eval_pdf(const Ggx &g, f3 L)
 {
     f3 H = normalize(g.wo + L);
+    if (g.ndf) {                                  // NDFKernel::evalPdf src/rlGgx.h:45-50, no floor
+        float IdotM = abs_m(dot(g.wo, H));
+        float MdotN = abs_m(dot(H, g.N));
+        return ggx_D(g, H) * MdotN * 0.25f / IdotM;
+    }
     float IdotN = abs_m(dot(g.wo, g.N));
     float pdf = ggx_D(g, H) * ggx_G1(g, g.wo, H, g.N) / IdotN * 0.25f;
     return max_m(pdf, kEps);

@@ -82,6 +82,7 @@ inline rls_disney_params disney_defaults()
     rls_disney_params p = {};
     p.base_color = uniform(1, 1, 1); p.opacity = uniform(1, 1, 1);
     p.indirectDiffuseScale = uniform(1.0f); p.indirectSpecularScale = uniform(1.0f);
+    p.sample_from_visible_normal = 1;   // src/rlDisney.cpp:191
     return p;   // the ten scalar parameters default to 0
 }
 inline rls_skin_params skin_defaults()

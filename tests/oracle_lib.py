@@ -287,6 +287,15 @@ class Oracle:
                                        C.byref(out))
         return dict(r=r, origin=np.stack(o), dir=np.stack(d), maxdist=md, flags=fl)
 
+    def skin_probe_mis_pdf(self, sg, params, disp, hit_normal):
+        n = disp.shape[1]
+        pdf = _z(n)
+        kd = [np.ascontiguousarray(disp[j], dtype=f32) for j in range(3)]
+        kn = [np.ascontiguousarray(hit_normal[j], dtype=f32) for j in range(3)]
+        self.lib.oracle_skin_probe_mis_pdf(C.c_size_t(n), C.byref(shading_struct(sg)), C.byref(params),
+                                           abi.vec3(kd), abi.vec3(kn), C.c_void_p(pdf.ctypes.data))
+        return pdf
+
     def albedo_sweep(self, grid, seed, spp_begin, spp_end):
         cells = grid.n_rough * grid.n_cos * grid.n_ior
         table = np.zeros((cells, abi.SWEEP_VALUES_PER_CELL), dtype=np.float64)

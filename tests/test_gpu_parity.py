@@ -393,3 +393,70 @@ def test_full_size_properties_config2(ctx):
     cpu = ol.load_port().ggx_dielectric(hs, p, rx[idx].cpu().numpy(), ry[idx].cpu().numpy())
     kinds = dict(fresnel="rel", wi_r="dir", f_r="rel", pdf_r="rel", wi_t="dir", f_t="rel", weight_t="rel", flags="flags")
     check(parity.summarize({k: v[..., idx] for k, v in a.items()}, cpu, kinds), "config 2 full size, strided subsample")
+
+
+# ------------------------------------------- sampler variants and probe rows
+def test_ggx_ndf_sampler_variant(ctx, orc):
+    """GgxSamplerT<NDFKernel> (src/rlGgx.h:24-56): sampling, un-floored pdf, dielectric unit."""
+    from rlshaders_b200 import api
+    sg, kw, rx, ry = parity.ggx_dielectric_inputs(N, aniso=True)
+    kw["KsColor"] = tuple(ol.hash_uniform(N, 3, 60 + j) for j in range(3))
+    kw["normal_sampler"] = abi.GGX_SAMPLER_NDF
+    p = abi.ggx_params(**kw)
+    s = api.GgxSampler(ctx, api.ShadingBatch.from_numpy(sg, ctx.device), **parity.params_to_dev(kw, ctx.device))
+    drx, dry = dev(rx, ctx), dev(ry, ctx)
+    kinds = dict(wi="dir", f="rel", pdf="rel", fresnel="rel", flags="flags")
+    fused = s.sampleEvalPdf(drx, dry)
+    check(parity.summarize(fused, orc.ggx_sample_eval_pdf(sg, p, rx, ry), kinds), f"NDF fused vs {orc.kind}")
+    kinds2 = dict(fresnel="rel", wi_r="dir", f_r="rel", pdf_r="rel", wi_t="dir", f_t="rel", weight_t="rel", flags="flags")
+    check(parity.summarize(s.dielectricSampleEvalPdf(drx, dry), orc.ggx_dielectric(sg, p, rx, ry), kinds2),
+          f"NDF dielectric vs {orc.kind}")
+    wi, _ = s.evalSample(drx, dry)
+    assert torch.equal(wi, fused["wi"]) and torch.equal(s.evalPdf(wi), fused["pdf"]) and torch.equal(s.evalBrdf(wi), fused["f"])
+
+
+def test_disney_non_visible_normal_variant(ctx, orc):
+    from rlshaders_b200 import api
+    sg, kw, u = parity.disney_inputs(N)
+    kw["sample_from_visible_normal"] = 0
+    cpu = orc.disney_sample_eval_pdf(sg, abi.disney_params(**kw), *u)
+    s = api.DisneySampler(ctx, api.ShadingBatch.from_numpy(sg, ctx.device), **parity.params_to_dev(kw, ctx.device))
+    gpu = s.sampleEvalPdf(*[dev(t, ctx) for t in u])
+    kinds = dict(wi_s="dir", f_s="rel", pdf_s="rel", wi_d="dir", f_d="rel", pdf_d="rel", flags="flags")
+    check(parity.summarize(gpu, cpu, kinds), f"Disney non-VN vs {orc.kind}")
+    s.setSampleType(abi.RLS_RAY_GLOSSY)
+    assert torch.equal(s.evalPdf(gpu["wi_s"]), gpu["pdf_s"])
+
+
+def test_probe_ray_and_mis_pdf(ctx, orc):
+    """SssSampler::getProbeRay and the 3-axis MIS pdf (src/rlSss.h:487-533, 252-263)."""
+    from rlshaders_b200 import api
+    kw, rx = parity.skin_inputs(N)
+    ry = ol.hash_uniform(N, 5, 9)
+    sgn = ol.make_shading(N, 77)
+    sp = abi.skin_params(**kw)
+    s = api.SkinProfile(ctx, N, **parity.params_to_dev(kw, ctx.device))
+    dsg = api.ShadingBatch.from_numpy(sgn, ctx.device)
+    gpu = s.getProbeRay(dsg, dev(rx, ctx), dev(ry, ctx))
+    cpu = orc.skin_probe_ray(sgn, sp, rx, ry)
+    stats = parity.summarize(gpu, cpu, dict(r="rel", origin="dir", dir="dir", maxdist="rel", flags="flags"))
+    check(stats, f"probe ray vs {orc.kind}")
+    axis = (cpu["flags"] & abi.FLAG_PROBE_AXIS_MASK) >> abi.FLAG_PROBE_AXIS_SHIFT
+    assert set(np.unique(axis)) == {0, 2, 3} and abs((axis == 0).mean() - 0.5) < 0.01
+    # golden fixture (reference library, build container)
+    g = gio.load("skin")
+    color, dist = (g["color_r"], g["color_g"], g["color_b"]), (g["dist_x"], g["dist_y"], g["dist_z"])
+    n = len(g["rx"])
+    sg2 = api.SkinProfile(ctx, n, **parity.params_to_dev(dict(sss_color=color, sss_scatter_dist=dist), ctx.device))
+    out = sg2.getProbeRay(api.ShadingBatch.from_numpy(gio.shading(g, "probe_sg_"), ctx.device), dev(g["rx"], ctx), dev(g["probe_ry"], ctx))
+    want = {k: g["probe_" + k] for k in ("r", "origin", "dir", "maxdist", "flags")}
+    st = parity.summarize(out, want, dict(r="rel", origin="dir", dir="dir", maxdist="rel", flags="flags"))
+    assert st["flags"]["mismatches"] == 0 and all(v["within"] == 1.0 for k, v in st.items() if k != "flags")
+    # MIS pdf at synthetic hits
+    disp = np.stack([ol.hash_uniform(N, 8, j, lo=-1.5, hi=1.5) for j in range(3)])
+    hn = ol.make_shading(N, 9)
+    hnv = np.stack([hn["Nx"], hn["Ny"], hn["Nz"]])
+    pdf = s.probeMisPdf(dsg, dev(disp, ctx), dev(hnv, ctx)).cpu().numpy()
+    sm = parity.stat_rel(pdf, orc.skin_probe_mis_pdf(sgn, sp, disp, hnv))
+    print(parity.format_report("probe MIS pdf", dict(pdf=sm)))
+    assert sm["within"] == 1.0

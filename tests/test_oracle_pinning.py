@@ -135,3 +135,40 @@ def test_port_vs_reference_profile(port, ref):
 def test_port_vs_reference_sweep(port, ref):
     g = abi.SweepGrid(3, 5, 2, 0.02, 1.0, 1.0, 2.5)
     assert np.array_equal(ref.albedo_sweep(g, 123, 0, 128), port.albedo_sweep(g, 123, 0, 128))
+
+
+def test_port_vs_reference_sampler_variants_and_mis(port, ref):
+    """NDFKernel as the GgxSamplerT argument (src/rlGgx.h:24-56), DisneySampler with
+    mSampleFromVisibleNormal = false (src/rlDisney.cpp:377-379,541-542), probe-hit MIS pdf
+    (src/rlSss.h:252-263)."""
+    n = N
+    sg = ol.make_shading(n, 3, backfacing_fraction=0.25)
+    rx, ry = ol.hash_uniform(n, 3, 0), ol.hash_uniform(n, 3, 1)
+    kw = dict(specularRoughness=ol.hash_uniform(n, 3, 2, lo=0.05, hi=1.0), ior=ol.hash_uniform(n, 3, 3, lo=1.05, hi=2.5),
+              anisotropic=ol.hash_uniform(n, 3, 4), KsColor=tuple(ol.hash_uniform(n, 3, 60 + j) for j in range(3)),
+              normal_sampler=abi.GGX_SAMPLER_NDF)
+    p = abi.ggx_params(**kw)
+    a = ref.ggx_sample_eval_pdf(sg, p, rx, ry)
+    assert_same(a, port.ggx_sample_eval_pdf(sg, p, rx, ry), "ndf fused")
+    assert_same(ref.ggx_dielectric(sg, p, rx, ry), port.ggx_dielectric(sg, p, rx, ry), "ndf dielectric")
+    assert gio.bits_equal(ref.ggx_eval_pdf(sg, p, a["wi"]), port.ggx_eval_pdf(sg, p, a["wi"]))
+    # the NDF pdf is not floored: it differs from the VNDF pdf on the same directions
+    vndf = port.ggx_eval_pdf(sg, abi.ggx_params(**dict(kw, normal_sampler=abi.GGX_SAMPLER_VNDF)), a["wi"])
+    assert not gio.bits_equal(vndf, port.ggx_eval_pdf(sg, p, a["wi"]))
+
+    sgd, _, u = ol.workload_disney(n)
+    names = ["subsurface", "metallic", "specular", "specular_tint", "roughness", "anisotropic",
+             "sheen", "sheen_tint", "clearcoat", "clearcoat_gloss"]
+    kwd = {nm: ol.hash_uniform(n, 0x5EED0003, 20 + j) for j, nm in enumerate(names)}
+    kwd["base_color"] = tuple(ol.hash_uniform(n, 0x5EED0003, 30 + j) for j in range(3))
+    pd = abi.disney_params(sample_from_visible_normal=0, **kwd)
+    b = ref.disney_sample_eval_pdf(sgd, pd, *u)
+    assert_same(b, port.disney_sample_eval_pdf(sgd, pd, *u), "disney non-visible-normal")
+    assert gio.bits_equal(ref.disney_eval_pdf(sgd, pd, abi.RLS_RAY_GLOSSY, b["wi_s"]),
+                          port.disney_eval_pdf(sgd, pd, abi.RLS_RAY_GLOSSY, b["wi_s"]))
+
+    sp, _ = ol.workload_skin(n)
+    disp = np.stack([ol.hash_uniform(n, 8, j, lo=-1.5, hi=1.5) for j in range(3)])
+    hn = ol.make_shading(n, 9)
+    hnv = np.stack([hn["Nx"], hn["Ny"], hn["Nz"]])
+    assert gio.bits_equal(ref.skin_probe_mis_pdf(sg, sp, disp, hnv), port.skin_probe_mis_pdf(sg, sp, disp, hnv))
