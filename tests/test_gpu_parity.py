@@ -7,7 +7,8 @@ Stated tolerances (BASELINE.json north_star; DESIGN.md "Parity policy"):
   * sampled directions: 1e-6 absolute; f, pdf, radii, weights: 1e-5 relative.
     Visible-normal sampling is ill-conditioned, so the value tolerances are
     asserted as fractions: >= FRAC_TOL of samples within tolerance and >= FRAC_LOOSE within
-    100x the tolerance;
+    100x the tolerance -- and, since the device maths reproduces the host bit for bit
+    (DESIGN.md 2), >= FRAC_EXACT of samples bit-identical;
   * everything that is free of transcendentals (rlGgx evalBrdf / evalPdf at a given
     direction, layer weights, the synthetic hash): bit-exact, every sample.
 """
@@ -25,8 +26,10 @@ from rlshaders_b200 import _abi as abi
 pytestmark = pytest.mark.gpu
 
 N = 1 << 20
-FRAC_TOL = 0.995      # fraction of samples within the stated tolerance
-FRAC_LOOSE = 0.9999   # fraction within 100x the stated tolerance
+FRAC_TOL = 0.9999     # fraction of samples within the stated tolerance
+FRAC_LOOSE = 0.99999  # fraction within 100x the stated tolerance
+FRAC_EXACT = 0.999    # fraction of samples bit-identical (measured: 1.0; the margin only covers a
+                      # host whose libm picks a non-FMA build of the binary64-based functions)
 
 
 @pytest.fixture(scope="module")
@@ -54,6 +57,7 @@ def check(stats, title):
             loose = s.get("within_1e4", s.get("within_1e3"))
             assert s["within"] >= FRAC_TOL, (title, name, s)
             assert loose >= FRAC_LOOSE, (title, name, s)
+            assert s["bit_exact"] >= FRAC_EXACT, (title, name, s)
 
 
 def dev(a, ctx):
