@@ -318,18 +318,10 @@ k_disney_sample_eval_pdf(size_t n, ShadingSoA sg, DisneyParamsDev p, const float
 {
     RLS_INDEX();
     Disney d; disney_init(d, load_shading(sg, i), p, i);
-    uint32_t lobe = 0;
-    f3 Ls = disney_sample_specular(d, __ldg(rx_s + i), __ldg(ry_s + i), lobe);
-    f3 fs = disney_eval_brdf(d, kRayGlossy, Ls);
-    float ps = disney_eval_pdf(d, kRayGlossy, Ls);
-    f3 Ld = disney_sample_diffuse(d, __ldg(rx_d + i), __ldg(ry_d + i));
-    f3 fd = disney_eval_brdf(d, kRayDiffuse, Ld);
-    float pd = disney_eval_pdf(d, kRayDiffuse, Ld);
-    store3(o.wi_s, i, Ls); store3(o.f_s, i, fs); o.pdf_s[i] = ps;
-    store3(o.wi_d, i, Ld); store3(o.f_d, i, fd); o.pdf_d[i] = pd;
-    uint32_t fls = (bsdf_flags(Ls, d.N, fs, ps) & ~RLS_FLAG_PDF_FLOORED) | (lobe << RLS_FLAG_LOBE_SHIFT);
-    uint32_t fld = bsdf_flags(Ld, d.N, fd, pd);
-    o.flags[i] = fls | (fld << RLS_FLAG_DIFFUSE_SHIFT);
+    DisneyOut1 r = disney_unit(d, __ldg(rx_s + i), __ldg(ry_s + i), __ldg(rx_d + i), __ldg(ry_d + i));
+    store3(o.wi_s, i, r.Ls); store3(o.f_s, i, r.fs); o.pdf_s[i] = r.ps;
+    store3(o.wi_d, i, r.Ld); store3(o.f_d, i, r.fd); o.pdf_d[i] = r.pd;
+    o.flags[i] = r.flags;
 }
 
 // ================================================================ profile kernels

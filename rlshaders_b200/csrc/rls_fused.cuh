@@ -167,3 +167,103 @@ RLS_DEV GgxBsdf ggx_unit(const Ggx &g, float rx, float ry)
 }
 
 } // namespace rls
+
+namespace rls {
+
+// ------------------------------------------------------------------ rlDisney fused unit
+// ctor + glossy triple + diffuse triple with the terms the reference recomputes shared:
+//   * the half vector M = normalize(L + V), L.M, N.M of evalSpecular (src/rlDisney.cpp:328-331)
+//     and evalSpecularPdf (:522-524) are the same IEEE operations on the same bits;
+//   * D_GTR2Aniso(M) and D_GTR1 (incl. its logf of a per-sample constant) are evaluated by both
+//     (:339,347 and :536-537);
+//   * V.N and the two view-side smithG_GGX terms depend on the shading point only.
+// The local microfacet normal of both specular lobes goes through ONE rotate/normalize/reflect tail.
+struct DisneyOut1 { f3 Ls, fs, Ld, fd; float ps, pd; uint32_t flags; };
+
+RLS_DEV DisneyOut1 disney_unit(const Disney &d, float rx_s, float ry_s, float rx_d, float ry_d)
+{
+    DisneyOut1 o;
+    const float VdotN = dot(d.wo, d.N);
+    // per-sample constants of D_GTR1 (src/rlDisney.cpp:547-549)
+    const float gtr1_alpha = lerp_m(d.clearcoatGloss, 0.1f, 0.001f);
+    const float gtr1_a2 = sqr(gtr1_alpha);
+    const float gtr1_log = rlm::logf_(gtr1_a2);
+    auto D_GTR1_shared = [&](float MdotN2) {
+        float denominator = gtr1_log * (1.0f + (gtr1_a2 - 1.0f) * MdotN2);
+        return (gtr1_a2 - 1.0f) * kInvPi / denominator;
+    };
+
+    // ---- specular sample (src/rlDisney.cpp:367-390)
+    uint32_t lobe;
+    f3 M;
+    {
+        float gtr2Weight = 1.0f / (d.clearcoat + 1.0f);
+        if (rx_s < gtr2Weight) {
+            float rx = rx_s / gtr2Weight;
+            M = d.visibleNormal ? sample_visible_normal(d.wo, d.U, d.V, d.N, d.ax, d.ay, rx, ry_s)
+                                : sample_ndf_normal(d.U, d.V, d.N, d.ax, d.ay, ry_s, rx);
+            lobe = 0;
+        } else {
+            float rx = (rx_s - gtr2Weight) / (1.0f - gtr2Weight);
+            M = disney_sample_gtr1(d, rx, ry_s);
+            lobe = 1;
+        }
+    }
+    const bool zeroS = dot(d.N, M) < 0.0f;
+    o.Ls = zeroS ? mk3(0.0f, 0.0f, 0.0f) : reflect_direction(d.wo, M);
+
+    // ---- specular eval + pdf at Ls, sharing the half vector and both D terms
+    if (zeroS) {
+        o.fs = mk3(0.0f, 0.0f, 0.0f);
+        o.ps = 0.0f;
+    } else {
+        const f3 L = o.Ls;
+        const float LdotN = dot(L, d.N);                     // == dot(N, L) bitwise
+        const f3 H = normalize(L + d.wo);
+        const float LdotM = dot(L, H);
+        const float NdotM = dot(d.N, H);                     // == dot(H, N) bitwise
+        const float NdotM2 = sqr(NdotM);
+        const float Ds = D_GTR2Aniso(d, H, NdotM2);
+        const float Dr = D_GTR1_shared(NdotM2);
+        // pdf (:520-543)
+        if (NdotM < 0.0f) {
+            o.ps = 0.0f;
+        } else {
+            const float IdotM = abs_m(LdotM);
+            const float clearcoatWeight = d.clearcoat / (d.clearcoat + 1.0f);
+            if (d.visibleNormal) {
+                const float Vn = max_m(1e-4f, VdotN);
+                const float Dw = smithG_GGX(IdotM, d.specRough) * Ds * 2.0f * IdotM / Vn;
+                o.ps = lerp_m(clearcoatWeight, Dw, Dr * abs_m(NdotM) / IdotM) * 0.25f;
+            } else {
+                o.ps = lerp_m(clearcoatWeight, Ds, Dr) * abs_m(NdotM) * 0.25f / IdotM;
+            }
+        }
+        // eval (:318-356) x N.L (:136)
+        if (LdotN < kEps || VdotN < kEps || NdotM < kEps || LdotM < kEps) {
+            o.fs = mk3(0.0f, 0.0f, 0.0f) * LdotN;            // black * NdotL keeps the sign of zero
+        } else {
+            const float FH = rlm::powf_(clamp_m(1.0f - LdotM, 0.0f, 1.0f), 5.0f);
+            const f3 Fs = lerp_m(FH, d.F0, mk3(1.0f, 1.0f, 1.0f));
+            const float Gs = smithG_GGX(LdotN, d.specRough) * smithG_GGX(VdotN, d.specRough);
+            const float Fr = lerp_m(FH, 0.04f, 1.0f);
+            const float Gr = smithG_GGX(LdotN, 0.25f) * smithG_GGX(VdotN, 0.25f);
+            const f3 Fsheen = d.sheenColor * FH * (1.0f - d.metallic);
+            const f3 spec = Fs * Ds * Gs;
+            const float coat = d.clearcoat * Dr * Fr * Gr;
+            o.fs = (mk3(spec.x + coat, spec.y + coat, spec.z + coat) + Fsheen) * LdotN;
+        }
+    }
+
+    // ---- diffuse triple (src/rlDisney.cpp:359-365, 199-236, 515-518)
+    o.Ld = disney_sample_diffuse(d, rx_d, ry_d);
+    o.fd = disney_eval_brdf(d, kRayDiffuse, o.Ld);
+    o.pd = disney_eval_pdf(d, kRayDiffuse, o.Ld);
+
+    const uint32_t fls = (bsdf_flags(o.Ls, d.N, o.fs, o.ps) & ~0x0040u) | (lobe << 8);
+    const uint32_t fld = bsdf_flags(o.Ld, d.N, o.fd, o.pd);
+    o.flags = fls | (fld << 16);
+    return o;
+}
+
+} // namespace rls
