@@ -165,6 +165,7 @@ def run_product(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = api.Context(local)
+    ctx.set_arith_policy(args.arith)
     dev = ctx.device
 
     def barrier():
@@ -206,15 +207,16 @@ def run_product(args):
     step = lambda: sampler.dielectricSampleEvalPdf(rx, ry, out=out)   # noqa: E731
 
     clocks = ClockSampler(local)
-    launches0 = ctx.kernel_launches
     for _ in range(args.warmup):
         step()
     barrier()
+    ctx.fallback_count(reset=True)
     clocks.start()
     launches1 = ctx.kernel_launches
     ms = timed(step, args.steps, 0)
     gpu_launches = ctx.kernel_launches - launches1
-    del launches0
+    # samples the fast arithmetic policy re-ran with the guarded IEEE operators (rls_fp.cuh)
+    arith = {"policy": args.arith, "exact_rerun_fraction": ctx.fallback_count(reset=True) / float(n * args.steps)}
     value = world * n / (ms * 1e-3)
     achieved = n * B_ALG["ggx_dielectric"] / (ms * 1e-3) / 1e9
     traffic = measured_traffic("k_ggx_dielectric")
@@ -263,7 +265,7 @@ def run_product(args):
             "config": {"workload": WORKLOAD, "samples_per_gpu": n,
                        "l2": "inputs+outputs per step = %.1f GB >> 126 MB L2, no flush needed" % (n * 113 / 1e9),
                        "sharding": "independent index ranges per rank, no collective"},
-            "roofline": roofline, "e2e": e2e, "e2e_matches_device": bool(same),
+            "roofline": roofline, "e2e": e2e, "e2e_matches_device": bool(same), "arith": arith,
             "gpu_launches": int(gpu_launches), "clocks": clock_info}
 
     # ---- CPU baseline beside it (rank 0, N = 1): same input bits, bounded prefix
@@ -320,9 +322,12 @@ def run_product(args):
             flush.zero_()
             s1.sampleEvalPdf(rx1, ry1, out=o1)
         t_flush = timed(lambda: flush.zero_(), steps_o, warm_o)
+        ctx.fallback_count(reset=True)
         t1 = timed(step1, steps_o, warm_o) - t_flush
+        fb1 = ctx.fallback_count(reset=True) / float(n1 * (steps_o + warm_o))
         others["ggx_conductor_1M"] = {"samples_per_s": world * n1 / (t1 * 1e-3), "ms": t1,
                                       "hbm_frac": n1 * B_ALG["ggx_conductor"] / (t1 * 1e-3) / 1e9 / peak,
+                                      "exact_rerun_fraction": fb1,
                                       "l2": "flushed between iterations (512 MB memset, its time subtracted)"}
         del flush, s1, o1
         del sampler, out, rough, ior
@@ -337,6 +342,7 @@ def run_product(args):
         o4 = s4.alloc_out(rx4)
         t4 = timed(lambda: s4.sampleEvalPdf(rx4, out=o4), steps_o, warm_o)
         others["skin_profile_256M"] = {"samples_per_s": world * n4 / (t4 * 1e-3), "ms": t4,
+                                       "exact_rerun_fraction": ctx.fallback_count(reset=True) / float(n4 * (steps_o + warm_o)),
                                        "hbm_frac": n4 * B_ALG["skin_profile"] / (t4 * 1e-3) / 1e9 / peak}
         del color, distv, rx4, s4, o4
         torch.cuda.empty_cache()
@@ -353,6 +359,7 @@ def run_product(args):
         o3 = s3.alloc_out(u[0])
         t3 = timed(lambda: s3.sampleEvalPdf(*u, out=o3), steps_o, warm_o)
         others["disney_256M"] = {"samples_per_s": world * n3 / (t3 * 1e-3), "ms": t3,
+                                 "exact_rerun_fraction": ctx.fallback_count(reset=True) / float(n3 * (steps_o + warm_o)),
                                  "hbm_frac": n3 * B_ALG["disney"] / (t3 * 1e-3) / 1e9 / peak}
         del sg3, kw, u, s3, o3
         torch.cuda.empty_cache()
@@ -369,6 +376,8 @@ def run_product(args):
                 dist.all_reduce(table, op=dist.ReduceOp.SUM)
         t5 = timed(step5, max(2, steps_o // 2), 1)
         others["albedo_sweep_65536x4096"] = {"samples_per_s": 64 * 64 * 16 * spp / (t5 * 1e-3), "ms": t5,
+                                             "exact_rerun_fraction": ctx.fallback_count(reset=True) /
+                                             float(64 * 64 * 16 * (k1 - k0) * (max(2, steps_o // 2) + 1)),
                                              "collective": "nccl all_reduce(sum) of the 2.6 MB FP64 table" if world > 1 else "none (1 GPU)"}
         line["other_workloads"] = others
 
@@ -404,6 +413,8 @@ def main():
     ap.add_argument("--e2e-samples", type=int, default=N_DIELECTRIC, help="samples per e2e step (per GPU)")
     ap.add_argument("--main-only", action="store_true", help="skip the other BASELINE configs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--arith", choices=["fast", "exact"], default="fast",
+                    help="arithmetic policy of the fused kernels (same bits; csrc/rls_fp.cuh)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -235,6 +235,16 @@ const char *rls_last_error_string(const rls_context *ctx);/* ctx may be NULL: in
 int  rls_abi_version(void);
 /* Number of kernels this context has launched since creation (bench bookkeeping). */
 uint64_t rls_kernel_launch_count(const rls_context *ctx);
+/* Arithmetic policy of the fused *_sample_eval_pdf kernels (rlshaders_b200/csrc/rls_fp.cuh).
+ * Both produce the same bits for every input; RLS_ARITH_FAST (default) runs guard-free
+ * division / sqrt / reciprocal sequences and re-runs a sample with the guarded IEEE operators
+ * when an operand left the window in which the two agree; RLS_ARITH_EXACT always uses the
+ * guarded operators (A/B testing, tests).  rls_fallback_count reports how many samples were
+ * re-run since creation / the last reset (synchronises the context's streams). */
+#define RLS_ARITH_FAST  0
+#define RLS_ARITH_EXACT 1
+int rls_set_arith_policy(rls_context *ctx, int policy);
+int rls_fallback_count(rls_context *ctx, uint64_t *out_count, int reset);
 /* The node names this library stands in for: "rlGgx", "rlDisney", "rlSkin"; NULL past
  * the end -- same enumeration contract as NodeLoader(i, ...). */
 const char *rls_node_name(int i);

@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("RLS_B200_LIB") or os.path.join(os.path.dirname(os.pat
 # Every extern "C" symbol include/rls_b200.h declares (tests check the export list).
 SYMBOLS = [
     "rls_init", "rls_shutdown", "rls_synchronize", "rls_last_error_string", "rls_abi_version",
-    "rls_kernel_launch_count", "rls_node_name",
+    "rls_kernel_launch_count", "rls_node_name", "rls_set_arith_policy", "rls_fallback_count",
     "rls_ggx_eval_sample", "rls_ggx_eval_brdf", "rls_ggx_eval_pdf", "rls_ggx_sample_eval_pdf",
     "rls_ggx_dielectric_sample_eval_pdf",
     "rls_disney_eval_sample", "rls_disney_eval_brdf", "rls_disney_eval_pdf",
@@ -94,6 +94,10 @@ def load():
     lib.rls_abi_version.restype = C.c_int
     lib.rls_kernel_launch_count.argtypes = [vp]
     lib.rls_kernel_launch_count.restype = C.c_uint64
+    lib.rls_set_arith_policy.argtypes = [vp, i32]
+    lib.rls_set_arith_policy.restype = C.c_int
+    lib.rls_fallback_count.argtypes = [vp, C.POINTER(C.c_uint64), i32]
+    lib.rls_fallback_count.restype = C.c_int
     lib.rls_node_name.argtypes = [i32]
     lib.rls_node_name.restype = C.c_char_p
     if lib.rls_abi_version() != abi.ABI_VERSION:

@@ -70,6 +70,19 @@ class Context:
     def kernel_launches(self):
         return int(self.lib.rls_kernel_launch_count(self.handle))
 
+    def set_arith_policy(self, policy):
+        """"fast" (default: guard-free IEEE sequences + exact re-run of out-of-window samples)
+        or "exact" (guarded operators only).  Same bits either way (csrc/rls_fp.cuh)."""
+        code = {"fast": 0, "exact": 1}[policy]
+        _check(self.handle, self.lib.rls_set_arith_policy(self.handle, code), self.lib)
+
+    def fallback_count(self, reset=False):
+        """Samples the fused kernels re-ran with the guarded operators (synchronises)."""
+        import ctypes
+        v = ctypes.c_uint64(0)
+        _check(self.handle, self.lib.rls_fallback_count(self.handle, ctypes.byref(v), int(bool(reset))), self.lib)
+        return int(v.value)
+
     # ---- allocation helpers -------------------------------------------------
     def empty(self, *shape, dtype=torch.float32, like=None):
         if like is not None and like.device.type == "cpu":

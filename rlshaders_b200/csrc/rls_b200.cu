@@ -44,6 +44,8 @@ struct rls_context {
     bool         own_stream = false;
     std::string  err;
     uint64_t     launches = 0;
+    int          arith = RLS_ARITH_FAST;          // policy of the fused kernels (rls_fp.cuh)
+    unsigned long long *fallbacks = nullptr;      // device counter: samples re-run with FpExact
     // host-staging resources (lazily created by the *_host entry points)
     cudaStream_t stage_stream[kStages] = { nullptr, nullptr, nullptr };
     cudaEvent_t  stage_done[kStages] = { nullptr, nullptr, nullptr };
@@ -109,7 +111,37 @@ extern "C" int rls_init(int device, void *stream, rls_context **out_ctx)
         if (e != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaStreamCreateWithFlags"); }
         ctx->own_stream = true;
     }
+    e = cudaMalloc((void **)&ctx->fallbacks, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ctx->fallbacks, 0, sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return cuda_fail(nullptr, e, "cudaMalloc(fallback counter)");
+    }
     *out_ctx = ctx;
+    return RLS_OK;
+}
+
+extern "C" int rls_set_arith_policy(rls_context *ctx, int policy)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (policy != RLS_ARITH_FAST && policy != RLS_ARITH_EXACT)
+        return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "rls_set_arith_policy: policy must be RLS_ARITH_FAST or RLS_ARITH_EXACT");
+    ctx->arith = policy;
+    return RLS_OK;
+}
+
+extern "C" int rls_fallback_count(rls_context *ctx, uint64_t *out_count, int reset)
+{
+    if (!ctx || !out_count) return RLS_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    unsigned long long v = 0;
+    RLS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < kStages; b++)
+        if (ctx->stage_stream[b]) RLS_CUDA(ctx, cudaStreamSynchronize(ctx->stage_stream[b]));
+    RLS_CUDA(ctx, cudaMemcpy(&v, ctx->fallbacks, sizeof(v), cudaMemcpyDeviceToHost));
+    if (reset) RLS_CUDA(ctx, cudaMemset(ctx->fallbacks, 0, sizeof(v)));
+    *out_count = (uint64_t)v;
     return RLS_OK;
 }
 
@@ -123,6 +155,7 @@ extern "C" int rls_shutdown(rls_context *ctx)
         if (ctx->stage_done[b]) cudaEventDestroy(ctx->stage_done[b]);
         if (ctx->stage_buf[b]) cudaFree(ctx->stage_buf[b]);
     }
+    if (ctx->fallbacks) cudaFree(ctx->fallbacks);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RLS_OK;
@@ -209,11 +242,24 @@ static inline unsigned grid_for(size_t n) { return (unsigned)((n + kBlock - 1) /
     if (i >= (uint32_t)n) return;
 
 // ================================================================ rlGgx kernels
-RLS_DEV Ggx ggx_make(const ShadingSoA &sg, const GgxParamsDev &p, uint32_t i)
+// Fused kernels: run the sample with the guard-free FpFast sequences; if any operand left the
+// window in which they equal the IEEE operators, run it again with FpExact (rls_fp.cuh).
+#define RLS_FAST_THEN_EXACT(kFast, result, expr)                                   \
+    do {                                                                            \
+        bool ok_ = false;                                                           \
+        if (kFast) { FpFast fp; result = (expr); ok_ = fp.ok(); }                   \
+        if (!ok_) {                                                                 \
+            FpExact fp; result = (expr);                                            \
+            if (kFast) atomicAdd(fallbacks, 1ull);                                  \
+        }                                                                           \
+    } while (0)
+
+template <class Fp>
+RLS_DEV Ggx ggx_make(Fp &fp, const ShadingSoA &sg, const GgxParamsDev &p, uint32_t i)
 {
     Shading s = load_shading(sg, i);
     Ggx g;
-    ggx_init(g, s, fetch(p.ks, i), fetch(p.ior, i), fetch(p.rough, i), fetch(p.aniso, i));
+    ggx_init(fp, g, s, fetch(p.ks, i), fetch(p.ior, i), fetch(p.rough, i), fetch(p.aniso, i));
     g.ndf = p.ndf != 0;
     return g;
 }
@@ -222,36 +268,52 @@ __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_ggx_eval_sample(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, V3 wi, float *fresnel)
 {
     RLS_INDEX();
-    Ggx g = ggx_make(sg, p, i);
-    f3 M = ggx_sample_normal(g, __ldg(rx + i), __ldg(ry + i));
+    FpExact fp;
+    Ggx g = ggx_make(fp, sg, p, i);
+    f3 M = ggx_sample_normal(fp, g, __ldg(rx + i), __ldg(ry + i));
     f3 L = reflect_direction(g.wo, M);                 // src/rlGgx.h:100-101
     store3(wi, i, L);
-    if (fresnel) fresnel[i] = ggx_fresnel(g, L, M);    // :103-104,181-184 with one sample
+    if (fresnel) fresnel[i] = ggx_fresnel(fp, g, L, M);    // :103-104,181-184 with one sample
 }
 
 __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_ggx_eval_brdf(size_t n, ShadingSoA sg, GgxParamsDev p, CV3 wi, V3 f)
 {
     RLS_INDEX();
-    Ggx g = ggx_make(sg, p, i);
-    store3(f, i, ggx_eval_brdf(g, load3(wi, i)));
+    FpExact fp;
+    Ggx g = ggx_make(fp, sg, p, i);
+    store3(f, i, ggx_eval_brdf(fp, g, load3(wi, i)));
 }
 
 __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_ggx_eval_pdf(size_t n, ShadingSoA sg, GgxParamsDev p, CV3 wi, float *pdf)
 {
     RLS_INDEX();
-    Ggx g = ggx_make(sg, p, i);
-    pdf[i] = ggx_eval_pdf(g, load3(wi, i));
+    FpExact fp;
+    Ggx g = ggx_make(fp, sg, p, i);
+    pdf[i] = ggx_eval_pdf(fp, g, load3(wi, i));
 }
 
+template <class Fp>
+RLS_DEV GgxBsdf ggx_unit_from(Fp &fp, const Shading &s, f3 ks, float ior, float rough, float aniso, bool ndf, float rx, float ry)
+{
+    Ggx g;
+    ggx_init(fp, g, s, ks, ior, rough, aniso);
+    g.ndf = ndf;
+    return ggx_unit(fp, g, rx, ry);
+}
+template <bool kFast>
 __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_ggx_sample_eval_pdf(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry,
-                      V3 wi, V3 f, float *pdf, float *fresnel, uint32_t *flags)
+                      V3 wi, V3 f, float *pdf, float *fresnel, uint32_t *flags, unsigned long long *fallbacks)
 {
     RLS_INDEX();
-    Ggx g = ggx_make(sg, p, i);
-    GgxBsdf o = ggx_unit(g, __ldg(rx + i), __ldg(ry + i));
+    const Shading s = load_shading(sg, i);
+    const f3 ks = fetch(p.ks, i);
+    const float ior = fetch(p.ior, i), rough = fetch(p.rough, i), aniso = fetch(p.aniso, i);
+    const float u1 = __ldg(rx + i), u2 = __ldg(ry + i);
+    GgxBsdf o;
+    RLS_FAST_THEN_EXACT(kFast, o, ggx_unit_from(fp, s, ks, ior, rough, aniso, p.ndf != 0, u1, u2));
     store3(wi, i, o.L);
     store3(f, i, o.f);
     pdf[i] = o.pdf;
@@ -261,13 +323,17 @@ k_ggx_sample_eval_pdf(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, 
 
 struct DielectricOutDev { float *fresnel; V3 wi_r; float *f_r, *pdf_r; V3 wi_t; float *f_t, *weight_t; uint32_t *flags; };
 
+template <bool kFast>
 __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
-k_ggx_dielectric(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, DielectricOutDev o)
+k_ggx_dielectric(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, DielectricOutDev o,
+                 unsigned long long *fallbacks)
 {
     RLS_INDEX();
-    Shading s = load_shading(sg, i);
-    Dielectric r = dielectric_unit(s, fetch(p.ior, i), fetch(p.rough, i), fetch(p.aniso, i), __ldg(rx + i), __ldg(ry + i),
-                                   p.ndf != 0);
+    const Shading s = load_shading(sg, i);
+    const float ior = fetch(p.ior, i), rough = fetch(p.rough, i), aniso = fetch(p.aniso, i);
+    const float u1 = __ldg(rx + i), u2 = __ldg(ry + i);
+    Dielectric r;
+    RLS_FAST_THEN_EXACT(kFast, r, dielectric_unit(fp, s, ior, rough, aniso, u1, u2, p.ndf != 0));
     o.fresnel[i] = r.F;
     store3(o.wi_r, i, r.wi_r);
     o.f_r[i] = r.f_r;
@@ -283,10 +349,11 @@ __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_disney_eval_sample(size_t n, ShadingSoA sg, DisneyParamsDev p, int type, const float *rx, const float *ry, V3 wi, uint32_t *flags)
 {
     RLS_INDEX();
-    Disney d; disney_init(d, load_shading(sg, i), p, i);
+    FpExact fp;
+    Disney d; disney_init(fp, d, load_shading(sg, i), p, i);
     uint32_t lobe = 0;
-    f3 L = (type == kRayDiffuse) ? disney_sample_diffuse(d, __ldg(rx + i), __ldg(ry + i))
-                                 : disney_sample_specular(d, __ldg(rx + i), __ldg(ry + i), lobe);
+    f3 L = (type == kRayDiffuse) ? disney_sample_diffuse(fp, d, __ldg(rx + i), __ldg(ry + i))
+                                 : disney_sample_specular(fp, d, __ldg(rx + i), __ldg(ry + i), lobe);
     store3(wi, i, L);
     if (flags) {
         uint32_t fl = lobe << RLS_FLAG_LOBE_SHIFT;
@@ -299,26 +366,38 @@ __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_disney_eval_brdf(size_t n, ShadingSoA sg, DisneyParamsDev p, int type, CV3 wi, V3 f)
 {
     RLS_INDEX();
-    Disney d; disney_init(d, load_shading(sg, i), p, i);
-    store3(f, i, disney_eval_brdf(d, type, load3(wi, i)));
+    FpExact fp;
+    Disney d; disney_init(fp, d, load_shading(sg, i), p, i);
+    store3(f, i, disney_eval_brdf(fp, d, type, load3(wi, i)));
 }
 __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_disney_eval_pdf(size_t n, ShadingSoA sg, DisneyParamsDev p, int type, CV3 wi, float *pdf)
 {
     RLS_INDEX();
-    Disney d; disney_init(d, load_shading(sg, i), p, i);
-    pdf[i] = disney_eval_pdf(d, type, load3(wi, i));
+    FpExact fp;
+    Disney d; disney_init(fp, d, load_shading(sg, i), p, i);
+    pdf[i] = disney_eval_pdf(fp, d, type, load3(wi, i));
 }
 
 struct DisneyOutDev { V3 wi_s, f_s; float *pdf_s; V3 wi_d, f_d; float *pdf_d; uint32_t *flags; };
 
+template <class Fp>
+RLS_DEV DisneyOut1 disney_unit_from(Fp &fp, const Shading &s, const DisneyParamsDev &p, uint32_t i,
+                                    float rx_s, float ry_s, float rx_d, float ry_d)
+{
+    Disney d; disney_init(fp, d, s, p, i);
+    return disney_unit(fp, d, rx_s, ry_s, rx_d, ry_d);
+}
+template <bool kFast>
 __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_disney_sample_eval_pdf(size_t n, ShadingSoA sg, DisneyParamsDev p, const float *rx_s, const float *ry_s,
-                         const float *rx_d, const float *ry_d, DisneyOutDev o)
+                         const float *rx_d, const float *ry_d, DisneyOutDev o, unsigned long long *fallbacks)
 {
     RLS_INDEX();
-    Disney d; disney_init(d, load_shading(sg, i), p, i);
-    DisneyOut1 r = disney_unit(d, __ldg(rx_s + i), __ldg(ry_s + i), __ldg(rx_d + i), __ldg(ry_d + i));
+    const Shading s = load_shading(sg, i);
+    const float u1 = __ldg(rx_s + i), u2 = __ldg(ry_s + i), u3 = __ldg(rx_d + i), u4 = __ldg(ry_d + i);
+    DisneyOut1 r;
+    RLS_FAST_THEN_EXACT(kFast, r, disney_unit_from(fp, s, p, i, u1, u2, u3, u4));
     store3(o.wi_s, i, r.Ls); store3(o.f_s, i, r.fs); o.pdf_s[i] = r.ps;
     store3(o.wi_d, i, r.Ld); store3(o.f_d, i, r.fd); o.pdf_d[i] = r.pd;
     o.flags[i] = r.flags;
@@ -339,7 +418,8 @@ __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_nd_set_distance(size_t n, CV3 dist, NdProfileSoADev o)
 {
     RLS_INDEX();
-    NdProfile p; nd_set_distance(p, load3(dist, i));
+    FpExact fp;
+    NdProfile p; nd_set_distance(fp, p, load3(dist, i));
     store3(o.distance, i, mk3(p.d[0], p.d[1], p.d[2]));
     store3(o.C1, i, mk3(p.C1[0], p.C1[1], p.C1[2]));
     store3(o.C2, i, mk3(p.C2[0], p.C2[1], p.C2[2]));
@@ -351,7 +431,8 @@ k_nd_get_radius(size_t n, NdProfileSoADev s, const float *rx, float *r, uint32_t
     RLS_INDEX();
     NdProfile p = nd_load(s, i);
     uint32_t fl;
-    r[i] = nd_get_radius(p, __ldg(rx + i), fl);
+    FpExact fp;
+    r[i] = nd_get_radius(fp, p, __ldg(rx + i), fl);
     if (flags) flags[i] = fl;
 }
 __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
@@ -359,27 +440,42 @@ k_nd_get_pdf(size_t n, NdProfileSoADev s, const float *r, float *pdf)
 {
     RLS_INDEX();
     NdProfile p = nd_load(s, i);
-    pdf[i] = nd_get_pdf(p, __ldg(r + i));
+    FpExact fp;
+    pdf[i] = nd_get_pdf(fp, p, __ldg(r + i));
 }
 __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_nd_eval_profile(size_t n, NdProfileSoADev s, const float *r, V3 rd)
 {
     RLS_INDEX();
     NdProfile p = nd_load(s, i);
-    store3(rd, i, nd_eval_profile(p, __ldg(r + i)));
+    FpExact fp;
+    store3(rd, i, nd_eval_profile(fp, p, __ldg(r + i)));
 }
 struct ProfileOutDev { float *r, *pdf; V3 Rd; uint32_t *flags; };
+struct Profile1 { float r, pdf; f3 Rd; uint32_t flags; };
+template <class Fp>
+RLS_DEV Profile1 skin_profile_unit(Fp &fp, f3 dist, float rx)
+{
+    Profile1 o;
+    NdProfile p; nd_set_distance(fp, p, dist);
+    o.r = nd_get_radius(fp, p, rx, o.flags);
+    o.pdf = nd_get_pdf(fp, p, o.r);
+    o.Rd = nd_eval_profile(fp, p, o.r);
+    return o;
+}
+template <bool kFast>
 __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
-k_skin_profile(size_t n, SkinParamsDev sp, const float *rx, ProfileOutDev o)
+k_skin_profile(size_t n, SkinParamsDev sp, const float *rx, ProfileOutDev o, unsigned long long *fallbacks)
 {
     RLS_INDEX();
-    NdProfile p; nd_set_distance(p, skin_scatter_dist(sp, i));
-    uint32_t fl;
-    float r = nd_get_radius(p, __ldg(rx + i), fl);
-    o.r[i] = r;
-    o.pdf[i] = nd_get_pdf(p, r);
-    store3(o.Rd, i, nd_eval_profile(p, r));
-    o.flags[i] = fl;
+    const f3 dist = skin_scatter_dist(sp, i);
+    const float u = __ldg(rx + i);
+    Profile1 r;
+    RLS_FAST_THEN_EXACT(kFast, r, skin_profile_unit(fp, dist, u));
+    o.r[i] = r.r;
+    o.pdf[i] = r.pdf;
+    store3(o.Rd, i, r.Rd);
+    o.flags[i] = r.flags;
 }
 // src/rlSkin.cpp:191,204,214,228,231,238
 __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
@@ -404,14 +500,15 @@ k_skin_probe_ray(size_t n, ShadingSoA sg, SkinParamsDev sp, const float *rx_in, 
 {
     RLS_INDEX();
     Shading s = load_shading(sg, i);
-    NdProfile p; nd_set_distance(p, skin_scatter_dist(sp, i));
+    FpExact fp;
+    NdProfile p; nd_set_distance(fp, p, skin_scatter_dist(sp, i));
     float rx = __ldg(rx_in + i), ry = __ldg(ry_in + i);
     int idx;
-    if (rx < 0.5f) { idx = 0; rx = linearstep_m(0.0f, 0.5f, rx); }
-    else if (rx < 0.75f) { idx = 2; rx = linearstep_m(0.5f, 0.75f, rx); }
-    else { idx = 3; rx = linearstep_m(0.75f, 1.0f, rx); }
+    if (rx < 0.5f) { idx = 0; rx = linearstep_m(fp, 0.0f, 0.5f, rx); }
+    else if (rx < 0.75f) { idx = 2; rx = linearstep_m(fp, 0.5f, 0.75f, rx); }
+    else { idx = 3; rx = linearstep_m(fp, 0.75f, 1.0f, rx); }
     uint32_t fl;
-    float r = nd_get_radius(p, rx, fl);
+    float r = nd_get_radius(fp, p, rx, fl);
     float rmax = p.R;
     float phi = kTwoPi * ry;
     float sn, cs;
@@ -434,14 +531,15 @@ k_skin_probe_mis_pdf(size_t n, ShadingSoA sg, SkinParamsDev sp, CV3 disp, CV3 hi
 {
     RLS_INDEX();
     Shading s = load_shading(sg, i);
-    NdProfile p; nd_set_distance(p, skin_scatter_dist(sp, i));
+    FpExact fp;
+    NdProfile p; nd_set_distance(fp, p, skin_scatter_dist(sp, i));
     f3 dp = load3(disp, i), hn = load3(hitN, i);
     f3 off = mk3(dot(dp, s.U), dot(dp, s.V), dot(dp, s.N));     // world -> local (AiM4VectorByMatrixMult)
     off = mk3(off.x * off.x, off.y * off.y, off.z * off.z);
     float rr0 = sqrtf(off.y + off.z), rr1 = sqrtf(off.x + off.z), rr2 = sqrtf(off.x + off.y);
-    pdf[i] = nd_get_pdf(p, rr0) * abs_m(dot(s.U, hn)) * 0.25f
-           + nd_get_pdf(p, rr1) * abs_m(dot(s.V, hn)) * 0.25f
-           + nd_get_pdf(p, rr2) * abs_m(dot(s.N, hn)) * 0.5f;
+    pdf[i] = nd_get_pdf(fp, p, rr0) * abs_m(dot(s.U, hn)) * 0.25f
+           + nd_get_pdf(fp, p, rr1) * abs_m(dot(s.V, hn)) * 0.25f
+           + nd_get_pdf(fp, p, rr2) * abs_m(dot(s.N, hn)) * 0.5f;
 }
 
 // ============================================================ synthetic generators
@@ -469,23 +567,24 @@ k_synth_shading(size_t n, uint64_t seed, uint64_t first, float cos_lo, float cos
                 V3 U, V3 V, V3 N, V3 wo, uint8_t *backfacing)
 {
     RLS_INDEX();
+    FpExact fp;
     uint64_t idx = first + i;
     float u1 = uniform24(seed, 10, idx), u2 = uniform24(seed, 11, idx), u3 = uniform24(seed, 12, idx);
     float u4 = uniform24(seed, 13, idx), u5 = uniform24(seed, 14, idx), u6 = uniform24(seed, 15, idx);
     float nz = 1.0f - 2.0f * u1;
     float rn = sqrtf(fmaxf(0.0f, 1.0f - nz * nz));
     float sn, cn; sincosf(kTwoPi * u2, &sn, &cn);
-    f3 Nn = normalize(mk3(rn * cn, rn * sn, nz));
+    f3 Nn = normalize(fp, mk3(rn * cn, rn * sn, nz));
     f3 A = fabsf(Nn.x) < 0.9f ? mk3(1.0f, 0.0f, 0.0f) : mk3(0.0f, 1.0f, 0.0f);
-    f3 T = normalize(A - Nn * dot(A, Nn));
+    f3 T = normalize(fp, A - Nn * dot(A, Nn));
     f3 B = mk3(Nn.y * T.z - Nn.z * T.y, Nn.z * T.x - Nn.x * T.z, Nn.x * T.y - Nn.y * T.x);
     float st, ct; sincosf(kTwoPi * u3, &st, &ct);
-    f3 Uu = normalize(T * ct + B * st);
+    f3 Uu = normalize(fp, T * ct + B * st);
     f3 Vv = mk3(Nn.y * Uu.z - Nn.z * Uu.y, Nn.z * Uu.x - Nn.x * Uu.z, Nn.x * Uu.y - Nn.y * Uu.x);
     float cz = cos_lo + (cos_hi - cos_lo) * u4;
     float sr = sqrtf(fmaxf(0.0f, 1.0f - cz * cz));
     float sv, cvv; sincosf(kTwoPi * u5, &sv, &cvv);
-    f3 w = normalize(Uu * (sr * cvv) + Vv * (sr * sv) + Nn * cz);
+    f3 w = normalize(fp, Uu * (sr * cvv) + Vv * (sr * sv) + Nn * cz);
     store3(U, i, Uu); store3(V, i, Vv); store3(N, i, Nn); store3(wo, i, w);
     if (backfacing) backfacing[i] = (u6 < back_frac) ? 1 : 0;
 }
@@ -493,8 +592,9 @@ k_synth_shading(size_t n, uint64_t seed, uint64_t first, float cos_lo, float cos
 // ================================================================= albedo sweep
 struct SweepGridDev { int n_rough, n_cos, n_ior; float rlo, rhi, ilo, ihi; };
 
+template <bool kFast>
 __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
-k_albedo_sweep(SweepGridDev g, uint64_t seed, uint32_t k0, uint32_t k1, double *table)
+k_albedo_sweep(SweepGridDev g, uint64_t seed, uint32_t k0, uint32_t k1, double *table, unsigned long long *fallbacks)
 {
     const uint32_t cell = blockIdx.x;
     uint32_t ie = cell % (uint32_t)g.n_ior;
@@ -516,7 +616,8 @@ k_albedo_sweep(SweepGridDev g, uint64_t seed, uint32_t k0, uint32_t k1, double *
         uint64_t idx = ((uint64_t)cell << 32) | (uint64_t)k;
         float rx = uniform24(seed, 0u, idx);
         float ry = uniform24(seed, 1u, idx);
-        Dielectric r = dielectric_unit(s, ior, rough, 0.0f, rx, ry);
+        Dielectric r;
+        RLS_FAST_THEN_EXACT(kFast, r, dielectric_unit(fp, s, ior, rough, 0.0f, rx, ry));
         bool valid = !(r.flags & (RLS_FLAG_ZERO_L | RLS_FLAG_BELOW_HORIZON));
         if (valid) { acc[0] += (double)(r.f_r / r.pdf_r); acc[3] += 1.0; }
         if (r.flags & RLS_FLAG_TIR) acc[4] += 1.0; else acc[1] += (double)r.w_t;
@@ -549,7 +650,10 @@ k_albedo_sweep(SweepGridDev g, uint64_t seed, uint32_t k0, uint32_t k1, double *
 static int launch_ggx_sample_eval_pdf(rls_context *ctx, cudaStream_t st, size_t n, const rls_shading_soa *sg,
                                       const rls_ggx_params *p, const float *rx, const float *ry, const rls_bsdf_out *o)
 {
-    k_ggx_sample_eval_pdf<<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), dev(*p), rx, ry, mv(o->wi), mv(o->f), o->pdf, o->fresnel, o->flags);
+    if (ctx->arith == RLS_ARITH_FAST)
+        k_ggx_sample_eval_pdf<true><<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), dev(*p), rx, ry, mv(o->wi), mv(o->f), o->pdf, o->fresnel, o->flags, ctx->fallbacks);
+    else
+        k_ggx_sample_eval_pdf<false><<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), dev(*p), rx, ry, mv(o->wi), mv(o->f), o->pdf, o->fresnel, o->flags, ctx->fallbacks);
     RLS_LAUNCH_CHECK(ctx);
     return RLS_OK;
 }
@@ -558,7 +662,10 @@ static int launch_ggx_dielectric(rls_context *ctx, cudaStream_t st, size_t n, co
 {
     DielectricOutDev d; d.fresnel = o->fresnel; d.wi_r = mv(o->wi_r); d.f_r = o->f_r; d.pdf_r = o->pdf_r;
     d.wi_t = mv(o->wi_t); d.f_t = o->f_t; d.weight_t = o->weight_t; d.flags = o->flags;
-    k_ggx_dielectric<<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), dev(*p), rx, ry, d);
+    if (ctx->arith == RLS_ARITH_FAST)
+        k_ggx_dielectric<true><<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), dev(*p), rx, ry, d, ctx->fallbacks);
+    else
+        k_ggx_dielectric<false><<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), dev(*p), rx, ry, d, ctx->fallbacks);
     RLS_LAUNCH_CHECK(ctx);
     return RLS_OK;
 }
@@ -568,7 +675,10 @@ static int launch_disney_sample_eval_pdf(rls_context *ctx, cudaStream_t st, size
 {
     DisneyOutDev d; d.wi_s = mv(o->wi_s); d.f_s = mv(o->f_s); d.pdf_s = o->pdf_s;
     d.wi_d = mv(o->wi_d); d.f_d = mv(o->f_d); d.pdf_d = o->pdf_d; d.flags = o->flags;
-    k_disney_sample_eval_pdf<<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), dev(*p), rx_s, ry_s, rx_d, ry_d, d);
+    if (ctx->arith == RLS_ARITH_FAST)
+        k_disney_sample_eval_pdf<true><<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), dev(*p), rx_s, ry_s, rx_d, ry_d, d, ctx->fallbacks);
+    else
+        k_disney_sample_eval_pdf<false><<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), dev(*p), rx_s, ry_s, rx_d, ry_d, d, ctx->fallbacks);
     RLS_LAUNCH_CHECK(ctx);
     return RLS_OK;
 }
@@ -576,7 +686,10 @@ static int launch_skin_profile(rls_context *ctx, cudaStream_t st, size_t n, cons
                                const float *rx, const rls_profile_out *o)
 {
     ProfileOutDev d; d.r = o->r; d.pdf = o->pdf; d.Rd = mv(o->Rd); d.flags = o->flags;
-    k_skin_profile<<<grid_for(n), kBlock, 0, st>>>(n, dev(*p), rx, d);
+    if (ctx->arith == RLS_ARITH_FAST)
+        k_skin_profile<true><<<grid_for(n), kBlock, 0, st>>>(n, dev(*p), rx, d, ctx->fallbacks);
+    else
+        k_skin_profile<false><<<grid_for(n), kBlock, 0, st>>>(n, dev(*p), rx, d, ctx->fallbacks);
     RLS_LAUNCH_CHECK(ctx);
     return RLS_OK;
 }
@@ -825,7 +938,10 @@ extern "C" int rls_albedo_sweep(rls_context *ctx, const rls_sweep_grid *grid, ui
     g.rlo = grid->roughness_lo; g.rhi = grid->roughness_hi; g.ilo = grid->ior_lo; g.ihi = grid->ior_hi;
     unsigned cells = (unsigned)(grid->n_rough * grid->n_cos * grid->n_ior);
     DeviceGuard guard(ctx->device);
-    k_albedo_sweep<<<cells, kBlock, 0, ctx->stream>>>(g, seed, spp_begin, spp_end, table);
+    if (ctx->arith == RLS_ARITH_FAST)
+        k_albedo_sweep<true><<<cells, kBlock, 0, ctx->stream>>>(g, seed, spp_begin, spp_end, table, ctx->fallbacks);
+    else
+        k_albedo_sweep<false><<<cells, kBlock, 0, ctx->stream>>>(g, seed, spp_begin, spp_end, table, ctx->fallbacks);
     RLS_LAUNCH_CHECK(ctx);
     return RLS_OK;
 }

@@ -20,22 +20,13 @@ namespace rls {
 struct Dielectric { float F, f_r, pdf_r, f_t, w_t; f3 wi_r, wi_t; uint32_t flags; };
 
 // G1's value part with the final 2/d as 2*(1/d): d = 1 + sqrt(..) lies in [2, 2^64] or is inf/NaN.
-RLS_DEV float ggx_G1_value2(const Ggx &g, float VdotN)
+template <class Fp>
+RLS_DEV float ggx_G1_value2(Fp &fp, const Ggx &g, float VdotN)
 {
     float cosSqr = sqr(VdotN);
-    float tanSqr = 1.0f / cosSqr - 1.0f;
-    float denominator = 1.0f + sqrtf(1.0f + sqr(g.rough) * tanSqr);
-    return 2.0f * (1.0f / denominator);
-}
-// Fresnel with the IOR ratio squared passed in (src/rlGgx.h:258: SQR(mIorOut / mIorIn)).
-RLS_DEV float ggx_fresnel_c(float ratio2, float c)
-{
-    float gSqr = ratio2 - 1.0f + c * c;
-    if (gSqr < 0.0f) return 1.0f;
-    float gg = sqrtf(gSqr);
-    float gmc = gg - c;
-    float gpc = gg + c;
-    return 0.5f * sqr(gmc / gpc) * (1.0f + sqr((c * gpc - 1.0f) / (c * gmc + 1.0f)));
+    float tanSqr = fp.rcp(cosSqr) - 1.0f;
+    float denominator = 1.0f + fp.sqrt(1.0f + sqr(g.rough) * tanSqr);
+    return 2.0f * fp.rcp(denominator);
 }
 
 // One GGX reflection evaluation + pdf at direction L, sharing the half vector, D and the
@@ -43,63 +34,66 @@ RLS_DEV float ggx_fresnel_c(float ratio2, float c)
 struct GgxShared {
     float VdotN, absVdotN, sgnV, G1v, ratio2;
 };
-RLS_DEV GgxShared ggx_shared(const Ggx &g)
+template <class Fp>
+RLS_DEV GgxShared ggx_shared(Fp &fp, const Ggx &g)
 {
     GgxShared s;
     s.VdotN = dot(g.wo, g.N);
     s.absVdotN = abs_m(s.VdotN);
     s.sgnV = sgn_m(s.VdotN);
-    s.G1v = ggx_G1_value2(g, s.VdotN);
-    s.ratio2 = sqr(g.iorOut / g.iorIn);
+    s.G1v = ggx_G1_value2(fp, g, s.VdotN);
+    s.ratio2 = sqr(fp.div(g.iorOut, g.iorIn));
     return s;
 }
 // Returns reflection(V, L, N) * dot(L, N) (KsColor applied by the caller) and the pdf.
-RLS_DEV void ggx_reflect_eval_pdf(const Ggx &g, const GgxShared &s, f3 L, float LdotN, float G1l,
+template <class Fp>
+RLS_DEV void ggx_reflect_eval_pdf(Fp &fp, const Ggx &g, const GgxShared &s, f3 L, float LdotN, float G1l,
                                   float &refl_cos, float &pdf)
 {
-    f3 H = normalize(L + g.wo);                       // o + i (brdf)  ==  V + L (pdf), bitwise
+    f3 H = normalize(fp, L + g.wo);                   // o + i (brdf)  ==  V + L (pdf), bitwise
     float VH = dot(g.wo, H);
     float LH = dot(L, H);
     // D(H): also D(hr) for hr = +-H
-    float D_H = ggx_D(g, H);
+    float D_H = ggx_D(fp, g, H);
     if (g.ndf) {                                      // NDFKernel::evalPdf (src/rlGgx.h:45-50)
-        pdf = D_H * abs_m(dot(H, g.N)) * 0.25f / abs_m(VH);
+        pdf = fp.div_pz(D_H * abs_m(dot(H, g.N)) * 0.25f, abs_m(VH));
     } else {                                          // VNDFKernel::evalPdf: G1(V, H, N), floored
         float G1_pdf = (VH * s.VdotN < 0.0f) ? 0.0f : s.G1v;
-        pdf = max_m(D_H * G1_pdf / s.absVdotN * 0.25f, kEps);
+        pdf = max_m(fp.div_pz(D_H * G1_pdf, s.absVdotN) * 0.25f, kEps);
     }
     // brdf: hr = sgn(V.N) * H
     float VHr = VH * s.sgnV, LHr = LH * s.sgnV;
-    float F = ggx_fresnel_c(s.ratio2, abs_m(VHr));
+    float F = ggx_fresnel_c(fp, s.ratio2, abs_m(VHr));
     float G1i = (VHr * s.VdotN < 0.0f) ? 0.0f : s.G1v;
     float G1o = (LHr * LdotN < 0.0f) ? 0.0f : G1l;
     float D_hr = (s.sgnV != 0.0f) ? D_H : __int_as_float(0x7f800000);   // D(0 vector) = 1/0
-    float refl = F * (G1i * G1o) * D_hr * 0.25f / (abs_m(LdotN) * s.absVdotN);
+    float refl = fp.div_pz(F * (G1i * G1o) * D_hr * 0.25f, abs_m(LdotN) * s.absVdotN);   // F or G may be 0
     refl_cos = refl;
 }
 
 // The rough-dielectric unit: src/rlGgx.h:228-243 loop body with the in-tree
 // getRefractDirection standing in for Arnold's AiRefractRay (same composition as the oracle).
-RLS_DEV Dielectric dielectric_unit(const Shading &sh, float ior, float rough, float aniso, float rx, float ry,
+template <class Fp>
+RLS_DEV Dielectric dielectric_unit(Fp &fp, const Shading &sh, float ior, float rough, float aniso, float rx, float ry,
                                    bool ndf = false)
 {
     Dielectric r;
     Ggx g;
-    ggx_init(g, sh, mk3(1.0f, 1.0f, 1.0f), ior, rough, aniso);
+    ggx_init(fp, g, sh, mk3(1.0f, 1.0f, 1.0f), ior, rough, aniso);
     g.ndf = ndf;
-    const GgxShared s = ggx_shared(g);
-    f3 m = ggx_sample_normal(g, rx, ry);
+    const GgxShared s = ggx_shared(fp, g);
+    f3 m = ggx_sample_normal(fp, g, rx, ry);
     float Vm = dot(g.wo, m);
     // reflectDirection(V, m) = 2|V.m| m - V
     r.wi_r = m * (2.0f * abs_m(Vm)) - g.wo;
-    r.F = ggx_fresnel_c(s.ratio2, abs_m(dot(r.wi_r, m)));
+    r.F = ggx_fresnel_c(fp, s.ratio2, abs_m(dot(r.wi_r, m)));
 
     // evalBrdf(wi_r) with white KsColor, evalPdf(wi_r)
     const f3 L = r.wi_r;
     const float LdotN = dot(L, g.N);
-    const float G1l = ggx_G1_value2(g, LdotN);
+    const float G1l = ggx_G1_value2(fp, g, LdotN);
     float refl;
-    ggx_reflect_eval_pdf(g, s, L, LdotN, G1l, refl, r.pdf_r);
+    ggx_reflect_eval_pdf(fp, g, s, L, LdotN, G1l, refl, r.pdf_r);
     const bool zeroL = is_zero(L);
     r.f_r = zeroL ? 0.0f : refl * LdotN;              // (1 * refl) * dot(L, N)
     uint32_t fl = 0;
@@ -111,7 +105,7 @@ RLS_DEV Dielectric dielectric_unit(const Shading &sh, float ior, float rough, fl
     if (g.entering) fl |= 0x0010u;
 
     // getRefractDirection(m, V): src/rlGgx.h:277-291
-    const float eta = g.iorIn / g.iorOut;
+    const float eta = fp.div(g.iorIn, g.iorOut);
     const float cosThetaTSqr = 1.0f + eta * (sqr(Vm) - 1.0f);
     const float mN = dot(m, g.N);
     float TdotN, G1t;
@@ -122,26 +116,26 @@ RLS_DEV Dielectric dielectric_unit(const Shading &sh, float ior, float rough, fl
         TdotN = LdotN;
         G1t = G1l;
     } else {
-        float sc = eta * Vm - s.sgnV * sqrtf(cosThetaTSqr);
+        float sc = eta * Vm - s.sgnV * fp.sqrt(cosThetaTSqr);
         f3 T = m * sc - g.wo * eta;
         r.wi_t = T;
         TdotN = dot(T, g.N);
-        G1t = ggx_G1_value2(g, TdotN);
+        G1t = ggx_G1_value2(fp, g, TdotN);
         // refraction(V, T, N): src/rlGgx.h:316-328
-        f3 ht = -normalize(g.wo * g.iorIn + T * g.iorOut);
+        f3 ht = -normalize(fp, g.wo * g.iorIn + T * g.iorOut);
         float IdotH = dot(g.wo, ht);
         float OdotH = dot(T, ht);
-        float refractWeight = 1.0f - ggx_fresnel_c(s.ratio2, abs_m(IdotH));
+        float refractWeight = 1.0f - ggx_fresnel_c(fp, s.ratio2, abs_m(IdotH));
         float denominator = abs_m(TdotN) * s.absVdotN * sqr(g.iorIn * IdotH + g.iorOut * OdotH);
         float G1i = (IdotH * s.VdotN < 0.0f) ? 0.0f : s.G1v;
         float G1o = (OdotH * TdotN < 0.0f) ? 0.0f : G1t;
-        r.f_t = abs_m(OdotH * IdotH) * sqr(g.iorOut) * refractWeight * (G1i * G1o) * ggx_D(g, ht) / denominator;
+        r.f_t = fp.div_pz(abs_m(OdotH * IdotH) * sqr(g.iorOut) * refractWeight * (G1i * G1o) * ggx_D(fp, g, ht), denominator);
     }
     // getSampleWeight(V, wi_t, m): src/rlGgx.h:294-301
     {
         float G1i = (Vm * s.VdotN < 0.0f) ? 0.0f : s.G1v;
         float G1o = (dot(r.wi_t, m) * TdotN < 0.0f) ? 0.0f : G1t;
-        r.w_t = (G1i * G1o) * abs_m(Vm / (s.absVdotN * abs_m(mN)));
+        r.w_t = (G1i * G1o) * abs_m(fp.div(Vm, s.absVdotN * abs_m(mN)));
     }
     r.flags = fl;
     return r;
@@ -149,16 +143,17 @@ RLS_DEV Dielectric dielectric_unit(const Shading &sh, float ior, float rough, fl
 
 // Fused rlGgx unit with a KsColor: ctor + evalSample + evalBrdf + evalPdf (+ the Fresnel term).
 struct GgxBsdf { f3 L, f; float pdf, fresnel; uint32_t flags; };
-RLS_DEV GgxBsdf ggx_unit(const Ggx &g, float rx, float ry)
+template <class Fp>
+RLS_DEV GgxBsdf ggx_unit(Fp &fp, const Ggx &g, float rx, float ry)
 {
     GgxBsdf o;
-    const GgxShared s = ggx_shared(g);
-    f3 m = ggx_sample_normal(g, rx, ry);
+    const GgxShared s = ggx_shared(fp, g);
+    f3 m = ggx_sample_normal(fp, g, rx, ry);
     o.L = m * (2.0f * abs_m(dot(g.wo, m))) - g.wo;
-    o.fresnel = ggx_fresnel_c(s.ratio2, abs_m(dot(o.L, m)));
+    o.fresnel = ggx_fresnel_c(fp, s.ratio2, abs_m(dot(o.L, m)));
     const float LdotN = dot(o.L, g.N);
     float refl;
-    ggx_reflect_eval_pdf(g, s, o.L, LdotN, ggx_G1_value2(g, LdotN), refl, o.pdf);
+    ggx_reflect_eval_pdf(fp, g, s, o.L, LdotN, ggx_G1_value2(fp, g, LdotN), refl, o.pdf);
     const bool black = is_zero(o.L) || (abs_m(g.ks.x) < kEps && abs_m(g.ks.y) < kEps && abs_m(g.ks.z) < kEps);
     o.f = black ? mk3(0.0f, 0.0f, 0.0f) : g.ks * refl * LdotN;
     o.flags = bsdf_flags(o.L, g.N, o.f, o.pdf);
@@ -180,7 +175,8 @@ namespace rls {
 // The local microfacet normal of both specular lobes goes through ONE rotate/normalize/reflect tail.
 struct DisneyOut1 { f3 Ls, fs, Ld, fd; float ps, pd; uint32_t flags; };
 
-RLS_DEV DisneyOut1 disney_unit(const Disney &d, float rx_s, float ry_s, float rx_d, float ry_d)
+template <class Fp>
+RLS_DEV DisneyOut1 disney_unit(Fp &fp, const Disney &d, float rx_s, float ry_s, float rx_d, float ry_d)
 {
     DisneyOut1 o;
     const float VdotN = dot(d.wo, d.N);
@@ -190,22 +186,22 @@ RLS_DEV DisneyOut1 disney_unit(const Disney &d, float rx_s, float ry_s, float rx
     const float gtr1_log = rlm::logf_(gtr1_a2);
     auto D_GTR1_shared = [&](float MdotN2) {
         float denominator = gtr1_log * (1.0f + (gtr1_a2 - 1.0f) * MdotN2);
-        return (gtr1_a2 - 1.0f) * kInvPi / denominator;
+        return fp.div((gtr1_a2 - 1.0f) * kInvPi, denominator);
     };
 
     // ---- specular sample (src/rlDisney.cpp:367-390)
     uint32_t lobe;
     f3 M;
     {
-        float gtr2Weight = 1.0f / (d.clearcoat + 1.0f);
+        float gtr2Weight = fp.rcp(d.clearcoat + 1.0f);
         if (rx_s < gtr2Weight) {
-            float rx = rx_s / gtr2Weight;
-            M = d.visibleNormal ? sample_visible_normal(d.wo, d.U, d.V, d.N, d.ax, d.ay, rx, ry_s)
-                                : sample_ndf_normal(d.U, d.V, d.N, d.ax, d.ay, ry_s, rx);
+            float rx = fp.div(rx_s, gtr2Weight);
+            M = d.visibleNormal ? sample_visible_normal(fp, d.wo, d.U, d.V, d.N, d.ax, d.ay, rx, ry_s)
+                                : sample_ndf_normal(fp, d.U, d.V, d.N, d.ax, d.ay, ry_s, rx);
             lobe = 0;
         } else {
-            float rx = (rx_s - gtr2Weight) / (1.0f - gtr2Weight);
-            M = disney_sample_gtr1(d, rx, ry_s);
+            float rx = fp.div_pz(rx_s - gtr2Weight, 1.0f - gtr2Weight);
+            M = disney_sample_gtr1(fp, d, rx, ry_s);
             lobe = 1;
         }
     }
@@ -219,24 +215,24 @@ RLS_DEV DisneyOut1 disney_unit(const Disney &d, float rx_s, float ry_s, float rx
     } else {
         const f3 L = o.Ls;
         const float LdotN = dot(L, d.N);                     // == dot(N, L) bitwise
-        const f3 H = normalize(L + d.wo);
+        const f3 H = normalize(fp, L + d.wo);
         const float LdotM = dot(L, H);
         const float NdotM = dot(d.N, H);                     // == dot(H, N) bitwise
         const float NdotM2 = sqr(NdotM);
-        const float Ds = D_GTR2Aniso(d, H, NdotM2);
+        const float Ds = D_GTR2Aniso(fp, d, H, NdotM2);
         const float Dr = D_GTR1_shared(NdotM2);
         // pdf (:520-543)
         if (NdotM < 0.0f) {
             o.ps = 0.0f;
         } else {
             const float IdotM = abs_m(LdotM);
-            const float clearcoatWeight = d.clearcoat / (d.clearcoat + 1.0f);
+            const float clearcoatWeight = fp.div_pz(d.clearcoat, d.clearcoat + 1.0f);
             if (d.visibleNormal) {
                 const float Vn = max_m(1e-4f, VdotN);
-                const float Dw = smithG_GGX(IdotM, d.specRough) * Ds * 2.0f * IdotM / Vn;
-                o.ps = lerp_m(clearcoatWeight, Dw, Dr * abs_m(NdotM) / IdotM) * 0.25f;
+                const float Dw = fp.div(smithG_GGX(fp, IdotM, d.specRough) * Ds * 2.0f * IdotM, Vn);
+                o.ps = lerp_m(clearcoatWeight, Dw, fp.div(Dr * abs_m(NdotM), IdotM)) * 0.25f;
             } else {
-                o.ps = lerp_m(clearcoatWeight, Ds, Dr) * abs_m(NdotM) * 0.25f / IdotM;
+                o.ps = fp.div(lerp_m(clearcoatWeight, Ds, Dr) * abs_m(NdotM) * 0.25f, IdotM);
             }
         }
         // eval (:318-356) x N.L (:136)
@@ -245,9 +241,9 @@ RLS_DEV DisneyOut1 disney_unit(const Disney &d, float rx_s, float ry_s, float rx
         } else {
             const float FH = rlm::powf_(clamp_m(1.0f - LdotM, 0.0f, 1.0f), 5.0f);
             const f3 Fs = lerp_m(FH, d.F0, mk3(1.0f, 1.0f, 1.0f));
-            const float Gs = smithG_GGX(LdotN, d.specRough) * smithG_GGX(VdotN, d.specRough);
+            const float Gs = smithG_GGX(fp, LdotN, d.specRough) * smithG_GGX(fp, VdotN, d.specRough);
             const float Fr = lerp_m(FH, 0.04f, 1.0f);
-            const float Gr = smithG_GGX(LdotN, 0.25f) * smithG_GGX(VdotN, 0.25f);
+            const float Gr = smithG_GGX(fp, LdotN, 0.25f) * smithG_GGX(fp, VdotN, 0.25f);
             const f3 Fsheen = d.sheenColor * FH * (1.0f - d.metallic);
             const f3 spec = Fs * Ds * Gs;
             const float coat = d.clearcoat * Dr * Fr * Gr;
@@ -256,9 +252,9 @@ RLS_DEV DisneyOut1 disney_unit(const Disney &d, float rx_s, float ry_s, float rx
     }
 
     // ---- diffuse triple (src/rlDisney.cpp:359-365, 199-236, 515-518)
-    o.Ld = disney_sample_diffuse(d, rx_d, ry_d);
-    o.fd = disney_eval_brdf(d, kRayDiffuse, o.Ld);
-    o.pd = disney_eval_pdf(d, kRayDiffuse, o.Ld);
+    o.Ld = disney_sample_diffuse(fp, d, rx_d, ry_d);
+    o.fd = disney_eval_brdf(fp, d, kRayDiffuse, o.Ld);
+    o.pd = disney_eval_pdf(fp, d, kRayDiffuse, o.Ld);
 
     const uint32_t fls = (bsdf_flags(o.Ls, d.N, o.fs, o.ps) & ~0x0040u) | (lobe << 8);
     const uint32_t fld = bsdf_flags(o.Ld, d.N, o.fd, o.pd);

@@ -10,11 +10,12 @@ namespace rls {
 
 // ---------------------------------------------------------------- rlUtil helpers
 // src/rlUtil.h:21-29
-RLS_DEV f3 spherical_direction(float cosTheta, float phi)
+template <class Fp>
+RLS_DEV f3 spherical_direction(Fp &fp, float cosTheta, float phi)
 {
     float s, c;
     rlm::sincosf_(phi, &s, &c);
-    float r = sqrtf(1.0f - sqr(cosTheta));
+    float r = fp.sqrt(1.0f - sqr(cosTheta));
     return mk3(r * c, r * s, cosTheta);
 }
 // src/rlUtil.h:31-34 -- 2*ABS(i.n)*n - i
@@ -26,7 +27,8 @@ RLS_DEV f3 reflect_direction(f3 i, f3 n)
 // src/rlUtil.h:36-39
 RLS_DEV float color_to_luminance(f3 c) { return c.x * 0.212671f + c.y * 0.715160f + c.z * 0.072169f; }
 // src/rlUtil.cpp:3-27 (x, y only; callers overwrite z)
-RLS_DEV f2 concentric_disk_sample(float rx, float ry)
+template <class Fp>
+RLS_DEV f2 concentric_disk_sample(Fp &fp, float rx, float ry)
 {
     rx = rx * 2.0f - 1.0f;
     ry = ry * 2.0f - 1.0f;
@@ -35,10 +37,10 @@ RLS_DEV f2 concentric_disk_sample(float rx, float ry)
     float r, phi;
     if (abs_m(rx) > abs_m(ry)) {
         r = rx;
-        phi = kHalfPi * 0.5f * ry / rx;
+        phi = fp.div(kHalfPi * 0.5f * ry, rx);
     } else {
         r = ry;
-        phi = kHalfPi * (1.0f - 0.5f * rx / ry);
+        phi = kHalfPi * (1.0f - fp.div(0.5f * rx, ry));
     }
     float s, c;
     rlm::sincosf_(phi, &s, &c);
@@ -49,9 +51,10 @@ RLS_DEV f2 concentric_disk_sample(float rx, float ry)
 
 // ------------------------------------------- visible-normal sampling (Heitz-d'Eon)
 // src/rlGgx.cpp:18-25
-RLS_DEV f2 uniform_slope(float rx, float ry)
+template <class Fp>
+RLS_DEV f2 uniform_slope(Fp &fp, float rx, float ry)
 {
-    float r = sqrtf(rx / (1.0f - rx));
+    float r = fp.sqrt(fp.div(rx, 1.0f - rx));
     float phi = kTwoPi * ry;
     float s, c;
     rlm::sincosf_(phi, &s, &c);
@@ -59,24 +62,25 @@ RLS_DEV f2 uniform_slope(float rx, float ry)
     return o;
 }
 // src/rlGgx.cpp:14-61 (VNDFKernel::sampleSlope); rlDisney.cpp:416-463 is the same code.
-RLS_DEV f2 sample_slope(float theta, float rx, float ry)
+template <class Fp>
+RLS_DEV f2 sample_slope(Fp &fp, float theta, float rx, float ry)
 {
-    if (theta < kEps) return uniform_slope(rx, ry);
+    if (theta < kEps) return uniform_slope(fp, rx, ry);
 
-    float B = rlm::tanf_(theta);
+    float B = rlm::tanf_(fp, theta);
     float B2 = sqr(B);
-    float G1 = 2.0f * (1.0f / (1.0f + sqrtf(1.0f + B2)));   // == 2/(..) bitwise: the divisor is in [2, 2^64]
+    float G1 = 2.0f * fp.rcp(1.0f + fp.sqrt(1.0f + B2));   // == 2/(..) bitwise: the divisor is in [2, 2^64]
 
-    float A = 2.0f * rx / G1 - 1.0f;
+    float A = fp.div(2.0f * rx, G1) - 1.0f;
     float A2 = sqr(A);
-    if (abs_m(A2 - 1.0f) < kEps) return uniform_slope(rx, ry);
+    if (abs_m(A2 - 1.0f) < kEps) return uniform_slope(fp, rx, ry);
 
-    float tmp = 1.0f / (A2 - 1.0f);
-    float D = sqrtf(max_m(0.0f, B2 * sqr(tmp) - (A2 - B2) * tmp));
+    float tmp = fp.rcp(A2 - 1.0f);
+    float D = fp.sqrt(max_m(0.0f, B2 * sqr(tmp) - (A2 - B2) * tmp));
     float slopeX1 = B * tmp - D;
     float slopeX2 = B * tmp + D;
     f2 slope;
-    slope.x = (A < 0.0f || slopeX2 > 1.0f / B) ? slopeX1 : slopeX2;
+    slope.x = (A < 0.0f || slopeX2 > fp.rcp(B)) ? slopeX1 : slopeX2;
 
     float sign = 1.0f;
     if (ry > 0.5f) {
@@ -85,28 +89,29 @@ RLS_DEV f2 sample_slope(float theta, float rx, float ry)
         sign = -1.0f;
         ry = 2.0f * (0.5f - ry);
     }
-    float z = (ry * (ry * (ry * 0.27385f - 0.73369f) + 0.46341f))
-            / (ry * (ry * (ry * 0.093073f + 0.309420f) - 1.0f) + 0.597999f);
-    slope.y = sign * z * sqrtf(1.0f + sqr(slope.x));
+    float z = fp.div(ry * (ry * (ry * 0.27385f - 0.73369f) + 0.46341f),
+                     ry * (ry * (ry * 0.093073f + 0.309420f) - 1.0f) + 0.597999f);
+    slope.y = sign * z * fp.sqrt(1.0f + sqr(slope.x));
     return slope;
 }
 // src/rlGgx.cpp:63-99 (VNDFKernel::evalSample); rlDisney.cpp:467-502 is the same code.
-RLS_DEV f3 sample_visible_normal(f3 view, f3 U, f3 Vax, f3 N, float ax, float ay, float rx, float ry)
+template <class Fp>
+RLS_DEV f3 sample_visible_normal(Fp &fp, f3 view, f3 U, f3 Vax, f3 N, float ax, float ay, float rx, float ry)
 {
     float cosThetaV = clamp_m(dot(N, view), -1.0f, 1.0f);
-    float phiV = rlm::atan2f_(dot(Vax, view), dot(U, view));
-    f3 V = spherical_direction(cosThetaV, phiV);
+    float phiV = rlm::atan2f_(fp, dot(Vax, view), dot(U, view));
+    f3 V = spherical_direction(fp, cosThetaV, phiV);
 
     V.x *= ax;
     V.y *= ay;
-    V = normalize(V);
+    V = normalize(fp, V);
 
     float theta = 0.0f, phi = 0.0f;
     if (V.z < (1.0f - kEps)) {
-        theta = rlm::acosf_(V.z);
-        phi = rlm::atan2f_(V.y, V.x);
+        theta = rlm::acosf_(fp, V.z);
+        phi = rlm::atan2f_(fp, V.y, V.x);
     }
-    f2 slope = sample_slope(theta, rx, ry);
+    f2 slope = sample_slope(fp, theta, rx, ry);
 
     float sinPhi, cosPhi;
     rlm::sincosf_(phi, &sinPhi, &cosPhi);
@@ -114,19 +119,20 @@ RLS_DEV f3 sample_visible_normal(f3 view, f3 U, f3 Vax, f3 N, float ax, float ay
     omega.x = -(cosPhi * slope.x - sinPhi * slope.y) * ax;
     omega.y = -(sinPhi * slope.x + cosPhi * slope.y) * ay;
     omega.z = 1.0f;
-    return normalize(rotate_to_frame(omega, U, Vax, N));
+    return normalize(fp, rotate_to_frame(omega, U, Vax, N));
 }
 
 // src/rlGgx.h:33-41 (NDFKernel::evalSample, Burley Eq.14): plain NDF sampling; also
 // DisneySampler::sampleGTR2AnisoDirection (src/rlDisney.cpp:406-414) with (rx, ry) swapped.
-RLS_DEV f3 sample_ndf_normal(f3 U, f3 Vax, f3 N, float ax, float ay, float rx, float ry)
+template <class Fp>
+RLS_DEV f3 sample_ndf_normal(Fp &fp, f3 U, f3 Vax, f3 N, float ax, float ay, float rx, float ry)
 {
-    float g = sqrtf(rx / (1.0f - rx));
+    float g = fp.sqrt(fp.div(rx, 1.0f - rx));
     float phi = kTwoPi * ry;
     float s, c;
     rlm::sincosf_(phi, &s, &c);
     f3 omega = mk3(g * ax * c, g * ay * s, 1.0f);
-    return normalize(rotate_to_frame(omega, U, Vax, N));
+    return normalize(fp, rotate_to_frame(omega, U, Vax, N));
 }
 
 // ------------------------------------------------------------------------ rlGgx
@@ -136,14 +142,16 @@ struct Ggx {
     bool entering;
     bool ndf;        // GgxSamplerT<NDFKernel> instead of the shipped GgxSamplerT<VNDFKernel>
 };
-RLS_DEV f3 ggx_sample_normal(const Ggx &g, float rx, float ry)
+template <class Fp>
+RLS_DEV f3 ggx_sample_normal(Fp &fp, const Ggx &g, float rx, float ry)
 {
-    if (g.ndf) return sample_ndf_normal(g.U, g.V, g.N, g.ax, g.ay, rx, ry);
-    return sample_visible_normal(g.wo, g.U, g.V, g.N, g.ax, g.ay, rx, ry);
+    if (g.ndf) return sample_ndf_normal(fp, g.U, g.V, g.N, g.ax, g.ay, rx, ry);
+    return sample_visible_normal(fp, g.wo, g.U, g.V, g.N, g.ax, g.ay, rx, ry);
 }
 
 // src/rlGgx.h:130-156 (GgxSamplerT ctor)
-RLS_DEV void ggx_init(Ggx &g, const Shading &sh, f3 ks, float ior, float roughness, float aniso)
+template <class Fp>
+RLS_DEV void ggx_init(Fp &fp, Ggx &g, const Shading &sh, f3 ks, float ior, float roughness, float aniso)
 {
     f3 Ngeo = sh.backfacing ? -sh.N : sh.N;      // sg->N
     f3 Rd = -sh.wo;                              // sg->Rd
@@ -153,112 +161,128 @@ RLS_DEV void ggx_init(Ggx &g, const Shading &sh, f3 ks, float ior, float roughne
     g.iorOut = g.entering ? b : a;
     g.wo = sh.wo;                                // :144  -(-wo) is exact
     g.U = sh.U; g.V = sh.V; g.N = sh.N;          // :145-146, explicit frame
-    float aspect = sqrtf(1.0f - aniso * 0.9f);   // :148
-    g.ax = max_m(1e-4f, sqr(roughness) / aspect);
+    float aspect = fp.sqrt(1.0f - aniso * 0.9f); // :148
+    g.ax = max_m(1e-4f, fp.div_pz(sqr(roughness), aspect));   // roughness 0 is a legal parameter
     g.ay = max_m(1e-4f, sqr(roughness) * aspect);
     g.rough = max_m(1e-5f, sqr(roughness));      // :155
     g.ks = ks;
     g.ndf = false;
 }
 // src/rlGgx.h:249-270
-RLS_DEV float ggx_fresnel(const Ggx &g, f3 i, f3 m)
+// Walter Eq.22 given c = |i.m| and ratio2 = SQR(mIorOut / mIorIn) (:258)
+template <class Fp>
+RLS_DEV float ggx_fresnel_c(Fp &fp, float ratio2, float c)
 {
-    float c = abs_m(dot(i, m));
-    float gSqr = sqr(g.iorOut / g.iorIn) - 1.0f + c * c;
+    float gSqr = ratio2 - 1.0f + c * c;
     if (gSqr < 0.0f) return 1.0f;
-    float gg = sqrtf(gSqr);
+    float gg = fp.sqrt(gSqr);
     float gmc = gg - c;
     float gpc = gg + c;
-    return 0.5f * sqr(gmc / gpc) * (1.0f + sqr((c * gpc - 1.0f) / (c * gmc + 1.0f)));
+    // gmc == 0 for ior 1 (a legal parameter): zero-tolerant numerator over gpc > 0
+    return 0.5f * sqr(fp.div_pz(gmc, gpc)) * (1.0f + sqr(fp.div(c * gpc - 1.0f, c * gmc + 1.0f)));
+}
+template <class Fp>
+RLS_DEV float ggx_fresnel(Fp &fp, const Ggx &g, f3 i, f3 m)
+{
+    return ggx_fresnel_c(fp, sqr(fp.div(g.iorOut, g.iorIn)), abs_m(dot(i, m)));
 }
 // src/rlGgx.h:343-357, split so the view-only half can be shared: the masking value
 // depends on (v.n) only, the zero test on sign(v.m * v.n).
-RLS_DEV float ggx_G1_value(const Ggx &g, float VdotN)
+template <class Fp>
+RLS_DEV float ggx_G1_value(Fp &fp, const Ggx &g, float VdotN)
 {
     float cosSqr = sqr(VdotN);
-    float tanSqr = 1.0f / cosSqr - 1.0f;
-    float denominator = 1.0f + sqrtf(1.0f + sqr(g.rough) * tanSqr);
-    return 2.0f / denominator;
+    float tanSqr = fp.rcp(cosSqr) - 1.0f;
+    float denominator = 1.0f + fp.sqrt(1.0f + sqr(g.rough) * tanSqr);
+    return fp.div(2.0f, denominator);
 }
-RLS_DEV float ggx_G1(const Ggx &g, f3 v, f3 m, f3 n)
+template <class Fp>
+RLS_DEV float ggx_G1(Fp &fp, const Ggx &g, f3 v, f3 m, f3 n)
 {
     float VdotM = dot(v, m);
     float VdotN = dot(v, n);
     if (VdotM * VdotN < 0.0f) return 0.0f;
-    return ggx_G1_value(g, VdotN);
+    return ggx_G1_value(fp, g, VdotN);
 }
 // src/rlGgx.h:332-340
-RLS_DEV float ggx_D(const Ggx &g, f3 m)
+template <class Fp>
+RLS_DEV float ggx_D(Fp &fp, const Ggx &g, f3 m)
 {
     float MdotU = dot(m, g.U);
     float MdotV = dot(m, g.V);
     float MdotN2 = sqr(dot(g.N, m));
-    float denominator = g.ax * g.ay * sqr(sqr(MdotU / g.ax) + sqr(MdotV / g.ay) + MdotN2);
-    return kInvPi / denominator;
+    float denominator = g.ax * g.ay * sqr(sqr(fp.div(MdotU, g.ax)) + sqr(fp.div(MdotV, g.ay)) + MdotN2);
+    return fp.div(kInvPi, denominator);
 }
 // src/rlGgx.h:304-313
-RLS_DEV float ggx_reflection(const Ggx &g, f3 i, f3 o, f3 n)
+template <class Fp>
+RLS_DEV float ggx_reflection(Fp &fp, const Ggx &g, f3 i, f3 o, f3 n)
 {
-    f3 hr = normalize(o + i) * sgn_m(dot(i, n));
-    float reflectWeight = ggx_fresnel(g, i, hr);
+    f3 hr = normalize(fp, o + i) * sgn_m(dot(i, n));
+    float reflectWeight = ggx_fresnel(fp, g, i, hr);
     float LdotN = abs_m(dot(o, n));
     float VdotN = abs_m(dot(i, n));
-    float G = ggx_G1(g, i, hr, n) * ggx_G1(g, o, hr, n);
-    return reflectWeight * G * ggx_D(g, hr) * 0.25f / (LdotN * VdotN);
+    float G = ggx_G1(fp, g, i, hr, n) * ggx_G1(fp, g, o, hr, n);
+    return fp.div_pz(reflectWeight * G * ggx_D(fp, g, hr) * 0.25f, LdotN * VdotN);   // F or G may be 0
 }
 // src/rlGgx.h:316-328
-RLS_DEV float ggx_refraction(const Ggx &g, f3 i, f3 o, f3 n)
+template <class Fp>
+RLS_DEV float ggx_refraction(Fp &fp, const Ggx &g, f3 i, f3 o, f3 n)
 {
-    f3 ht = -normalize(i * g.iorIn + o * g.iorOut);
-    float refractWeight = 1.0f - ggx_fresnel(g, i, ht);
+    f3 ht = -normalize(fp, i * g.iorIn + o * g.iorOut);
+    float refractWeight = 1.0f - ggx_fresnel(fp, g, i, ht);
     float OdotN = abs_m(dot(o, n));
     float IdotN = abs_m(dot(i, n));
     float OdotH = dot(o, ht);
     float IdotH = dot(i, ht);
     float denominator = OdotN * IdotN * sqr(g.iorIn * IdotH + g.iorOut * OdotH);
-    float G = ggx_G1(g, i, ht, n) * ggx_G1(g, o, ht, n);
-    return abs_m(OdotH * IdotH) * sqr(g.iorOut) * refractWeight * G * ggx_D(g, ht) / denominator;
+    float G = ggx_G1(fp, g, i, ht, n) * ggx_G1(fp, g, o, ht, n);
+    return fp.div_pz(abs_m(OdotH * IdotH) * sqr(g.iorOut) * refractWeight * G * ggx_D(fp, g, ht), denominator);
 }
 // src/rlGgx.h:277-291 (eta is NOT squared, as in the reference)
-RLS_DEV bool ggx_refract_direction(const Ggx &g, f3 m, f3 i, f3 &dir)
+template <class Fp>
+RLS_DEV bool ggx_refract_direction(Fp &fp, const Ggx &g, f3 m, f3 i, f3 &dir)
 {
     float sign = sgn_m(dot(i, g.N));
     float IdotM = dot(i, m);
-    float eta = g.iorIn / g.iorOut;
+    float eta = fp.div(g.iorIn, g.iorOut);
     float cosThetaTSqr = 1.0f + eta * (sqr(IdotM) - 1.0f);
     if (cosThetaTSqr < 0.0f) return false;
-    float s = eta * IdotM - sign * sqrtf(cosThetaTSqr);
+    float s = eta * IdotM - sign * fp.sqrt(cosThetaTSqr);
     dir = m * s - i * eta;
     return true;
 }
 // src/rlGgx.h:294-301
-RLS_DEV float ggx_sample_weight(const Ggx &g, f3 i, f3 o, f3 m)
+template <class Fp>
+RLS_DEV float ggx_sample_weight(Fp &fp, const Ggx &g, f3 i, f3 o, f3 m)
 {
     float IdotH = dot(i, m);
     float MdotN = abs_m(dot(m, g.N));
     float IdotN = abs_m(dot(i, g.N));
-    float G = ggx_G1(g, i, m, g.N) * ggx_G1(g, o, m, g.N);
-    return G * abs_m(IdotH / (IdotN * MdotN));
+    float G = ggx_G1(fp, g, i, m, g.N) * ggx_G1(fp, g, o, m, g.N);
+    return G * abs_m(fp.div(IdotH, IdotN * MdotN));
 }
 // src/rlGgx.h:110-119,158-165
-RLS_DEV f3 ggx_eval_brdf(const Ggx &g, f3 L)
+template <class Fp>
+RLS_DEV f3 ggx_eval_brdf(Fp &fp, const Ggx &g, f3 L)
 {
     if (is_zero(L)) return mk3(0.0f, 0.0f, 0.0f);
     if (abs_m(g.ks.x) < kEps && abs_m(g.ks.y) < kEps && abs_m(g.ks.z) < kEps) return mk3(0.0f, 0.0f, 0.0f);
-    float refl = ggx_reflection(g, g.wo, L, g.N);
+    float refl = ggx_reflection(fp, g, g.wo, L, g.N);
     return g.ks * refl * dot(L, g.N);
 }
 // src/rlGgx.h:121-127 with VNDFKernel::evalPdf :72-80 (floored at AI_EPSILON, no zero-L guard)
-RLS_DEV float ggx_eval_pdf(const Ggx &g, f3 L)
+template <class Fp>
+RLS_DEV float ggx_eval_pdf(Fp &fp, const Ggx &g, f3 L)
 {
-    f3 H = normalize(g.wo + L);
+    f3 H = normalize(fp, g.wo + L);
     if (g.ndf) {                                  // NDFKernel::evalPdf src/rlGgx.h:45-50, no floor
         float IdotM = abs_m(dot(g.wo, H));
         float MdotN = abs_m(dot(H, g.N));
-        return ggx_D(g, H) * MdotN * 0.25f / IdotM;
+        return fp.div_pz(ggx_D(fp, g, H) * MdotN * 0.25f, IdotM);
     }
     float IdotN = abs_m(dot(g.wo, g.N));
-    float pdf = ggx_D(g, H) * ggx_G1(g, g.wo, H, g.N) / IdotN * 0.25f;
+    float pdf = fp.div_pz(ggx_D(fp, g, H) * ggx_G1(fp, g, g.wo, H, g.N), IdotN) * 0.25f;
     return max_m(pdf, kEps);
 }
 

@@ -33,6 +33,7 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
+#include "rls_fp.cuh"
 
 #if defined(__CUDACC__)
 #define RLM_HD __host__ __device__ __forceinline__
@@ -228,7 +229,8 @@ RLM_HD void sincosf_(float y, float *sinp, float *cosp)
 // fdlibm k_tanf.c (binary32), written with selects instead of branches: every lane runs the
 // same instruction stream (one polynomial, one division) whichever of the routine's three
 // regimes it is in.  Each regime's arithmetic is operation-for-operation the original.
-RLM_HD float kernel_tanf(float x, float y, int iy)
+template <class Fp>
+RLM_HD float kernel_tanf(Fp &fp, float x, float y, int iy)
 {
     const float pio4 = 7.8539812565e-01f, pio4lo = 3.7748947079e-08f;
     const float T0 = 3.3333334327e-01f, T1 = 1.3333334029e-01f, T2 = 5.3968254477e-02f,
@@ -260,7 +262,7 @@ RLM_HD float kernel_tanf(float x, float y, int iy)
     r += T0 * s;
     w = x + r;
     // the one division: w*w/(w+iy) (big) or -1/w (small, iy == -1)
-    float q = (big ? w * w : -1.0f) / (big ? w + fiy : w);
+    float q = fp.div(big ? w * w : -1.0f, big ? w + fiy : w);
     float res_big = sgn_big * (fiy - 2.0f * (x - (q - r)));
     // -1/(x+r), accurately
     float zt = u2f(f2u(w) & 0xfffff000u);
@@ -282,7 +284,8 @@ RLM_HD float kernel_tanf(float x, float y, int iy)
 // glibc 2.39 s_tanf.c with the binary64 reduce_fast of e_rem_pio2f.c.  For |x| <= pi/4 the host
 // skips the reduction; reducing anyway gives n = 0, y0 = x, y1 = 0 -- the same kernel call -- so
 // one path serves both.
-RLM_HD float tanf_(float x)
+template <class Fp>
+RLM_HD float tanf_(Fp &fp, float x)
 {
     uint32_t ix = f2u(x) & 0x7fffffffu;
     if (ix >= 0x7f800000u) return x - x;
@@ -299,13 +302,15 @@ RLM_HD float tanf_(float x)
     }
     float y0 = (float)dx;
     float y1 = (float)(dx - (double)y0);
-    return kernel_tanf(y0, y1, 1 - ((n & 1) << 1));
+    return kernel_tanf(fp, y0, y1, 1 - ((n & 1) << 1));
 }
+RLM_HD float tanf_(float x) { rls::FpExact fp; return tanf_(fp, x); }
 
 // ==================================================================== atanf
 // fdlibm s_atanf.c (binary32) with the five argument-reduction branches folded into selects:
 // one division (x/1 == x in the unreduced range), one polynomial.
-RLM_HD float atanf_(float x)
+template <class Fp>
+RLM_HD float atanf_(Fp &fp, float x)
 {
     const float aT0 = 3.3333334327e-01f, aT1 = -2.0000000298e-01f, aT2 = 1.4285714924e-01f,
                 aT3 = -1.1111110449e-01f, aT4 = 9.0908870101e-02f, aT5 = -7.6918758452e-02f,
@@ -327,7 +332,7 @@ RLM_HD float atanf_(float x)
     float den = r0 ? 1.0f : (r1 ? 2.0f + ax : (r2 ? ax + 1.0f : (r3 ? 1.0f + 1.5f * ax : ax)));
     float hi = r1 ? 4.6364760399e-01f : (r2 ? 7.8539812565e-01f : (r3 ? 9.8279368877e-01f : 1.5707962513e+00f));
     float lo = r1 ? 5.0121582440e-09f : (r2 ? 3.7748947079e-08f : (r3 ? 3.4473217170e-08f : 7.5497894159e-08f));
-    float t = num / den;
+    float t = fp.div_pz(num, den);               // den >= 1; num is 0 for |x| == 0, 0.5, 1, 1.5
     float z = t * t;
     float w = z * z;
     float s1 = z * (aT0 + w * (aT2 + w * (aT4 + w * (aT6 + w * (aT8 + w * aT10)))));
@@ -337,10 +342,12 @@ RLM_HD float atanf_(float x)
     float zz = hi - ((ts - lo) - t);
     return (hx < 0) ? -zz : zz;
 }
+RLM_HD float atanf_(float x) { rls::FpExact fp; return atanf_(fp, x); }
 
 // =================================================================== atan2f
 // fdlibm e_atan2f.c (binary32)
-RLM_HD float atan2f_(float y, float x)
+template <class Fp>
+RLM_HD float atan2f_(Fp &fp, float y, float x)
 {
     const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f,
                 pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f;
@@ -348,7 +355,7 @@ RLM_HD float atan2f_(float y, float x)
     int32_t hx = (int32_t)f2u(x), hy = (int32_t)f2u(y);
     int32_t ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
     if (ix > 0x7f800000 || iy > 0x7f800000) return x + y;
-    if (hx == 0x3f800000) return atanf_(y);
+    if (hx == 0x3f800000) return atanf_(fp, y);
     int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
     if (iy == 0) {
         switch (m) {
@@ -379,7 +386,7 @@ RLM_HD float atan2f_(float y, float x)
     int32_t k = (iy - ix) >> 23;
     if (k > 60) z = pi_o_2 + 0.5f * pi_lo;
     else if (hx < 0 && k < -60) z = 0.0f;
-    else z = atanf_(fabsf_(y / x));
+    else z = atanf_(fp, fabsf_(fp.div_z(y, x)));     // only |y/x| is used
     switch (m) {
     case 0: return z;
     case 1: return u2f(f2u(z) ^ 0x80000000u);
@@ -387,12 +394,14 @@ RLM_HD float atan2f_(float y, float x)
     default: return (z - pi_lo) - pi;
     }
 }
+RLM_HD float atan2f_(float y, float x) { rls::FpExact fp; return atan2f_(fp, y, x); }
 
 // ==================================================================== acosf
 // fdlibm e_acosf.c (binary32) as shipped by glibc 2.39 (six-term P, four-term Q), with the
 // three ranges sharing one P/Q evaluation: z = x*x for |x| < 0.5, else (1 - |x|)/2
 // ((1 + x)*0.5 for x < -0.5 is the same IEEE operation as (1 - |x|)*0.5).
-RLM_HD float acosf_(float x)
+template <class Fp>
+RLM_HD float acosf_(Fp &fp, float x)
 {
     const float pi = 3.1415925026e+00f, pio2_hi = 1.5707962513e+00f, pio2_lo = 7.5497894159e-08f;
     const float pS0 = 1.6666667163e-01f, pS1 = -3.2556581497e-01f, pS2 = 2.0121252537e-01f,
@@ -409,21 +418,22 @@ RLM_HD float acosf_(float x)
     const float z = small ? x * x : (1.0f - fabsf_(x)) * 0.5f;
     const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
     const float q = 1.0f + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
-    const float r = p / q;
+    const float r = fp.div_pz(p, q);           // q in (0.2, 1]; p == 0 for x == 0
     if (small) {
         if (ix <= 0x32800000) return pio2_hi + pio2_lo;
         return pio2_hi - (x - (pio2_lo - x * r));
     }
-    const float s = sqrtf_(z);
+    const float s = fp.sqrt(z);
     if (hx < 0) {                              // x < -0.5
         float w = r * s - pio2_lo;
         return pi - 2.0f * (s + w);
     }
     const float df = u2f(f2u(s) & 0xfffff000u);
-    const float c = (z - df * df) / (s + df);
+    const float c = fp.div_pz(z - df * df, s + df);
     const float w = r * s + c;
     return 2.0f * (df + w);
 }
+RLM_HD float acosf_(float x) { rls::FpExact fp; return acosf_(fp, x); }
 
 // ===================================================================== expf
 // glibc 2.39 e_expf.c (ARM Optimized Routines), FMA build

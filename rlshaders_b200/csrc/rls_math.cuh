@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "rls_fp.cuh"
 
 #define RLS_DEV __device__ __forceinline__
 
@@ -43,14 +44,16 @@ RLS_DEV float clamp_m(float v, float lo, float hi) { return (v < lo) ? lo : ((v 
 RLS_DEV float sgn_m(float a) { return (a < 0.0f) ? -1.0f : ((a > 0.0f) ? 1.0f : 0.0f); }
 RLS_DEV float lerp_m(float t, float a, float b) { return (1.0f - t) * a + b * t; }
 RLS_DEV f3    lerp_m(float t, f3 a, f3 b) { return a * (1.0f - t) + b * t; }
-RLS_DEV float linearstep_m(float lo, float hi, float t) { return clamp_m((t - lo) / (hi - lo), 0.0f, 1.0f); }
+template <class Fp>
+RLS_DEV float linearstep_m(Fp &fp, float lo, float hi, float t) { return clamp_m(fp.div_pz(t - lo, hi - lo), 0.0f, 1.0f); }
 
 // AiV3Normalize: reciprocal, then three multiplies; the zero vector stays zero.
-RLS_DEV f3 normalize(f3 a)
+template <class Fp>
+RLS_DEV f3 normalize(Fp &fp, f3 a)
 {
-    float len = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
-    if (len != 0.0f) {
-        float inv = 1.0f / len;
+    float len = fp.sqrt(a.x * a.x + a.y * a.y + a.z * a.z);
+    if (Fp::kFast || len != 0.0f) {              // fast policy: a zero length has already left the window
+        float inv = fp.rcp(len);
         return mk3(a.x * inv, a.y * inv, a.z * inv);
     }
     return a;

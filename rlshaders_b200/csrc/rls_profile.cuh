@@ -11,65 +11,70 @@ struct NdProfile { float d[3], C1[3], C2[3], R; };
 
 // src/rlSss.cpp:20-34.  The `s` of :23 (powf of the albedo luminance) is dead code in the
 // reference and is not evaluated; the albedo therefore does not enter the profile.
-RLS_DEV void nd_set_distance(NdProfile &p, f3 dist)
+template <class Fp>
+RLS_DEV void nd_set_distance(Fp &fp, NdProfile &p, f3 dist)
 {
     p.d[0] = dist.x; p.d[1] = dist.y; p.d[2] = dist.z;
     p.R = max_m(dist.x, max_m(dist.y, dist.z)) * 3.0f;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         float d = p.d[i];
-        p.C1[i] = 1.0f - rlm::expf_(-p.R / d);
-        p.C2[i] = 1.0f - rlm::expf_(-p.R / d / 3.0f);
+        p.C1[i] = 1.0f - rlm::expf_(fp.div(-p.R, d));
+        p.C2[i] = 1.0f - rlm::expf_(fp.div(fp.div(-p.R, d), 3.0f));
     }
 }
 // src/rlSss.h:30-42 (thirds at 0.3333f / 0.6666f)
-RLS_DEV int nd_select_dist_lobe(float &x)
+template <class Fp>
+RLS_DEV int nd_select_dist_lobe(Fp &fp, float &x)
 {
-    if (x < 0.3333f) { x = linearstep_m(0.0f, 0.3333f, x); return 0; }
-    else if (x > 0.6666f) { x = linearstep_m(0.6666f, 1.0f, x); return 2; }
-    x = linearstep_m(0.3333f, 0.6666f, x);
+    if (x < 0.3333f) { x = linearstep_m(fp, 0.0f, 0.3333f, x); return 0; }
+    else if (x > 0.6666f) { x = linearstep_m(fp, 0.6666f, 1.0f, x); return 2; }
+    x = linearstep_m(fp, 0.3333f, 0.6666f, x);
     return 1;
 }
 RLS_DEV float pick3(const float (&a)[3], int i) { return i == 0 ? a[0] : (i == 1 ? a[1] : a[2]); }
 
 // src/rlSss.cpp:36-66; also reports the channel / exponential-lobe / degenerate flags.
-RLS_DEV float nd_get_radius(const NdProfile &p, float rx, uint32_t &flags)
+template <class Fp>
+RLS_DEV float nd_get_radius(Fp &fp, const NdProfile &p, float rx, uint32_t &flags)
 {
     float x = rx;
-    int ch = nd_select_dist_lobe(x);
+    int ch = nd_select_dist_lobe(fp, x);
     flags = (uint32_t)ch << 8;                       // RLS_FLAG_LOBE_SHIFT
     float d = pick3(p.d, ch);
     if (p.R < kEps || d < kEps) { flags |= 0x0800u; return 0.0f; }   // RLS_FLAG_DEGENERATE
     float w1 = pick3(p.C1, ch);
     float w2 = pick3(p.C2, ch);
-    float w = w1 / (w1 + w2 * 3.0f);
+    float w = fp.div(w1, w1 + w2 * 3.0f);
     float r;
     if (x > w) {
         flags |= 0x0400u;                            // RLS_FLAG_EXP_LOBE
-        x = linearstep_m(w, 1.0f, x);
+        x = linearstep_m(fp, w, 1.0f, x);
         r = rlm::logf_(1.0f - x * w2) * (-d * 3.0f);
     } else {
-        x = linearstep_m(0.0f, w, x);
+        x = linearstep_m(fp, 0.0f, w, x);
         r = rlm::logf_(1.0f - x * w1) * (-d);
     }
     return r;
 }
 // src/rlSss.cpp:68-84
-RLS_DEV float nd_get_pdf(const NdProfile &p, float r)
+template <class Fp>
+RLS_DEV float nd_get_pdf(Fp &fp, const NdProfile &p, float r)
 {
     if (p.R < kEps) return 1.0f;
     float pdf = 0.0f;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         float d = max_m(p.d[i], kEps);
-        float p1 = rlm::expf_(-r / d);
-        float p2 = rlm::expf_(-r / d / 3.0f);
-        pdf += (p1 + p2) / d / (p.C1[i] + p.C2[i] * 3.0f);
+        float p1 = rlm::expf_(fp.div(-r, d));
+        float p2 = rlm::expf_(fp.div(fp.div(-r, d), 3.0f));
+        pdf += fp.div(fp.div(p1 + p2, d), p.C1[i] + p.C2[i] * 3.0f);
     }
-    return pdf / (kTwoPi * r * 3.0f);
+    return fp.div(pdf, kTwoPi * r * 3.0f);
 }
 // src/rlSss.cpp:86-106
-RLS_DEV f3 nd_eval_profile(const NdProfile &p, float r)
+template <class Fp>
+RLS_DEV f3 nd_eval_profile(Fp &fp, const NdProfile &p, float r)
 {
     if (p.R < kEps) return mk3(0.0f, 0.0f, 0.0f);
     else if (r < kEps) return mk3(1.0f, 1.0f, 1.0f);
@@ -78,7 +83,8 @@ RLS_DEV f3 nd_eval_profile(const NdProfile &p, float r)
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         float d = p.d[i];
-        o[i] = d < kEps ? 1.0f : (rlm::expf_(-r / d) + rlm::expf_(-r / (3.0f * d))) / (denom * d);
+        o[i] = 1.0f;
+        if (!(d < kEps)) o[i] = fp.div(rlm::expf_(fp.div(-r, d)) + rlm::expf_(fp.div(-r, 3.0f * d)), denom * d);
     }
     return mk3(o[0], o[1], o[2]);
 }

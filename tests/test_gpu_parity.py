@@ -464,3 +464,115 @@ def test_probe_ray_and_mis_pdf(ctx, orc):
     sm = parity.stat_rel(pdf, orc.skin_probe_mis_pdf(sgn, sp, disp, hnv))
     print(parity.format_report("probe MIS pdf", dict(pdf=sm)))
     assert sm["within"] == 1.0
+
+
+# ------------------------------------------------- arithmetic policies (csrc/rls_fp.cuh)
+def _adversarial_shading(n, seed):
+    """Shading points that push operands out of the fast window: grazing and exactly normal
+    views, axis-aligned frames (exact-zero dot products), views below the horizon."""
+    sg = ol.make_shading(n, seed, backfacing_fraction=0.25)
+    U, V, Nn, wo = (np.stack([sg[k + c] for c in "xyz"]).astype(np.float32) for k in ("U", "V", "N", "wo"))
+    idx = np.arange(n)
+    k = idx % 8
+    axis = (k == 1) | (k == 2) | (k == 5)
+    U[:, axis] = np.array([[1], [0], [0]], np.float32)
+    V[:, axis] = np.array([[0], [1], [0]], np.float32)
+    Nn[:, axis] = np.array([[0], [0], [1]], np.float32)
+    u = ol.hash_uniform(n, seed, 60)
+    cosv = np.where(k == 2, 1.0, np.where(k == 3, u * 1e-4, np.where(k == 4, 10.0 ** (-30.0 * u), u))).astype(np.float32)
+    cosv = np.where(k == 6, -u, cosv).astype(np.float32)          # below the horizon
+    phi = (ol.hash_uniform(n, seed, 61) * np.float32(2 * np.pi)).astype(np.float32)
+    phi = np.where(k == 5, 0.0, phi).astype(np.float32)           # wo in the U-N plane: atan2(0, x)
+    sr = np.sqrt(np.maximum(0.0, 1.0 - cosv.astype(np.float64) ** 2))
+    w = U * (sr * np.cos(phi)) + V * (sr * np.sin(phi)) + Nn * cosv
+    w = (w / np.linalg.norm(w, axis=0)).astype(np.float32)
+    sel = k != 0
+    wo[:, sel] = w[:, sel]
+    out = dict(sg)
+    for name, M in (("U", U), ("V", V), ("N", Nn), ("wo", wo)):
+        for j, c in enumerate("xyz"):
+            out[name + c] = np.ascontiguousarray(M[j], dtype=np.float32)
+    return out
+
+
+def _pick(n, seed, stream, values):
+    u = ol.hash_uniform(n, seed, stream)
+    v = np.asarray(values, dtype=np.float32)
+    return v[np.minimum((u * len(v)).astype(np.int64), len(v) - 1)]
+
+
+def _same_bits(a, b, name):
+    a, b = a.cpu().numpy(), b.cpu().numpy()
+    au, bu = a.view(np.uint32), b.view(np.uint32)
+    bad = (au != bu) & ~(np.isnan(a.view(np.float32)) & np.isnan(b.view(np.float32))) if a.dtype == np.float32 else (au != bu)
+    assert not bad.any(), f"{name}: {int(bad.sum())} / {bad.size} elements differ between the fast and exact policies"
+
+
+def _run_both(ctx, fn):
+    ctx.fallback_count(reset=True)
+    ctx.set_arith_policy("fast")
+    fast = {k: v.clone() for k, v in fn().items()}
+    ctx.synchronize()
+    fb = ctx.fallback_count(reset=True)
+    ctx.set_arith_policy("exact")
+    try:
+        exact = fn()
+        ctx.synchronize()
+        assert ctx.fallback_count(reset=True) == 0
+    finally:
+        ctx.set_arith_policy("fast")
+    for k in fast:
+        _same_bits(fast[k], exact[k], k)
+    return fb
+
+
+@pytest.mark.parametrize("adversarial", [False, True])
+def test_fast_policy_equals_exact_policy(ctx, adversarial):
+    """The guard-free sequences + out-of-window re-run produce the bits of the guarded IEEE
+    operators for every sample, on the benchmark distributions and on operands chosen to
+    leave the window (zero / tiny / huge / exactly representable special values)."""
+    from rlshaders_b200 import api
+    n = 1 << 21
+    seed = 0x5EEDFA57 + int(adversarial)
+    special = [2.0 ** -24, 1.0 - 2.0 ** -24, 0.5, 0.25, 0.75, 0.3333, 0.6666, 1e-3, 0.999]
+    if adversarial:
+        sg = _adversarial_shading(n, seed)
+        rough = _pick(n, seed, 2, [0.0, 1e-3, 0.01, 0.05, 0.3, 1.0, 1.0, 0.7])
+        ior = _pick(n, seed, 3, [1.0, 1.0, 0.47, 1e-4, 1.5, 2.5, 1.33, 1.0001])
+        aniso = _pick(n, seed, 4, [0.0, 0.0, 1.0, 0.5])
+        rx = np.where(ol.hash_uniform(n, seed, 5) < 0.3, _pick(n, seed, 6, special), ol.hash_uniform(n, seed, 0)).astype(np.float32)
+        ry = np.where(ol.hash_uniform(n, seed, 7) < 0.3, _pick(n, seed, 8, special), ol.hash_uniform(n, seed, 1)).astype(np.float32)
+    else:
+        sg, kw, rx, ry = parity.ggx_dielectric_inputs(n, seed, aniso=True)
+        rough, ior, aniso = kw["specularRoughness"], kw["ior"], kw["anisotropic"]
+    dsg = api.ShadingBatch.from_numpy(sg, ctx.device)
+    drx, dry = dev(rx, ctx), dev(ry, ctx)
+    g = api.GgxSampler(ctx, dsg, KsColor=(1.0, 0.5, 0.25), specularRoughness=dev(rough, ctx), ior=dev(ior, ctx),
+                       anisotropic=dev(aniso, ctx))
+    fb = {}
+    fb["dielectric"] = _run_both(ctx, lambda: g.dielectricSampleEvalPdf(drx, dry))
+    fb["ggx"] = _run_both(ctx, lambda: g.sampleEvalPdf(drx, dry))
+
+    _, dk, du = parity.disney_inputs(n, seed)
+    if adversarial:
+        for j, nm in enumerate(["subsurface", "metallic", "specular", "specular_tint", "roughness", "anisotropic",
+                                "sheen", "sheen_tint", "clearcoat", "clearcoat_gloss"]):
+            dk[nm] = _pick(n, seed, 70 + j, [0.0, 0.0, 1.0, 0.5, 1e-3, 0.25])
+        dk["base_color"] = tuple(_pick(n, seed, 90 + j, [0.0, 1.0, 0.5, 0.18]) for j in range(3))
+        du = [rx, ry, np.where(ol.hash_uniform(n, seed, 9) < 0.3, _pick(n, seed, 10, special), du[2]).astype(np.float32),
+              np.where(ol.hash_uniform(n, seed, 11) < 0.3, _pick(n, seed, 12, special), du[3]).astype(np.float32)]
+    d = api.DisneySampler(ctx, dsg, **parity.params_to_dev(dk, ctx.device))
+    ddu = [dev(t, ctx) for t in du]
+    fb["disney"] = _run_both(ctx, lambda: d.sampleEvalPdf(*ddu))
+
+    sk, srx = parity.skin_inputs(n, seed)
+    if adversarial:
+        sk["sss_scatter_dist"] = tuple(_pick(n, seed, 100 + j, [0.0, 1e-5, 1e-3, 0.05, 1.0, 2.0, 50.0, 1.0]) for j in range(3))
+        srx = rx
+    s = api.SkinProfile(ctx, n, **parity.params_to_dev(sk, ctx.device))
+    dsrx = dev(srx, ctx)
+    fb["skin"] = _run_both(ctx, lambda: s.sampleEvalPdf(dsrx))
+    print(f"fast-policy fallbacks per {n} samples (adversarial={adversarial}): {fb}")
+    if not adversarial:     # the benchmark distributions stay inside the window
+        for k, v in fb.items():
+            assert v <= n * 2e-3, (k, v)
