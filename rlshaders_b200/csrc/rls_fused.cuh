@@ -26,7 +26,7 @@ RLS_DEV float ggx_G1_value2(Fp &fp, const Ggx &g, float VdotN)
     float cosSqr = sqr(VdotN);
     float tanSqr = fp.rcp(cosSqr) - 1.0f;
     float denominator = 1.0f + fp.sqrt(1.0f + sqr(g.rough) * tanSqr);
-    return 2.0f * fp.rcp(denominator);
+    return 2.0f * fp.rcp_in_window(denominator);      // 1 + sqrt(t), t tracked: in [1, 2^60 + 1]
 }
 
 // One GGX reflection evaluation + pdf at direction L, sharing the half vector, D and the

@@ -61,15 +61,15 @@ RLS_DEV f2 uniform_slope(Fp &fp, float rx, float ry)
     f2 o; o.x = r * c; o.y = r * s;
     return o;
 }
-// src/rlGgx.cpp:14-61 (VNDFKernel::sampleSlope); rlDisney.cpp:416-463 is the same code.
+// src/rlGgx.cpp:14-61 (VNDFKernel::sampleSlope) for theta >= AI_EPSILON; rlDisney.cpp:416-463 is
+// the same code.  The theta < AI_EPSILON early-out (:27) is taken by the caller.
 template <class Fp>
 RLS_DEV f2 sample_slope(Fp &fp, float theta, float rx, float ry)
 {
-    if (theta < kEps) return uniform_slope(fp, rx, ry);
-
     float B = rlm::tanf_(fp, theta);
     float B2 = sqr(B);
-    float G1 = 2.0f * fp.rcp(1.0f + fp.sqrt(1.0f + B2));   // == 2/(..) bitwise: the divisor is in [2, 2^64]
+    // == 2/(..) bitwise: the divisor 1 + sqrt(t) is in [1, 2^60 + 1] once t is tracked
+    float G1 = 2.0f * fp.rcp_in_window(1.0f + fp.sqrt(1.0f + B2));
 
     float A = fp.div(2.0f * rx, G1) - 1.0f;
     float A2 = sqr(A);
@@ -95,6 +95,12 @@ RLS_DEV f2 sample_slope(Fp &fp, float theta, float rx, float ry)
     return slope;
 }
 // src/rlGgx.cpp:63-99 (VNDFKernel::evalSample); rlDisney.cpp:467-502 is the same code.
+//
+// Control flow is arranged so that a warp runs ONE sincosf for the slope/rotation stage: when
+// the stretched view is (nearly) the normal the reference leaves theta = phi = 0 (:82), takes
+// the uniform-slope early-out (sincosf(2 pi ry), :18-25) and then rotates by phi = 0, for which
+// sincosf returns exactly (0, 1); otherwise it rotates by sincosf(phi).  theta = acosf(V.z) with
+// V.z < 1 - 1e-4 is >= 0.0141 (or NaN), so the early-out is taken exactly when theta was left 0.
 template <class Fp>
 RLS_DEV f3 sample_visible_normal(Fp &fp, f3 view, f3 U, f3 Vax, f3 N, float ax, float ay, float rx, float ry)
 {
@@ -106,15 +112,27 @@ RLS_DEV f3 sample_visible_normal(Fp &fp, f3 view, f3 U, f3 Vax, f3 N, float ax, 
     V.y *= ay;
     V = normalize(fp, V);
 
+    const bool along_normal = !(V.z < (1.0f - kEps));
     float theta = 0.0f, phi = 0.0f;
-    if (V.z < (1.0f - kEps)) {
+    if (!along_normal) {
         theta = rlm::acosf_(fp, V.z);
         phi = rlm::atan2f_(fp, V.y, V.x);
     }
-    f2 slope = sample_slope(fp, theta, rx, ry);
-
+    float s, c;
+    rlm::sincosf_(along_normal ? kTwoPi * ry : phi, &s, &c);
+    f2 slope;
     float sinPhi, cosPhi;
-    rlm::sincosf_(phi, &sinPhi, &cosPhi);
+    if (along_normal) {                          // uniform_slope(rx, ry), then a rotation by phi = 0
+        float r = fp.sqrt(fp.div(rx, 1.0f - rx));
+        slope.x = r * c;
+        slope.y = r * s;
+        sinPhi = 0.0f;
+        cosPhi = 1.0f;
+    } else {
+        slope = sample_slope(fp, theta, rx, ry);
+        sinPhi = s;
+        cosPhi = c;
+    }
     f3 omega;
     omega.x = -(cosPhi * slope.x - sinPhi * slope.y) * ax;
     omega.y = -(sinPhi * slope.x + cosPhi * slope.y) * ay;

@@ -151,14 +151,14 @@ RLM_TABLE uint32_t kInvPio4[24] = {
 
 // ================================================================== sincosf
 // glibc 2.39 sysdeps/ieee754/flt-32/s_sincosf.{c,h} (ARM Optimized Routines), FMA build.
+// The cosine coefficients of quadrants 2,3 (__sincosf_table[1]) are the negated coefficients of
+// quadrants 0,1: every fma/multiply below is odd in them under round-to-nearest, so the host's
+// result there is exactly -(result with table[0]) -- evaluate once, flip the sign bit.  The
+// cosine polynomial is >= 0.7 on the reduced range, so no signed-zero case arises.
 RLM_HD void sincosf_poly(double x, double x2, bool neg_cos, int n, float *sinp, float *cosp)
 {
-    // cosine coefficients flip sign in quadrants 2,3 (__sincosf_table[1])
-    const double c0 = neg_cos ? -0x1p0 : 0x1p0;
-    const double c1 = neg_cos ? 0x1.ffffffd0c621cp-2 : -0x1.ffffffd0c621cp-2;
-    const double c2 = neg_cos ? -0x1.55553e1068f19p-5 : 0x1.55553e1068f19p-5;
-    const double c3 = neg_cos ? 0x1.6c087e89a359dp-10 : -0x1.6c087e89a359dp-10;
-    const double c4 = neg_cos ? -0x1.99343027bf8c3p-16 : 0x1.99343027bf8c3p-16;
+    const double c0 = 0x1p0, c1 = -0x1.ffffffd0c621cp-2, c2 = 0x1.55553e1068f19p-5,
+                 c3 = -0x1.6c087e89a359dp-10, c4 = 0x1.99343027bf8c3p-16;
     const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
 
     double x4 = x2 * x2;
@@ -172,9 +172,15 @@ RLM_HD void sincosf_poly(double x, double x2, bool neg_cos, int n, float *sinp, 
     double c = fma_(x4, c2, cc1);
     float sv = (float)fma_(x5, ss1, s);
     float cv = (float)fma_(x6, cc2, c);
+    cv = u2f(f2u(cv) ^ (neg_cos ? 0x80000000u : 0u));
     // swap sin/cos result based on quadrant
     *sinp = (n & 1) ? cv : sv;
     *cosp = (n & 1) ? sv : cv;
+}
+// x * sign[q & 3] with sign = {1, -1, -1, 1}: a multiplication by +-1 is a sign-bit flip.
+RLM_HD double sincosf_signed(double x, int q)
+{
+    return u2d(d2u(x) ^ ((uint64_t)((uint32_t)(q + 1) & 2u) << 62));
 }
 // Slow path for |y| >= 120: 192-bit 4/pi multiply (reduce_large).  Never taken on the path
 // (arguments are angles in [-2pi, 2pi]); kept so the function is total.
@@ -206,9 +212,8 @@ RLM_HD void sincosf_(float y, float *sinp, float *cosp)
         double r = x * 0x1.45F306DC9C883p+23;  // 2/pi * 2^24
         int n = ((int32_t)r + 0x800000) >> 24;
         x = fma_(-(double)n, 0x1.921FB54442D18p0, x);
-        double s = ((n + 1) & 2) ? -1.0 : 1.0; // sign[n & 3] = {1, -1, -1, 1}
         float sv, cv;
-        sincosf_poly(x * s, x * x, (n & 2) != 0, n, &sv, &cv);
+        sincosf_poly(sincosf_signed(x, n), x * x, (n & 2) != 0, n, &sv, &cv);
         const bool tiny = top < 0x398u;        // |y| < 2^-12: sin = y, cos = 1
         *sinp = tiny ? y : sv;
         *cosp = tiny ? 1.0f : cv;
@@ -218,8 +223,7 @@ RLM_HD void sincosf_(float y, float *sinp, float *cosp)
         int sign = (int)(xi >> 31);
         x = sincosf_reduce_large(xi, &n);
         int q = n + sign;
-        double s = ((q + 1) & 2) ? -1.0 : 1.0;
-        sincosf_poly(x * s, x * x, (q & 2) != 0, n, sinp, cosp);
+        sincosf_poly(sincosf_signed(x, q), x * x, (q & 2) != 0, n, sinp, cosp);
     } else {
         *sinp = *cosp = y - y;
     }
@@ -344,6 +348,35 @@ RLM_HD float atanf_(Fp &fp, float x)
 }
 RLM_HD float atanf_(float x) { rls::FpExact fp; return atanf_(fp, x); }
 
+// Fast-policy form of atanf_ for a finite argument ax >= 0 (the |y/x| of atan2f_): the same
+// five regimes; the |x| >= 2^25 shortcut of the original is not carried (fp.require).
+template <class Fp>
+RLM_HD float atanf_nonneg_(Fp &fp, float ax)
+{
+    const float aT0 = 3.3333334327e-01f, aT1 = -2.0000000298e-01f, aT2 = 1.4285714924e-01f,
+                aT3 = -1.1111110449e-01f, aT4 = 9.0908870101e-02f, aT5 = -7.6918758452e-02f,
+                aT6 = 6.6610731184e-02f, aT7 = -5.8335702866e-02f, aT8 = 4.9768779427e-02f,
+                aT9 = -3.6531571299e-02f, aT10 = 1.6285819933e-02f;
+    const int32_t ix = (int32_t)f2u(ax);
+    fp.require((uint32_t)ix < 0x4c000000u);    // also excludes NaN / Inf / negative arguments
+    const bool r0 = ix < 0x3ee00000;
+    const bool r1 = ix < 0x3f300000;
+    const bool r2 = ix < 0x3f980000;
+    const bool r3 = ix < 0x401c0000;
+    float num = r0 ? ax : (r1 ? 2.0f * ax - 1.0f : (r2 ? ax - 1.0f : (r3 ? ax - 1.5f : -1.0f)));
+    float den = r0 ? 1.0f : (r1 ? 2.0f + ax : (r2 ? ax + 1.0f : (r3 ? 1.0f + 1.5f * ax : ax)));
+    float hi = r1 ? 4.6364760399e-01f : (r2 ? 7.8539812565e-01f : (r3 ? 9.8279368877e-01f : 1.5707962513e+00f));
+    float lo = r1 ? 5.0121582440e-09f : (r2 ? 3.7748947079e-08f : (r3 ? 3.4473217170e-08f : 7.5497894159e-08f));
+    float t = fp.div_pz(num, den);
+    float z = t * t;
+    float w = z * z;
+    float s1 = z * (aT0 + w * (aT2 + w * (aT4 + w * (aT6 + w * (aT8 + w * aT10)))));
+    float s2 = w * (aT1 + w * (aT3 + w * (aT5 + w * (aT7 + w * aT9))));
+    float ts = t * (s1 + s2);
+    float small = (ix < 0x31000000) ? ax : t - ts;
+    return r0 ? small : hi - ((ts - lo) - t);
+}
+
 // =================================================================== atan2f
 // fdlibm e_atan2f.c (binary32)
 template <class Fp>
@@ -351,6 +384,16 @@ RLM_HD float atan2f_(Fp &fp, float y, float x)
 {
     const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f,
                 pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f;
+    if (Fp::kFast) {
+        // Main path only.  The operand window of div_z (x finite, non-zero; y finite) and the
+        // fp.require of atanf_nonneg_ exclude every special case except y == +-0, x == 1 and
+        // |k| > 60 with a quotient below 2^25, for which the generic formulas below give the
+        // original's bits: atanf(0) = 0; y/1 == y; pi - (0 - pi_lo) == pi + tiny == pi;
+        // a quotient < 2^-60 does not change z - pi_lo; (z - pi_lo) - pi == -(pi - (z - pi_lo)).
+        float z0 = atanf_nonneg_(fp, fabsf_(fp.div_z(y, x)));      // only |y/x| is used
+        float w0 = ((int32_t)f2u(x) < 0) ? pi - (z0 - pi_lo) : z0; // >= +0
+        return u2f(f2u(w0) | (f2u(y) & 0x80000000u));
+    }
     float z;
     int32_t hx = (int32_t)f2u(x), hy = (int32_t)f2u(y);
     int32_t ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;

@@ -53,7 +53,7 @@ RLS_DEV f3 normalize(Fp &fp, f3 a)
 {
     float len = fp.sqrt(a.x * a.x + a.y * a.y + a.z * a.z);
     if (Fp::kFast || len != 0.0f) {              // fast policy: a zero length has already left the window
-        float inv = fp.rcp(len);
+        float inv = fp.rcp_in_window(len);       // len = sqrt(t), t in [2^-60, 2^120] once tracked
         return mk3(a.x * inv, a.y * inv, a.z * inv);
     }
     return a;
