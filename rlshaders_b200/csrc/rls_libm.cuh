@@ -141,6 +141,25 @@ RLM_TABLE double kLog2Tab[32] = {
     0x1.886e6037841edp-1, 0x1.88e9c2c1b9ff8p-2, 0x1.767dcf5534862p-1, 0x1.ce0a44eb17bccp-2,
 };
 
+// Binary64 coefficients live in the constant bank on the device: DFMA / DMUL take a c[bank][offset]
+// operand directly, whereas a literal costs two 32-bit moves into a register pair per use.
+#if defined(__CUDA_ARCH__)
+#define RLM_COEF static __constant__ double
+#else
+#define RLM_COEF static const double
+#endif
+RLM_COEF kExpC[5] = { 0x1.71547652b82fep+5, 0x1.8p+52,                       // InvLn2N, Shift   (__exp2f_data, N = 32)
+                      0x1.c6af84b912394p-20, 0x1.ebfce50fac4f3p-13, 0x1.62e42ff0c52d6p-6 };   // C0, C1, C2
+RLM_COEF kExp2C[4] = { 0x1.8p+47,                                                // ShiftScaled (powf's exp2_inline)
+                       0x1.c6af84b912394p-5, 0x1.ebfce50fac4f3p-3, 0x1.62e42ff0c52d6p-1 };
+RLM_COEF kSinCosC[9] = { -0x1.ffffffd0c621cp-2, 0x1.55553e1068f19p-5, -0x1.6c087e89a359dp-10,    // c1..c4
+                         0x1.99343027bf8c3p-16,
+                         -0x1.555545995a603p-3, 0x1.1107605230bc4p-7, -0x1.994eb3774cf24p-13,    // s1..s3
+                         0x1.45F306DC9C883p+23, 0x1.921FB54442D18p0 };                           // 2/pi * 2^24, pi/2
+RLM_COEF kLogC[4] = { 0x1.62e42fefa39efp-1, -0x1.00ea348b88334p-2, 0x1.5575b0be00b6ap-2, -0x1.ffffef20a4123p-2 };  // Ln2, A0..A2
+RLM_COEF kLog2C[5] = { 0x1.27616c9496e0bp-2, -0x1.71969a075c67ap-2, 0x1.ec70a6ca7baddp-2,
+                       -0x1.7154748bef6c8p-1, 0x1.71547652ab82bp+0 };                            // A0..A4 (__powf_log2_data)
+
 // 4/pi in 32-bit words, for the |x| >= 120 argument reduction   (__inv_pio4)
 RLM_TABLE uint32_t kInvPio4[24] = {
     0xa2u, 0xa2f9u, 0xa2f983u, 0xa2f9836eu, 0xf9836e4eu, 0x836e4e44u, 0x6e4e4415u, 0x4e441529u,
@@ -157,9 +176,8 @@ RLM_TABLE uint32_t kInvPio4[24] = {
 // cosine polynomial is >= 0.7 on the reduced range, so no signed-zero case arises.
 RLM_HD void sincosf_poly(double x, double x2, bool neg_cos, int n, float *sinp, float *cosp)
 {
-    const double c0 = 0x1p0, c1 = -0x1.ffffffd0c621cp-2, c2 = 0x1.55553e1068f19p-5,
-                 c3 = -0x1.6c087e89a359dp-10, c4 = 0x1.99343027bf8c3p-16;
-    const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
+    const double c0 = 0x1p0, c1 = kSinCosC[0], c2 = kSinCosC[1], c3 = kSinCosC[2], c4 = kSinCosC[3];
+    const double s1 = kSinCosC[4], s2 = kSinCosC[5], s3 = kSinCosC[6];
 
     double x4 = x2 * x2;
     double x3 = x2 * x;
@@ -205,19 +223,19 @@ RLM_HD double sincosf_reduce_large(uint32_t xi, int *np)
 RLM_HD void sincosf_(float y, float *sinp, float *cosp)
 {
     double x = (double)y;
-    uint32_t top = abstop12(y);
-    if (top < 0x42fu) {                        // |y| < 120
+    // abstop12(y) < 0x42f  <=>  |y| < 120 (one FSETP with an |.| operand instead of shift/mask/compare)
+    if (fabsf_(y) < 120.0f) {
         // For |y| < pi/4 the host takes a shortcut that is bit-identical to reduce_fast with
         // n = 0 (x - 0*hpi == x, sign 1), so one uniform path serves both -- no divergence.
-        double r = x * 0x1.45F306DC9C883p+23;  // 2/pi * 2^24
+        double r = x * kSinCosC[7];            // 2/pi * 2^24
         int n = ((int32_t)r + 0x800000) >> 24;
-        x = fma_(-(double)n, 0x1.921FB54442D18p0, x);
+        x = fma_(-(double)n, kSinCosC[8], x);
         float sv, cv;
         sincosf_poly(sincosf_signed(x, n), x * x, (n & 2) != 0, n, &sv, &cv);
-        const bool tiny = top < 0x398u;        // |y| < 2^-12: sin = y, cos = 1
+        const bool tiny = fabsf_(y) < 0x1p-12f;  // abstop12(y) < 0x398: sin = y, cos = 1
         *sinp = tiny ? y : sv;
         *cosp = tiny ? 1.0f : cv;
-    } else if (top < 0x7f8u) {
+    } else if (abstop12(y) < 0x7f8u) {
         int n;
         uint32_t xi = f2u(y);
         int sign = (int)(xi >> 31);
@@ -295,10 +313,10 @@ RLM_HD float tanf_(Fp &fp, float x)
     if (ix >= 0x7f800000u) return x - x;
     double dx = (double)x;
     int n;
-    if (abstop12(x) < 0x42fu) {
-        double r = dx * 0x1.45F306DC9C883p+23;
+    if (fabsf_(x) < 120.0f) {                               // abstop12(x) < 0x42f
+        double r = dx * kSinCosC[7];
         n = ((int32_t)r + 0x800000) >> 24;
-        dx = dx - (double)n * 0x1.921FB54442D18p0;          // not fused in this routine
+        dx = dx - (double)n * kSinCosC[8];                  // not fused in this routine
     } else {
         uint32_t xi = f2u(x);
         dx = sincosf_reduce_large(xi, &n);
@@ -483,21 +501,20 @@ RLM_HD float acosf_(float x) { rls::FpExact fp; return acosf_(fp, x); }
 RLM_HD float expf_(float x)
 {
     double xd = (double)x;
-    uint32_t abstop = abstop12(x);
-    if (abstop >= 0x42bu) {                    // |x| >= 88 or NaN
+    if (!(fabsf_(x) < 88.0f)) {                // abstop12(x) >= 0x42b: |x| >= 88 or NaN
         if (f2u(x) == 0xff800000u) return 0.0f;
-        if (abstop >= 0x7f8u) return x + x;
+        if (abstop12(x) >= 0x7f8u) return x + x;
         if (x > 0x1.62e42ep6f) return u2f(0x7f800000u);             // overflow
         if (x < -0x1.9fe368p6f) return 0.0f;                        // underflow
         if (x < -0x1.9d1d9ep6f) return 0x1.4p-75f * 0x1.4p-75f;     // may-underflow value
     }
-    const double InvLn2N = 0x1.71547652b82fep+5, Shift = 0x1.8p+52;
-    const double C0 = 0x1.c6af84b912394p-20, C1 = 0x1.ebfce50fac4f3p-13, C2 = 0x1.62e42ff0c52d6p-6;
+    const double InvLn2N = kExpC[0], Shift = kExpC[1];
+    const double C0 = kExpC[2], C1 = kExpC[3], C2 = kExpC[4];
     double kd = fma_(InvLn2N, xd, Shift);
     uint64_t ki = d2u(kd);
     kd -= Shift;
     double r = fma_(InvLn2N, xd, -kd);
-    uint64_t t = RLM_LD(kExp2Tab[ki & 31]);
+    uint64_t t = RLM_LD(kExp2Tab[(uint32_t)ki & 31u]);
     t += ki << 47;
     double s = u2d(t);
     double z = fma_(C0, r, C1);
@@ -521,8 +538,8 @@ RLM_HD float logf_(float x)
         ix = f2u(x * 0x1p23f);                              // subnormal: normalise
         ix -= 23u << 23;
     }
-    const double Ln2 = 0x1.62e42fefa39efp-1;
-    const double A0 = -0x1.00ea348b88334p-2, A1 = 0x1.5575b0be00b6ap-2, A2 = -0x1.ffffef20a4123p-2;
+    const double Ln2 = kLogC[0];
+    const double A0 = kLogC[1], A1 = kLogC[2], A2 = kLogC[3];
     uint32_t tmp = ix - 0x3f330000u;
     int i = (int)((tmp >> 19) & 15u);
     int k = (int32_t)tmp >> 23;
@@ -568,8 +585,7 @@ RLM_HD float powf_(float x, float y)
         }
     }
     // log2_inline
-    const double A0 = 0x1.27616c9496e0bp-2, A1 = -0x1.71969a075c67ap-2, A2 = 0x1.ec70a6ca7baddp-2,
-                 A3 = -0x1.7154748bef6c8p-1, A4 = 0x1.71547652ab82bp+0;
+    const double A0 = kLog2C[0], A1 = kLog2C[1], A2 = kLog2C[2], A3 = kLog2C[3], A4 = kLog2C[4];
     uint32_t tmp = ix - 0x3f330000u;
     int i = (int)((tmp >> 19) & 15u);
     uint32_t top = tmp & 0xff800000u;
@@ -595,13 +611,13 @@ RLM_HD float powf_(float x, float y)
         if (ylogx < -149.0) return 0x1.4p-75f * 0x1.4p-75f;                 // may-underflow value
     }
     // exp2_inline
-    const double ShiftScaled = 0x1.8p+47;
-    const double C0 = 0x1.c6af84b912394p-5, C1 = 0x1.ebfce50fac4f3p-3, C2 = 0x1.62e42ff0c52d6p-1;
+    const double ShiftScaled = kExp2C[0];
+    const double C0 = kExp2C[1], C1 = kExp2C[2], C2 = kExp2C[3];
     double kd = ylogx + ShiftScaled;
     uint64_t ki = d2u(kd);
     kd -= ShiftScaled;
     double rr = ylogx - kd;
-    uint64_t t = RLM_LD(kExp2Tab[ki & 31]);
+    uint64_t t = RLM_LD(kExp2Tab[(uint32_t)ki & 31u]);
     t += ki << 47;
     double s = u2d(t);
     double zz = fma_(C0, rr, C1);

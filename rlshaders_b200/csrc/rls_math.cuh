@@ -75,6 +75,13 @@ RLS_DEV f3 fetch(const P3 &p, uint32_t i)
     return mk3(p.x ? __ldg(p.x + i) : p.value[0], p.y ? __ldg(p.y + i) : p.value[1],
                p.z ? __ldg(p.z + i) : p.value[2]);
 }
+// kArrays = true: the launch site has checked that the parameter IS a per-sample array, so the
+// kernel skips the per-parameter pointer tests (a dozen of them per rlDisney sample).
+template <bool kArrays> RLS_DEV float fetch_t(const P1 &p, uint32_t i) { return kArrays ? __ldg(p.array + i) : fetch(p, i); }
+template <bool kArrays> RLS_DEV f3 fetch_t(const P3 &p, uint32_t i)
+{
+    return kArrays ? mk3(__ldg(p.x + i), __ldg(p.y + i), __ldg(p.z + i)) : fetch(p, i);
+}
 struct CV3 { const float *x, *y, *z; };
 struct V3  { float *x, *y, *z; };
 RLS_DEV f3 load3(const CV3 &v, uint32_t i) { return mk3(__ldg(v.x + i), __ldg(v.y + i), __ldg(v.z + i)); }

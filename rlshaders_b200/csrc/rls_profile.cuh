@@ -89,6 +89,35 @@ RLS_DEV f3 nd_eval_profile(Fp &fp, const NdProfile &p, float r)
     return mk3(o[0], o[1], o[2]);
 }
 
+// getPdf(r) and evalProfile(r) at the same radius (the fused skin unit): exp(-r/d) of a channel
+// is the same IEEE operation in both (src/rlSss.cpp:78 and :102) whenever d >= AI_EPSILON, where
+// getPdf's floored distance MAX(d, AI_EPSILON) is d itself -- evaluate it once.
+template <class Fp>
+RLS_DEV void nd_pdf_and_profile(Fp &fp, const NdProfile &p, float r, float &pdf_out, f3 &rd_out)
+{
+    if (p.R < kEps) { pdf_out = 1.0f; rd_out = mk3(0.0f, 0.0f, 0.0f); return; }
+    const bool white = r < kEps;                 // evalProfile: white for r < AI_EPSILON
+    const float denom = 8.0f * kPi * r;
+    float pdf = 0.0f;
+    float o[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float d = p.d[i];
+        const float dm = max_m(d, kEps);
+        const float q1 = fp.div(-r, dm);
+        const float p1 = rlm::expf_(q1);
+        const float p2 = rlm::expf_(fp.div(q1, 3.0f));
+        pdf += fp.div(fp.div(p1 + p2, dm), p.C1[i] + p.C2[i] * 3.0f);
+        o[i] = 1.0f;
+        if (!white && !(d < kEps)) {             // dm == d here (unless d is NaN): exp(-r/d) == p1
+            const float e1 = (dm == d) ? p1 : rlm::expf_(fp.div(-r, d));
+            o[i] = fp.div(e1 + rlm::expf_(fp.div(-r, 3.0f * d)), denom * d);
+        }
+    }
+    pdf_out = fp.div(pdf, kTwoPi * r * 3.0f);
+    rd_out = mk3(o[0], o[1], o[2]);
+}
+
 struct SkinParamsDev {
     P3 sss_color, sss_scatter_dist;
     P1 sss_weight, sss_dist_multiplier, specular_weight, sheen_weight;
