@@ -357,6 +357,87 @@ typedef struct rls_sweep_grid {
 int rls_albedo_sweep(rls_context *ctx, const rls_sweep_grid *grid, uint64_t seed,
                      uint32_t spp_begin, uint32_t spp_end, double *table);
 
+/* ------------------------- callers of the triple */
+/* f2 -- rlSkin's two glossy layers for P shading points with K BRDF samples each
+ * (src/rlSkin.cpp:184-238).  Per point and per layer (sheen first, then specular) exactly the
+ * calls the node makes: GgxSampler(sg, color, ior, roughness) (:192,:215; anisotropic 0), then for
+ * k = 0..K-1 the triple AiBRDFIntegrate drives (src/rlGgx.h:172-179): L = evalSample(rx, ry) --
+ * which accumulates fresnel(L, m) and the sample count (src/rlGgx.h:100-104) --, evalBrdf(L),
+ * evalPdf(L); getAvgReflectWeight() (src/rlGgx.h:181-184) and the layer hand-off
+ * (src/rlSkin.cpp:204,:228,:231,:238,:244).  A layer whose weight is <= 1e-4 is skipped (:191,:214).
+ * Arnold's integrator itself is proprietary; the layer estimate is DEFINED here as
+ *     (1/K) sum_k evalBrdf(L_k) / evalPdf(L_k) * Li_k        (Li = 1 when li_* is all-NULL)
+ * accumulated in binary32 in sample order, then scaled as the node does.
+ * Sample arrays are sample-major: element [k * n_points + p]. */
+typedef struct rls_skin_layers_out {
+    rls_vec3  sheen;             /* sheen estimate * sheen_weight                          (:207) */
+    rls_vec3  specular;          /* specular estimate * specular_weight * (1 - sheenFresnel) (:231) */
+    float    *sheen_fresnel;     /* getAvgReflectWeight() * sheen_weight, 0 if skipped      (:204) */
+    float    *specular_fresnel;  /* getAvgReflectWeight() * specular_weight, 0 if skipped   (:228) */
+    float    *sss_weight;        /* sss_weight * (1 - specularFresnel * (1 - sheenFresnel)) (:238) */
+    uint32_t *flags;             /* RLS_SKIN_* */
+} rls_skin_layers_out;
+#define RLS_SKIN_SHEEN_EVALUATED    0x1u   /* sheen_weight > 1e-4     */
+#define RLS_SKIN_SPECULAR_EVALUATED 0x2u   /* specular_weight > 1e-4  */
+#define RLS_SKIN_SSS_SKIPPED        0x4u   /* sss weight < 1e-4 (:244) */
+int rls_skin_glossy_layers(rls_context *ctx, size_t n_points, uint32_t k, const rls_shading_soa *sg,
+                           const rls_skin_params *params,
+                           const float *rx_sheen, const float *ry_sheen,
+                           const float *rx_specular, const float *ry_specular,
+                           rls_cvec3 li_sheen, rls_cvec3 li_specular,     /* all-NULL = radiance 1 */
+                           const rls_skin_layers_out *out);
+
+/* f3 -- one light sample evaluated against a BRDF with multiple importance sampling: the shape
+ * of AiEvaluateLightSample(sg, brdf, evalSample, evalBrdf, evalPdf) (src/rlGgx.h:167-170,
+ * src/rlDisney.cpp:266-277; called from the light loops src/rlGgx.cpp:286-295,
+ * src/rlDisney.cpp:695-704).  Arnold's estimator is proprietary; DEFINED here as the two-sample
+ * power heuristic (beta = 2):
+ *     light half : f(Ld) * Li * w(p_l, p_b(Ld)) / p_l          f = evalBrdf, p_b = evalPdf
+ *     BRDF half  : L = evalSample(rx, ry);  f(L) * Li_b * w(p_b(L), p_lb) / p_b(L)
+ *     w(a, b) = a^2 / (a^2 + b^2)
+ * `light` describes the light sample (sg->Ld, sg->Li, its pdf); `light_at_l` (may be NULL: no
+ * BRDF half) the same light evaluated along the sampled direction L, which the caller obtains
+ * from rls_*_eval_sample with the same (rx, ry).  A half whose pdf is 0 or whose direction is
+ * the zero vector contributes 0. */
+typedef struct rls_light_sample {
+    rls_cvec3    dir;       /* sg->Ld (unit); ignored for light_at_l (the direction is L)   */
+    rls_cvec3    radiance;  /* sg->Li                                                       */
+    const float *pdf;       /* light pdf w.r.t. solid angle                                 */
+} rls_light_sample;
+int rls_ggx_evaluate_light_sample(rls_context *ctx, size_t n, const rls_shading_soa *sg,
+                                  const rls_ggx_params *params, const rls_light_sample *light,
+                                  const float *rx, const float *ry, const rls_light_sample *light_at_l,
+                                  rls_vec3 out_rgb, float *out_w_light /* may be NULL */,
+                                  float *out_w_brdf /* may be NULL */);
+int rls_disney_evaluate_light_sample(rls_context *ctx, size_t n, const rls_shading_soa *sg,
+                                     const rls_disney_params *params, int sample_type,
+                                     const rls_light_sample *light, const float *rx, const float *ry,
+                                     const rls_light_sample *light_at_l, rls_vec3 out_rgb,
+                                     float *out_w_light, float *out_w_brdf);
+
+/* f4 -- the developer's visual check SampleWriter (src/rlUtil.h:44-171; driven from the
+ * commented sweep src/rlGgx.cpp:202-224, src/rlDisney.cpp:642-653) for ONE shading point
+ * (element `point` of sg / params):
+ *   radiance image (writeRadiance :98-114): pixel (i, j) = evalBrdf(sphericalDirection(
+ *       cosf(pi/2 * j / height), 2 pi * i / width)) -- the direction is used as is, i.e. the
+ *       image is in the frame of the shading normal only when the frame is the identity;
+ *   sample scatter (writeSample :116-156): for each uniform pair L = evalSample(rx, ry); a
+ *       zero L is skipped; pixel (clamp(int(phi / 2pi * width)), clamp(int(theta / (pi/2) *
+ *       height))) is painted green, or red when theta > pi/2; where several samples hit a
+ *       pixel the LAST one wins, as in the sequential loop.
+ * `image` is a device array of 3 * width * height floats in the writer's plane order B, G, R
+ * (writePixel :158-163).  The radiance pass overwrites it; the scatter pass paints over it, so
+ * calling both reproduces the file the writer saves.  out_missing (device, may be NULL)
+ * receives the count of samples with theta > pi/2 (:152). */
+#define RLS_NODE_GGX    0
+#define RLS_NODE_DISNEY 1
+int rls_sample_writer_radiance(rls_context *ctx, int node, const rls_shading_soa *sg, const void *params,
+                               size_t point, int sample_type, int width, int height, float *image);
+int rls_sample_writer_scatter(rls_context *ctx, int node, const rls_shading_soa *sg, const void *params,
+                              size_t point, int sample_type, size_t n_samples, const float *rx,
+                              const float *ry, int width, int height, float *image,
+                              uint32_t *scratch /* width * height, device */, uint32_t *out_missing);
+
 /* ------------------------------------------- synthetic workload generators */
 /* Counter-based integer hash h(seed, stream, index) -> 24-bit uniform in
  * [2^-24, 1 - 2^-24]; out[i] = lo + (hi - lo) * u(first_index + i).  The integer part is

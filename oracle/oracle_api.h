@@ -72,6 +72,25 @@ void oracle_skin_probe_ray(size_t n, const rls_shading_soa *sg, const rls_skin_p
 void oracle_skin_probe_mis_pdf(size_t n, const rls_shading_soa *sg, const rls_skin_params *p,
                                rls_cvec3 disp, rls_cvec3 hit_normal, float *out_pdf);
 
+/* the callers of the triple; definitions in include/rls_b200.h. */
+void oracle_skin_glossy_layers(size_t n_points, uint32_t k, const rls_shading_soa *sg,
+                               const rls_skin_params *p, const float *rx_sheen, const float *ry_sheen,
+                               const float *rx_specular, const float *ry_specular,
+                               rls_cvec3 li_sheen, rls_cvec3 li_specular, const rls_skin_layers_out *out);
+void oracle_ggx_evaluate_light_sample(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
+                                      const rls_light_sample *light, const float *rx, const float *ry,
+                                      const rls_light_sample *light_at_l, rls_vec3 out_rgb,
+                                      float *out_w_light, float *out_w_brdf);
+void oracle_disney_evaluate_light_sample(size_t n, const rls_shading_soa *sg, const rls_disney_params *p,
+                                         int sample_type, const rls_light_sample *light, const float *rx,
+                                         const float *ry, const rls_light_sample *light_at_l,
+                                         rls_vec3 out_rgb, float *out_w_light, float *out_w_brdf);
+void oracle_sample_writer_radiance(int node, const rls_shading_soa *sg, const void *params, size_t point,
+                                   int sample_type, int width, int height, float *image);
+void oracle_sample_writer_scatter(int node, const rls_shading_soa *sg, const void *params, size_t point,
+                                  int sample_type, size_t n_samples, const float *rx, const float *ry,
+                                  int width, int height, float *image, uint32_t *out_missing);
+
 void oracle_albedo_sweep(const rls_sweep_grid *grid, uint64_t seed, uint32_t spp_begin,
                          uint32_t spp_end, double *table);
 

@@ -553,6 +553,234 @@ void oracle_skin_probe_mis_pdf(size_t n, const rls_shading_soa *sg, const rls_sk
     }
 }
 
+/* ---- rlSkin's glossy layers.  src/rlSkin.cpp:184-238 lives inside
+ * shader_evaluate, so the node's statements are restated around the reference's own GgxSampler
+ * (its evalSample accumulates the Fresnel average exactly as in the plugin). */
+static void skinLayerRef(Shading &sh, const float *c, float ior, float rough, uint32_t K, size_t P, size_t p,
+                         const float *rx, const float *ry, rls_cvec3 li, float *avg, float *est)
+{
+    AtColor color = rls_shim_rgb(c[0], c[1], c[2]);
+    rls::GgxSampler s(&sh.sg, color, ior, rough);                    /* src/rlSkin.cpp:192,215 */
+    float acc[3] = { 0.0f, 0.0f, 0.0f };
+    if (!AiColorIsSmall(color)) {                                    /* integrateGlossy, src/rlGgx.h:174-176 */
+        for (uint32_t k = 0; k < K; k++) {
+            size_t idx = (size_t)k * P + p;
+            AtVector L = rls::GgxSampler::evalSample(&s, rx[idx], ry[idx]);
+            AtColor f = rls::GgxSampler::evalBrdf(&s, &L);
+            float pdf = rls::GgxSampler::evalPdf(&s, &L);
+            float w[3] = { f.r / pdf, f.g / pdf, f.b / pdf };
+            if (li.x) { w[0] *= li.x[idx]; w[1] *= li.y[idx]; w[2] *= li.z[idx]; }
+            acc[0] += w[0]; acc[1] += w[1]; acc[2] += w[2];
+        }
+    }
+    *avg = s.getAvgReflectWeight();
+    float invK = 1.0f / (float)K;
+    est[0] = acc[0] * invK; est[1] = acc[1] * invK; est[2] = acc[2] * invK;
+}
+
+void oracle_skin_glossy_layers(size_t n, uint32_t K, const rls_shading_soa *sg, const rls_skin_params *sp,
+                               const float *rx_a, const float *ry_a, const float *rx_b, const float *ry_b,
+                               rls_cvec3 li_a, rls_cvec3 li_b, const rls_skin_layers_out *out)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        Shading sh; loadShading(sg, i, sh);
+        uint32_t flags = 0;
+        float sheenFresnel = 0.0f, specularFresnel = 0.0f;
+        float sheen[3] = { 0, 0, 0 }, specular[3] = { 0, 0, 0 }, c[3], avg;
+        float sheenWeight = orc_p1(&sp->sheen_weight, i);
+        if (sheenWeight > AI_EPSILON) {
+            orc_p3(&sp->sheen_color, i, c);
+            skinLayerRef(sh, c, orc_p1(&sp->sheen_ior, i), orc_p1(&sp->sheen_roughness, i), K, n, i, rx_a, ry_a, li_a, &avg, sheen);
+            sheenFresnel = avg * sheenWeight;
+            flags |= RLS_SKIN_SHEEN_EVALUATED;
+        }
+        for (int j = 0; j < 3; j++) sheen[j] *= sheenWeight;
+        float specularWeight = orc_p1(&sp->specular_weight, i);
+        if (specularWeight > AI_EPSILON) {
+            orc_p3(&sp->specular_color, i, c);
+            skinLayerRef(sh, c, orc_p1(&sp->specular_ior, i), orc_p1(&sp->specular_roughness, i), K, n, i, rx_b, ry_b, li_b, &avg, specular);
+            specularFresnel = avg * specularWeight;
+            flags |= RLS_SKIN_SPECULAR_EVALUATED;
+        }
+        float scale = specularWeight * (1.0f - sheenFresnel);
+        for (int j = 0; j < 3; j++) specular[j] *= scale;
+        float sssWeight = orc_p1(&sp->sss_weight, i);
+        sssWeight *= 1.0f - specularFresnel * (1.0f - sheenFresnel);
+        if (sssWeight < AI_EPSILON) flags |= RLS_SKIN_SSS_SKIPPED;
+        store3(out->sheen, i, sheen[0], sheen[1], sheen[2]);
+        store3(out->specular, i, specular[0], specular[1], specular[2]);
+        out->sheen_fresnel[i] = sheenFresnel;
+        out->specular_fresnel[i] = specularFresnel;
+        out->sss_weight[i] = sssWeight;
+        out->flags[i] = flags;
+    }
+}
+
+/* ---- 8(f) f3: one MIS light sample (two-sample power heuristic, include/rls_b200.h). */
+extern "C++" {
+namespace {
+inline float powerHeuristic(float a, float b) { float a2 = a * a; return a2 / (a2 + b * b); }
+struct MisOut { float rgb[3], wl, wb; };
+inline MisOut misCombine(const AtVector &Ld, const float *Li, float pl, const AtColor &fl, float pbl, bool have,
+                         const AtVector &L, const AtColor &fb, float pb, const float *Lib, float plb)
+{
+    MisOut o = { { 0.0f, 0.0f, 0.0f }, 0.0f, 0.0f };
+    if (!(Ld == AI_V3_ZERO) && pl > 0.0f) {
+        o.wl = powerHeuristic(pl, pbl);
+        float s = o.wl / pl;
+        o.rgb[0] = fl.r * Li[0] * s; o.rgb[1] = fl.g * Li[1] * s; o.rgb[2] = fl.b * Li[2] * s;
+    }
+    if (have && !(L == AI_V3_ZERO) && pb > 0.0f) {
+        o.wb = powerHeuristic(pb, plb);
+        float s = o.wb / pb;
+        o.rgb[0] = o.rgb[0] + fb.r * Lib[0] * s; o.rgb[1] = o.rgb[1] + fb.g * Lib[1] * s; o.rgb[2] = o.rgb[2] + fb.b * Lib[2] * s;
+    }
+    return o;
+}
+template <typename Brdf, typename SampleFn>
+inline void lightSampleOne(Brdf &brdf, SampleFn sample, size_t i, const rls_light_sample *light, const rls_light_sample *at_l,
+                           rls_vec3 out_rgb, float *wl, float *wb)
+{
+    AtVector Ld; AiV3Create(Ld, light->dir.x[i], light->dir.y[i], light->dir.z[i]);
+    float Li[3] = { light->radiance.x[i], light->radiance.y[i], light->radiance.z[i] };
+    AtColor fl = Brdf::evalBrdf(&brdf, &Ld);
+    float pbl = Brdf::evalPdf(&brdf, &Ld);
+    AtVector L = AI_V3_ZERO; AtColor fb = AI_RGB_BLACK; float pb = 0.0f, plb = 0.0f, Lib[3] = { 0, 0, 0 };
+    if (at_l) {
+        L = sample();
+        fb = Brdf::evalBrdf(&brdf, &L);
+        pb = Brdf::evalPdf(&brdf, &L);
+        Lib[0] = at_l->radiance.x[i]; Lib[1] = at_l->radiance.y[i]; Lib[2] = at_l->radiance.z[i];
+        plb = at_l->pdf[i];
+    }
+    MisOut m = misCombine(Ld, Li, light->pdf[i], fl, pbl, at_l != nullptr, L, fb, pb, Lib, plb);
+    store3(out_rgb, i, m.rgb[0], m.rgb[1], m.rgb[2]);
+    if (wl) wl[i] = m.wl;
+    if (wb) wb[i] = m.wb;
+}
+template <typename Sampler>
+void ggxLightSampleT(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p, const rls_light_sample *light,
+                     const float *rx, const float *ry, const rls_light_sample *at_l, rls_vec3 out_rgb, float *wl, float *wb)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        Shading sh; loadShading(sg, i, sh);
+        GgxArgs a = ggxArgs(p, i);
+        Sampler s(&sh.sg, a.ks, a.ior, a.rough, a.aniso);
+        lightSampleOne(s, [&]() { return Sampler::evalSample(&s, rx[i], ry[i]); }, i, light, at_l, out_rgb, wl, wb);
+    }
+}
+} // namespace
+} // extern "C++"
+
+void oracle_ggx_evaluate_light_sample(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
+                                      const rls_light_sample *light, const float *rx, const float *ry,
+                                      const rls_light_sample *at_l, rls_vec3 out_rgb, float *wl, float *wb)
+{
+    GGX_DISPATCH(p, ggxLightSampleT, n, sg, p, light, rx, ry, at_l, out_rgb, wl, wb);
+}
+
+void oracle_disney_evaluate_light_sample(size_t n, const rls_shading_soa *sg, const rls_disney_params *p, int sample_type,
+                                         const rls_light_sample *light, const float *rx, const float *ry,
+                                         const rls_light_sample *at_l, rls_vec3 out_rgb, float *wl, float *wb)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        Shading sh; loadShading(sg, i, sh);
+        float table[64 * 3];
+        disneyTable(p, i, table);
+        rls_shim_set_param_table(table);
+        DisneySampler s(nullptr, &sh.sg);
+        s.mSampleFromVisibleNormal = p->sample_from_visible_normal != 0;
+        s.setSampleType((AtUInt16)sample_type);
+        lightSampleOne(s, [&]() { return DisneySampler::evalSample(&s, rx[i], ry[i]); }, i, light, at_l, out_rgb, wl, wb);
+    }
+}
+
+/* ---- 8(f) f4: SampleWriter (src/rlUtil.h:44-171).  The class itself needs tinyexr and an
+ * Arnold sampler; its two loops are restated around the reference's own triple. */
+extern "C++" {
+namespace {
+inline void writerPixel(float *image, int W, int H, int x, int y, const AtColor &c)     /* writePixel :158-163 */
+{
+    size_t stride = (size_t)W * H, at = (size_t)x + (size_t)y * W;
+    image[at] = c.b; image[at + stride] = c.g; image[at + stride * 2] = c.r;
+}
+template <typename Brdf>
+void writerRadiance(Brdf &brdf, int W, int H, float *image)                                /* :98-114 */
+{
+    for (int j = 0; j < H; j++) {
+        float theta = AI_PIOVER2 * j / H;
+        for (int i = 0; i < W; i++) {
+            float phi = AI_PITIMES2 * i / W;
+            AtVector dir = rls::sphericalDirection(cosf(theta), phi);
+            writerPixel(image, W, H, i, j, Brdf::evalBrdf(&brdf, &dir));
+        }
+    }
+}
+template <typename Brdf>
+void writerScatter(Brdf &brdf, size_t n, const float *rx, const float *ry, int W, int H, float *image, uint32_t *missing)   /* :116-156 */
+{
+    uint32_t missingCount = 0;
+    for (size_t k = 0; k < n; k++) {
+        AtVector dir = Brdf::evalSample(&brdf, rx[k], ry[k]);
+        if (AiV3IsZero(dir)) continue;
+        float theta = acosf(dir.z);
+        float phi = atan2f(dir.y, dir.x);
+        if (phi < 0.0f) phi += AI_PITIMES2;
+        int i = CLAMP(static_cast<int>(phi * AI_ONEOVER2PI * W), 0, W - 1);
+        int j = CLAMP(static_cast<int>(theta / AI_PIOVER2 * H), 0, H - 1);
+        if (theta > AI_PIOVER2) { writerPixel(image, W, H, i, j, AI_RGB_RED); missingCount++; }
+        else writerPixel(image, W, H, i, j, AI_RGB_GREEN);
+    }
+    if (missing) *missing = missingCount;
+}
+} // namespace
+} // extern "C++"
+
+void oracle_sample_writer_radiance(int node, const rls_shading_soa *sg, const void *params, size_t point, int sample_type,
+                                   int W, int H, float *image)
+{
+    Shading sh; loadShading(sg, point, sh);
+    if (node == RLS_NODE_GGX) {
+        const rls_ggx_params *p = (const rls_ggx_params *)params;
+        GgxArgs a = ggxArgs(p, point);
+        if (p->normal_sampler == RLS_GGX_SAMPLER_NDF) { GgxNdfSampler s(&sh.sg, a.ks, a.ior, a.rough, a.aniso); writerRadiance(s, W, H, image); }
+        else { rls::GgxSampler s(&sh.sg, a.ks, a.ior, a.rough, a.aniso); writerRadiance(s, W, H, image); }
+    } else {
+        const rls_disney_params *p = (const rls_disney_params *)params;
+        float table[64 * 3];
+        disneyTable(p, point, table);
+        rls_shim_set_param_table(table);
+        DisneySampler s(nullptr, &sh.sg);
+        s.mSampleFromVisibleNormal = p->sample_from_visible_normal != 0;
+        s.setSampleType((AtUInt16)sample_type);
+        writerRadiance(s, W, H, image);
+    }
+}
+
+void oracle_sample_writer_scatter(int node, const rls_shading_soa *sg, const void *params, size_t point, int sample_type,
+                                  size_t n, const float *rx, const float *ry, int W, int H, float *image, uint32_t *missing)
+{
+    Shading sh; loadShading(sg, point, sh);
+    if (node == RLS_NODE_GGX) {
+        const rls_ggx_params *p = (const rls_ggx_params *)params;
+        GgxArgs a = ggxArgs(p, point);
+        if (p->normal_sampler == RLS_GGX_SAMPLER_NDF) { GgxNdfSampler s(&sh.sg, a.ks, a.ior, a.rough, a.aniso); writerScatter(s, n, rx, ry, W, H, image, missing); }
+        else { rls::GgxSampler s(&sh.sg, a.ks, a.ior, a.rough, a.aniso); writerScatter(s, n, rx, ry, W, H, image, missing); }
+    } else {
+        const rls_disney_params *p = (const rls_disney_params *)params;
+        float table[64 * 3];
+        disneyTable(p, point, table);
+        rls_shim_set_param_table(table);
+        DisneySampler s(nullptr, &sh.sg);
+        s.mSampleFromVisibleNormal = p->sample_from_visible_normal != 0;
+        s.setSampleType((AtUInt16)sample_type);
+        writerScatter(s, n, rx, ry, W, H, image, missing);
+    }
+}
+
 void oracle_albedo_sweep(const rls_sweep_grid *g, uint64_t seed, uint32_t spp_begin,
                          uint32_t spp_end, double *table)
 {

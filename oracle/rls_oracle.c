@@ -986,6 +986,202 @@ void oracle_skin_probe_mis_pdf(size_t n, const rls_shading_soa *sg, const rls_sk
     }
 }
 
+/* ---- rlSkin's glossy layers (src/rlSkin.cpp:184-238) */
+static void skin_layer(v3 U, v3 V, v3 N, v3 wo, int back, const float *c, float ior, float rough, uint32_t K, size_t P,
+                       size_t p, const float *rx, const float *ry, rls_cvec3 li, float *avg, float *est)
+{
+    ggx_t g;
+    v3 color = mk3(c[0], c[1], c[2]);
+    ggx_init(&g, U, V, N, wo, back, color, ior, rough, 0.0f);          /* src/rlSkin.cpp:192,215 */
+    float reflectWeight = 0.0f, count = 0.0f;                          /* src/rlGgx.h:371-372 */
+    float acc[3] = { 0.0f, 0.0f, 0.0f };
+    int small = ABSF(color.x) < EPS && ABSF(color.y) < EPS && ABSF(color.z) < EPS;   /* src/rlGgx.h:174-176 */
+    if (!small) {
+        for (uint32_t k = 0; k < K; k++) {
+            size_t idx = (size_t)k * P + p;
+            v3 M = ggx_sample_normal(&g, rx[idx], ry[idx]);            /* src/rlGgx.h:97-107 */
+            v3 L = reflect_direction(g.wo, M);
+            reflectWeight += ggx_fresnel(&g, L, M);
+            count += 1.0f;
+            v3 f = ggx_eval_brdf(&g, L);
+            float pdf = ggx_eval_pdf(&g, L);
+            float w[3] = { f.x / pdf, f.y / pdf, f.z / pdf };
+            if (li.x) { w[0] *= li.x[idx]; w[1] *= li.y[idx]; w[2] *= li.z[idx]; }
+            acc[0] += w[0]; acc[1] += w[1]; acc[2] += w[2];
+        }
+    }
+    *avg = count > 0.0f ? reflectWeight / count : 1.0f;                /* src/rlGgx.h:181-184 */
+    float invK = 1.0f / (float)K;
+    est[0] = acc[0] * invK; est[1] = acc[1] * invK; est[2] = acc[2] * invK;
+}
+
+void oracle_skin_glossy_layers(size_t n, uint32_t K, const rls_shading_soa *sg, const rls_skin_params *sp,
+                               const float *rx_a, const float *ry_a, const float *rx_b, const float *ry_b,
+                               rls_cvec3 li_a, rls_cvec3 li_b, const rls_skin_layers_out *out)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        v3 U, V, N, wo; int back;
+        load_shading(sg, i, &U, &V, &N, &wo, &back);
+        uint32_t flags = 0;
+        float sheenFresnel = 0.0f, specularFresnel = 0.0f;
+        float sheen[3] = { 0, 0, 0 }, specular[3] = { 0, 0, 0 }, c[3], avg;
+        float sheenWeight = orc_p1(&sp->sheen_weight, i);
+        if (sheenWeight > EPS) {                                                           /* :191 */
+            orc_p3(&sp->sheen_color, i, c);
+            skin_layer(U, V, N, wo, back, c, orc_p1(&sp->sheen_ior, i), orc_p1(&sp->sheen_roughness, i), K, n, i,
+                       rx_a, ry_a, li_a, &avg, sheen);
+            sheenFresnel = avg * sheenWeight;                                              /* :204 */
+            flags |= RLS_SKIN_SHEEN_EVALUATED;
+        }
+        for (int j = 0; j < 3; j++) sheen[j] *= sheenWeight;                               /* :207 */
+        float specularWeight = orc_p1(&sp->specular_weight, i);
+        if (specularWeight > EPS) {                                                        /* :214 */
+            orc_p3(&sp->specular_color, i, c);
+            skin_layer(U, V, N, wo, back, c, orc_p1(&sp->specular_ior, i), orc_p1(&sp->specular_roughness, i), K, n, i,
+                       rx_b, ry_b, li_b, &avg, specular);
+            specularFresnel = avg * specularWeight;                                        /* :228 */
+            flags |= RLS_SKIN_SPECULAR_EVALUATED;
+        }
+        float scale = specularWeight * (1.0f - sheenFresnel);                              /* :231 */
+        for (int j = 0; j < 3; j++) specular[j] *= scale;
+        float sssWeight = orc_p1(&sp->sss_weight, i);
+        sssWeight *= 1.0f - specularFresnel * (1.0f - sheenFresnel);                       /* :238 */
+        if (sssWeight < EPS) flags |= RLS_SKIN_SSS_SKIPPED;                                /* :244 */
+        st3(out->sheen, i, mk3(sheen[0], sheen[1], sheen[2]));
+        st3(out->specular, i, mk3(specular[0], specular[1], specular[2]));
+        out->sheen_fresnel[i] = sheenFresnel;
+        out->specular_fresnel[i] = specularFresnel;
+        out->sss_weight[i] = sssWeight;
+        out->flags[i] = flags;
+    }
+}
+
+/* ---- 8(f) f3: one MIS light sample (two-sample power heuristic; include/rls_b200.h) */
+static inline float power_heuristic(float a, float b) { float a2 = a * a; return a2 / (a2 + b * b); }
+typedef struct { v3 rgb; float wl, wb; } mis_t;
+static mis_t mis_combine(v3 Ld, v3 Li, float pl, v3 fl, float pbl, int have, v3 L, v3 fb, float pb, v3 Lib, float plb)
+{
+    mis_t o; o.rgb = mk3(0.0f, 0.0f, 0.0f); o.wl = 0.0f; o.wb = 0.0f;
+    if (!iszero3(Ld) && pl > 0.0f) {
+        o.wl = power_heuristic(pl, pbl);
+        float s = o.wl / pl;
+        o.rgb = mk3(fl.x * Li.x * s, fl.y * Li.y * s, fl.z * Li.z * s);
+    }
+    if (have && !iszero3(L) && pb > 0.0f) {
+        o.wb = power_heuristic(pb, plb);
+        float s = o.wb / pb;
+        o.rgb = add3(o.rgb, mk3(fb.x * Lib.x * s, fb.y * Lib.y * s, fb.z * Lib.z * s));
+    }
+    return o;
+}
+static inline v3 ld3(rls_cvec3 v, size_t i) { return mk3(v.x[i], v.y[i], v.z[i]); }
+
+void oracle_ggx_evaluate_light_sample(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
+                                      const rls_light_sample *light, const float *rx, const float *ry,
+                                      const rls_light_sample *at_l, rls_vec3 out_rgb, float *wl, float *wb)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        ggx_t g; ggx_from_params(&g, sg, p, i);
+        v3 Ld = ld3(light->dir, i);
+        v3 fl = ggx_eval_brdf(&g, Ld);
+        float pbl = ggx_eval_pdf(&g, Ld);
+        v3 L = mk3(0.0f, 0.0f, 0.0f), fb = L, Lib = L;
+        float pb = 0.0f, plb = 0.0f;
+        if (at_l) {
+            L = ggx_eval_sample(&g, rx[i], ry[i], NULL);
+            fb = ggx_eval_brdf(&g, L);
+            pb = ggx_eval_pdf(&g, L);
+            Lib = ld3(at_l->radiance, i);
+            plb = at_l->pdf[i];
+        }
+        mis_t m = mis_combine(Ld, ld3(light->radiance, i), light->pdf[i], fl, pbl, at_l != NULL, L, fb, pb, Lib, plb);
+        st3(out_rgb, i, m.rgb);
+        if (wl) wl[i] = m.wl;
+        if (wb) wb[i] = m.wb;
+    }
+}
+
+void oracle_disney_evaluate_light_sample(size_t n, const rls_shading_soa *sg, const rls_disney_params *p, int sample_type,
+                                         const rls_light_sample *light, const float *rx, const float *ry,
+                                         const rls_light_sample *at_l, rls_vec3 out_rgb, float *wl, float *wb)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        disney_t d; disney_init(&d, sg, p, i);
+        v3 Ld = ld3(light->dir, i);
+        v3 fl = disney_eval_brdf(&d, sample_type, Ld);
+        float pbl = disney_eval_pdf(&d, sample_type, Ld);
+        v3 L = mk3(0.0f, 0.0f, 0.0f), fb = L, Lib = L;
+        float pb = 0.0f, plb = 0.0f;
+        if (at_l) {
+            uint32_t lobe = 0;
+            L = sample_type == RLS_RAY_DIFFUSE ? disney_sample_diffuse(&d, rx[i], ry[i])
+                                               : disney_sample_specular(&d, rx[i], ry[i], &lobe);
+            fb = disney_eval_brdf(&d, sample_type, L);
+            pb = disney_eval_pdf(&d, sample_type, L);
+            Lib = ld3(at_l->radiance, i);
+            plb = at_l->pdf[i];
+        }
+        mis_t m = mis_combine(Ld, ld3(light->radiance, i), light->pdf[i], fl, pbl, at_l != NULL, L, fb, pb, Lib, plb);
+        st3(out_rgb, i, m.rgb);
+        if (wl) wl[i] = m.wl;
+        if (wb) wb[i] = m.wb;
+    }
+}
+
+/* ---- 8(f) f4: SampleWriter (src/rlUtil.h:98-163) */
+static inline void writer_pixel(float *image, int W, int H, int x, int y, v3 rgb)        /* writePixel :158-163 */
+{
+    size_t stride = (size_t)W * H, at = (size_t)x + (size_t)y * W;
+    image[at] = rgb.z; image[at + stride] = rgb.y; image[at + stride * 2] = rgb.x;
+}
+typedef struct { int node, type; ggx_t g; disney_t d; } writer_brdf_t;
+static void writer_setup(writer_brdf_t *b, int node, const rls_shading_soa *sg, const void *params, size_t point, int type)
+{
+    b->node = node; b->type = type;
+    if (node == RLS_NODE_GGX) ggx_from_params(&b->g, sg, (const rls_ggx_params *)params, point);
+    else disney_init(&b->d, sg, (const rls_disney_params *)params, point);
+}
+void oracle_sample_writer_radiance(int node, const rls_shading_soa *sg, const void *params, size_t point, int sample_type,
+                                   int W, int H, float *image)
+{
+    writer_brdf_t b; writer_setup(&b, node, sg, params, point, sample_type);
+    for (int j = 0; j < H; j++) {                                                        /* :103-113 */
+        float theta = HALF_PI_F * j / H;
+        for (int i = 0; i < W; i++) {
+            float phi = TWO_PI_F * i / W;
+            v3 dir = spherical_direction(cosf(theta), phi);
+            v3 c = node == RLS_NODE_GGX ? ggx_eval_brdf(&b.g, dir) : disney_eval_brdf(&b.d, sample_type, dir);
+            writer_pixel(image, W, H, i, j, c);
+        }
+    }
+}
+void oracle_sample_writer_scatter(int node, const rls_shading_soa *sg, const void *params, size_t point, int sample_type,
+                                  size_t n, const float *rx, const float *ry, int W, int H, float *image, uint32_t *missing)
+{
+    writer_brdf_t b; writer_setup(&b, node, sg, params, point, sample_type);
+    uint32_t missingCount = 0;
+    for (size_t k = 0; k < n; k++) {                                                     /* :127-150 */
+        uint32_t lobe = 0;
+        v3 dir = node == RLS_NODE_GGX ? ggx_eval_sample(&b.g, rx[k], ry[k], NULL)
+               : (sample_type == RLS_RAY_DIFFUSE ? disney_sample_diffuse(&b.d, rx[k], ry[k])
+                                                 : disney_sample_specular(&b.d, rx[k], ry[k], &lobe));
+        if (iszero3(dir)) continue;
+        float theta = acosf(dir.z);
+        float phi = atan2f(dir.y, dir.x);
+        if (phi < 0.0f) phi += TWO_PI_F;
+        int i = (int)(phi * 0.15915494309189533577f * W);
+        int j = (int)(theta / HALF_PI_F * H);
+        i = i < 0 ? 0 : (i > W - 1 ? W - 1 : i);
+        j = j < 0 ? 0 : (j > H - 1 ? H - 1 : j);
+        if (theta > HALF_PI_F) { writer_pixel(image, W, H, i, j, mk3(1.0f, 0.0f, 0.0f)); missingCount++; }
+        else writer_pixel(image, W, H, i, j, mk3(0.0f, 1.0f, 0.0f));
+    }
+    if (missing) *missing = missingCount;
+}
+
 void oracle_albedo_sweep(const rls_sweep_grid *g, uint64_t seed, uint32_t spp_begin,
                          uint32_t spp_end, double *table)
 {

@@ -120,6 +120,26 @@ class ProbeOut(C.Structure):
                 ("flags", C.c_void_p)]
 
 
+class SkinLayersOut(C.Structure):
+    _fields_ = [("sheen", Vec3), ("specular", Vec3), ("sheen_fresnel", C.c_void_p),
+                ("specular_fresnel", C.c_void_p), ("sss_weight", C.c_void_p), ("flags", C.c_void_p)]
+
+
+class LightSample(C.Structure):
+    _fields_ = [("dir", CVec3), ("radiance", CVec3), ("pdf", C.c_void_p)]
+
+
+def light_sample(direction, radiance, pdf):
+    """rls_light_sample from ([3] arrays or None, [3] arrays, array)."""
+    s = LightSample(vec3(direction), vec3(radiance), _addr(pdf))
+    s._keepalive = (direction, radiance, pdf)
+    return s
+
+
+NODE_GGX, NODE_DISNEY = 0, 1
+SKIN_SHEEN_EVALUATED, SKIN_SPECULAR_EVALUATED, SKIN_SSS_SKIPPED = 1, 2, 4
+
+
 class SweepGrid(C.Structure):
     _fields_ = [("n_rough", C.c_int32), ("n_cos", C.c_int32), ("n_ior", C.c_int32),
                 ("roughness_lo", C.c_float), ("roughness_hi", C.c_float),

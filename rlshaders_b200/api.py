@@ -194,6 +194,12 @@ class GgxSampler:
             _f32(ry, "ry", n).data_ptr(), abi.vec3(_f32rows(wi, "wi")), F.data_ptr() if F is not None else None), c.lib)
         return wi, F
 
+    def evalLightSample(self, Ld, Li, light_pdf, rx=None, ry=None, Li_at_l=None, pdf_at_l=None):
+        """AiEvaluateLightSample-shaped MIS of one light sample (src/rlGgx.h:167-170); the BRDF
+        half is included when the light's radiance / pdf along L = evalSample(rx, ry) are given."""
+        return _eval_light_sample(self.ctx.lib.rls_ggx_evaluate_light_sample, self, (), Ld, Li, light_pdf,
+                                  rx, ry, Li_at_l, pdf_at_l)
+
     def evalBrdf(self, wi):
         n, c = self.sg.n, self.ctx
         f = c.empty(3, n, like=wi)
@@ -253,6 +259,77 @@ class GgxSampler:
         return out
 
 
+def _light(direction, radiance, pdf, n):
+    d = _f32rows(direction, "Ld") if direction is not None else None
+    return abi.light_sample(d, _f32rows(radiance, "Li"), _f32(pdf, "light pdf", n))
+
+
+def _eval_light_sample(fn, sampler, head_args, Ld, Li, light_pdf, rx, ry, Li_at_l, pdf_at_l):
+    """Shared body of {GgxSampler,DisneySampler}.evalLightSample (include/rls_b200.h, f3)."""
+    n, c = sampler.sg.n, sampler.ctx
+    light = _light(Ld, Li, light_pdf, n)
+    at_l = None
+    if Li_at_l is not None:
+        at_l = _light(None, Li_at_l, pdf_at_l, n)
+    rgb = c.empty(3, n, like=light_pdf)
+    wl, wb = c.empty(n, like=light_pdf), c.empty(n, like=light_pdf)
+    _check(c.handle, fn(c.handle, n, C.byref(sampler.sg.struct), C.byref(sampler.params), *head_args, C.byref(light),
+                        _f32(rx, "rx", n).data_ptr() if rx is not None else None,
+                        _f32(ry, "ry", n).data_ptr() if ry is not None else None,
+                        C.byref(at_l) if at_l is not None else None,
+                        abi.vec3(_f32rows(rgb, "rgb")), wl.data_ptr(), wb.data_ptr()), c.lib)
+    return dict(rgb=rgb, w_light=wl, w_brdf=wb)
+
+
+class SampleWriter:
+    """rls::SampleWriter (src/rlUtil.h:44-171) for one shading point of a sampler: writeRadiance
+    fills the lat-long BRDF image, writeSample paints the sample scatter over it (green; red
+    below the horizon).  `image` is [3, height, width] float32 in the writer's B, G, R plane
+    order; save() writes the scanline OpenEXR file the reference's writer produces (HALF
+    channels B, G, R), or a .npy."""
+
+    def __init__(self, ctx, width, height, outpath=""):
+        self.ctx, self.width, self.height, self.outpath = ctx, int(width), int(height), outpath
+        self.image = torch.zeros(3, self.height, self.width, dtype=torch.float32, device=ctx.device)
+        self._scratch = torch.empty(self.height * self.width, dtype=torch.int32, device=ctx.device)
+        self.missing = torch.zeros(1, dtype=torch.int32, device=ctx.device)
+
+    def _node(self, brdf):
+        if isinstance(brdf, GgxSampler):
+            return abi.NODE_GGX, 0
+        return abi.NODE_DISNEY, brdf.sample_type
+
+    def writeRadiance(self, brdf, point=0):
+        c = self.ctx
+        node, st = self._node(brdf)
+        _check(c.handle, c.lib.rls_sample_writer_radiance(c.handle, node, C.byref(brdf.sg.struct),
+                                                          C.cast(C.byref(brdf.params), C.c_void_p), point, st,
+                                                          self.width, self.height, self.image.data_ptr()), c.lib)
+        return self.image
+
+    def writeSample(self, brdf, rx, ry, point=0):
+        c = self.ctx
+        node, st = self._node(brdf)
+        n = rx.shape[0]
+        _check(c.handle, c.lib.rls_sample_writer_scatter(c.handle, node, C.byref(brdf.sg.struct),
+                                                         C.cast(C.byref(brdf.params), C.c_void_p), point, st, n,
+                                                         _f32(rx, "rx", n).data_ptr(), _f32(ry, "ry", n).data_ptr(),
+                                                         self.width, self.height, self.image.data_ptr(),
+                                                         self._scratch.data_ptr(), self.missing.data_ptr()), c.lib)
+        return self.image
+
+    def save(self, path=None):
+        from . import exr
+        path = path or self.outpath
+        img = self.image.cpu().numpy()
+        if path.endswith(".npy"):
+            import numpy as np
+            np.save(path, img)
+        else:
+            exr.write_scanline_exr(path, img, ("B", "G", "R"), half=True)
+        return path
+
+
 class DisneySampler:
     """Batched DisneySampler (src/rlDisney.cpp:105-602).  Node parameters by name
     (src/rlDisney.cpp:606-610); setSampleType mirrors :194."""
@@ -266,6 +343,12 @@ class DisneySampler:
         if sample_type not in (abi.RLS_RAY_DIFFUSE, abi.RLS_RAY_GLOSSY):
             raise ValueError("sample type must be RLS_RAY_DIFFUSE or RLS_RAY_GLOSSY")
         self.sample_type = sample_type
+
+    def evalLightSample(self, Ld, Li, light_pdf, rx=None, ry=None, Li_at_l=None, pdf_at_l=None):
+        """evalDiffuseLightSample / evalSpecularLightSample (src/rlDisney.cpp:266-277) for the
+        current sample type, as a two-sample power-heuristic MIS (include/rls_b200.h, f3)."""
+        return _eval_light_sample(self.ctx.lib.rls_disney_evaluate_light_sample, self, (self.sample_type,),
+                                  Ld, Li, light_pdf, rx, ry, Li_at_l, pdf_at_l)
 
     def evalSample(self, rx, ry):
         n, c = self.sg.n, self.ctx
@@ -410,6 +493,26 @@ class SkinProfile:
                                                       abi.vec3(_f32rows(hit_normal, "hit_normal")),
                                                       pdf.data_ptr()), c.lib)
         return pdf
+
+    def glossyLayers(self, sg, k, rx_sheen, ry_sheen, rx_specular, ry_specular, li_sheen=None, li_specular=None):
+        """rlSkin's sheen + specular layers with K BRDF samples per shading point and the
+        average-Fresnel hand-off to the SSS weight (src/rlSkin.cpp:184-238).  Sample arrays are
+        sample-major [k * n]; li_* are optional [3, k * n] incoming radiances."""
+        c, n = self.ctx, self.n
+        for nm, t in (("rx_sheen", rx_sheen), ("ry_sheen", ry_sheen), ("rx_specular", rx_specular), ("ry_specular", ry_specular)):
+            _f32(t, nm, n * k)
+        out = dict(sheen=c.empty(3, n, like=rx_sheen), specular=c.empty(3, n, like=rx_sheen),
+                   sheen_fresnel=c.empty(n, like=rx_sheen), specular_fresnel=c.empty(n, like=rx_sheen),
+                   sss_weight=c.empty(n, like=rx_sheen), flags=c.empty(n, dtype=torch.int32, like=rx_sheen))
+        o = abi.SkinLayersOut(abi.vec3(_f32rows(out["sheen"], "sheen")), abi.vec3(_f32rows(out["specular"], "specular")),
+                              out["sheen_fresnel"].data_ptr(), out["specular_fresnel"].data_ptr(),
+                              out["sss_weight"].data_ptr(), out["flags"].data_ptr())
+        la = abi.vec3(_f32rows(li_sheen, "li_sheen")) if li_sheen is not None else abi.vec3(None)
+        lb = abi.vec3(_f32rows(li_specular, "li_specular")) if li_specular is not None else abi.vec3(None)
+        _check(c.handle, c.lib.rls_skin_glossy_layers(c.handle, n, k, C.byref(sg.struct), C.byref(self.params),
+                                                      rx_sheen.data_ptr(), ry_sheen.data_ptr(), rx_specular.data_ptr(),
+                                                      ry_specular.data_ptr(), la, lb, C.byref(o)), c.lib)
+        return out
 
     def layerWeights(self, avg_fresnel_sheen, avg_fresnel_specular):
         c, n = self.ctx, self.n

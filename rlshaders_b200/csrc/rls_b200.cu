@@ -23,6 +23,7 @@
 #include "rls_disney.cuh"
 #include "rls_profile.cuh"
 #include "rls_fused.cuh"
+#include "rls_callers.cuh"
 
 using namespace rls;
 
@@ -542,6 +543,155 @@ k_skin_probe_mis_pdf(size_t n, ShadingSoA sg, SkinParamsDev sp, CV3 disp, CV3 hi
            + nd_get_pdf(fp, p, rr2) * abs_m(dot(s.N, hn)) * 0.5f;
 }
 
+// ============================================ callers of the triple (8(f) rows f2-f4)
+struct SkinLayersOutDev { V3 sheen, spec; float *sheenF, *specF, *sssW; uint32_t *flags; };
+template <bool kFast>
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+k_skin_glossy_layers(size_t n, uint32_t K, ShadingSoA sg, SkinLayersDev sp, const float *rx_a, const float *ry_a,
+                     const float *rx_b, const float *ry_b, CV3 li_a, CV3 li_b, SkinLayersOutDev o,
+                     unsigned long long *fallbacks)
+{
+    RLS_INDEX();
+    const Shading s = load_shading(sg, i);
+    SkinLayers1 r;
+    RLS_FAST_THEN_EXACT(kFast, r, skin_layers_unit(fp, s, sp, K, n, i, rx_a, ry_a, rx_b, ry_b, li_a, li_b));
+    store3(o.sheen, i, r.sheen);
+    store3(o.spec, i, r.spec);
+    o.sheenF[i] = r.sheenF;
+    o.specF[i] = r.specF;
+    o.sssW[i] = r.sssW;
+    o.flags[i] = r.flags;
+}
+
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+k_ggx_light_sample(size_t n, ShadingSoA sg, GgxParamsDev p, LightDev light, const float *rx, const float *ry,
+                   LightDev at_l, V3 out, float *w_light, float *w_brdf)
+{
+    RLS_INDEX();
+    FpExact fp;
+    Ggx g = ggx_make(fp, sg, p, i);
+    const f3 Ld = load3(light.dir, i), Li = load3(light.radiance, i);
+    const float pl = __ldg(light.pdf + i);
+    const f3 f_l = ggx_eval_brdf(fp, g, Ld);
+    const float p_bl = ggx_eval_pdf(fp, g, Ld);
+    const bool have = at_l.pdf != nullptr;
+    f3 L = mk3(0.0f, 0.0f, 0.0f), f_b = L, Li_b = L;
+    float p_b = 0.0f, p_lb = 0.0f;
+    if (have) {
+        GgxBsdf u = ggx_unit(fp, g, __ldg(rx + i), __ldg(ry + i));
+        L = u.L; f_b = u.f; p_b = u.pdf;
+        Li_b = load3(at_l.radiance, i);
+        p_lb = __ldg(at_l.pdf + i);
+    }
+    Mis1 m = mis_combine(Ld, Li, pl, f_l, p_bl, have, L, f_b, p_b, Li_b, p_lb);
+    store3(out, i, m.rgb);
+    if (w_light) w_light[i] = m.w_light;
+    if (w_brdf) w_brdf[i] = m.w_brdf;
+}
+
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+k_disney_light_sample(size_t n, ShadingSoA sg, DisneyParamsDev p, int type, LightDev light, const float *rx,
+                      const float *ry, LightDev at_l, V3 out, float *w_light, float *w_brdf)
+{
+    RLS_INDEX();
+    FpExact fp;
+    Disney d; disney_init(fp, d, load_shading(sg, i), p, i);
+    const f3 Ld = load3(light.dir, i), Li = load3(light.radiance, i);
+    const float pl = __ldg(light.pdf + i);
+    const f3 f_l = disney_eval_brdf(fp, d, type, Ld);
+    const float p_bl = disney_eval_pdf(fp, d, type, Ld);
+    const bool have = at_l.pdf != nullptr;
+    f3 L = mk3(0.0f, 0.0f, 0.0f), f_b = L, Li_b = L;
+    float p_b = 0.0f, p_lb = 0.0f;
+    if (have) {
+        uint32_t lobe = 0;
+        L = (type == kRayDiffuse) ? disney_sample_diffuse(fp, d, __ldg(rx + i), __ldg(ry + i))
+                                  : disney_sample_specular(fp, d, __ldg(rx + i), __ldg(ry + i), lobe);
+        f_b = disney_eval_brdf(fp, d, type, L);
+        p_b = disney_eval_pdf(fp, d, type, L);
+        Li_b = load3(at_l.radiance, i);
+        p_lb = __ldg(at_l.pdf + i);
+    }
+    Mis1 m = mis_combine(Ld, Li, pl, f_l, p_bl, have, L, f_b, p_b, Li_b, p_lb);
+    store3(out, i, m.rgb);
+    if (w_light) w_light[i] = m.w_light;
+    if (w_brdf) w_brdf[i] = m.w_brdf;
+}
+
+// SampleWriter::writeRadiance (src/rlUtil.h:98-114): one thread per pixel of one shading point.
+RLS_DEV f3 writer_direction(int i, int j, int W, int H)
+{
+    FpExact fp;
+    float theta = kHalfPi * (float)j / (float)H;
+    float phi = kTwoPi * (float)i / (float)W;
+    float sn, cs;
+    rlm::sincosf_(theta, &sn, &cs);                    // cosf(theta): same binary64 kernel as sincosf
+    return spherical_direction(fp, cs, phi);
+}
+RLS_DEV void write_pixel(float *image, int W, int H, int x, int y, f3 rgb)     // writePixel :158-163
+{
+    const size_t stride = (size_t)W * H, at = (size_t)x + (size_t)y * W;
+    image[at] = rgb.z; image[at + stride] = rgb.y; image[at + stride * 2] = rgb.x;
+}
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+k_writer_radiance_ggx(size_t n, ShadingSoA sg, GgxParamsDev p, uint32_t point, int W, int H, float *image)
+{
+    RLS_INDEX();
+    FpExact fp;
+    Ggx g = ggx_make(fp, sg, p, point);
+    const int x = (int)(i % (uint32_t)W), y = (int)(i / (uint32_t)W);
+    write_pixel(image, W, H, x, y, ggx_eval_brdf(fp, g, writer_direction(x, y, W, H)));
+}
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+k_writer_radiance_disney(size_t n, ShadingSoA sg, DisneyParamsDev p, int type, uint32_t point, int W, int H, float *image)
+{
+    RLS_INDEX();
+    FpExact fp;
+    Disney d; disney_init(fp, d, load_shading(sg, point), p, point);
+    const int x = (int)(i % (uint32_t)W), y = (int)(i / (uint32_t)W);
+    write_pixel(image, W, H, x, y, disney_eval_brdf(fp, d, type, writer_direction(x, y, W, H)));
+}
+// SampleWriter::writeSample (:116-156).  scratch[pixel] = max over samples of ((k + 1) << 1 | red):
+// the sample with the largest index wins, as the last write does in the sequential loop.
+RLS_DEV void scatter_mark(f3 L, uint32_t k, int W, int H, uint32_t *scratch, uint32_t *missing)
+{
+    int x, y; bool red;
+    if (!scatter_pixel(L, W, H, x, y, red)) return;
+    atomicMax(scratch + (size_t)x + (size_t)y * W, ((k + 1u) << 1) | (red ? 1u : 0u));
+    if (red && missing) atomicAdd(missing, 1u);
+}
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+k_writer_scatter_ggx(size_t n, ShadingSoA sg, GgxParamsDev p, uint32_t point, const float *rx, const float *ry,
+                     int W, int H, uint32_t *scratch, uint32_t *missing)
+{
+    RLS_INDEX();
+    FpExact fp;
+    Ggx g = ggx_make(fp, sg, p, point);
+    f3 M = ggx_sample_normal(fp, g, __ldg(rx + i), __ldg(ry + i));
+    scatter_mark(reflect_direction(g.wo, M), i, W, H, scratch, missing);
+}
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+k_writer_scatter_disney(size_t n, ShadingSoA sg, DisneyParamsDev p, int type, uint32_t point, const float *rx,
+                        const float *ry, int W, int H, uint32_t *scratch, uint32_t *missing)
+{
+    RLS_INDEX();
+    FpExact fp;
+    Disney d; disney_init(fp, d, load_shading(sg, point), p, point);
+    uint32_t lobe = 0;
+    f3 L = (type == kRayDiffuse) ? disney_sample_diffuse(fp, d, __ldg(rx + i), __ldg(ry + i))
+                                 : disney_sample_specular(fp, d, __ldg(rx + i), __ldg(ry + i), lobe);
+    scatter_mark(L, i, W, H, scratch, missing);
+}
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+k_writer_scatter_paint(size_t n, int W, int H, const uint32_t *scratch, float *image)
+{
+    RLS_INDEX();
+    const uint32_t v = scratch[i];
+    if (v == 0u) return;
+    const f3 c = (v & 1u) ? mk3(1.0f, 0.0f, 0.0f) : mk3(0.0f, 1.0f, 0.0f);     // AI_RGB_RED / AI_RGB_GREEN
+    write_pixel(image, W, H, (int)(i % (uint32_t)W), (int)(i / (uint32_t)W), c);
+}
+
 // ============================================================ synthetic generators
 RLS_DEV uint64_t hash64(uint64_t seed, uint32_t stream, uint64_t index)
 {
@@ -1007,6 +1157,137 @@ extern "C" int rls_synth_shading(rls_context *ctx, size_t n, uint64_t seed, uint
     V3 W = { (float *)sg->wo.x, (float *)sg->wo.y, (float *)sg->wo.z };
     k_synth_shading<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, seed, first_index, cos_lo, cos_hi, backfacing_fraction,
                                                             U, V, N, W, (uint8_t *)sg->backfacing);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+
+// ===================================================== C ABI: callers (8(f) f2-f4)
+static inline bool none3(const rls_cvec3 &v) { return !v.x && !v.y && !v.z; }
+static inline SkinLayerDev layer_dev(const rls_param3 &c, const rls_param1 &w, const rls_param1 &r, const rls_param1 &ior)
+{
+    SkinLayerDev o; o.color = p3(c); o.weight = p1(w); o.roughness = p1(r); o.ior = p1(ior); return o;
+}
+extern "C" int rls_skin_glossy_layers(rls_context *ctx, size_t n, uint32_t k, const rls_shading_soa *sg,
+                                      const rls_skin_params *p, const float *rx_a, const float *ry_a,
+                                      const float *rx_b, const float *ry_b, rls_cvec3 li_a, rls_cvec3 li_b,
+                                      const rls_skin_layers_out *out)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
+    RLS_REQUIRE(ctx, k >= 1, "rls_skin_glossy_layers: k must be at least 1");
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_skin_params(p) && ok_p3(p->sheen_color) && ok_p3(p->specular_color) &&
+                rx_a && ry_a && rx_b && ry_b && out && has3(out->sheen) && has3(out->specular) && out->sheen_fresnel &&
+                out->specular_fresnel && out->sss_weight && out->flags, "rls_skin_glossy_layers: NULL argument");
+    RLS_REQUIRE(ctx, (none3(li_a) || has3(li_a)) && (none3(li_b) || has3(li_b)),
+                "rls_skin_glossy_layers: a radiance input must have all three channels or none");
+    DeviceGuard guard(ctx->device);
+    SkinLayersDev sp;
+    sp.sheen = layer_dev(p->sheen_color, p->sheen_weight, p->sheen_roughness, p->sheen_ior);
+    sp.spec = layer_dev(p->specular_color, p->specular_weight, p->specular_roughness, p->specular_ior);
+    sp.sss_weight = p1(p->sss_weight);
+    SkinLayersOutDev o; o.sheen = mv(out->sheen); o.spec = mv(out->specular); o.sheenF = out->sheen_fresnel;
+    o.specF = out->specular_fresnel; o.sssW = out->sss_weight; o.flags = out->flags;
+    if (ctx->arith == RLS_ARITH_FAST)
+        k_skin_glossy_layers<true><<<grid_for(n), kBlock, 0, ctx->stream>>>(n, k, sh(*sg), sp, rx_a, ry_a, rx_b, ry_b, cv(li_a), cv(li_b), o, ctx->fallbacks);
+    else
+        k_skin_glossy_layers<false><<<grid_for(n), kBlock, 0, ctx->stream>>>(n, k, sh(*sg), sp, rx_a, ry_a, rx_b, ry_b, cv(li_a), cv(li_b), o, ctx->fallbacks);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+
+static inline bool ok_light(const rls_light_sample *l, bool need_dir)
+{
+    return l && (!need_dir || has3(l->dir)) && has3(l->radiance) && l->pdf;
+}
+static inline LightDev light_dev(const rls_light_sample *l)
+{
+    LightDev o; o.dir = CV3{ nullptr, nullptr, nullptr }; o.radiance = o.dir; o.pdf = nullptr;
+    if (l) { o.dir = cv(l->dir); o.radiance = cv(l->radiance); o.pdf = l->pdf; }
+    return o;
+}
+extern "C" int rls_ggx_evaluate_light_sample(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
+                                             const rls_light_sample *light, const float *rx, const float *ry,
+                                             const rls_light_sample *at_l, rls_vec3 out_rgb, float *w_light, float *w_brdf)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && ok_light(light, true) && has3(out_rgb) &&
+                (!at_l || (ok_light(at_l, false) && rx && ry)), "rls_ggx_evaluate_light_sample: NULL argument");
+    DeviceGuard guard(ctx->device);
+    k_ggx_light_sample<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), light_dev(light), rx, ry, light_dev(at_l),
+                                                               mv(out_rgb), w_light, w_brdf);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+extern "C" int rls_disney_evaluate_light_sample(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_disney_params *p,
+                                                int sample_type, const rls_light_sample *light, const float *rx, const float *ry,
+                                                const rls_light_sample *at_l, rls_vec3 out_rgb, float *w_light, float *w_brdf)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_disney_params(p) && ok_light(light, true) && has3(out_rgb) &&
+                (!at_l || (ok_light(at_l, false) && rx && ry)), "rls_disney_evaluate_light_sample: NULL argument");
+    RLS_REQUIRE(ctx, ok_sample_type(sample_type), "rls_disney_evaluate_light_sample: sample_type must be RLS_RAY_DIFFUSE or RLS_RAY_GLOSSY");
+    DeviceGuard guard(ctx->device);
+    k_disney_light_sample<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), sample_type, light_dev(light), rx, ry,
+                                                                  light_dev(at_l), mv(out_rgb), w_light, w_brdf);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+
+extern "C" int rls_sample_writer_radiance(rls_context *ctx, int node, const rls_shading_soa *sg, const void *params, size_t point,
+                                          int sample_type, int width, int height, float *image)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, (node == RLS_NODE_GGX || node == RLS_NODE_DISNEY) && ok_shading(sg) && params && image,
+                "rls_sample_writer_radiance: bad argument");
+    RLS_REQUIRE(ctx, width > 0 && height > 0 && (size_t)width * height < (1ull << 31) && !(point >> 32),
+                "rls_sample_writer_radiance: bad image size or point index");
+    DeviceGuard guard(ctx->device);
+    const size_t n = (size_t)width * height;
+    if (node == RLS_NODE_GGX) {
+        const rls_ggx_params *p = (const rls_ggx_params *)params;
+        RLS_REQUIRE(ctx, ok_ggx_params(p), "rls_sample_writer_radiance: bad rlGgx parameters");
+        k_writer_radiance_ggx<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), (uint32_t)point, width, height, image);
+    } else {
+        const rls_disney_params *p = (const rls_disney_params *)params;
+        RLS_REQUIRE(ctx, ok_disney_params(p) && ok_sample_type(sample_type), "rls_sample_writer_radiance: bad rlDisney parameters");
+        k_writer_radiance_disney<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), sample_type, (uint32_t)point, width, height, image);
+    }
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+extern "C" int rls_sample_writer_scatter(rls_context *ctx, int node, const rls_shading_soa *sg, const void *params, size_t point,
+                                         int sample_type, size_t n_samples, const float *rx, const float *ry, int width,
+                                         int height, float *image, uint32_t *scratch, uint32_t *out_missing)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, (node == RLS_NODE_GGX || node == RLS_NODE_DISNEY) && ok_shading(sg) && params && image && scratch &&
+                (n_samples == 0 || (rx && ry)), "rls_sample_writer_scatter: bad argument");
+    RLS_REQUIRE(ctx, width > 0 && height > 0 && (size_t)width * height < (1ull << 31) && !(point >> 32) && n_samples < (1ull << 31),
+                "rls_sample_writer_scatter: bad image size, point index or sample count");
+    DeviceGuard guard(ctx->device);
+    const size_t npix = (size_t)width * height;
+    RLS_CUDA(ctx, cudaMemsetAsync(scratch, 0, npix * sizeof(uint32_t), ctx->stream));
+    if (out_missing) RLS_CUDA(ctx, cudaMemsetAsync(out_missing, 0, sizeof(uint32_t), ctx->stream));
+    if (n_samples) {
+        if (node == RLS_NODE_GGX) {
+            const rls_ggx_params *p = (const rls_ggx_params *)params;
+            RLS_REQUIRE(ctx, ok_ggx_params(p), "rls_sample_writer_scatter: bad rlGgx parameters");
+            k_writer_scatter_ggx<<<grid_for(n_samples), kBlock, 0, ctx->stream>>>(n_samples, sh(*sg), dev(*p), (uint32_t)point, rx, ry,
+                                                                                  width, height, scratch, out_missing);
+        } else {
+            const rls_disney_params *p = (const rls_disney_params *)params;
+            RLS_REQUIRE(ctx, ok_disney_params(p) && ok_sample_type(sample_type), "rls_sample_writer_scatter: bad rlDisney parameters");
+            k_writer_scatter_disney<<<grid_for(n_samples), kBlock, 0, ctx->stream>>>(n_samples, sh(*sg), dev(*p), sample_type, (uint32_t)point,
+                                                                                     rx, ry, width, height, scratch, out_missing);
+        }
+        RLS_LAUNCH_CHECK(ctx);
+    }
+    k_writer_scatter_paint<<<grid_for(npix), kBlock, 0, ctx->stream>>>(npix, width, height, scratch, image);
     RLS_LAUNCH_CHECK(ctx);
     return RLS_OK;
 }

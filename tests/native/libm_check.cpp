@@ -1,7 +1,7 @@
 // tests/native/libm_check.cpp -- TEST INFRASTRUCTURE.
 // Runs the product's device libm (rlshaders_b200/csrc/rls_libm.cuh, which is __host__
 // __device__) on the CPU against the host C library, bit for bit.
-//   libm_check <function> [stride]     function: sincos tan atan acos exp log atan2 pow
+//   libm_check <function> [stride]     function: sincos cos tan atan acos exp log atan2 pow
 // Univariate functions walk every binary32 bit pattern (stride 1) or every stride-th one;
 // bivariate ones draw (stride-scaled) pseudo-random pairs from the path's domains.
 // Prints "<function> checked N mismatches M first <hex args>" and exits 0.
@@ -63,6 +63,10 @@ int main(int argc, char **argv)
                 sincosf(x, &s0, &c0);
                 rlm::sincosf_(x, &s1, &c1);
                 ok = same(s0, s1) && same(c0, c1);
+            } else if (fn == "cos") {                   // SampleWriter's cosf(theta) is served by sincosf_
+                float s1, c1;
+                rlm::sincosf_(x, &s1, &c1);
+                ok = same(cosf(x), c1);
             } else if (fn == "tan") ok = same(tanf(x), rlm::tanf_(x));
             else if (fn == "atan") ok = same(atanf(x), rlm::atanf_(x));
             else if (fn == "acos") ok = same(acosf(x), rlm::acosf_(x));

@@ -296,6 +296,57 @@ class Oracle:
                                            abi.vec3(kd), abi.vec3(kn), C.c_void_p(pdf.ctypes.data))
         return pdf
 
+    # ---- SURVEY.md 8(f) f2-f4
+    def skin_glossy_layers(self, sg, params, k, rx_a, ry_a, rx_b, ry_b, li_a=None, li_b=None):
+        n = len(rx_a) // k
+        sheen, spec, sf, pf, w, fl = _v3(n), _v3(n), _z(n), _z(n), _z(n), _z(n, np.uint32)
+        out = abi.SkinLayersOut(abi.vec3(sheen), abi.vec3(spec), sf.ctypes.data, pf.ctypes.data, w.ctypes.data,
+                                fl.ctypes.data)
+        ka = [np.ascontiguousarray(li_a[j], dtype=f32) for j in range(3)] if li_a is not None else None
+        kb = [np.ascontiguousarray(li_b[j], dtype=f32) for j in range(3)] if li_b is not None else None
+        self.lib.oracle_skin_glossy_layers(C.c_size_t(n), C.c_uint32(k), C.byref(shading_struct(sg)), C.byref(params),
+                                           C.c_void_p(rx_a.ctypes.data), C.c_void_p(ry_a.ctypes.data),
+                                           C.c_void_p(rx_b.ctypes.data), C.c_void_p(ry_b.ctypes.data),
+                                           abi.vec3(ka), abi.vec3(kb), C.byref(out))
+        return dict(sheen=np.stack(sheen), specular=np.stack(spec), sheen_fresnel=sf, specular_fresnel=pf,
+                    sss_weight=w, flags=fl)
+
+    def _light_sample(self, fn, head, sg, params, Ld, Li, pl, rx, ry, Li_b, pl_b):
+        n = len(pl)
+        keep = [[np.ascontiguousarray(a[j], dtype=f32) for j in range(3)] for a in (Ld, Li)]
+        light = abi.light_sample(keep[0], keep[1], pl)
+        at_l = None
+        if Li_b is not None:
+            kb = [np.ascontiguousarray(Li_b[j], dtype=f32) for j in range(3)]
+            at_l = abi.light_sample(None, kb, pl_b)
+        rgb, wl, wb = _v3(n), _z(n), _z(n)
+        fn(C.c_size_t(n), C.byref(shading_struct(sg)), C.byref(params), *head, C.byref(light),
+           C.c_void_p(rx.ctypes.data if rx is not None else None), C.c_void_p(ry.ctypes.data if ry is not None else None),
+           C.byref(at_l) if at_l is not None else None, abi.vec3(rgb), C.c_void_p(wl.ctypes.data), C.c_void_p(wb.ctypes.data))
+        return dict(rgb=np.stack(rgb), w_light=wl, w_brdf=wb)
+
+    def ggx_light_sample(self, sg, params, Ld, Li, pl, rx=None, ry=None, Li_b=None, pl_b=None):
+        return self._light_sample(self.lib.oracle_ggx_evaluate_light_sample, (), sg, params, Ld, Li, pl, rx, ry, Li_b, pl_b)
+
+    def disney_light_sample(self, sg, params, sample_type, Ld, Li, pl, rx=None, ry=None, Li_b=None, pl_b=None):
+        return self._light_sample(self.lib.oracle_disney_evaluate_light_sample, (C.c_int(sample_type),), sg, params,
+                                  Ld, Li, pl, rx, ry, Li_b, pl_b)
+
+    def sample_writer(self, node, sg, params, point, sample_type, width, height, rx=None, ry=None):
+        """writeRadiance, then (if samples are given) writeSample painted over it."""
+        image = np.zeros((3, height, width), dtype=f32)
+        self.lib.oracle_sample_writer_radiance(C.c_int(node), C.byref(shading_struct(sg)), C.byref(params),
+                                               C.c_size_t(point), C.c_int(sample_type), C.c_int(width), C.c_int(height),
+                                               C.c_void_p(image.ctypes.data))
+        missing = np.zeros(1, dtype=np.uint32)
+        if rx is not None:
+            self.lib.oracle_sample_writer_scatter(C.c_int(node), C.byref(shading_struct(sg)), C.byref(params),
+                                                  C.c_size_t(point), C.c_int(sample_type), C.c_size_t(len(rx)),
+                                                  C.c_void_p(rx.ctypes.data), C.c_void_p(ry.ctypes.data),
+                                                  C.c_int(width), C.c_int(height), C.c_void_p(image.ctypes.data),
+                                                  C.c_void_p(missing.ctypes.data))
+        return image, int(missing[0])
+
     def albedo_sweep(self, grid, seed, spp_begin, spp_end):
         cells = grid.n_rough * grid.n_cos * grid.n_ior
         table = np.zeros((cells, abi.SWEEP_VALUES_PER_CELL), dtype=np.float64)

@@ -177,3 +177,55 @@ if __name__ == "__main__":
         print(format_report("GGX dielectric, anisotropic", run_ggx_dielectric(ctx, orc, n, aniso=True)[0]))
         print(format_report("Disney (config 3)", run_disney(ctx, orc, n)[0]))
         print(format_report("Skin profile (config 4)", run_skin(ctx, orc, n)[0]))
+
+
+# ------------------------------------------- callers of the triple
+def skin_layers_inputs(n, k, seed=0x5EED00F2, with_radiance=True):
+    """P shading points x K samples (sample-major), every rlSkin layer parameter varying; a few
+    points have a zero / tiny layer weight or a black layer colour (the node's skip branches)."""
+    sg = ol.make_shading(n, seed)
+    u = lambda s, lo=0.0, hi=1.0: ol.hash_uniform(n, seed, s, lo=lo, hi=hi)     # noqa: E731
+    sel = ol.hash_uniform(n, seed, 99)
+    kw = dict(sheen_color=tuple(u(20 + j) for j in range(3)), sheen_weight=np.where(sel < 0.1, 0.0, u(23)).astype(np.float32),
+              sheen_roughness=u(24, 0.05, 1.0), sheen_ior=u(25, 1.05, 2.0),
+              specular_color=tuple(np.where((sel > 0.9) & (sel < 0.95), 0.0, u(26 + j)).astype(np.float32) for j in range(3)),
+              specular_weight=np.where(sel > 0.97, 5e-5, u(29)).astype(np.float32),
+              specular_roughness=u(30, 0.05, 1.0), specular_ior=u(31, 1.05, 2.0), sss_weight=u(32))
+    uu = [ol.hash_uniform(n * k, seed, 40 + j) for j in range(4)]
+    li = [np.stack([ol.hash_uniform(n * k, seed, 50 + 3 * j + c, lo=0.0, hi=4.0) for c in range(3)]) for j in range(2)] \
+        if with_radiance else [None, None]
+    return sg, kw, uu, li
+
+
+def run_skin_layers(ctx, oracle, n, k, seed=0x5EED00F2, with_radiance=True):
+    sg, kw, uu, li = skin_layers_inputs(n, k, seed, with_radiance)
+    cpu = oracle.skin_glossy_layers(sg, abi.skin_params(**kw), k, *uu, li[0], li[1])
+    dsg = api.ShadingBatch.from_numpy(sg, ctx.device)
+    s = api.SkinProfile(ctx, n, **params_to_dev(kw, ctx.device))
+    dli = [to_dev(t, ctx.device) if t is not None else None for t in li]
+    gpu = s.glossyLayers(dsg, k, *[to_dev(t, ctx.device) for t in uu], dli[0], dli[1])
+    ctx.synchronize()
+    kinds = dict(sheen="rel", specular="rel", sheen_fresnel="rel", specular_fresnel="rel", sss_weight="rel", flags="flags")
+    return summarize(gpu, cpu, kinds), gpu, cpu
+
+
+def light_inputs(n, sg, seed):
+    """A light sample per shading point: direction in the upper hemisphere of the frame (a few
+    below it and a few zero vectors), radiance, pdf (some zero); and the same light evaluated
+    along the BRDF-sampled direction."""
+    N = np.stack([sg["N" + c] for c in "xyz"]); U = np.stack([sg["U" + c] for c in "xyz"]); V = np.stack([sg["V" + c] for c in "xyz"])
+    cz = ol.hash_uniform(n, seed, 70, lo=-0.2, hi=1.0)
+    ph = ol.hash_uniform(n, seed, 71, lo=0.0, hi=2.0 * np.pi)
+    sr = np.sqrt(np.maximum(0.0, 1.0 - cz.astype(np.float64) ** 2))
+    Ld = U * (sr * np.cos(ph)) + V * (sr * np.sin(ph)) + N * cz
+    Ld = (Ld / np.linalg.norm(Ld, axis=0)).astype(np.float32)
+    sel = ol.hash_uniform(n, seed, 72)
+    Ld[:, sel < 0.02] = 0.0
+    Li = np.stack([ol.hash_uniform(n, seed, 73 + c, lo=0.0, hi=10.0) for c in range(3)])
+    pl = np.where(sel > 0.97, 0.0, ol.hash_uniform(n, seed, 76, lo=0.01, hi=5.0)).astype(np.float32)
+    Lib = np.stack([ol.hash_uniform(n, seed, 77 + c, lo=0.0, hi=10.0) for c in range(3)])
+    plb = np.where((sel > 0.5) & (sel < 0.55), 0.0, ol.hash_uniform(n, seed, 80, lo=0.01, hi=5.0)).astype(np.float32)
+    return np.ascontiguousarray(Ld), Li, pl, Lib, plb
+
+
+MIS_KINDS = dict(rgb="rel", w_light="rel", w_brdf="rel")

@@ -38,7 +38,8 @@ def test_struct_layouts_match_header():
                "rls_bsdf_out": abi.BsdfOut, "rls_ggx_dielectric_out": abi.GgxDielectricOut,
                "rls_disney_out": abi.DisneyOut, "rls_ndprofile_soa": abi.NdProfileSoA,
                "rls_profile_out": abi.ProfileOut, "rls_probe_out": abi.ProbeOut,
-               "rls_sweep_grid": abi.SweepGrid}
+               "rls_sweep_grid": abi.SweepGrid, "rls_skin_layers_out": abi.SkinLayersOut,
+               "rls_light_sample": abi.LightSample}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){']
     for cname, cls in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

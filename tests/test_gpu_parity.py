@@ -576,3 +576,98 @@ def test_fast_policy_equals_exact_policy(ctx, adversarial):
     if not adversarial:     # the benchmark distributions stay inside the window
         for k, v in fb.items():
             assert v <= n * 2e-3, (k, v)
+
+
+# ------------------------------------------- callers of the triple
+@pytest.mark.parametrize("with_radiance", [True, False])
+def test_skin_glossy_layers(ctx, orc, with_radiance):
+    """f2: K GGX triples per shading point and layer, sequential Fresnel average, layer hand-off."""
+    stats, gpu, cpu = parity.run_skin_layers(ctx, orc, 1 << 16, 9, with_radiance=with_radiance)
+    check(stats, f"f2 skin glossy layers (radiance={with_radiance}) vs {orc.kind}")
+    fl = gpu["flags"].cpu().numpy()
+    assert ((fl & abi.SKIN_SHEEN_EVALUATED) == 0).any() and ((fl & abi.SKIN_SPECULAR_EVALUATED) == 0).any()
+    # K = 1 with both layers on reproduces the single-sample entry points
+    from rlshaders_b200 import api
+    n = 1 << 14
+    sg, kw, uu, _ = parity.skin_layers_inputs(n, 1, with_radiance=False)
+    dsg = api.ShadingBatch.from_numpy(sg, ctx.device)
+    s = api.SkinProfile(ctx, n, **parity.params_to_dev(kw, ctx.device))
+    one = s.glossyLayers(dsg, 1, *[dev(t, ctx) for t in uu])
+    g = api.GgxSampler(ctx, dsg, KsColor=tuple(dev(t, ctx) for t in kw["sheen_color"]), ior=dev(kw["sheen_ior"], ctx),
+                       specularRoughness=dev(kw["sheen_roughness"], ctx))
+    unit = g.sampleEvalPdf(dev(uu[0], ctx), dev(uu[1], ctx))
+    on = (one["flags"] & abi.SKIN_SHEEN_EVALUATED) != 0
+    w = dev(kw["sheen_weight"], ctx)
+    assert torch.equal(one["sheen_fresnel"][on], (unit["fresnel"] / 1.0 * w)[on])
+    assert torch.equal(one["sheen"][:, on], ((unit["f"] / unit["pdf"]) * 1.0 * w)[:, on])
+
+
+def test_light_sample_mis(ctx, orc):
+    """f3: AiEvaluateLightSample-shaped two-sample MIS for rlGgx and both rlDisney sample types."""
+    from rlshaders_b200 import api
+    n = 1 << 18
+    sg, kw, rx, ry = parity.ggx_dielectric_inputs(n, 0x5EED00F3, aniso=True)
+    Ld, Li, pl, Lib, plb = parity.light_inputs(n, sg, 0x5EED00F3)
+    dsg = api.ShadingBatch.from_numpy(sg, ctx.device)
+    g = api.GgxSampler(ctx, dsg, KsColor=(0.9, 0.6, 0.3), **parity.params_to_dev(kw, ctx.device))
+    p = abi.ggx_params(KsColor=(0.9, 0.6, 0.3), **kw)
+    d = lambda a: dev(a, ctx)     # noqa: E731
+    gpu = g.evalLightSample(d(Ld), d(Li), d(pl))
+    check(parity.summarize(gpu, orc.ggx_light_sample(sg, p, Ld, Li, pl), parity.MIS_KINDS), "f3 ggx, light half only")
+    gpu = g.evalLightSample(d(Ld), d(Li), d(pl), d(rx), d(ry), d(Lib), d(plb))
+    cpu = orc.ggx_light_sample(sg, p, Ld, Li, pl, rx, ry, Lib, plb)
+    check(parity.summarize(gpu, cpu, parity.MIS_KINDS), f"f3 ggx, both halves vs {orc.kind}")
+    # the two power-heuristic weights of one direction pair sum to one where both pdfs are positive
+    wl, wb = gpu["w_light"].cpu().numpy(), gpu["w_brdf"].cpu().numpy()
+    assert ((wl >= 0) & (wl <= 1) & (wb >= 0) & (wb <= 1)).all()
+
+    dsg_np, dkw, du = parity.disney_inputs(n, 0x5EED00F3)
+    Ld, Li, pl, Lib, plb = parity.light_inputs(n, dsg_np, 0x5EED00F4)
+    ds = api.DisneySampler(ctx, api.ShadingBatch.from_numpy(dsg_np, ctx.device), **parity.params_to_dev(dkw, ctx.device))
+    dp = abi.disney_params(**dkw)
+    for st, (ux, uy) in ((abi.RLS_RAY_GLOSSY, du[:2]), (abi.RLS_RAY_DIFFUSE, du[2:])):
+        ds.setSampleType(st)
+        gpu = ds.evalLightSample(d(Ld), d(Li), d(pl), d(ux), d(uy), d(Lib), d(plb))
+        cpu = orc.disney_light_sample(dsg_np, dp, st, Ld, Li, pl, ux, uy, Lib, plb)
+        check(parity.summarize(gpu, cpu, parity.MIS_KINDS), f"f3 disney type {st:#x} vs {orc.kind}")
+
+
+def test_sample_writer_images(ctx, orc, tmp_path):
+    """f4: SampleWriter's lat-long BRDF image + sample scatter, bit for bit, and the EXR it saves."""
+    from rlshaders_b200 import api, exr
+    n = 64
+    sg, kw, rx, ry = parity.ggx_dielectric_inputs(n, 0x5EED00F5)
+    for name, val in (("U", (1, 0, 0)), ("V", (0, 1, 0)), ("N", (0, 0, 1)), ("wo", (np.sqrt(0.5), 0, np.sqrt(0.5)))):
+        for c, v in zip("xyz", val):
+            sg[name + c][0] = np.float32(v)
+    sx, sy = ol.hash_uniform(1 << 16, 7, 0), ol.hash_uniform(1 << 16, 7, 1)
+    dsg = api.ShadingBatch.from_numpy(sg, ctx.device)
+    g = api.GgxSampler(ctx, dsg, specularRoughness=0.35, ior=1.5)
+    p = abi.ggx_params(specularRoughness=0.35, ior=1.5)
+    W, H = 256, 128
+    for point in (0, 5):
+        w = api.SampleWriter(ctx, W, H)
+        w.writeRadiance(g, point)
+        want, _ = orc.sample_writer(abi.NODE_GGX, sg, p, point, 0, W, H)
+        ctx.synchronize()
+        assert gio.bits_equal(w.image.cpu().numpy(), want), "radiance image"
+        w.writeSample(g, dev(sx, ctx), dev(sy, ctx), point)
+        want, missing = orc.sample_writer(abi.NODE_GGX, sg, p, point, 0, W, H, sx, sy)
+        ctx.synchronize()
+        assert gio.bits_equal(w.image.cpu().numpy(), want), "radiance + scatter image"
+        assert int(w.missing.item()) == missing
+    path = w.save(str(tmp_path / "rls_sampling_pattern.exr"))
+    planes, _ = exr.read_scanline_exr(path)
+    assert np.array_equal(planes["G"], want[1].astype(np.float16))
+
+    dsg_np, dkw, _ = parity.disney_inputs(n, 0x5EED00F6)
+    ds = api.DisneySampler(ctx, api.ShadingBatch.from_numpy(dsg_np, ctx.device), **parity.params_to_dev(dkw, ctx.device))
+    dp = abi.disney_params(**dkw)
+    for st in (abi.RLS_RAY_GLOSSY, abi.RLS_RAY_DIFFUSE):
+        ds.setSampleType(st)
+        w = api.SampleWriter(ctx, 128, 64)
+        w.writeRadiance(ds, 3)
+        w.writeSample(ds, dev(sx, ctx), dev(sy, ctx), 3)
+        want, missing = orc.sample_writer(abi.NODE_DISNEY, dsg_np, dp, 3, st, 128, 64, sx, sy)
+        ctx.synchronize()
+        assert gio.bits_equal(w.image.cpu().numpy(), want) and int(w.missing.item()) == missing

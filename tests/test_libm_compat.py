@@ -28,7 +28,7 @@ def checker():
     return EXE
 
 
-@pytest.mark.parametrize("fn", ["sincos", "tan", "atan", "acos", "exp", "log", "atan2", "pow", "pow5"])
+@pytest.mark.parametrize("fn", ["sincos", "cos", "tan", "atan", "acos", "exp", "log", "atan2", "pow", "pow5"])
 def test_device_libm_source_matches_host_libm(checker, fn):
     stride = "1" if os.environ.get("RLS_LIBM_EXHAUSTIVE") else ("61" if fn in ("atan2", "pow", "pow5") else "253")
     out = subprocess.run([checker, fn, stride], check=True, capture_output=True, text=True).stdout.split()

@@ -172,3 +172,76 @@ def test_port_vs_reference_sampler_variants_and_mis(port, ref):
     hn = ol.make_shading(n, 9)
     hnv = np.stack([hn["Nx"], hn["Ny"], hn["Nz"]])
     assert gio.bits_equal(ref.skin_probe_mis_pdf(sg, sp, disp, hnv), port.skin_probe_mis_pdf(sg, sp, disp, hnv))
+
+
+# ------------------------------------------- callers of the triple
+def test_port_vs_reference_skin_glossy_layers(port, ref):
+    import parity
+    n, k = 1 << 12, 9
+    for with_li in (True, False):
+        sg, kw, uu, li = parity.skin_layers_inputs(n, k, with_radiance=with_li)
+        p = abi.skin_params(**kw)
+        a = port.skin_glossy_layers(sg, p, k, *uu, li[0], li[1])
+        b = ref.skin_glossy_layers(sg, p, k, *uu, li[0], li[1])
+        assert_same(b, a, f"skin glossy layers (radiance={with_li})")
+        assert (a["flags"] & abi.SKIN_SHEEN_EVALUATED).any() and not (a["flags"] & abi.SKIN_SHEEN_EVALUATED).all()
+    # a skipped layer leaves its Fresnel term at 0 and the estimate black (src/rlSkin.cpp:191,207)
+    off = (a["flags"] & abi.SKIN_SHEEN_EVALUATED) == 0
+    assert not a["sheen_fresnel"][off].any() and not a["sheen"][:, off].any()
+
+
+def test_port_vs_reference_light_sample(port, ref):
+    import parity
+    n = 1 << 14
+    sg, kw, rx, ry = parity.ggx_dielectric_inputs(n, 0x5EED00F3, aniso=True)
+    Ld, Li, pl, Lib, plb = parity.light_inputs(n, sg, 0x5EED00F3)
+    p = abi.ggx_params(KsColor=(0.9, 0.6, 0.3), **kw)
+    for half in (False, True):
+        extra = (rx, ry, Lib, plb) if half else ()
+        a, b = port.ggx_light_sample(sg, p, Ld, Li, pl, *extra), ref.ggx_light_sample(sg, p, Ld, Li, pl, *extra)
+        assert_same(b, a, f"ggx light sample (brdf half={half})")
+    assert (a["w_light"] == 0).any() and (a["w_brdf"] == 1).any() and (a["w_light"] > 0).any()
+    dsg, dkw, du = parity.disney_inputs(n, 0x5EED00F3)
+    dp = abi.disney_params(**dkw)
+    Ld, Li, pl, Lib, plb = parity.light_inputs(n, dsg, 0x5EED00F4)
+    for st, (ux, uy) in ((abi.RLS_RAY_GLOSSY, du[:2]), (abi.RLS_RAY_DIFFUSE, du[2:])):
+        a = port.disney_light_sample(dsg, dp, st, Ld, Li, pl, ux, uy, Lib, plb)
+        b = ref.disney_light_sample(dsg, dp, st, Ld, Li, pl, ux, uy, Lib, plb)
+        assert_same(b, a, f"disney light sample type {st:#x}")
+
+
+def test_port_vs_reference_sample_writer(port, ref):
+    import parity
+    n = 64
+    sg, kw, rx, ry = parity.ggx_dielectric_inputs(n, 0x5EED00F5)
+    # the writer's own use (src/rlGgx.cpp:202-224): identity frame, view at 45 degrees
+    for name, val in (("U", (1, 0, 0)), ("V", (0, 1, 0)), ("N", (0, 0, 1)), ("wo", (np.sqrt(0.5), 0, np.sqrt(0.5)))):
+        for c, v in zip("xyz", val):
+            sg[name + c][0] = np.float32(v)
+    sx, sy = ol.hash_uniform(4096, 7, 0), ol.hash_uniform(4096, 7, 1)
+    p = abi.ggx_params(specularRoughness=0.35, ior=1.5)
+    for point in (0, 5):
+        a, ma = port.sample_writer(abi.NODE_GGX, sg, p, point, 0, 96, 48, sx, sy)
+        b, mb = ref.sample_writer(abi.NODE_GGX, sg, p, point, 0, 96, 48, sx, sy)
+        assert gio.bits_equal(a, b) and ma == mb
+    assert (a[1] == 1.0).any()                          # green scatter pixels (plane order B, G, R)
+    dsg, dkw, _ = parity.disney_inputs(n, 0x5EED00F6)
+    dp = abi.disney_params(**{k: (float(v[3]) if not isinstance(v, tuple) else tuple(float(t[3]) for t in v)) for k, v in dkw.items()})
+    for st in (abi.RLS_RAY_GLOSSY, abi.RLS_RAY_DIFFUSE):
+        a, ma = port.sample_writer(abi.NODE_DISNEY, dsg, dp, 3, st, 64, 32, sx, sy)
+        b, mb = ref.sample_writer(abi.NODE_DISNEY, dsg, dp, 3, st, 64, 32, sx, sy)
+        assert gio.bits_equal(a, b) and ma == mb
+
+
+def test_exr_writer_round_trip(tmp_path):
+    from rlshaders_b200 import exr
+    rng = np.random.default_rng(5)
+    img = rng.random((3, 17, 33), dtype=np.float32) * 4.0
+    for half in (True, False):
+        path = exr.write_scanline_exr(str(tmp_path / f"w{int(half)}.exr"), img, ("B", "G", "R"), half=half)
+        planes, attrs = exr.read_scanline_exr(path)
+        assert sorted(planes) == ["B", "G", "R"] and attrs["compression"][1] == b"\0"
+        for j, nm in enumerate(("B", "G", "R")):
+            want = img[j].astype(np.float16) if half else img[j]
+            assert planes[nm].dtype == want.dtype and np.array_equal(planes[nm], want)
+    assert open(path, "rb").read(4) == bytes([0x76, 0x2f, 0x31, 0x01])       # OpenEXR magic
