@@ -29,14 +29,15 @@ using namespace rls;
 
 // ============================================================== context
 static constexpr int kStages = 3;          // host-staging pipeline depth
-// Launch shape: 512 threads x >= 2 resident CTAs per SM (<= 64 registers/thread).  Chosen from a
-// sweep on B200 (tools/sweep_variants.sh; profiles/r01_launch_sweep.txt): the kernels are
-// instruction-issue bound, so occupancy beyond ~50 % does not help and tighter register caps spill.
+// Launch shape: 256 threads x >= 4 resident CTAs per SM (<= 64 registers/thread).  Chosen from
+// sweeps on B200 (tools/sweep_variants.sh; profiles/r01_launch_sweep.txt): the kernels are
+// instruction-issue bound, so occupancy beyond ~50 % does not help and tighter register caps
+// spill; among the 64-register shapes the smaller CTA wins by 2-7 % (finer-grained tail).
 #ifndef RLS_BLOCK
-#define RLS_BLOCK 512
+#define RLS_BLOCK 256
 #endif
 #ifndef RLS_MIN_BLOCKS
-#define RLS_MIN_BLOCKS 2
+#define RLS_MIN_BLOCKS 4
 #endif
 static constexpr int kBlock = RLS_BLOCK;
 

@@ -189,21 +189,44 @@ RLS_DEV DisneyOut1 disney_unit(Fp &fp, const Disney &d, float rx_s, float ry_s, 
         return fp.div((gtr1_a2 - 1.0f) * kInvPi, denominator);
     };
 
-    // ---- specular sample (src/rlDisney.cpp:367-390)
+    // ---- specular sample (src/rlDisney.cpp:367-390).  Both lobes go through ONE sincosf and
+    // one rotate/normalize tail: GTR2 (visible normals) needs sincosf(phi or 2 pi ry), GTR1
+    // sincosf(2 pi rx'), plain GTR2 sincosf(2 pi rx) -- the angle is selected per lane.
     uint32_t lobe;
     f3 M;
     {
         float gtr2Weight = fp.rcp(d.clearcoat + 1.0f);
+        VndfState st;
+        float rx, angle, cosThetaH = 0.0f, g = 0.0f;
         if (rx_s < gtr2Weight) {
-            float rx = fp.div(rx_s, gtr2Weight);
-            M = d.visibleNormal ? sample_visible_normal(fp, d.wo, d.U, d.V, d.N, d.ax, d.ay, rx, ry_s)
-                                : sample_ndf_normal(fp, d.U, d.V, d.N, d.ax, d.ay, ry_s, rx);
             lobe = 0;
+            rx = fp.div(rx_s, gtr2Weight);
+            if (d.visibleNormal) {
+                st = vndf_prepare(fp, d.wo, d.U, d.V, d.N, d.ax, d.ay);
+                angle = vndf_angle(st, ry_s);
+            } else {                                              // sampleGTR2AnisoDirection (:406-414)
+                g = fp.sqrt(fp.div(ry_s, 1.0f - ry_s));           // sample_ndf_normal(.., ry_s, rx)
+                angle = kTwoPi * rx;
+            }
         } else {
-            float rx = fp.div_pz(rx_s - gtr2Weight, 1.0f - gtr2Weight);
-            M = disney_sample_gtr1(fp, d, rx, ry_s);
             lobe = 1;
+            rx = fp.div_pz(rx_s - gtr2Weight, 1.0f - gtr2Weight);
+            angle = kTwoPi * rx;                                  // sampleGTR1Direction (:393-404)
+            float a2 = sqr(d.roughness);
+            cosThetaH = (a2 == 1.0f) ? fp.sqrt(1.0f - ry_s)
+                                     : fp.sqrt(fp.div(1.0f - rlm::powf_(a2, 1.0f - ry_s), 1.0f - a2));
         }
+        float s, c;
+        rlm::sincosf_(angle, &s, &c);
+        f3 omega;
+        if (lobe == 0) {
+            omega = d.visibleNormal ? vndf_omega(fp, st, s, c, d.ax, d.ay, rx, ry_s)
+                                    : mk3(g * d.ax * c, g * d.ay * s, 1.0f);
+        } else {                                                  // sphericalDirection(cosThetaH, phiH)
+            float r = fp.sqrt(1.0f - sqr(cosThetaH));
+            omega = mk3(r * c, r * s, cosThetaH);
+        }
+        M = normalize(fp, rotate_to_frame(omega, d.U, d.V, d.N));
     }
     const bool zeroS = dot(d.N, M) < 0.0f;
     o.Ls = zeroS ? mk3(0.0f, 0.0f, 0.0f) : reflect_direction(d.wo, M);

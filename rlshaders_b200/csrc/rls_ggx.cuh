@@ -101,8 +101,15 @@ RLS_DEV f2 sample_slope(Fp &fp, float theta, float rx, float ry)
 // the uniform-slope early-out (sincosf(2 pi ry), :18-25) and then rotates by phi = 0, for which
 // sincosf returns exactly (0, 1); otherwise it rotates by sincosf(phi).  theta = acosf(V.z) with
 // V.z < 1 - 1e-4 is >= 0.0141 (or NaN), so the early-out is taken exactly when theta was left 0.
+// The sampler in three stages, so that a caller with other lobes in the same warp (rlDisney's
+// GTR1 clearcoat) can share the one sincosf and the rotate/normalize tail:
+//   vndf_prepare  view -> stretched polar angles (theta, phi), or `along_normal`
+//   vndf_angle    the argument of the slope/rotation sincosf
+//   vndf_omega    (sin, cos) of that angle -> un-normalised local microfacet normal
+struct VndfState { bool along_normal; float theta, phi; };
+
 template <class Fp>
-RLS_DEV f3 sample_visible_normal(Fp &fp, f3 view, f3 U, f3 Vax, f3 N, float ax, float ay, float rx, float ry)
+RLS_DEV VndfState vndf_prepare(Fp &fp, f3 view, f3 U, f3 Vax, f3 N, float ax, float ay)
 {
     float cosThetaV = clamp_m(dot(N, view), -1.0f, 1.0f);
     float phiV = rlm::atan2f_(fp, dot(Vax, view), dot(U, view));
@@ -112,24 +119,30 @@ RLS_DEV f3 sample_visible_normal(Fp &fp, f3 view, f3 U, f3 Vax, f3 N, float ax, 
     V.y *= ay;
     V = normalize(fp, V);
 
-    const bool along_normal = !(V.z < (1.0f - kEps));
-    float theta = 0.0f, phi = 0.0f;
-    if (!along_normal) {
-        theta = rlm::acosf_(fp, V.z);
-        phi = rlm::atan2f_(fp, V.y, V.x);
+    VndfState st;
+    st.along_normal = !(V.z < (1.0f - kEps));
+    st.theta = 0.0f; st.phi = 0.0f;
+    if (!st.along_normal) {
+        st.theta = rlm::acosf_(fp, V.z);
+        st.phi = rlm::atan2f_(fp, V.y, V.x);
     }
-    float s, c;
-    rlm::sincosf_(along_normal ? kTwoPi * ry : phi, &s, &c);
+    return st;
+}
+RLS_DEV float vndf_angle(const VndfState &st, float ry) { return st.along_normal ? kTwoPi * ry : st.phi; }
+
+template <class Fp>
+RLS_DEV f3 vndf_omega(Fp &fp, const VndfState &st, float s, float c, float ax, float ay, float rx, float ry)
+{
     f2 slope;
     float sinPhi, cosPhi;
-    if (along_normal) {                          // uniform_slope(rx, ry), then a rotation by phi = 0
+    if (st.along_normal) {                       // uniform_slope(rx, ry), then a rotation by phi = 0
         float r = fp.sqrt(fp.div(rx, 1.0f - rx));
         slope.x = r * c;
         slope.y = r * s;
         sinPhi = 0.0f;
         cosPhi = 1.0f;
     } else {
-        slope = sample_slope(fp, theta, rx, ry);
+        slope = sample_slope(fp, st.theta, rx, ry);
         sinPhi = s;
         cosPhi = c;
     }
@@ -137,7 +150,16 @@ RLS_DEV f3 sample_visible_normal(Fp &fp, f3 view, f3 U, f3 Vax, f3 N, float ax, 
     omega.x = -(cosPhi * slope.x - sinPhi * slope.y) * ax;
     omega.y = -(sinPhi * slope.x + cosPhi * slope.y) * ay;
     omega.z = 1.0f;
-    return normalize(fp, rotate_to_frame(omega, U, Vax, N));
+    return omega;
+}
+
+template <class Fp>
+RLS_DEV f3 sample_visible_normal(Fp &fp, f3 view, f3 U, f3 Vax, f3 N, float ax, float ay, float rx, float ry)
+{
+    const VndfState st = vndf_prepare(fp, view, U, Vax, N, ax, ay);
+    float s, c;
+    rlm::sincosf_(vndf_angle(st, ry), &s, &c);
+    return normalize(fp, rotate_to_frame(vndf_omega(fp, st, s, c, ax, ay, rx, ry), U, Vax, N));
 }
 
 // src/rlGgx.h:33-41 (NDFKernel::evalSample, Burley Eq.14): plain NDF sampling; also
