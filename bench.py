@@ -148,6 +148,26 @@ def run_reference(args):
     emit(line)
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so that the pinned host
+    buffers of the e2e leg are allocated (first touch) on the GPU's own NUMA node and the
+    H2D / D2H copies do not cross the socket interconnect.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ============================================================== product arm (GPU)
 def run_product(args):
     import torch
@@ -162,6 +182,7 @@ def run_product(args):
         raise SystemExit("bench.py: no CUDA device; the product arm has no CPU path "
                          "(use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = api.Context(local)
@@ -255,7 +276,8 @@ def run_product(args):
     e2e_s = max_over_ranks(e2e_s * 1e3) * 1e-3
     clock_info = clocks.stop()
     e2e = {"value": world * ne / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "steps": e2e_steps, "ms_per_step": e2e_s * 1e3, "samples_per_gpu_per_step": ne}
+           "steps": e2e_steps, "ms_per_step": e2e_s * 1e3, "samples_per_gpu_per_step": ne,
+           "host_cpus_bound_to_gpu_numa_node": numa}
     # e2e outputs must equal the device-resident outputs bit for bit
     same = all(torch.equal(hout[k], out[k][..., :ne].cpu()) for k in hout)
 
