@@ -14,6 +14,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <initializer_list>
 #include <new>
 
 #include "../../include/rls_b200.h"
@@ -24,6 +25,7 @@
 #include "rls_profile.cuh"
 #include "rls_fused.cuh"
 #include "rls_callers.cuh"
+#include "rls_packed.cuh"
 
 using namespace rls;
 
@@ -48,6 +50,9 @@ struct rls_context {
     std::string  err;
     uint64_t     launches = 0;
     int          arith = RLS_ARITH_FAST;          // policy of the fused kernels (rls_fp.cuh)
+    bool         packed = false;                  // two-samples-per-thread kernel (rls_packed.cuh): bit-exact but
+                                                  // measured slower on B200 (latency bound at 128 registers), so
+                                                  // it is off unless RLS_PACKED=1 (kept for A/B runs and its test)
     unsigned long long *fallbacks = nullptr;      // device counter: samples re-run with FpExact
     // host-staging resources (lazily created by the *_host entry points)
     cudaStream_t stage_stream[kStages] = { nullptr, nullptr, nullptr };
@@ -105,6 +110,7 @@ extern "C" int rls_init(int device, void *stream, rls_context **out_ctx)
                     "; kernels are built for sm_100a only");
     rls_context *ctx = new (std::nothrow) rls_context();
     if (!ctx) return fail(nullptr, RLS_ERR_OUT_OF_MEMORY, "rls_init: host allocation failed");
+    if (const char *v = getenv("RLS_PACKED")) ctx->packed = atoi(v) != 0;     // A/B switch for tuning runs
     ctx->device = device;
     DeviceGuard guard(device);
     if (stream) {
@@ -113,6 +119,15 @@ extern "C" int rls_init(int device, void *stream, rls_context **out_ctx)
         e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaStreamCreateWithFlags"); }
         ctx->own_stream = true;
+    }
+    {   // {-0, -0} for the packed kernels' multiplies (rls_packed.cuh): a run-time value on purpose
+        const unsigned long long negzero2 = 0x8000000080000000ull;
+        e = cudaMemcpyToSymbol(pk::c_negzero2, &negzero2, sizeof(negzero2));
+        if (e != cudaSuccess) {
+            if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+            delete ctx;
+            return cuda_fail(nullptr, e, "cudaMemcpyToSymbol(c_negzero2)");
+        }
     }
     e = cudaMalloc((void **)&ctx->fallbacks, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(ctx->fallbacks, 0, sizeof(unsigned long long));
@@ -238,6 +253,11 @@ static inline SkinParamsDev dev(const rls_skin_params &p)
 }
 
 static inline unsigned grid_for(size_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+static inline bool aligned8(std::initializer_list<const void *> ptrs)
+{
+    for (const void *q : ptrs) if ((uintptr_t)q & 7u) return false;
+    return true;
+}
 // 32-bit sample index: one IMAD.WIDE per array address instead of a 64-bit add pair; the entry
 // points reject n >= 2^32 (that many samples would not fit in HBM anyway).
 #define RLS_INDEX()                                                            \
@@ -345,6 +365,68 @@ k_ggx_dielectric(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const
     o.f_t[i] = r.f_t;
     o.weight_t[i] = r.w_t;
     o.flags[i] = r.flags;
+}
+
+// Two samples per thread, packed f32x2 arithmetic (rls_packed.cuh): thread t owns samples 2t and
+// 2t + 1 of every SoA array (one 64-bit load / store each).  Fast policy only; a pair whose
+// tracker left the window is re-run lane by lane with the scalar FpExact unit.
+// EXPERIMENT, off by default (RLS_PACKED=1): 22 % fewer issue slots per sample (1092 vs 1396 per
+// 32 samples) but 128 registers/thread leave 4 warps per scheduler, issue utilisation drops from
+// 85 % to 48 % and the kernel runs at 16.2 instead of 22.6 G samples/s; capping registers at
+// 80 / 64 spills and is slower still (15.9 / 14.5).  profiles/r01_packed_experiment.md.
+#ifndef RLS_PACKED_MIN_BLOCKS
+#define RLS_PACKED_MIN_BLOCKS 2
+#endif
+template <bool kArrays>
+__global__ void __launch_bounds__(kBlock, RLS_PACKED_MIN_BLOCKS)
+k_ggx_dielectric2(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, DielectricOutDev o,
+                  unsigned long long *fallbacks)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint32_t)((n + 1) / 2)) return;
+    const bool tail = 2u * t + 1u >= (uint32_t)n;
+    const pk::V2 U = pk::ld2(sg.U, t, tail), V = pk::ld2(sg.V, t, tail), N = pk::ld2(sg.N, t, tail), wo = pk::ld2(sg.wo, t, tail);
+    pk::B2 back; back.a = false; back.b = false;
+    if (sg.backfacing) {
+        back.a = __ldg(sg.backfacing + 2u * t) != 0;
+        back.b = tail ? back.a : (__ldg(sg.backfacing + 2u * t + 1u) != 0);
+    }
+    const pk::F2 ior = kArrays ? pk::ld2(p.ior.array, t, tail) : pk::fetch2(p.ior, t, tail);
+    const pk::F2 rough = kArrays ? pk::ld2(p.rough.array, t, tail) : pk::fetch2(p.rough, t, tail);
+    const pk::F2 aniso = pk::fetch2(p.aniso, t, tail);
+    const pk::F2 u1 = pk::ld2(rx, t, tail), u2 = pk::ld2(ry, t, tail);
+    pk::Fp2 fp;
+    pk::Dielectric2 r = pk::dielectric_unit(fp, U, V, N, wo, back, ior, rough, aniso, u1, u2);
+    if (!fp.ok()) {
+        atomicAdd(fallbacks, tail ? 1ull : 2ull);
+#pragma unroll 1
+        for (int l = 0; l < 2; l++) {
+            Shading s;
+            s.U = l ? pk::lane1(U) : pk::lane0(U); s.V = l ? pk::lane1(V) : pk::lane0(V);
+            s.N = l ? pk::lane1(N) : pk::lane0(N); s.wo = l ? pk::lane1(wo) : pk::lane0(wo);
+            s.backfacing = l ? back.b : back.a;
+            FpExact fe;
+            const Dielectric e = dielectric_unit(fe, s, l ? pk::hi(ior) : pk::lo(ior), l ? pk::hi(rough) : pk::lo(rough),
+                                                 l ? pk::hi(aniso) : pk::lo(aniso), l ? pk::hi(u1) : pk::lo(u1),
+                                                 l ? pk::hi(u2) : pk::lo(u2), false);
+#define RLS_SET_LANE(dst, val) dst = l ? pk::mk(pk::lo(dst), (val)) : pk::mk((val), pk::hi(dst))
+            RLS_SET_LANE(r.F, e.F); RLS_SET_LANE(r.f_r, e.f_r); RLS_SET_LANE(r.pdf_r, e.pdf_r);
+            RLS_SET_LANE(r.f_t, e.f_t); RLS_SET_LANE(r.w_t, e.w_t);
+            RLS_SET_LANE(r.wi_r.x, e.wi_r.x); RLS_SET_LANE(r.wi_r.y, e.wi_r.y); RLS_SET_LANE(r.wi_r.z, e.wi_r.z);
+            RLS_SET_LANE(r.wi_t.x, e.wi_t.x); RLS_SET_LANE(r.wi_t.y, e.wi_t.y); RLS_SET_LANE(r.wi_t.z, e.wi_t.z);
+#undef RLS_SET_LANE
+            if (l) r.flags1 = e.flags; else r.flags0 = e.flags;
+        }
+    }
+    pk::st2(o.fresnel, t, tail, r.F);
+    pk::st2(o.wi_r, t, tail, r.wi_r);
+    pk::st2(o.f_r, t, tail, r.f_r);
+    pk::st2(o.pdf_r, t, tail, r.pdf_r);
+    pk::st2(o.wi_t, t, tail, r.wi_t);
+    pk::st2(o.f_t, t, tail, r.f_t);
+    pk::st2(o.weight_t, t, tail, r.w_t);
+    if (tail) o.flags[2u * t] = r.flags0;
+    else reinterpret_cast<uint2 *>(o.flags)[t] = make_uint2(r.flags0, r.flags1);
 }
 
 // ============================================================= rlDisney kernels
@@ -829,6 +911,17 @@ static int launch_ggx_dielectric(rls_context *ctx, cudaStream_t st, size_t n, co
     const GgxParamsDev pd = dev(*p);
     const bool arrays = pd.ior.array && pd.rough.array;
     const bool fast = ctx->arith == RLS_ARITH_FAST;
+    // Packed two-samples-per-thread kernel: fast policy, shipped sampler, every array 8-byte aligned.
+    if (fast && !pd.ndf && ctx->packed &&
+        aligned8({ sg->U.x, sg->U.y, sg->U.z, sg->V.x, sg->V.y, sg->V.z, sg->N.x, sg->N.y, sg->N.z, sg->wo.x, sg->wo.y, sg->wo.z,
+                   pd.ior.array, pd.rough.array, pd.aniso.array, rx, ry, d.fresnel, d.wi_r.x, d.wi_r.y, d.wi_r.z, d.f_r, d.pdf_r,
+                   d.wi_t.x, d.wi_t.y, d.wi_t.z, d.f_t, d.weight_t, d.flags })) {
+        const unsigned grid = (unsigned)(((n + 1) / 2 + kBlock - 1) / kBlock);
+        if (arrays) k_ggx_dielectric2<true><<<grid, kBlock, 0, st>>>(n, sh(*sg), pd, rx, ry, d, ctx->fallbacks);
+        else k_ggx_dielectric2<false><<<grid, kBlock, 0, st>>>(n, sh(*sg), pd, rx, ry, d, ctx->fallbacks);
+        RLS_LAUNCH_CHECK(ctx);
+        return RLS_OK;
+    }
 #define RLS_DIELECTRIC_LAUNCH(F, A) \
     k_ggx_dielectric<F, A><<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), pd, rx, ry, d, ctx->fallbacks)
     if (fast && arrays) RLS_DIELECTRIC_LAUNCH(true, true);

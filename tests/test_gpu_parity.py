@@ -671,3 +671,28 @@ def test_sample_writer_images(ctx, orc, tmp_path):
         want, missing = orc.sample_writer(abi.NODE_DISNEY, dsg_np, dp, 3, st, 128, 64, sx, sy)
         ctx.synchronize()
         assert gio.bits_equal(w.image.cpu().numpy(), want) and int(w.missing.item()) == missing
+
+
+def test_packed_kernel_is_bit_exact(orc, monkeypatch):
+    """The two-samples-per-thread f32x2 kernel (rls_packed.cuh; off by default, RLS_PACKED=1): same
+    bits as the oracle and as the scalar kernel, for even / odd batch sizes (tail lane), uniform
+    and per-sample parameters, and operands that force the exact re-run of a pair."""
+    from rlshaders_b200 import api
+    monkeypatch.setenv("RLS_PACKED", "1")
+    c = api.Context(0)
+    try:
+        check(parity.run_ggx_dielectric(c, orc, N, aniso=True)[0], f"packed dielectric vs {orc.kind}")
+        check(parity.run_ggx_dielectric(c, orc, 100003)[0], f"packed dielectric, odd n, vs {orc.kind}")
+        assert c.fallback_count(reset=True) > 0
+        n = 1 << 18
+        sg = _adversarial_shading(n, 77)
+        rx, ry = ol.hash_uniform(n, 77, 0), ol.hash_uniform(n, 77, 1)
+        kw = dict(specularRoughness=_pick(n, 77, 2, [0.0, 1e-3, 0.05, 0.3, 1.0]), ior=_pick(n, 77, 3, [1.0, 0.47, 1.5, 2.5]))
+        cpu = orc.ggx_dielectric(sg, abi.ggx_params(**kw), rx, ry)
+        s = api.GgxSampler(c, api.ShadingBatch.from_numpy(sg, c.device), **parity.params_to_dev(kw, c.device))
+        gpu = s.dielectricSampleEvalPdf(dev(rx, c), dev(ry, c))
+        c.synchronize()
+        kinds = dict(fresnel="rel", wi_r="dir", f_r="rel", pdf_r="rel", wi_t="dir", f_t="rel", weight_t="rel", flags="flags")
+        check(parity.summarize(gpu, cpu, kinds), "packed dielectric, adversarial operands")
+    finally:
+        c.close()
