@@ -25,6 +25,8 @@
 #include "rls_profile.cuh"
 #include "rls_fused.cuh"
 #include "rls_callers.cuh"
+#include "rls_pair.cuh"
+#include "rls_tile.cuh"
 #include "rls_packed.cuh"
 
 using namespace rls;
@@ -42,6 +44,17 @@ static constexpr int kStages = 3;          // host-staging pipeline depth
 #define RLS_MIN_BLOCKS 4
 #endif
 static constexpr int kBlock = RLS_BLOCK;
+// The two fused rlGgx kernels fit 56 registers once the exact re-run reloads its inputs, so 9 CTAs of
+// 128 threads (36 warps / SM) are resident instead of 4 x 256 (32 warps); smaller CTAs also turn over
+// more evenly.  B200 sweep (profiles/r01_launch_sweep.txt, third sweep): dielectric 22.66 -> 22.96, conductor
+// 23.37 -> 24.07 G samples/s; rlDisney and the skin profile keep 256 x 4.
+#ifndef RLS_GGX_BLOCK
+#define RLS_GGX_BLOCK 128
+#endif
+#ifndef RLS_GGX_MIN_BLOCKS
+#define RLS_GGX_MIN_BLOCKS 9
+#endif
+static constexpr int kBlockGgx = RLS_GGX_BLOCK;
 
 struct rls_context {
     int          device = 0;
@@ -50,6 +63,11 @@ struct rls_context {
     std::string  err;
     uint64_t     launches = 0;
     int          arith = RLS_ARITH_FAST;          // policy of the fused kernels (rls_fp.cuh)
+    bool         paired = false;                  // lane-paired evaluations inside one sample (rls_pair.cuh):
+                                                  // bit-exact, 5 % fewer issue slots, measured slower (RLS_PAIRED=1)
+    bool         tma = false;                     // persistent TMA-staged fused kernels (rls_tile.cuh); RLS_TMA=1
+    int          sm_count = 0;
+    int          persistent = 0;                  // CTAs per SM of the persistent grid-stride kernels; 0 = one CTA per tile (RLS_PERSISTENT)
     bool         packed = false;                  // two-samples-per-thread kernel (rls_packed.cuh): bit-exact but
                                                   // measured slower on B200 (latency bound at 128 registers), so
                                                   // it is off unless RLS_PACKED=1 (kept for A/B runs and its test)
@@ -111,7 +129,11 @@ extern "C" int rls_init(int device, void *stream, rls_context **out_ctx)
     rls_context *ctx = new (std::nothrow) rls_context();
     if (!ctx) return fail(nullptr, RLS_ERR_OUT_OF_MEMORY, "rls_init: host allocation failed");
     if (const char *v = getenv("RLS_PACKED")) ctx->packed = atoi(v) != 0;     // A/B switch for tuning runs
+    if (const char *v = getenv("RLS_PAIRED")) ctx->paired = atoi(v) != 0;     // A/B switch for tuning runs
+    if (const char *v = getenv("RLS_TMA")) ctx->tma = atoi(v) != 0;           // A/B switch for tuning runs
+    if (const char *v = getenv("RLS_PERSISTENT")) ctx->persistent = atoi(v);  // A/B switch for tuning runs
     ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
     DeviceGuard guard(device);
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
@@ -252,7 +274,7 @@ static inline SkinParamsDev dev(const rls_skin_params &p)
     return o;
 }
 
-static inline unsigned grid_for(size_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+static inline unsigned grid_for(size_t n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
 static inline bool aligned8(std::initializer_list<const void *> ptrs)
 {
     for (const void *q : ptrs) if ((uintptr_t)q & 7u) return false;
@@ -326,17 +348,27 @@ RLS_DEV GgxBsdf ggx_unit_from(Fp &fp, const Shading &s, f3 ks, float ior, float 
     return ggx_unit(fp, g, rx, ry);
 }
 template <bool kFast>
-__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+__global__ void __launch_bounds__(kBlockGgx, RLS_GGX_MIN_BLOCKS)
 k_ggx_sample_eval_pdf(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry,
                       V3 wi, V3 f, float *pdf, float *fresnel, uint32_t *flags, unsigned long long *fallbacks)
 {
     RLS_INDEX();
-    const Shading s = load_shading(sg, i);
-    const f3 ks = fetch(p.ks, i);
-    const float ior = fetch(p.ior, i), rough = fetch(p.rough, i), aniso = fetch(p.aniso, i);
-    const float u1 = __ldg(rx + i), u2 = __ldg(ry + i);
     GgxBsdf o;
-    RLS_FAST_THEN_EXACT(kFast, o, ggx_unit_from(fp, s, ks, ior, rough, aniso, p.ndf != 0, u1, u2));
+    bool ok = false;
+    if (kFast) {
+        const Shading s = load_shading(sg, i);
+        FpFast fp;
+        o = ggx_unit_from(fp, s, fetch(p.ks, i), fetch(p.ior, i), fetch(p.rough, i), fetch(p.aniso, i), p.ndf != 0,
+                          __ldg(rx + i), __ldg(ry + i));
+        ok = fp.ok();
+    }
+    if (!ok) {          // the exact re-run reloads its inputs (see k_ggx_dielectric)
+        const Shading s = load_shading<true>(sg, i);
+        FpExact fp;
+        o = ggx_unit_from(fp, s, fetch<true>(p.ks, i), fetch<true>(p.ior, i), fetch<true>(p.rough, i), fetch<true>(p.aniso, i),
+                          p.ndf != 0, __ldcg(rx + i), __ldcg(ry + i));
+        if (kFast) atomicAdd(fallbacks, 1ull);
+    }
     store3(wi, i, o.L);
     store3(f, i, o.f);
     pdf[i] = o.pdf;
@@ -346,17 +378,31 @@ k_ggx_sample_eval_pdf(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, 
 
 struct DielectricOutDev { float *fresnel; V3 wi_r; float *f_r, *pdf_r; V3 wi_t; float *f_t, *weight_t; uint32_t *flags; };
 
-template <bool kFast, bool kArrays>      // kArrays: ior and specularRoughness are per-sample arrays
-__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
-k_ggx_dielectric(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, DielectricOutDev o,
-                 unsigned long long *fallbacks)
+template <bool kFast, bool kArrays, bool kPair>   // kArrays: ior and specularRoughness are per-sample arrays
+RLS_DEV void dielectric_sample(uint32_t i, const ShadingSoA &sg, const GgxParamsDev &p, const float *rx, const float *ry,
+                               const DielectricOutDev &o, unsigned long long *fallbacks)
 {
-    RLS_INDEX();
-    const Shading s = load_shading(sg, i);
-    const float ior = fetch_t<kArrays>(p.ior, i), rough = fetch_t<kArrays>(p.rough, i), aniso = fetch(p.aniso, i);
-    const float u1 = __ldg(rx + i), u2 = __ldg(ry + i);
     Dielectric r;
-    RLS_FAST_THEN_EXACT(kFast, r, dielectric_unit(fp, s, ior, rough, aniso, u1, u2, p.ndf != 0));
+    bool ok = false;
+    if (kFast) {        // kPair: reflection and refraction evaluations paired lane-wise (rls_pair.cuh)
+        const Shading s = load_shading(sg, i);
+        const float ior = fetch_t<kArrays>(p.ior, i), rough = fetch_t<kArrays>(p.rough, i), aniso = fetch(p.aniso, i);
+        const float u1 = __ldg(rx + i), u2 = __ldg(ry + i);
+        FpFast fp;
+        r = kPair ? pk::dielectric_unit_paired(fp, s, ior, rough, aniso, u1, u2, p.ndf != 0)
+                  : dielectric_unit(fp, s, ior, rough, aniso, u1, u2, p.ndf != 0);
+        ok = fp.ok();
+    }
+    if (!ok) {
+        // The exact re-run RELOADS its inputs (ld.global.cg, which the compiler cannot merge with the
+        // ld.global.nc above): the fast path then need not keep 17 input registers alive for it.
+        const Shading s = load_shading<true>(sg, i);
+        const float ior = fetch_t<kArrays, true>(p.ior, i), rough = fetch_t<kArrays, true>(p.rough, i), aniso = fetch<true>(p.aniso, i);
+        const float u1 = __ldcg(rx + i), u2 = __ldcg(ry + i);
+        FpExact fp;
+        r = dielectric_unit(fp, s, ior, rough, aniso, u1, u2, p.ndf != 0);
+        if (kFast) atomicAdd(fallbacks, 1ull);
+    }
     o.fresnel[i] = r.F;
     store3(o.wi_r, i, r.wi_r);
     o.f_r[i] = r.f_r;
@@ -365,6 +411,97 @@ k_ggx_dielectric(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const
     o.f_t[i] = r.f_t;
     o.weight_t[i] = r.w_t;
     o.flags[i] = r.flags;
+}
+template <bool kFast, bool kArrays, bool kPair>
+__global__ void __launch_bounds__(kBlockGgx, RLS_GGX_MIN_BLOCKS)
+k_ggx_dielectric(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, DielectricOutDev o,
+                 unsigned long long *fallbacks)
+{
+    RLS_INDEX();
+    dielectric_sample<kFast, kArrays, kPair>(i, sg, p, rx, ry, o, fallbacks);
+}
+// Persistent form: grid = resident CTAs (a multiple of the SM count), every thread strides over the
+// batch.  No CTA turnover (a CTA slot of the plain kernel stays partly empty until its slowest warp
+// retires) and the warps of a CTA drift apart, so their load phases stop coinciding.
+template <bool kFast, bool kArrays, bool kPair>
+__global__ void __launch_bounds__(kBlockGgx, RLS_GGX_MIN_BLOCKS)
+k_ggx_dielectric_persistent(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, DielectricOutDev o,
+                            unsigned long long *fallbacks)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+#pragma unroll 1
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)n; i += stride)
+        dielectric_sample<kFast, kArrays, kPair>(i, sg, p, rx, ry, o, fallbacks);
+}
+
+// Persistent, TMA-staged form of k_ggx_dielectric (rls_tile.cuh): grid = resident CTAs, every CTA
+// walks whole 256-sample tiles; the inputs of the next tile are in flight while this one computes.
+// Fast policy only (the launch site keeps the plain kernel for the exact policy, unaligned arrays
+// and the ragged tail); a sample whose operands left the window reloads its inputs from global
+// memory and is re-run with FpExact, as in the plain kernel.
+namespace dielectric_slots {
+enum In { U = 0, V = 3, N = 6, WO = 9, RX = 12, RY = 13, ROUGH = 14, IOR = 15, ANISO = 16, BACK = 17, kIn = 18 };
+enum Out { FRESNEL = 0, WI_R = 1, F_R = 4, PDF_R = 5, WI_T = 6, F_T = 9, WEIGHT_T = 10, FLAGS = 11, kOut = 12 };
+}
+template <bool kArrays, bool kPair>
+__global__ void __launch_bounds__(tile::kTile, 4)
+k_ggx_dielectric_tma(uint32_t n_tiles, const __grid_constant__ tile::Arrays arr, ShadingSoA sg, GgxParamsDev p,
+                     const float *rx, const float *ry, unsigned long long *fallbacks)
+{
+    using namespace dielectric_slots;
+    __shared__ __align__(128) unsigned char smem[tile::Pipe<kIn, kOut>::kSmemBytes];
+    __shared__ uint64_t bar;
+    tile::Pipe<kIn, kOut> pipe;
+    pipe.init(&arr, smem, &bar);
+    const uint32_t tid = threadIdx.x;
+    uint32_t t = blockIdx.x;
+    if (t < n_tiles) pipe.issue_loads(t);
+#pragma unroll 1
+    for (; t < n_tiles; t += gridDim.x) {
+        pipe.wait_inputs();
+#define RLS_IN(k) pipe.in_slot(k)[tid]
+        Shading s;
+        s.U = mk3(RLS_IN(U), RLS_IN(U + 1), RLS_IN(U + 2));
+        s.V = mk3(RLS_IN(V), RLS_IN(V + 1), RLS_IN(V + 2));
+        s.N = mk3(RLS_IN(N), RLS_IN(N + 1), RLS_IN(N + 2));
+        s.wo = mk3(RLS_IN(WO), RLS_IN(WO + 1), RLS_IN(WO + 2));
+        s.backfacing = sg.backfacing ? (reinterpret_cast<const uint8_t *>(pipe.in_slot(BACK))[tid] != 0) : false;
+        const float ior = (kArrays || p.ior.array) ? RLS_IN(IOR) : p.ior.value;
+        const float rough = (kArrays || p.rough.array) ? RLS_IN(ROUGH) : p.rough.value;
+        const float aniso = p.aniso.array ? RLS_IN(ANISO) : p.aniso.value;
+        const float u1 = RLS_IN(RX), u2 = RLS_IN(RY);
+#undef RLS_IN
+        pipe.inputs_consumed(t + gridDim.x, n_tiles);
+        Dielectric r;
+        bool ok;
+        {
+            FpFast fp;
+            r = kPair ? pk::dielectric_unit_paired(fp, s, ior, rough, aniso, u1, u2, p.ndf != 0)
+                      : dielectric_unit(fp, s, ior, rough, aniso, u1, u2, p.ndf != 0);
+            ok = fp.ok();
+        }
+        if (!ok) {
+            const uint32_t i = t * tile::kTile + tid;
+            const Shading se = load_shading<true>(sg, i);
+            FpExact fp;
+            r = dielectric_unit(fp, se, fetch<true>(p.ior, i), fetch<true>(p.rough, i), fetch<true>(p.aniso, i),
+                                __ldcg(rx + i), __ldcg(ry + i), p.ndf != 0);
+            atomicAdd(fallbacks, 1ull);
+        }
+        pipe.begin_store();
+#define RLS_OUT(k) pipe.out_slot(k)[tid]
+        RLS_OUT(FRESNEL) = r.F;
+        RLS_OUT(WI_R) = r.wi_r.x; RLS_OUT(WI_R + 1) = r.wi_r.y; RLS_OUT(WI_R + 2) = r.wi_r.z;
+        RLS_OUT(F_R) = r.f_r;
+        RLS_OUT(PDF_R) = r.pdf_r;
+        RLS_OUT(WI_T) = r.wi_t.x; RLS_OUT(WI_T + 1) = r.wi_t.y; RLS_OUT(WI_T + 2) = r.wi_t.z;
+        RLS_OUT(F_T) = r.f_t;
+        RLS_OUT(WEIGHT_T) = r.w_t;
+        RLS_OUT(FLAGS) = __uint_as_float(r.flags);
+#undef RLS_OUT
+        pipe.end_store(t);
+    }
+    pipe.finish();
 }
 
 // Two samples per thread, packed f32x2 arithmetic (rls_packed.cuh): thread t owns samples 2t and
@@ -466,11 +603,11 @@ k_disney_eval_pdf(size_t n, ShadingSoA sg, DisneyParamsDev p, int type, CV3 wi, 
 
 struct DisneyOutDev { V3 wi_s, f_s; float *pdf_s; V3 wi_d, f_d; float *pdf_d; uint32_t *flags; };
 
-template <bool kArrays, class Fp>
+template <bool kArrays, bool kReload, class Fp>
 RLS_DEV DisneyOut1 disney_unit_from(Fp &fp, const Shading &s, const DisneyParamsDev &p, uint32_t i,
                                     float rx_s, float ry_s, float rx_d, float ry_d)
 {
-    Disney d; disney_init<kArrays>(fp, d, s, p, i);
+    Disney d; disney_init<kArrays, kReload>(fp, d, s, p, i);
     return disney_unit(fp, d, rx_s, ry_s, rx_d, ry_d);
 }
 template <bool kFast, bool kArrays>
@@ -479,10 +616,20 @@ k_disney_sample_eval_pdf(size_t n, ShadingSoA sg, DisneyParamsDev p, const float
                          const float *rx_d, const float *ry_d, DisneyOutDev o, unsigned long long *fallbacks)
 {
     RLS_INDEX();
-    const Shading s = load_shading(sg, i);
-    const float u1 = __ldg(rx_s + i), u2 = __ldg(ry_s + i), u3 = __ldg(rx_d + i), u4 = __ldg(ry_d + i);
     DisneyOut1 r;
-    RLS_FAST_THEN_EXACT(kFast, r, disney_unit_from<kArrays>(fp, s, p, i, u1, u2, u3, u4));
+    bool ok = false;
+    if (kFast) {
+        const Shading s = load_shading(sg, i);
+        FpFast fp;
+        r = disney_unit_from<kArrays, false>(fp, s, p, i, __ldg(rx_s + i), __ldg(ry_s + i), __ldg(rx_d + i), __ldg(ry_d + i));
+        ok = fp.ok();
+    }
+    if (!ok) {          // the exact re-run reloads its 29 inputs (see k_ggx_dielectric)
+        const Shading s = load_shading<true>(sg, i);
+        FpExact fp;
+        r = disney_unit_from<kArrays, true>(fp, s, p, i, __ldcg(rx_s + i), __ldcg(ry_s + i), __ldcg(rx_d + i), __ldcg(ry_d + i));
+        if (kFast) atomicAdd(fallbacks, 1ull);
+    }
     store3(o.wi_s, i, r.Ls); store3(o.f_s, i, r.fs); o.pdf_s[i] = r.ps;
     store3(o.wi_d, i, r.Ld); store3(o.f_d, i, r.fd); o.pdf_d[i] = r.pd;
     o.flags[i] = r.flags;
@@ -552,10 +699,18 @@ __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_skin_profile(size_t n, SkinParamsDev sp, const float *rx, ProfileOutDev o, unsigned long long *fallbacks)
 {
     RLS_INDEX();
-    const f3 dist = skin_scatter_dist(sp, i);
-    const float u = __ldg(rx + i);
     Profile1 r;
-    RLS_FAST_THEN_EXACT(kFast, r, skin_profile_unit(fp, dist, u));
+    bool ok = false;
+    if (kFast) {
+        FpFast fp;
+        r = skin_profile_unit(fp, skin_scatter_dist(sp, i), __ldg(rx + i));
+        ok = fp.ok();
+    }
+    if (!ok) {          // the exact re-run reloads its inputs (see k_ggx_dielectric)
+        FpExact fp;
+        r = skin_profile_unit(fp, skin_scatter_dist<true>(sp, i), __ldcg(rx + i));
+        if (kFast) atomicAdd(fallbacks, 1ull);
+    }
     o.r[i] = r.r;
     o.pdf[i] = r.pdf;
     store3(o.Rd, i, r.Rd);
@@ -897,15 +1052,94 @@ static int launch_ggx_sample_eval_pdf(rls_context *ctx, cudaStream_t st, size_t 
                                       const rls_ggx_params *p, const float *rx, const float *ry, const rls_bsdf_out *o)
 {
     if (ctx->arith == RLS_ARITH_FAST)
-        k_ggx_sample_eval_pdf<true><<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), dev(*p), rx, ry, mv(o->wi), mv(o->f), o->pdf, o->fresnel, o->flags, ctx->fallbacks);
+        k_ggx_sample_eval_pdf<true><<<grid_for(n, kBlockGgx), kBlockGgx, 0, st>>>(n, sh(*sg), dev(*p), rx, ry, mv(o->wi), mv(o->f), o->pdf, o->fresnel, o->flags, ctx->fallbacks);
     else
-        k_ggx_sample_eval_pdf<false><<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), dev(*p), rx, ry, mv(o->wi), mv(o->f), o->pdf, o->fresnel, o->flags, ctx->fallbacks);
+        k_ggx_sample_eval_pdf<false><<<grid_for(n, kBlockGgx), kBlockGgx, 0, st>>>(n, sh(*sg), dev(*p), rx, ry, mv(o->wi), mv(o->f), o->pdf, o->fresnel, o->flags, ctx->fallbacks);
     RLS_LAUNCH_CHECK(ctx);
     return RLS_OK;
+}
+// ---- persistent TMA-staged launches (rls_tile.cuh): helpers shared by the fused entry points
+static inline rls_cvec3 adv(rls_cvec3 v, size_t k) { rls_cvec3 o = { v.x ? v.x + k : nullptr, v.y ? v.y + k : nullptr, v.z ? v.z + k : nullptr }; return o; }
+static inline rls_vec3 adv(rls_vec3 v, size_t k) { rls_vec3 o = { v.x ? v.x + k : nullptr, v.y ? v.y + k : nullptr, v.z ? v.z + k : nullptr }; return o; }
+template <typename T> static inline T *adv(T *q, size_t k) { return q ? q + k : nullptr; }
+static inline rls_param1 adv(rls_param1 q, size_t k) { q.array = adv(q.array, k); return q; }
+static inline rls_param3 adv(rls_param3 q, size_t k) { q.array = adv(q.array, k); return q; }
+static inline rls_shading_soa adv(const rls_shading_soa &s, size_t k)
+{
+    rls_shading_soa o; o.U = adv(s.U, k); o.V = adv(s.V, k); o.N = adv(s.N, k); o.wo = adv(s.wo, k);
+    o.backfacing = adv(s.backfacing, k); return o;
+}
+struct TileArrays {
+    tile::Arrays a;
+    bool aligned = true;
+    TileArrays() { memset(&a, 0, sizeof(a)); }
+    void in(int slot, const void *q, int elem = 4)
+    {
+        a.in[slot] = q; a.in_elem[slot] = (uint8_t)elem;
+        if (q) { a.in_bytes_per_tile += (uint32_t)(tile::kTile * elem); aligned = aligned && !((uintptr_t)q & 15u); }
+    }
+    void in3(int slot, const rls_cvec3 &v) { in(slot, v.x); in(slot + 1, v.y); in(slot + 2, v.z); }
+    void out(int slot, void *q) { a.out[slot] = q; if (q) aligned = aligned && !((uintptr_t)q & 15u); }
+    void out3(int slot, const rls_vec3 &v) { out(slot, v.x); out(slot + 1, v.y); out(slot + 2, v.z); }
+};
+// grid of a persistent kernel: every CTA resident at once (a multiple of the SM count), never more CTAs than tiles
+template <typename K> static unsigned persistent_grid(rls_context *ctx, K kernel, size_t n_tiles)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, tile::kTile, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const size_t resident = (size_t)per_sm * (size_t)ctx->sm_count;
+    return (unsigned)(n_tiles < resident ? n_tiles : resident);
+}
+
+static int launch_ggx_dielectric(rls_context *ctx, cudaStream_t st, size_t n, const rls_shading_soa *sg,
+                                 const rls_ggx_params *p, const float *rx, const float *ry, const rls_ggx_dielectric_out *o);
+static int launch_ggx_dielectric_tma(rls_context *ctx, cudaStream_t st, size_t n, const rls_shading_soa *sg,
+                                     const rls_ggx_params *p, const float *rx, const float *ry, const rls_ggx_dielectric_out *o,
+                                     bool *taken)
+{
+    using namespace dielectric_slots;
+    *taken = false;
+    if (!ctx->tma || ctx->arith != RLS_ARITH_FAST || n < (size_t)tile::kTile) return RLS_OK;
+    const GgxParamsDev pd = dev(*p);
+    TileArrays ta;
+    ta.in3(U, sg->U); ta.in3(V, sg->V); ta.in3(N, sg->N); ta.in3(WO, sg->wo);
+    ta.in(RX, rx); ta.in(RY, ry); ta.in(ROUGH, pd.rough.array); ta.in(IOR, pd.ior.array); ta.in(ANISO, pd.aniso.array);
+    ta.in(BACK, sg->backfacing, 1);
+    ta.out(FRESNEL, o->fresnel); ta.out3(WI_R, o->wi_r); ta.out(F_R, o->f_r); ta.out(PDF_R, o->pdf_r);
+    ta.out3(WI_T, o->wi_t); ta.out(F_T, o->f_t); ta.out(WEIGHT_T, o->weight_t); ta.out(FLAGS, o->flags);
+    if (!ta.aligned) return RLS_OK;
+    *taken = true;
+    const size_t n_tiles = n / tile::kTile;
+    const bool arrays = pd.ior.array && pd.rough.array;
+#define RLS_DIELECTRIC_TMA(A, P) \
+    k_ggx_dielectric_tma<A, P><<<persistent_grid(ctx, k_ggx_dielectric_tma<A, P>, n_tiles), tile::kTile, 0, st>>>( \
+        (uint32_t)n_tiles, ta.a, sh(*sg), pd, rx, ry, ctx->fallbacks)
+    if (arrays && ctx->paired) RLS_DIELECTRIC_TMA(true, true);
+    else if (arrays) RLS_DIELECTRIC_TMA(true, false);
+    else if (ctx->paired) RLS_DIELECTRIC_TMA(false, true);
+    else RLS_DIELECTRIC_TMA(false, false);
+#undef RLS_DIELECTRIC_TMA
+    RLS_LAUNCH_CHECK(ctx);
+    const size_t done = n_tiles * tile::kTile;
+    if (done == n) return RLS_OK;
+    // ragged tail: the plain kernel on the remaining n - done < 256 samples
+    const rls_shading_soa sg2 = adv(*sg, done);
+    rls_ggx_params p2 = *p;
+    p2.specularRoughness = adv(p->specularRoughness, done); p2.ior = adv(p->ior, done); p2.anisotropic = adv(p->anisotropic, done);
+    p2.KsColor = adv(p->KsColor, done);
+    rls_ggx_dielectric_out o2;
+    o2.fresnel = adv(o->fresnel, done); o2.wi_r = adv(o->wi_r, done); o2.f_r = adv(o->f_r, done); o2.pdf_r = adv(o->pdf_r, done);
+    o2.wi_t = adv(o->wi_t, done); o2.f_t = adv(o->f_t, done); o2.weight_t = adv(o->weight_t, done); o2.flags = adv(o->flags, done);
+    return launch_ggx_dielectric(ctx, st, n - done, &sg2, &p2, rx + done, ry + done, &o2);
 }
 static int launch_ggx_dielectric(rls_context *ctx, cudaStream_t st, size_t n, const rls_shading_soa *sg,
                                  const rls_ggx_params *p, const float *rx, const float *ry, const rls_ggx_dielectric_out *o)
 {
+    {
+        bool taken = false;
+        const int rc = launch_ggx_dielectric_tma(ctx, st, n, sg, p, rx, ry, o, &taken);
+        if (taken || rc != RLS_OK) return rc;
+    }
     DielectricOutDev d; d.fresnel = o->fresnel; d.wi_r = mv(o->wi_r); d.f_r = o->f_r; d.pdf_r = o->pdf_r;
     d.wi_t = mv(o->wi_t); d.f_t = o->f_t; d.weight_t = o->weight_t; d.flags = o->flags;
     const GgxParamsDev pd = dev(*p);
@@ -922,12 +1156,16 @@ static int launch_ggx_dielectric(rls_context *ctx, cudaStream_t st, size_t n, co
         RLS_LAUNCH_CHECK(ctx);
         return RLS_OK;
     }
-#define RLS_DIELECTRIC_LAUNCH(F, A) \
-    k_ggx_dielectric<F, A><<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), pd, rx, ry, d, ctx->fallbacks)
-    if (fast && arrays) RLS_DIELECTRIC_LAUNCH(true, true);
-    else if (fast) RLS_DIELECTRIC_LAUNCH(true, false);
-    else if (arrays) RLS_DIELECTRIC_LAUNCH(false, true);
-    else RLS_DIELECTRIC_LAUNCH(false, false);
+#define RLS_DIELECTRIC_LAUNCH(F, A, P) \
+    do { if (ctx->persistent && grid_for(n, kBlockGgx) > (unsigned)(ctx->sm_count * ctx->persistent)) \
+             k_ggx_dielectric_persistent<F, A, P><<<ctx->sm_count * ctx->persistent, kBlockGgx, 0, st>>>(n, sh(*sg), pd, rx, ry, d, ctx->fallbacks); \
+         else k_ggx_dielectric<F, A, P><<<grid_for(n, kBlockGgx), kBlockGgx, 0, st>>>(n, sh(*sg), pd, rx, ry, d, ctx->fallbacks); } while (0)
+    if (fast && arrays && ctx->paired) RLS_DIELECTRIC_LAUNCH(true, true, true);
+    else if (fast && arrays) RLS_DIELECTRIC_LAUNCH(true, true, false);
+    else if (fast && ctx->paired) RLS_DIELECTRIC_LAUNCH(true, false, true);
+    else if (fast) RLS_DIELECTRIC_LAUNCH(true, false, false);
+    else if (arrays) RLS_DIELECTRIC_LAUNCH(false, true, false);
+    else RLS_DIELECTRIC_LAUNCH(false, false, false);
 #undef RLS_DIELECTRIC_LAUNCH
     RLS_LAUNCH_CHECK(ctx);
     return RLS_OK;

@@ -23,21 +23,21 @@ struct Disney {
 };
 
 // src/rlDisney.cpp:155-192
-template <bool kArrays = false, class Fp>
+template <bool kArrays = false, bool kReload = false, class Fp>
 RLS_DEV void disney_init(Fp &fp, Disney &d, const Shading &sh, const DisneyParamsDev &p, uint32_t i)
 {
     d.U = sh.U; d.V = sh.V; d.N = sh.N; d.wo = sh.wo;
-    d.base = fetch_t<kArrays>(p.base_color, i);
-    d.roughness = fetch_t<kArrays>(p.roughness, i);
-    d.subsurface = fetch_t<kArrays>(p.subsurface, i);
-    float specular = fetch_t<kArrays>(p.specular, i) * 0.08f;            // :163
-    float specularTint = fetch_t<kArrays>(p.specular_tint, i);
-    d.metallic = fetch_t<kArrays>(p.metallic, i);
-    float sheen = fetch_t<kArrays>(p.sheen, i);
-    float sheenTint = fetch_t<kArrays>(p.sheen_tint, i);
-    float anisotropic = fetch_t<kArrays>(p.anisotropic, i);
-    d.clearcoat = fetch_t<kArrays>(p.clearcoat, i) * 0.25f;              // :169
-    d.clearcoatGloss = fetch_t<kArrays>(p.clearcoat_gloss, i);
+    d.base = fetch_t<kArrays, kReload>(p.base_color, i);
+    d.roughness = fetch_t<kArrays, kReload>(p.roughness, i);
+    d.subsurface = fetch_t<kArrays, kReload>(p.subsurface, i);
+    float specular = fetch_t<kArrays, kReload>(p.specular, i) * 0.08f;            // :163
+    float specularTint = fetch_t<kArrays, kReload>(p.specular_tint, i);
+    d.metallic = fetch_t<kArrays, kReload>(p.metallic, i);
+    float sheen = fetch_t<kArrays, kReload>(p.sheen, i);
+    float sheenTint = fetch_t<kArrays, kReload>(p.sheen_tint, i);
+    float anisotropic = fetch_t<kArrays, kReload>(p.anisotropic, i);
+    d.clearcoat = fetch_t<kArrays, kReload>(p.clearcoat, i) * 0.25f;              // :169
+    d.clearcoatGloss = fetch_t<kArrays, kReload>(p.clearcoat_gloss, i);
 
     float aspect = fp.sqrt(1.0f - anisotropic * 0.9f);        // :177
     d.ax = max_m(1e-2f, fp.div_pz(sqr(d.roughness), aspect)); // :178 (floor 1e-2, not 1e-4)

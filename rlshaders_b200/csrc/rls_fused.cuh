@@ -9,7 +9,9 @@
 //   * a + b == b + a, a * b == b * a bitwise (IEEE commutativity);
 //   * dot(v, s*h) == s*dot(v, h) and (s*x)^2 == x^2 bitwise for s = +-1 (negation is exact and
 //     round-to-nearest is sign-symmetric);
-//   * 2/d == 2*(1/d) bitwise while neither side over/underflows (power-of-two scaling is exact).
+//   * 2/d == 2*(1/d) bitwise while neither side over/underflows (power-of-two scaling is exact);
+//   * x/1 == x bitwise: one of mIorIn, mIorOut is the unit index (src/rlGgx.h:138-142), so the
+//     two quotients mIorOut/mIorIn (:258) and mIorIn/mIorOut (:282) are b and 1/b in some order.
 // tests/test_gpu_parity.py asserts fused == separate entry points == oracle, bit for bit.
 #pragma once
 #include "rls_ggx.cuh"
@@ -33,6 +35,7 @@ RLS_DEV float ggx_G1_value2(Fp &fp, const Ggx &g, float VdotN)
 // view-side G1 between evalBrdf (src/rlGgx.h:304-313) and evalPdf (:121-127, :72-80).
 struct GgxShared {
     float VdotN, absVdotN, sgnV, G1v, ratio2;
+    float eta;       // mIorIn / mIorOut (getRefractDirection, src/rlGgx.h:282)
 };
 template <class Fp>
 RLS_DEV GgxShared ggx_shared(Fp &fp, const Ggx &g)
@@ -42,7 +45,10 @@ RLS_DEV GgxShared ggx_shared(Fp &fp, const Ggx &g)
     s.absVdotN = abs_m(s.VdotN);
     s.sgnV = sgn_m(s.VdotN);
     s.G1v = ggx_G1_value2(fp, g, s.VdotN);
-    s.ratio2 = sqr(fp.div(g.iorOut, g.iorIn));
+    // entering: iorIn = 1, iorOut = b  ->  ratio = b/1 = b, eta = 1/b; leaving: the other way round
+    const float invB = fp.rcp(g.iorB);
+    s.ratio2 = sqr(g.entering ? g.iorB : invB);
+    s.eta = g.entering ? invB : g.iorB;
     return s;
 }
 // Returns reflection(V, L, N) * dot(L, N) (KsColor applied by the caller) and the pdf.
@@ -105,7 +111,7 @@ RLS_DEV Dielectric dielectric_unit(Fp &fp, const Shading &sh, float ior, float r
     if (g.entering) fl |= 0x0010u;
 
     // getRefractDirection(m, V): src/rlGgx.h:277-291
-    const float eta = fp.div(g.iorIn, g.iorOut);
+    const float eta = s.eta;
     const float cosThetaTSqr = 1.0f + eta * (sqr(Vm) - 1.0f);
     const float mN = dot(m, g.N);
     float TdotN, G1t;

@@ -179,6 +179,7 @@ RLS_DEV f3 sample_ndf_normal(Fp &fp, f3 U, f3 Vax, f3 N, float ax, float ay, flo
 struct Ggx {
     f3 U, V, N, wo, ks;
     float iorIn, iorOut, rough, ax, ay;
+    float iorB;      // max(ior, 1e-4): the side of the interface that is not the unit index (:138-142)
     bool entering;
     bool ndf;        // GgxSamplerT<NDFKernel> instead of the shipped GgxSamplerT<VNDFKernel>
 };
@@ -199,6 +200,7 @@ RLS_DEV void ggx_init(Fp &fp, Ggx &g, const Shading &sh, f3 ks, float ior, float
     float a = 1.0f, b = max_m(ior, 1e-4f);       // :138-139
     g.iorIn = g.entering ? a : b;                // :140-142 (swap)
     g.iorOut = g.entering ? b : a;
+    g.iorB = b;
     g.wo = sh.wo;                                // :144  -(-wo) is exact
     g.U = sh.U; g.V = sh.V; g.N = sh.N;          // :145-146, explicit frame
     float aspect = fp.sqrt(1.0f - aniso * 0.9f); // :148

@@ -69,32 +69,42 @@ RLS_DEV f3 rotate_to_frame(f3 a, f3 u, f3 v, f3 w)
 // ---- parameter fetch: uniform value or per-sample array (include/rls_b200.h rls_param1/3)
 struct P1 { float value; const float *array; };
 struct P3 { float value[3]; const float *x, *y, *z; };
-RLS_DEV float fetch(const P1 &p, uint32_t i) { return p.array ? __ldg(p.array + i) : p.value; }
-RLS_DEV f3 fetch(const P3 &p, uint32_t i)
+// kReload = true: ld.global.cg instead of ld.global.nc -- used by the exact re-run of the fused
+// kernels, which reloads its inputs so that the fast path need not keep them in registers (the
+// compiler cannot merge the two kinds of load).
+template <bool kReload = false> RLS_DEV float ld_in(const float *p) { return kReload ? __ldcg(p) : __ldg(p); }
+template <bool kReload = false> RLS_DEV float fetch(const P1 &p, uint32_t i) { return p.array ? ld_in<kReload>(p.array + i) : p.value; }
+template <bool kReload = false> RLS_DEV f3 fetch(const P3 &p, uint32_t i)
 {
-    return mk3(p.x ? __ldg(p.x + i) : p.value[0], p.y ? __ldg(p.y + i) : p.value[1],
-               p.z ? __ldg(p.z + i) : p.value[2]);
+    return mk3(p.x ? ld_in<kReload>(p.x + i) : p.value[0], p.y ? ld_in<kReload>(p.y + i) : p.value[1],
+               p.z ? ld_in<kReload>(p.z + i) : p.value[2]);
 }
 // kArrays = true: the launch site has checked that the parameter IS a per-sample array, so the
 // kernel skips the per-parameter pointer tests (a dozen of them per rlDisney sample).
-template <bool kArrays> RLS_DEV float fetch_t(const P1 &p, uint32_t i) { return kArrays ? __ldg(p.array + i) : fetch(p, i); }
-template <bool kArrays> RLS_DEV f3 fetch_t(const P3 &p, uint32_t i)
+template <bool kArrays, bool kReload = false> RLS_DEV float fetch_t(const P1 &p, uint32_t i)
 {
-    return kArrays ? mk3(__ldg(p.x + i), __ldg(p.y + i), __ldg(p.z + i)) : fetch(p, i);
+    return kArrays ? ld_in<kReload>(p.array + i) : fetch<kReload>(p, i);
+}
+template <bool kArrays, bool kReload = false> RLS_DEV f3 fetch_t(const P3 &p, uint32_t i)
+{
+    return kArrays ? mk3(ld_in<kReload>(p.x + i), ld_in<kReload>(p.y + i), ld_in<kReload>(p.z + i)) : fetch<kReload>(p, i);
 }
 struct CV3 { const float *x, *y, *z; };
 struct V3  { float *x, *y, *z; };
-RLS_DEV f3 load3(const CV3 &v, uint32_t i) { return mk3(__ldg(v.x + i), __ldg(v.y + i), __ldg(v.z + i)); }
+template <bool kReload = false> RLS_DEV f3 load3(const CV3 &v, uint32_t i)
+{
+    return mk3(ld_in<kReload>(v.x + i), ld_in<kReload>(v.y + i), ld_in<kReload>(v.z + i));
+}
 RLS_DEV void store3(const V3 &v, uint32_t i, f3 a) { v.x[i] = a.x; v.y[i] = a.y; v.z[i] = a.z; }
 
 // Shading inputs of one sample (include/rls_b200.h rls_shading_soa).
 struct ShadingSoA { CV3 U, V, N, wo; const uint8_t *backfacing; };
 struct Shading { f3 U, V, N, wo; bool backfacing; };
-RLS_DEV Shading load_shading(const ShadingSoA &s, uint32_t i)
+template <bool kReload = false> RLS_DEV Shading load_shading(const ShadingSoA &s, uint32_t i)
 {
     Shading o;
-    o.U = load3(s.U, i); o.V = load3(s.V, i); o.N = load3(s.N, i); o.wo = load3(s.wo, i);
-    o.backfacing = s.backfacing ? (__ldg(s.backfacing + i) != 0) : false;
+    o.U = load3<kReload>(s.U, i); o.V = load3<kReload>(s.V, i); o.N = load3<kReload>(s.N, i); o.wo = load3<kReload>(s.wo, i);
+    o.backfacing = s.backfacing ? ((kReload ? __ldcg(s.backfacing + i) : __ldg(s.backfacing + i)) != 0) : false;
     return o;
 }
 

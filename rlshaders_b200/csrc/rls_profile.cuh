@@ -123,9 +123,10 @@ struct SkinParamsDev {
     P1 sss_weight, sss_dist_multiplier, specular_weight, sheen_weight;
 };
 // src/rlSkin.cpp:236
+template <bool kReload = false>
 RLS_DEV f3 skin_scatter_dist(const SkinParamsDev &p, uint32_t i)
 {
-    return fetch(p.sss_scatter_dist, i) * fetch(p.sss_dist_multiplier, i);
+    return fetch<kReload>(p.sss_scatter_dist, i) * fetch<kReload>(p.sss_dist_multiplier, i);
 }
 
 } // namespace rls

@@ -696,3 +696,55 @@ def test_packed_kernel_is_bit_exact(orc, monkeypatch):
         check(parity.summarize(gpu, cpu, kinds), "packed dielectric, adversarial operands")
     finally:
         c.close()
+
+
+# ------------------------------------ persistent TMA-staged kernels (rls_tile.cuh) vs plain kernels
+def _tma_cases(c, n, seed, adversarial):
+    """Outputs of every fused entry point that has a TMA-staged form, for one context."""
+    from rlshaders_b200 import api
+    out = {}
+    if adversarial:
+        sg = _adversarial_shading(n, seed)
+        rough = _pick(n, seed, 2, [0.0, 1e-3, 0.01, 0.05, 0.3, 1.0, 1.0, 0.7])
+        ior = _pick(n, seed, 3, [1.0, 1.0, 0.47, 1e-4, 1.5, 2.5, 1.33, 1.0001])
+        aniso = _pick(n, seed, 4, [0.0, 0.0, 1.0, 0.5])
+        rx, ry = ol.hash_uniform(n, seed, 0), ol.hash_uniform(n, seed, 1)
+    else:
+        sg, kw, rx, ry = parity.ggx_dielectric_inputs(n, seed, aniso=True)
+        rough, ior, aniso = kw["specularRoughness"], kw["ior"], kw["anisotropic"]
+    dsg = api.ShadingBatch.from_numpy(sg, c.device)
+    drx, dry = dev(rx, c), dev(ry, c)
+    g = api.GgxSampler(c, dsg, KsColor=(1.0, 0.5, 0.25), specularRoughness=dev(rough, c), ior=dev(ior, c),
+                       anisotropic=dev(aniso, c))
+    out["dielectric"] = g.dielectricSampleEvalPdf(drx, dry)
+    gu = api.GgxSampler(c, dsg, KsColor=(1.0, 0.5, 0.25), specularRoughness=0.3, ior=1.5, anisotropic=0.25)
+    out["dielectric_uniform"] = gu.dielectricSampleEvalPdf(drx, dry)
+    c.synchronize()
+    return {k: {kk: vv.cpu().numpy() for kk, vv in v.items()} for k, v in out.items()}
+
+
+@pytest.mark.parametrize("n,adversarial", [(256, False), (256 * 7 + 37, False), (100003, True), (1 << 20, False)])
+def test_tma_staged_kernels_match_plain_kernels(monkeypatch, n, adversarial):
+    """The persistent TMA-staged forms (default) and the plain one-LDG-per-array kernels (RLS_TMA=0)
+    give the same bits, for whole tiles, a ragged tail, uniform parameters and operands that force
+    the exact re-run (which reloads its inputs from global memory)."""
+    from rlshaders_b200 import api
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("RLS_TMA", mode)
+        c = api.Context(0)
+        try:
+            res[mode] = _tma_cases(c, n, 0x7A11 + n, adversarial)
+            fb = c.fallback_count(reset=True)
+            if adversarial:
+                assert fb > 0
+        finally:
+            c.close()
+    for case, outs in res["1"].items():
+        for k, a in outs.items():
+            b = res["0"][case][k]
+            au, bu = a.view(np.uint32), b.view(np.uint32)
+            bad = (au != bu)
+            if a.dtype == np.float32:
+                bad &= ~(np.isnan(a) & np.isnan(b))
+            assert not bad.any(), f"{case}.{k}: {int(bad.sum())} / {bad.size} elements differ (TMA vs plain), n={n}"
