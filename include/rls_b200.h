@@ -461,6 +461,16 @@ int rls_synth_shading(rls_context *ctx, size_t n, uint64_t seed, uint64_t first_
 int rls_debug_libm(rls_context *ctx, int fn, size_t n, const float *a, const float *b,
                    float *out0, float *out1);
 
+/* Fast arithmetic policy == exact policy over a RANGE OF BIT PATTERNS (rlshaders_b200/csrc/rls_fp.cuh):
+ * argument k is the binary32 with bits first_bits + k * stride, k < count.  For every argument whose
+ * fast-policy evaluation leaves the operand tracker satisfied the result must equal the guarded
+ * IEEE evaluation bit for bit.  counts (device, 3 x uint64, caller-zeroed): [0] arguments accepted
+ * by the tracker, [1] mismatches among them (must stay 0), [2] arguments sent to the exact re-run.
+ * fn: 0 sqrt(a); 1 1/a; 2 a/b; 3 tanf(a); 4 acosf(a); 5 atan2f(a, b); 6 atan2f(b, a);
+ *     7 a/b with a zero-tolerant numerator and b > 0; 8 b/a. */
+int rls_debug_policy_check(rls_context *ctx, int fn, uint32_t first_bits, uint64_t count, uint32_t stride,
+                           float b, unsigned long long *counts);
+
 #ifdef __cplusplus
 }
 #endif

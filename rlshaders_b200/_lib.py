@@ -28,7 +28,7 @@ SYMBOLS = [
     "rls_ggx_sample_eval_pdf_host", "rls_ggx_dielectric_sample_eval_pdf_host",
     "rls_disney_sample_eval_pdf_host", "rls_skin_profile_sample_eval_pdf_host",
     "rls_host_alloc", "rls_host_free",
-    "rls_albedo_sweep", "rls_synth_uniform", "rls_synth_shading", "rls_debug_libm",
+    "rls_albedo_sweep", "rls_synth_uniform", "rls_synth_shading", "rls_debug_libm", "rls_debug_policy_check",
     "rls_skin_glossy_layers", "rls_ggx_evaluate_light_sample", "rls_disney_evaluate_light_sample",
     "rls_sample_writer_radiance", "rls_sample_writer_scatter",
 ]
@@ -85,6 +85,7 @@ def load():
         "rls_synth_uniform": [vp, sz, u64, u32, u64, f, f, vp],
         "rls_synth_shading": [vp, sz, u64, u64, f, f, f, P(abi.ShadingSoA)],
         "rls_debug_libm": [vp, i32, sz, vp, vp, vp, vp],
+        "rls_debug_policy_check": [vp, i32, u32, u64, u32, f, vp],
         "rls_skin_glossy_layers": [vp, sz, u32, P(abi.ShadingSoA), P(abi.SkinParams), vp, vp, vp, vp,
                                    abi.CVec3, abi.CVec3, P(abi.SkinLayersOut)],
         "rls_ggx_evaluate_light_sample": [vp, sz, P(abi.ShadingSoA), P(abi.GgxParams), P(abi.LightSample), vp, vp,

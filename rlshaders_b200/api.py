@@ -116,6 +116,17 @@ class Context:
                                                     out1.data_ptr() if out1 is not None else None), self.lib)
         return (out0, out1) if fn == 0 else out0
 
+    POLICY_CHECKS = dict(sqrt=0, rcp=1, div=2, tanf=3, acosf=4, atan2f_yx=5, atan2f_xy=6, div_pz=7, rdiv=8)
+
+    def debug_policy_check(self, name, first_bits, count, stride=1, b=1.0):
+        """Fast-policy == exact-policy over the binary32 bit patterns first_bits + k*stride, k < count.
+        Returns (accepted by the operand tracker, mismatches among them, sent to the exact re-run)."""
+        counts = torch.zeros(3, dtype=torch.int64, device=self.device)
+        _check(self.handle, self.lib.rls_debug_policy_check(self.handle, self.POLICY_CHECKS[name], int(first_bits) & 0xffffffff,
+                                                            int(count), int(stride), float(b), counts.data_ptr()), self.lib)
+        self.synchronize()
+        return tuple(int(v) for v in counts.cpu().tolist())
+
     # ---- albedo sweep ----------------------------------------------------------
     def albedo_sweep(self, grid, seed, spp_begin, spp_end, out=None):
         cells = grid.n_rough * grid.n_cos * grid.n_ior

@@ -1655,6 +1655,64 @@ extern "C" int rls_debug_libm(rls_context *ctx, int fn, size_t n, const float *a
     return RLS_OK;
 }
 
+// Fast-policy == exact-policy over RANGES OF BIT PATTERNS (no input arrays): argument k of the range
+// is the binary32 with bits first + k * stride.  For every argument whose fast-policy evaluation
+// leaves the operand tracker satisfied (FpFast::ok) the result must equal the exact policy's bit
+// for bit; counts[0] = such arguments, counts[1] = mismatches among them, counts[2] = arguments sent
+// to the exact re-run.  fn: 0 sqrt(a), 1 1/a, 2 a/b, 3 tanf(a), 4 acosf(a), 5 atan2f(a, b),
+// 6 atan2f(b, a), 7 a/b with a zero-tolerant numerator (div_pz, b > 0), 8 b/a.
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+k_debug_policy_check(int fn, uint32_t first, uint64_t count, uint32_t stride, float b, unsigned long long *counts)
+{
+    unsigned long long okc = 0, bad = 0, rerun = 0;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (uint64_t)gridDim.x * blockDim.x) {
+        const float a = __uint_as_float(first + (uint32_t)k * stride);
+        FpFast ff; FpExact fe;
+        float rf, re;
+        switch (fn) {
+        case 0: rf = ff.sqrt(a); re = fe.sqrt(a); break;
+        case 1: rf = ff.rcp(a); re = fe.rcp(a); break;
+        case 2: rf = ff.div(a, b); re = fe.div(a, b); break;
+        case 3: rf = rlm::tanf_(ff, a); re = rlm::tanf_(fe, a); break;
+        case 4: rf = rlm::acosf_(ff, a); re = rlm::acosf_(fe, a); break;
+        case 5: rf = rlm::atan2f_(ff, a, b); re = rlm::atan2f_(fe, a, b); break;
+        case 6: rf = rlm::atan2f_(ff, b, a); re = rlm::atan2f_(fe, b, a); break;
+        case 7: rf = ff.div_pz(a, b); re = fe.div_pz(a, b); break;
+        default: rf = ff.div(b, a); re = fe.div(b, a); break;
+        }
+        if (ff.ok()) {
+            okc++;
+            const bool both_nan = (rf != rf) && (re != re);
+            if (__float_as_uint(rf) != __float_as_uint(re) && !both_nan) bad++;
+        } else {
+            rerun++;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        okc += __shfl_down_sync(0xffffffffu, okc, o);
+        bad += __shfl_down_sync(0xffffffffu, bad, o);
+        rerun += __shfl_down_sync(0xffffffffu, rerun, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(counts + 0, okc);
+        atomicAdd(counts + 1, bad);
+        atomicAdd(counts + 2, rerun);
+    }
+}
+extern "C" int rls_debug_policy_check(rls_context *ctx, int fn, uint32_t first_bits, uint64_t count, uint32_t stride, float b,
+                                      unsigned long long *counts)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    RLS_REQUIRE(ctx, fn >= 0 && fn <= 8 && counts && stride >= 1, "rls_debug_policy_check: bad argument");
+    if (count == 0) return RLS_OK;
+    DeviceGuard guard(ctx->device);
+    const uint64_t blocks = (count + kBlock - 1) / kBlock;
+    const unsigned grid = (unsigned)(blocks < (uint64_t)ctx->sm_count * 32 ? blocks : (uint64_t)ctx->sm_count * 32);
+    k_debug_policy_check<<<grid, kBlock, 0, ctx->stream>>>(fn, first_bits, count, stride, b, counts);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+
 // ===================================================== host-buffer (end-to-end) forms
 // A chunk of samples is staged through one of kStages device buffers: H2D of every input
 // slice, the kernel, D2H of every output slice, all on that stage's stream, so that chunk

@@ -42,7 +42,7 @@ RLS_DEV GgxShared ggx_shared(Fp &fp, const Ggx &g)
 {
     GgxShared s;
     s.VdotN = dot(g.wo, g.N);
-    s.absVdotN = abs_m(s.VdotN);
+    s.absVdotN = fp.abs_nz(s.VdotN);                  // a factor of the divisors of refl and pdf
     s.sgnV = sgn_m(s.VdotN);
     s.G1v = ggx_G1_value2(fp, g, s.VdotN);
     // entering: iorIn = 1, iorOut = b  ->  ratio = b/1 = b, eta = 1/b; leaving: the other way round
@@ -69,11 +69,11 @@ RLS_DEV void ggx_reflect_eval_pdf(Fp &fp, const Ggx &g, const GgxShared &s, f3 L
     }
     // brdf: hr = sgn(V.N) * H
     float VHr = VH * s.sgnV, LHr = LH * s.sgnV;
-    float F = ggx_fresnel_c(fp, s.ratio2, abs_m(VHr));
+    float F = ggx_fresnel_c(fp, s.ratio2, fabsf(VHr));
     float G1i = (VHr * s.VdotN < 0.0f) ? 0.0f : s.G1v;
     float G1o = (LHr * LdotN < 0.0f) ? 0.0f : G1l;
     float D_hr = (s.sgnV != 0.0f) ? D_H : __int_as_float(0x7f800000);   // D(0 vector) = 1/0
-    float refl = fp.div_pz(F * (G1i * G1o) * D_hr * 0.25f, abs_m(LdotN) * s.absVdotN);   // F or G may be 0
+    float refl = fp.div_pz(F * (G1i * G1o) * D_hr * 0.25f, fp.abs_nz(LdotN) * s.absVdotN);   // F or G may be 0
     refl_cos = refl;
 }
 
@@ -91,8 +91,8 @@ RLS_DEV Dielectric dielectric_unit(Fp &fp, const Shading &sh, float ior, float r
     f3 m = ggx_sample_normal(fp, g, rx, ry);
     float Vm = dot(g.wo, m);
     // reflectDirection(V, m) = 2|V.m| m - V
-    r.wi_r = m * (2.0f * abs_m(Vm)) - g.wo;
-    r.F = ggx_fresnel_c(fp, s.ratio2, abs_m(dot(r.wi_r, m)));
+    r.wi_r = m * (2.0f * fp.abs_nz(Vm)) - g.wo;       // Vm is the tracked numerator of w_t below
+    r.F = ggx_fresnel_c(fp, s.ratio2, fabsf(dot(r.wi_r, m)));
 
     // evalBrdf(wi_r) with white KsColor, evalPdf(wi_r)
     const f3 L = r.wi_r;
@@ -131,8 +131,8 @@ RLS_DEV Dielectric dielectric_unit(Fp &fp, const Shading &sh, float ior, float r
         f3 ht = -normalize(fp, g.wo * g.iorIn + T * g.iorOut);
         float IdotH = dot(g.wo, ht);
         float OdotH = dot(T, ht);
-        float refractWeight = 1.0f - ggx_fresnel_c(fp, s.ratio2, abs_m(IdotH));
-        float denominator = abs_m(TdotN) * s.absVdotN * sqr(g.iorIn * IdotH + g.iorOut * OdotH);
+        float refractWeight = 1.0f - ggx_fresnel_c(fp, s.ratio2, fabsf(IdotH));
+        float denominator = fp.abs_nz(TdotN) * s.absVdotN * sqr(g.iorIn * IdotH + g.iorOut * OdotH);
         float G1i = (IdotH * s.VdotN < 0.0f) ? 0.0f : s.G1v;
         float G1o = (OdotH * TdotN < 0.0f) ? 0.0f : G1t;
         r.f_t = fp.div_pz(abs_m(OdotH * IdotH) * sqr(g.iorOut) * refractWeight * (G1i * G1o) * ggx_D(fp, g, ht), denominator);
@@ -141,7 +141,7 @@ RLS_DEV Dielectric dielectric_unit(Fp &fp, const Shading &sh, float ior, float r
     {
         float G1i = (Vm * s.VdotN < 0.0f) ? 0.0f : s.G1v;
         float G1o = (dot(r.wi_t, m) * TdotN < 0.0f) ? 0.0f : G1t;
-        r.w_t = (G1i * G1o) * abs_m(fp.div(Vm, s.absVdotN * abs_m(mN)));
+        r.w_t = (G1i * G1o) * fp.abs_nz(fp.div(Vm, s.absVdotN * fp.abs_nz(mN)));   // a tracked quotient is not 0
     }
     r.flags = fl;
     return r;
@@ -156,7 +156,7 @@ RLS_DEV GgxBsdf ggx_unit(Fp &fp, const Ggx &g, float rx, float ry)
     const GgxShared s = ggx_shared(fp, g);
     f3 m = ggx_sample_normal(fp, g, rx, ry);
     o.L = m * (2.0f * abs_m(dot(g.wo, m))) - g.wo;
-    o.fresnel = ggx_fresnel_c(fp, s.ratio2, abs_m(dot(o.L, m)));
+    o.fresnel = ggx_fresnel_c(fp, s.ratio2, fabsf(dot(o.L, m)));
     const float LdotN = dot(o.L, g.N);
     float refl;
     ggx_reflect_eval_pdf(fp, g, s, o.L, LdotN, ggx_G1_value2(fp, g, LdotN), refl, o.pdf);
@@ -254,7 +254,7 @@ RLS_DEV DisneyOut1 disney_unit(Fp &fp, const Disney &d, float rx_s, float ry_s, 
         if (NdotM < 0.0f) {
             o.ps = 0.0f;
         } else {
-            const float IdotM = abs_m(LdotM);
+            const float IdotM = fp.abs_nz(LdotM);            // the divisor of both pdf forms
             const float clearcoatWeight = fp.div_pz(d.clearcoat, d.clearcoat + 1.0f);
             if (d.visibleNormal) {
                 const float Vn = max_m(1e-4f, VdotN);
@@ -268,7 +268,7 @@ RLS_DEV DisneyOut1 disney_unit(Fp &fp, const Disney &d, float rx_s, float ry_s, 
         if (LdotN < kEps || VdotN < kEps || NdotM < kEps || LdotM < kEps) {
             o.fs = mk3(0.0f, 0.0f, 0.0f) * LdotN;            // black * NdotL keeps the sign of zero
         } else {
-            const float FH = rlm::powf_(clamp_m(1.0f - LdotM, 0.0f, 1.0f), 5.0f);
+            const float FH = rlm::pow5_unit_(clamp_m(1.0f - LdotM, 0.0f, 1.0f));
             const f3 Fs = lerp_m(FH, d.F0, mk3(1.0f, 1.0f, 1.0f));
             const float Gs = smithG_GGX(fp, LdotN, d.specRough) * smithG_GGX(fp, VdotN, d.specRough);
             const float Fr = lerp_m(FH, 0.04f, 1.0f);

@@ -194,34 +194,47 @@ RLS_DEV f3 ggx_sample_normal(Fp &fp, const Ggx &g, float rx, float ry)
 template <class Fp>
 RLS_DEV void ggx_init(Fp &fp, Ggx &g, const Shading &sh, f3 ks, float ior, float roughness, float aniso)
 {
-    f3 Ngeo = sh.backfacing ? -sh.N : sh.N;      // sg->N
-    f3 Rd = -sh.wo;                              // sg->Rd
-    g.entering = dot(Ngeo, Rd) < kEps;           // :137
+    // :137  dot(sg->N, sg->Rd) with sg->N = +-N, sg->Rd = -wo: the products are those of dot(wo, N)
+    // with the signs applied exactly, the sum is +-dot(wo, N) up to the sign of an exact zero, which
+    // the comparison does not see.  The fused units reuse the value as V.N (same products, same order).
+    const float woN = dot(sh.wo, sh.N);
+    g.entering = (sh.backfacing ? woN : -woN) < kEps;
     float a = 1.0f, b = max_m(ior, 1e-4f);       // :138-139
     g.iorIn = g.entering ? a : b;                // :140-142 (swap)
     g.iorOut = g.entering ? b : a;
     g.iorB = b;
     g.wo = sh.wo;                                // :144  -(-wo) is exact
     g.U = sh.U; g.V = sh.V; g.N = sh.N;          // :145-146, explicit frame
-    float aspect = fp.sqrt(1.0f - aniso * 0.9f); // :148
-    g.ax = max_m(1e-4f, fp.div_pz(sqr(roughness), aspect));   // roughness 0 is a legal parameter
-    g.ay = max_m(1e-4f, sqr(roughness) * aspect);
+    if (aniso == 0.0f) {
+        // The isotropic node (a uniform branch when `anisotropic` is a uniform parameter): aspect =
+        // sqrt(1 - 0) = 1 and r^2/1 = r^2*1 = r^2 exactly -- no root, no quotient.
+        g.ax = g.ay = max_m(1e-4f, sqr(roughness));
+    } else {
+        float aspect = fp.sqrt(1.0f - aniso * 0.9f); // :148
+        g.ax = max_m(1e-4f, fp.div_pz(sqr(roughness), aspect));   // roughness 0 is a legal parameter
+        g.ay = max_m(1e-4f, sqr(roughness) * aspect);
+    }
     g.rough = max_m(1e-5f, sqr(roughness));      // :155
     g.ks = ks;
     g.ndf = false;
 }
 // src/rlGgx.h:249-270
-// Walter Eq.22 given c = |i.m| and ratio2 = SQR(mIorOut / mIorIn) (:258)
+// Walter Eq.22 given c = |i.m| and ratio2 = SQR(mIorOut / mIorIn) (:258).
+// c = -0 (ABS keeps the sign of a zero) and c = +0 give the same bits: c*c = +0, g -+ (-0) = g -+ 0
+// (also for g = 0), (-0)*x -+ 1 = -+1.  The fused units therefore pass fabsf(i.m), an operand modifier.
 template <class Fp>
 RLS_DEV float ggx_fresnel_c(Fp &fp, float ratio2, float c)
 {
     float gSqr = ratio2 - 1.0f + c * c;
-    if (gSqr < 0.0f) return 1.0f;
-    float gg = fp.sqrt(gSqr);
+    // :260-263 returns 1 for g^2 < 0.  Select instead of branch (a warp almost always holds both
+    // kinds of lane): those lanes run the formula on the in-window dummy g^2 = 1 and drop the result.
+    const bool tir = gSqr < 0.0f;
+    float gg = fp.sqrt(tir ? 1.0f : gSqr);
     float gmc = gg - c;
     float gpc = gg + c;
     // gmc == 0 for ior 1 (a legal parameter): zero-tolerant numerator over gpc > 0
-    return 0.5f * sqr(fp.div_pz(gmc, gpc)) * (1.0f + sqr(fp.div(c * gpc - 1.0f, c * gmc + 1.0f)));
+    float v = 0.5f * sqr(fp.div_pz(gmc, gpc)) * (1.0f + sqr(fp.div(c * gpc - 1.0f, c * gmc + 1.0f)));
+    return tir ? 1.0f : v;
 }
 template <class Fp>
 RLS_DEV float ggx_fresnel(Fp &fp, const Ggx &g, f3 i, f3 m)

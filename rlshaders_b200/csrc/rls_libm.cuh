@@ -293,6 +293,12 @@ RLM_HD float kernel_tanf(Fp &fp, float x, float y, int iy)
     float st = 1.0f + t * zt;
     float res_inv = t + q * (st + t * vt);
     float res = big ? res_big : ((iy == 1) ? w : res_inv);
+    if (Fp::kFast) {
+        // The two special returns of the original (|pi/4 - |x|| < 2^-13; |x| < 2^-13) are not
+        // carried by the fast stream: such arguments go to the exact re-run.
+        fp.require(!big_tiny && ix >= 0x39000000);
+        return res;
+    }
     if (big_tiny) res = (float)((1 - ((hx >> 30) & 2)) * iy) * (1.0f - (float)(2 * iy) * x);
     if (ix < 0x39000000) {                     // |x| < 2^-13
         if ((int)x_in == 0) {
@@ -368,6 +374,15 @@ RLM_HD float atanf_(float x) { rls::FpExact fp; return atanf_(fp, x); }
 
 // Fast-policy form of atanf_ for a finite argument ax >= 0 (the |y/x| of atan2f_): the same
 // five regimes; the |x| >= 2^25 shortcut of the original is not carried (fp.require).
+// The five argument reductions are ONE expression (A*ax + B) / (-B*ax + A) with per-regime
+// constants, each regime's operations being the original's up to exact steps:
+//   regime            original                      A    B      A*ax + B          -B*ax + A
+//   |x| < 7/16        x                             1    0      1*x + 0 = x       (-0)*x + 1 = 1
+//   < 11/16           (2x - 1) / (2 + x)            2   -1      2x - 1            1*x + 2
+//   < 19/16           (x - 1) / (x + 1)             1   -1      1*x - 1           1*x + 1
+//   < 39/16           (x - 1.5) / (1 + 1.5x)        1   -1.5    1*x - 1.5         1.5x + 1
+//   else              -1 / x                        0   -1      0*x - 1 = -1      1*x + 0 = x
+// (a product by 1, 2 or 0 and a sum with 0 are exact; IEEE addition commutes.)
 template <class Fp>
 RLM_HD float atanf_nonneg_(Fp &fp, float ax)
 {
@@ -381,8 +396,10 @@ RLM_HD float atanf_nonneg_(Fp &fp, float ax)
     const bool r1 = ix < 0x3f300000;
     const bool r2 = ix < 0x3f980000;
     const bool r3 = ix < 0x401c0000;
-    float num = r0 ? ax : (r1 ? 2.0f * ax - 1.0f : (r2 ? ax - 1.0f : (r3 ? ax - 1.5f : -1.0f)));
-    float den = r0 ? 1.0f : (r1 ? 2.0f + ax : (r2 ? ax + 1.0f : (r3 ? 1.0f + 1.5f * ax : ax)));
+    const float A = r0 ? 1.0f : (r1 ? 2.0f : (r3 ? 1.0f : 0.0f));
+    const float B = r0 ? 0.0f : ((r3 && !r2) ? -1.5f : -1.0f);
+    const float num = A * ax + B;
+    const float den = (-B) * ax + A;
     float hi = r1 ? 4.6364760399e-01f : (r2 ? 7.8539812565e-01f : (r3 ? 9.8279368877e-01f : 1.5707962513e+00f));
     float lo = r1 ? 5.0121582440e-09f : (r2 ? 3.7748947079e-08f : (r3 ? 3.4473217170e-08f : 7.5497894159e-08f));
     float t = fp.div_pz(num, den);
@@ -611,6 +628,50 @@ RLM_HD float powf_(float x, float y)
         if (ylogx < -149.0) return 0x1.4p-75f * 0x1.4p-75f;                 // may-underflow value
     }
     // exp2_inline
+    const double ShiftScaled = kExp2C[0];
+    const double C0 = kExp2C[1], C1 = kExp2C[2], C2 = kExp2C[3];
+    double kd = ylogx + ShiftScaled;
+    uint64_t ki = d2u(kd);
+    kd -= ShiftScaled;
+    double rr = ylogx - kd;
+    uint64_t t = RLM_LD(kExp2Tab[(uint32_t)ki & 31u]);
+    t += ki << 47;
+    double s = u2d(t);
+    double zz = fma_(C0, rr, C1);
+    double rr2 = rr * rr;
+    double out = fma_(C2, rr, 1.0);
+    out = fma_(zz, rr2, out);
+    out = out * s;
+    return (float)out;
+}
+
+// powf(x, 5.0f) for x in [0, 1] or NaN -- the Schlick weights pow(clamp(1 - cos, 0, 1), 5) of
+// rlDisney (src/rlDisney.cpp:218-219,335).  The main path of powf_ without the tests that cannot
+// fire on this domain: x normal (1 - cos is 0 or >= 2^-24), 5 log2(x) in [-120, 0] (no overflow /
+// underflow range test).  x == 0 and NaN (and subnormals, for totality) go through powf_.
+RLM_HD float pow5_unit_(float x)
+{
+    uint32_t ix = f2u(x);
+    if (!(ix - 0x00800000u < 0x3f800000u - 0x00800000u + 1u)) return powf_(x, 5.0f);   // not a normal number in (0, 1]
+    const double A0 = kLog2C[0], A1 = kLog2C[1], A2 = kLog2C[2], A3 = kLog2C[3], A4 = kLog2C[4];
+    uint32_t tmp = ix - 0x3f330000u;
+    int i = (int)((tmp >> 19) & 15u);
+    uint32_t top = tmp & 0xff800000u;
+    uint32_t iz = ix - top;
+    int k = (int32_t)top >> 23;
+    double invc = RLM_LD(kLog2Tab[2 * i]);
+    double logc = RLM_LD(kLog2Tab[2 * i + 1]);
+    double z = (double)u2f(iz);
+    double r = fma_(z, invc, -1.0);
+    double y0 = logc + (double)k;
+    double r2 = r * r;
+    double yy = fma_(A0, r, A1);
+    double p = fma_(A2, r, A3);
+    double r4 = r2 * r2;
+    double q = fma_(A4, r, y0);
+    q = fma_(p, r2, q);
+    double logx = fma_(yy, r4, q);
+    double ylogx = 5.0 * logx;
     const double ShiftScaled = kExp2C[0];
     const double C0 = kExp2C[1], C1 = kExp2C[2], C2 = kExp2C[3];
     double kd = ylogx + ShiftScaled;

@@ -67,8 +67,8 @@ RLS_DEV Dielectric dielectric_unit_paired(FpFast &fp, const Shading &sh, float i
     const GgxShared s = ggx_shared(fp, g);
     const f3 m = ggx_sample_normal(fp, g, rx, ry);
     const float Vm = dot(g.wo, m);
-    r.wi_r = m * (2.0f * rls::abs_m(Vm)) - g.wo;
-    r.F = rls::ggx_fresnel_c(fp, s.ratio2, rls::abs_m(dot(r.wi_r, m)));
+    r.wi_r = m * (2.0f * fp.abs_nz(Vm)) - g.wo;
+    r.F = rls::ggx_fresnel_c(fp, s.ratio2, fabsf(dot(r.wi_r, m)));
     const f3 L = r.wi_r;
     const float LdotN = dot(L, g.N);
 
@@ -143,7 +143,7 @@ RLS_DEV Dielectric dielectric_unit_paired(FpFast &fp, const Shading &sh, float i
         const float mN = dot(m, g.N);
         const float G1i_w = (Vm * s.VdotN < 0.0f) ? 0.0f : s.G1v;
         const float G1o_w = (dot(T, m) * TdotN < 0.0f) ? 0.0f : hi(G1x);
-        r.w_t = (G1i_w * G1o_w) * rls::abs_m(fp.div(Vm, s.absVdotN * rls::abs_m(mN)));
+        r.w_t = (G1i_w * G1o_w) * fp.abs_nz(fp.div(Vm, s.absVdotN * fp.abs_nz(mN)));
     }
     r.flags = fl;
     return r;

@@ -1,7 +1,7 @@
 // tests/native/libm_check.cpp -- TEST INFRASTRUCTURE.
 // Runs the product's device libm (rlshaders_b200/csrc/rls_libm.cuh, which is __host__
 // __device__) on the CPU against the host C library, bit for bit.
-//   libm_check <function> [stride]     function: sincos cos tan atan acos exp log atan2 pow
+//   libm_check <function> [stride]     function: sincos cos tan atan acos exp log atan2 pow pow5 pow5unit
 // Univariate functions walk every binary32 bit pattern (stride 1) or every stride-th one;
 // bivariate ones draw (stride-scaled) pseudo-random pairs from the path's domains.
 // Prints "<function> checked N mismatches M first <hex args>" and exits 0.
@@ -72,6 +72,10 @@ int main(int argc, char **argv)
             else if (fn == "acos") ok = same(acosf(x), rlm::acosf_(x));
             else if (fn == "exp") ok = same(expf(x), rlm::expf_(x));
             else if (fn == "log") ok = same(logf(x), rlm::logf_(x));
+            else if (fn == "pow5unit") {                // Schlick weights: every x in [0, 1] (subnormals too) and NaN
+                // (1 - c is never -0 in round-to-nearest, so the sign bit is clear on the path)
+                if ((x != x) || (x >= 0.0f && x <= 1.0f && !(fbits(x) >> 31))) ok = same(powf(x, 5.0f), rlm::pow5_unit_(x));
+            }
             else { fprintf(stderr, "unknown function %s\n", fn.c_str()); exit(2); }
             checked++;
             if (!ok) { bad++; if (u < first) first = u; }

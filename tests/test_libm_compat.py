@@ -28,7 +28,7 @@ def checker():
     return EXE
 
 
-@pytest.mark.parametrize("fn", ["sincos", "cos", "tan", "atan", "acos", "exp", "log", "atan2", "pow", "pow5"])
+@pytest.mark.parametrize("fn", ["sincos", "cos", "tan", "atan", "acos", "exp", "log", "atan2", "pow", "pow5", "pow5unit"])
 def test_device_libm_source_matches_host_libm(checker, fn):
     stride = "1" if os.environ.get("RLS_LIBM_EXHAUSTIVE") else ("61" if fn in ("atan2", "pow", "pow5") else "253")
     out = subprocess.run([checker, fn, stride], check=True, capture_output=True, text=True).stdout.split()
@@ -82,3 +82,32 @@ def test_compiled_device_libm_matches_host_libm():
     got = ctx.debug_libm("powf", dev(base), dev(ex)).cpu().numpy()
     assert np.array_equal(_bits(got[:m]), _bits(_host(libm, "powf", base[:m], ex[:m])))
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_fast_policy_equals_exact_policy_exhaustively():
+    """rls_fp.cuh / rls_libm.cuh: for EVERY binary32 argument (all 2^32 bit patterns of the univariate
+    operations; 2^32 numerators / angles against a set of second operands for the bivariate ones) the
+    guard-free fast-policy sequence either leaves the operand tracker unsatisfied (the sample is then
+    re-run with the guarded operators) or returns the bits of the exact policy."""
+    from rlshaders_b200 import api
+    ctx = api.Context(0)
+    try:
+        full = 1 << 32
+        for name in ("sqrt", "rcp", "tanf", "acosf"):
+            ok, bad, rerun = ctx.debug_policy_check(name, 0, full)
+            assert ok + rerun == full and bad == 0, (name, ok, bad, rerun)
+            assert ok > (1 << 28), (name, ok)          # the window is not vacuous
+        seconds = [1.0, -1.0, 3.0, 0.3, -0.7071068, 1e-4, 0.9999999, 1.0000001, 2.0 ** -30, 2.0 ** 40, 1e-20, -123456.7,
+                   float(np.float32(np.pi)), 0.5, 1.5, 7.0]
+        for name in ("div", "rdiv", "div_pz", "atan2f_yx", "atan2f_xy"):
+            total_ok = 0
+            for b in seconds:
+                if name == "div_pz" and b <= 0.0:
+                    continue
+                ok, bad, rerun = ctx.debug_policy_check(name, 0, full // 16, stride=16, b=b)
+                assert bad == 0, (name, b, ok, bad, rerun)
+                total_ok += ok
+            assert total_ok > (1 << 28), (name, total_ok)
+    finally:
+        ctx.close()
