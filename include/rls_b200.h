@@ -467,7 +467,8 @@ int rls_debug_libm(rls_context *ctx, int fn, size_t n, const float *a, const flo
  * IEEE evaluation bit for bit.  counts (device, 3 x uint64, caller-zeroed): [0] arguments accepted
  * by the tracker, [1] mismatches among them (must stay 0), [2] arguments sent to the exact re-run.
  * fn: 0 sqrt(a); 1 1/a; 2 a/b; 3 tanf(a); 4 acosf(a); 5 atan2f(a, b); 6 atan2f(b, a);
- *     7 a/b with a zero-tolerant numerator and b > 0; 8 b/a. */
+ *     7 a/b with a zero-tolerant numerator and b > 0; 8 b/a; 9 a/3 with the literal reciprocal;
+ *     10 a/b through the shared refined reciprocal of b. */
 int rls_debug_policy_check(rls_context *ctx, int fn, uint32_t first_bits, uint64_t count, uint32_t stride,
                            float b, unsigned long long *counts);
 

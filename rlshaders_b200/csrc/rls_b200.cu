@@ -1660,7 +1660,8 @@ extern "C" int rls_debug_libm(rls_context *ctx, int fn, size_t n, const float *a
 // leaves the operand tracker satisfied (FpFast::ok) the result must equal the exact policy's bit
 // for bit; counts[0] = such arguments, counts[1] = mismatches among them, counts[2] = arguments sent
 // to the exact re-run.  fn: 0 sqrt(a), 1 1/a, 2 a/b, 3 tanf(a), 4 acosf(a), 5 atan2f(a, b),
-// 6 atan2f(b, a), 7 a/b with a zero-tolerant numerator (div_pz, b > 0), 8 b/a.
+// 6 atan2f(b, a), 7 a/b with a zero-tolerant numerator (div_pz, b > 0), 8 b/a, 9 a/3 (div3),
+// 10 a/b through the shared refined reciprocal of b (shared_rcp + div_by).
 __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_debug_policy_check(int fn, uint32_t first, uint64_t count, uint32_t stride, float b, unsigned long long *counts)
 {
@@ -1678,7 +1679,9 @@ k_debug_policy_check(int fn, uint32_t first, uint64_t count, uint32_t stride, fl
         case 5: rf = rlm::atan2f_(ff, a, b); re = rlm::atan2f_(fe, a, b); break;
         case 6: rf = rlm::atan2f_(ff, b, a); re = rlm::atan2f_(fe, b, a); break;
         case 7: rf = ff.div_pz(a, b); re = fe.div_pz(a, b); break;
-        default: rf = ff.div(b, a); re = fe.div(b, a); break;
+        case 8: rf = ff.div(b, a); re = fe.div(b, a); break;
+        case 9: rf = ff.div3(a); re = fe.div3(a); break;
+        default: rf = ff.div_by(a, b, ff.shared_rcp(b)); re = fe.div(a, b); break;
         }
         if (ff.ok()) {
             okc++;
@@ -1703,7 +1706,7 @@ extern "C" int rls_debug_policy_check(rls_context *ctx, int fn, uint32_t first_b
                                       unsigned long long *counts)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
-    RLS_REQUIRE(ctx, fn >= 0 && fn <= 8 && counts && stride >= 1, "rls_debug_policy_check: bad argument");
+    RLS_REQUIRE(ctx, fn >= 0 && fn <= 10 && counts && stride >= 1, "rls_debug_policy_check: bad argument");
     if (count == 0) return RLS_OK;
     DeviceGuard guard(ctx->device);
     const uint64_t blocks = (count + kBlock - 1) / kBlock;

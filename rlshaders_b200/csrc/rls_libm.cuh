@@ -649,73 +649,46 @@ RLM_HD float powf_(float x, float y)
 // rlDisney (src/rlDisney.cpp:218-219,335).  The main path of powf_ without the tests that cannot
 // fire on this domain: x normal (1 - cos is 0 or >= 2^-24), 5 log2(x) in [-120, 0] (no overflow /
 // underflow range test).  x == 0 and NaN (and subnormals, for totality) go through powf_.
-// N independent evaluations step by step: every binary64 coefficient is fetched ONCE for the N
-// chains (a DFMA cannot take a 64-bit constant-bank operand: each use of a coefficient is otherwise
-// its own LDC) and the chains interleave.  Measured on B200 with N = 2 for rlDisney's FL, FV: the
-// two interleaved binary64 chains spill at 64 registers and lose 1 % -- the kernels call N = 1.
-template <int N>
-RLM_HD void pow5_unit_n_(const float (&x)[N], float (&res)[N])
-{
-    const double A0 = kLog2C[0], A1 = kLog2C[1], A2 = kLog2C[2], A3 = kLog2C[3], A4 = kLog2C[4];
-    const double ShiftScaled = kExp2C[0];
-    const double C0 = kExp2C[1], C1 = kExp2C[2], C2 = kExp2C[3];
-    bool main_path[N];
-    double ylogx[N];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 0; j < N; j++) {
-        uint32_t ix = f2u(x[j]);
-        main_path[j] = ix - 0x00800000u < 0x3f800000u - 0x00800000u + 1u;     // a normal number in (0, 1]
-        ix = main_path[j] ? ix : 0x3f000000u;                                  // dummy 0.5 for the others
-        uint32_t tmp = ix - 0x3f330000u;
-        int i = (int)((tmp >> 19) & 15u);
-        uint32_t top = tmp & 0xff800000u;
-        uint32_t iz = ix - top;
-        int k = (int32_t)top >> 23;
-        double invc = RLM_LD(kLog2Tab[2 * i]);
-        double logc = RLM_LD(kLog2Tab[2 * i + 1]);
-        double z = (double)u2f(iz);
-        double r = fma_(z, invc, -1.0);
-        double y0 = logc + (double)k;
-        double r2 = r * r;
-        double yy = fma_(A0, r, A1);
-        double p = fma_(A2, r, A3);
-        double r4 = r2 * r2;
-        double q = fma_(A4, r, y0);
-        q = fma_(p, r2, q);
-        ylogx[j] = 5.0 * fma_(yy, r4, q);
-    }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 0; j < N; j++) {
-        double kd = ylogx[j] + ShiftScaled;
-        uint64_t ki = d2u(kd);
-        kd -= ShiftScaled;
-        double rr = ylogx[j] - kd;
-        uint64_t t = RLM_LD(kExp2Tab[(uint32_t)ki & 31u]);
-        t += ki << 47;
-        double s = u2d(t);
-        double zz = fma_(C0, rr, C1);
-        double rr2 = rr * rr;
-        double out = fma_(C2, rr, 1.0);
-        out = fma_(zz, rr2, out);
-        out = out * s;
-        res[j] = (float)out;
-    }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 0; j < N; j++)
-        if (!main_path[j]) res[j] = powf_(x[j], 5.0f);      // x == 0 (L.M == 1 exactly), NaN
-}
 RLM_HD float pow5_unit_(float x)
 {
-    const float xs[1] = { x };
-    float r[1];
-    pow5_unit_n_<1>(xs, r);
-    return r[0];
+    uint32_t ix = f2u(x);
+    if (!(ix - 0x00800000u < 0x3f800000u - 0x00800000u + 1u)) return powf_(x, 5.0f);   // not a normal number in (0, 1]
+    const double A0 = kLog2C[0], A1 = kLog2C[1], A2 = kLog2C[2], A3 = kLog2C[3], A4 = kLog2C[4];
+    uint32_t tmp = ix - 0x3f330000u;
+    int i = (int)((tmp >> 19) & 15u);
+    uint32_t top = tmp & 0xff800000u;
+    uint32_t iz = ix - top;
+    int k = (int32_t)top >> 23;
+    double invc = RLM_LD(kLog2Tab[2 * i]);
+    double logc = RLM_LD(kLog2Tab[2 * i + 1]);
+    double z = (double)u2f(iz);
+    double r = fma_(z, invc, -1.0);
+    double y0 = logc + (double)k;
+    double r2 = r * r;
+    double yy = fma_(A0, r, A1);
+    double p = fma_(A2, r, A3);
+    double r4 = r2 * r2;
+    double q = fma_(A4, r, y0);
+    q = fma_(p, r2, q);
+    double logx = fma_(yy, r4, q);
+    double ylogx = 5.0 * logx;
+    const double ShiftScaled = kExp2C[0];
+    const double C0 = kExp2C[1], C1 = kExp2C[2], C2 = kExp2C[3];
+    double kd = ylogx + ShiftScaled;
+    uint64_t ki = d2u(kd);
+    kd -= ShiftScaled;
+    double rr = ylogx - kd;
+    uint64_t t = RLM_LD(kExp2Tab[(uint32_t)ki & 31u]);
+    t += ki << 47;
+    double s = u2d(t);
+    double zz = fma_(C0, rr, C1);
+    double rr2 = rr * rr;
+    double out = fma_(C2, rr, 1.0);
+    out = fma_(zz, rr2, out);
+    out = out * s;
+    return (float)out;
 }
+// (A step-wise N-chain form that fetched every binary64 coefficient once for the two Schlick weights
+// FL, FV of rlDisney was measured on B200: the interleaved chains spill at 64 registers, -1 %.)
 
 } // namespace rlm

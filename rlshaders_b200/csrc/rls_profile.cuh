@@ -7,7 +7,10 @@
 
 namespace rls {
 
-struct NdProfile { float d[3], C1[3], C2[3], R; };
+struct NdProfile {
+    float d[3], C1[3], C2[3], R;
+    float yd[3];     // fused unit only: the refined reciprocal of d[i] that its quotients by d[i] share (Fp::shared_rcp)
+};
 
 // src/rlSss.cpp:20-34.  The `s` of :23 (powf of the albedo luminance) is dead code in the
 // reference and is not evaluated; the albedo therefore does not enter the profile.
@@ -19,8 +22,10 @@ RLS_DEV void nd_set_distance(Fp &fp, NdProfile &p, f3 dist)
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         float d = p.d[i];
-        p.C1[i] = 1.0f - rlm::expf_(fp.div(-p.R, d));
-        p.C2[i] = 1.0f - rlm::expf_(fp.div(fp.div(-p.R, d), 3.0f));
+        p.yd[i] = fp.shared_rcp(d);
+        const float q = fp.div_by(-p.R, d, p.yd[i]);         // -R/d, evaluated once for :31 and :32
+        p.C1[i] = 1.0f - rlm::expf_(q);
+        p.C2[i] = 1.0f - rlm::expf_(fp.div3(q));
     }
 }
 // src/rlSss.h:30-42 (thirds at 0.3333f / 0.6666f)
@@ -104,10 +109,13 @@ RLS_DEV void nd_pdf_and_profile(Fp &fp, const NdProfile &p, float r, float &pdf_
     for (int i = 0; i < 3; i++) {
         const float d = p.d[i];
         const float dm = max_m(d, kEps);
-        const float q1 = fp.div(-r, dm);
+        // dm == d unless d < AI_EPSILON (or NaN): the quotients by dm then share setDistance's reciprocal of d
+        const bool same = dm == d;
+        const float q1 = same ? fp.div_by(-r, d, p.yd[i]) : fp.div(-r, dm);
         const float p1 = rlm::expf_(q1);
-        const float p2 = rlm::expf_(fp.div(q1, 3.0f));
-        pdf += fp.div(fp.div(p1 + p2, dm), p.C1[i] + p.C2[i] * 3.0f);
+        const float p2 = rlm::expf_(fp.div3(q1));
+        const float s12 = p1 + p2;
+        pdf += fp.div(same ? fp.div_by(s12, d, p.yd[i]) : fp.div(s12, dm), p.C1[i] + p.C2[i] * 3.0f);
         o[i] = 1.0f;
         if (!white && !(d < kEps)) {             // dm == d here (unless d is NaN): exp(-r/d) == p1
             const float e1 = (dm == d) ? p1 : rlm::expf_(fp.div(-r, d));

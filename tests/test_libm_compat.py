@@ -94,13 +94,13 @@ def test_fast_policy_equals_exact_policy_exhaustively():
     ctx = api.Context(0)
     try:
         full = 1 << 32
-        for name in ("sqrt", "rcp", "tanf", "acosf"):
+        for name in ("sqrt", "rcp", "tanf", "acosf", "div3"):
             ok, bad, rerun = ctx.debug_policy_check(name, 0, full)
             assert ok + rerun == full and bad == 0, (name, ok, bad, rerun)
             assert ok > (1 << 28), (name, ok)          # the window is not vacuous
         seconds = [1.0, -1.0, 3.0, 0.3, -0.7071068, 1e-4, 0.9999999, 1.0000001, 2.0 ** -30, 2.0 ** 40, 1e-20, -123456.7,
                    float(np.float32(np.pi)), 0.5, 1.5, 7.0]
-        for name in ("div", "rdiv", "div_pz", "atan2f_yx", "atan2f_xy"):
+        for name in ("div", "rdiv", "div_pz", "div_shared", "atan2f_yx", "atan2f_xy"):
             total_ok = 0
             for b in seconds:
                 if name == "div_pz" and b <= 0.0:
