@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Summarise an ncu report (ncu -i rep --page raw --csv) as a markdown table of the counters
-this repository's roofline discussion uses.  Usage: ncu_summary.py rep.ncu-rep [rep2 ...]"""
+this repository's roofline discussion uses.  Usage: ncu_summary.py rep.ncu-rep|rep.raw.csv [...]
+(a .csv argument is the already exported raw page: gpurun brings back at most 64 MiB)."""
 import csv
 import io
 import subprocess
@@ -28,7 +29,10 @@ WANT = [
 
 def main():
     for rep in sys.argv[1:]:
-        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        if rep.endswith(".csv"):
+            out = open(rep).read()
+        else:
+            out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(out)))
         hdr, units = rows[0], rows[1]
         print(f"### {rep.split('/')[-1]}\n")
