@@ -468,7 +468,7 @@ int rls_debug_libm(rls_context *ctx, int fn, size_t n, const float *a, const flo
  * by the tracker, [1] mismatches among them (must stay 0), [2] arguments sent to the exact re-run.
  * fn: 0 sqrt(a); 1 1/a; 2 a/b; 3 tanf(a); 4 acosf(a); 5 atan2f(a, b); 6 atan2f(b, a);
  *     7 a/b with a zero-tolerant numerator and b > 0; 8 b/a; 9 a/3 with the literal reciprocal;
- *     10 a/b through the shared refined reciprocal of b. */
+ *     10 a/b through the shared refined reciprocal of b; 11 expf(a); 12 sincosf(a) (sine and cosine). */
 int rls_debug_policy_check(rls_context *ctx, int fn, uint32_t first_bits, uint64_t count, uint32_t stride,
                            float b, unsigned long long *counts);
 

@@ -116,7 +116,7 @@ class Context:
                                                     out1.data_ptr() if out1 is not None else None), self.lib)
         return (out0, out1) if fn == 0 else out0
 
-    POLICY_CHECKS = dict(sqrt=0, rcp=1, div=2, tanf=3, acosf=4, atan2f_yx=5, atan2f_xy=6, div_pz=7, rdiv=8, div3=9, div_shared=10)
+    POLICY_CHECKS = dict(sqrt=0, rcp=1, div=2, tanf=3, acosf=4, atan2f_yx=5, atan2f_xy=6, div_pz=7, rdiv=8, div3=9, div_shared=10, expf=11, sincosf=12)
 
     def debug_policy_check(self, name, first_bits, count, stride=1, b=1.0):
         """Fast-policy == exact-policy over the binary32 bit patterns first_bits + k*stride, k < count.

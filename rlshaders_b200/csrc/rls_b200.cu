@@ -620,7 +620,7 @@ k_disney_sample_eval_pdf(size_t n, ShadingSoA sg, DisneyParamsDev p, const float
     bool ok = false;
     if (kFast) {
         const Shading s = load_shading(sg, i);
-        FpFast fp;
+        FpFastLeanTrig fp;
         r = disney_unit_from<kArrays, false>(fp, s, p, i, __ldg(rx_s + i), __ldg(ry_s + i), __ldg(rx_d + i), __ldg(ry_d + i));
         ok = fp.ok();
     }
@@ -1661,14 +1661,14 @@ extern "C" int rls_debug_libm(rls_context *ctx, int fn, size_t n, const float *a
 // for bit; counts[0] = such arguments, counts[1] = mismatches among them, counts[2] = arguments sent
 // to the exact re-run.  fn: 0 sqrt(a), 1 1/a, 2 a/b, 3 tanf(a), 4 acosf(a), 5 atan2f(a, b),
 // 6 atan2f(b, a), 7 a/b with a zero-tolerant numerator (div_pz, b > 0), 8 b/a, 9 a/3 (div3),
-// 10 a/b through the shared refined reciprocal of b (shared_rcp + div_by).
+// 10 a/b through the shared refined reciprocal of b (shared_rcp + div_by), 11 expf(a), 12 sincosf(a).
 __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_debug_policy_check(int fn, uint32_t first, uint64_t count, uint32_t stride, float b, unsigned long long *counts)
 {
     unsigned long long okc = 0, bad = 0, rerun = 0;
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (uint64_t)gridDim.x * blockDim.x) {
         const float a = __uint_as_float(first + (uint32_t)k * stride);
-        FpFast ff; FpExact fe;
+        FpFastLeanTrig ff; FpExact fe;       // the lean-trigonometry flavour, so that fn 12 checks the branch-free sincosf
         float rf, re;
         switch (fn) {
         case 0: rf = ff.sqrt(a); re = fe.sqrt(a); break;
@@ -1681,7 +1681,14 @@ k_debug_policy_check(int fn, uint32_t first, uint64_t count, uint32_t stride, fl
         case 7: rf = ff.div_pz(a, b); re = fe.div_pz(a, b); break;
         case 8: rf = ff.div(b, a); re = fe.div(b, a); break;
         case 9: rf = ff.div3(a); re = fe.div3(a); break;
-        default: rf = ff.div_by(a, b, ff.shared_rcp(b)); re = fe.div(a, b); break;
+        case 10: rf = ff.div_by(a, b, ff.shared_rcp(b)); re = fe.div(a, b); break;
+        case 11: rf = rlm::expf_(ff, a); re = rlm::expf_(fe, a); break;
+        default: {      // sincosf: both results must match (the sine is returned, the cosine is folded in)
+            float sf, cf, se, ce;
+            rlm::sincosf_(ff, a, &sf, &cf); rlm::sincosf_(fe, a, &se, &ce);
+            const bool cos_same = __float_as_uint(cf) == __float_as_uint(ce) || (cf != cf && ce != ce);
+            rf = sf; re = cos_same ? se : __uint_as_float(__float_as_uint(sf) ^ 1u);
+            break; }
         }
         if (ff.ok()) {
             okc++;
@@ -1706,7 +1713,7 @@ extern "C" int rls_debug_policy_check(rls_context *ctx, int fn, uint32_t first_b
                                       unsigned long long *counts)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
-    RLS_REQUIRE(ctx, fn >= 0 && fn <= 10 && counts && stride >= 1, "rls_debug_policy_check: bad argument");
+    RLS_REQUIRE(ctx, fn >= 0 && fn <= 12 && counts && stride >= 1, "rls_debug_policy_check: bad argument");
     if (count == 0) return RLS_OK;
     DeviceGuard guard(ctx->device);
     const uint64_t blocks = (count + kBlock - 1) / kBlock;

@@ -68,7 +68,7 @@ RLS_DEV float D_GTR1(Fp &fp, const Disney &d, float MdotN2)
 {
     float alpha = lerp_m(d.clearcoatGloss, 0.1f, 0.001f);
     float a2 = sqr(alpha);
-    float denominator = rlm::logf_(a2) * (1.0f + (a2 - 1.0f) * MdotN2);
+    float denominator = rlm::logf_(fp, a2) * (1.0f + (a2 - 1.0f) * MdotN2);
     return fp.div((a2 - 1.0f) * kInvPi, denominator);
 }
 // src/rlDisney.cpp:561-568

@@ -189,7 +189,7 @@ RLS_DEV DisneyOut1 disney_unit(Fp &fp, const Disney &d, float rx_s, float ry_s, 
     // per-sample constants of D_GTR1 (src/rlDisney.cpp:547-549)
     const float gtr1_alpha = lerp_m(d.clearcoatGloss, 0.1f, 0.001f);
     const float gtr1_a2 = sqr(gtr1_alpha);
-    const float gtr1_log = rlm::logf_(gtr1_a2);
+    const float gtr1_log = rlm::logf_(fp, gtr1_a2);
     auto D_GTR1_shared = [&](float MdotN2) {
         float denominator = gtr1_log * (1.0f + (gtr1_a2 - 1.0f) * MdotN2);
         return fp.div((gtr1_a2 - 1.0f) * kInvPi, denominator);
@@ -223,7 +223,7 @@ RLS_DEV DisneyOut1 disney_unit(Fp &fp, const Disney &d, float rx_s, float ry_s, 
                                      : fp.sqrt(fp.div(1.0f - rlm::powf_(a2, 1.0f - ry_s), 1.0f - a2));
         }
         float s, c;
-        rlm::sincosf_(angle, &s, &c);
+        rlm::sincosf_(fp, angle, &s, &c);
         f3 omega;
         if (lobe == 0) {
             omega = d.visibleNormal ? vndf_omega(fp, st, s, c, d.ax, d.ay, rx, ry_s)

@@ -14,7 +14,7 @@ template <class Fp>
 RLS_DEV f3 spherical_direction(Fp &fp, float cosTheta, float phi)
 {
     float s, c;
-    rlm::sincosf_(phi, &s, &c);
+    rlm::sincosf_(fp, phi, &s, &c);
     float r = fp.sqrt(1.0f - sqr(cosTheta));
     return mk3(r * c, r * s, cosTheta);
 }
@@ -43,7 +43,7 @@ RLS_DEV f2 concentric_disk_sample(Fp &fp, float rx, float ry)
         phi = kHalfPi * (1.0f - fp.div(0.5f * rx, ry));
     }
     float s, c;
-    rlm::sincosf_(phi, &s, &c);
+    rlm::sincosf_(fp, phi, &s, &c);
     o.x = r * c;
     o.y = r * s;
     return o;
@@ -57,7 +57,7 @@ RLS_DEV f2 uniform_slope(Fp &fp, float rx, float ry)
     float r = fp.sqrt(fp.div(rx, 1.0f - rx));
     float phi = kTwoPi * ry;
     float s, c;
-    rlm::sincosf_(phi, &s, &c);
+    rlm::sincosf_(fp, phi, &s, &c);
     f2 o; o.x = r * c; o.y = r * s;
     return o;
 }
@@ -158,7 +158,7 @@ RLS_DEV f3 sample_visible_normal(Fp &fp, f3 view, f3 U, f3 Vax, f3 N, float ax, 
 {
     const VndfState st = vndf_prepare(fp, view, U, Vax, N, ax, ay);
     float s, c;
-    rlm::sincosf_(vndf_angle(st, ry), &s, &c);
+    rlm::sincosf_(fp, vndf_angle(st, ry), &s, &c);
     return normalize(fp, rotate_to_frame(vndf_omega(fp, st, s, c, ax, ay, rx, ry), U, Vax, N));
 }
 
@@ -170,7 +170,7 @@ RLS_DEV f3 sample_ndf_normal(Fp &fp, f3 U, f3 Vax, f3 N, float ax, float ay, flo
     float g = fp.sqrt(fp.div(rx, 1.0f - rx));
     float phi = kTwoPi * ry;
     float s, c;
-    rlm::sincosf_(phi, &s, &c);
+    rlm::sincosf_(fp, phi, &s, &c);
     f3 omega = mk3(g * ax * c, g * ay * s, 1.0f);
     return normalize(fp, rotate_to_frame(omega, U, Vax, N));
 }

@@ -220,6 +220,20 @@ RLM_HD double sincosf_reduce_large(uint32_t xi, int *np)
     *np = (int)n;
     return x * 0x1.921FB54442D18p-62;
 }
+// The |y| < 120 path alone, WITHOUT the host's |y| < 2^-12 shortcut (sin = y, cos = 1): the
+// polynomial rounds to exactly those values there except for sin(-0) (tests/native/libm_check
+// "sincoslean": equal to the host for every |y| < 120), so the fast policy carries neither the range
+// branch nor the two selects of the shortcut.
+RLM_HD void sincosf_main_(float y, float *sinp, float *cosp)
+{
+    double x = (double)y;
+    double r = x * kSinCosC[7];            // 2/pi * 2^24
+    int n = ((int32_t)r + 0x800000) >> 24;
+    x = fma_(-(double)n, kSinCosC[8], x);
+    float sv;
+    sincosf_poly(sincosf_signed(x, n), x * x, (n & 2) != 0, n, &sv, cosp);
+    *sinp = (y == 0.0f) ? y : sv;          // sin(-0) = -0: the one argument the polynomial gets wrong (+0)
+}
 RLM_HD void sincosf_(float y, float *sinp, float *cosp)
 {
     double x = (double)y;
@@ -245,6 +259,16 @@ RLM_HD void sincosf_(float y, float *sinp, float *cosp)
     } else {
         *sinp = *cosp = y - y;
     }
+}
+// Policy form: |y| >= 120, Inf and NaN go to the exact re-run.
+template <class Fp>
+RLM_HD void sincosf_(Fp &fp, float y, float *sinp, float *cosp)
+{
+    // Measured on B200: the branch-free form gains 2 % in the rlDisney unit (three calls) and LOSES
+    // 1-3 % in the two rlGgx units, so it is a property of the policy type (FpFastLeanTrig).
+    if (!(Fp::kFast && Fp::kLeanTrig)) { sincosf_(y, sinp, cosp); return; }
+    fp.require(fabsf_(y) < 120.0f);
+    sincosf_main_(y, sinp, cosp);
 }
 
 // ===================================================================== tanf
@@ -515,9 +539,9 @@ RLM_HD float acosf_(float x) { rls::FpExact fp; return acosf_(fp, x); }
 
 // ===================================================================== expf
 // glibc 2.39 e_expf.c (ARM Optimized Routines), FMA build
+RLM_HD float expf_main_(float x);
 RLM_HD float expf_(float x)
 {
-    double xd = (double)x;
     if (!(fabsf_(x) < 88.0f)) {                // abstop12(x) >= 0x42b: |x| >= 88 or NaN
         if (f2u(x) == 0xff800000u) return 0.0f;
         if (abstop12(x) >= 0x7f8u) return x + x;
@@ -525,6 +549,15 @@ RLM_HD float expf_(float x)
         if (x < -0x1.9fe368p6f) return 0.0f;                        // underflow
         if (x < -0x1.9d1d9ep6f) return 0x1.4p-75f * 0x1.4p-75f;     // may-underflow value
     }
+    return expf_main_(x);
+}
+// The main path of expf_ alone.  With the argument clamped from below at -104.5 it returns the host's
+// bits for EVERY x < 88 (tests/native/libm_check "explean", exhaustive): on [-103.97, -88) the host
+// itself falls through to this path, and below it both round to the values the host's underflow
+// returns produce (2^-149 down to -103.97, then 0).
+RLM_HD float expf_main_(float x)
+{
+    double xd = (double)x;
     const double InvLn2N = kExpC[0], Shift = kExpC[1];
     const double C0 = kExpC[2], C1 = kExpC[3], C2 = kExpC[4];
     double kd = fma_(InvLn2N, xd, Shift);
@@ -541,9 +574,24 @@ RLM_HD float expf_(float x)
     y = y * s;
     return (float)y;
 }
+// Policy form: the fast stream carries neither the range ladder nor its branch -- one clamp, and
+// x >= 88 / NaN go to the exact re-run.
+template <class Fp>
+RLM_HD float expf_(Fp &fp, float x)
+{
+    if (!Fp::kFast) return expf_(x);
+    fp.require(x < 88.0f);
+#if defined(__CUDA_ARCH__)
+    return expf_main_(fmaxf(x, -104.5f));
+#else
+    return expf_main_(x > -104.5f ? x : -104.5f);
+#endif
+}
+
 
 // ===================================================================== logf
 // glibc 2.39 e_logf.c (ARM Optimized Routines), FMA build
+RLM_HD float logf_main_(uint32_t ix);
 RLM_HD float logf_(float x)
 {
     uint32_t ix = f2u(x);
@@ -555,6 +603,13 @@ RLM_HD float logf_(float x)
         ix = f2u(x * 0x1p23f);                              // subnormal: normalise
         ix -= 23u << 23;
     }
+    return logf_main_(ix);
+}
+// The main path of logf_ for the bits ix of a positive normal number.  It also returns the host's +0
+// for x == 1 (the host's shortcut is a speed-up, not a special value): tests/native/libm_check
+// "loglean" walks every positive normal binary32.
+RLM_HD float logf_main_(uint32_t ix)
+{
     const double Ln2 = kLogC[0];
     const double A0 = kLogC[1], A1 = kLogC[2], A2 = kLogC[3];
     uint32_t tmp = ix - 0x3f330000u;
@@ -572,6 +627,16 @@ RLM_HD float logf_(float x)
     y = fma_(y, r2, y0 + r);
     return (float)y;
 }
+// Policy form: zero, subnormal, negative, Inf and NaN arguments go to the exact re-run.
+template <class Fp>
+RLM_HD float logf_(Fp &fp, float x)
+{
+    if (!Fp::kFast) return logf_(x);
+    const uint32_t ix = f2u(x);
+    fp.require(ix - 0x00800000u < 0x7f800000u - 0x00800000u);
+    return logf_main_(ix);
+}
+
 
 // ===================================================================== powf
 // glibc 2.39 e_powf.c (ARM Optimized Routines), FMA build.  Main path for x > 0; the

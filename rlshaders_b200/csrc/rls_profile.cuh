@@ -24,8 +24,8 @@ RLS_DEV void nd_set_distance(Fp &fp, NdProfile &p, f3 dist)
         float d = p.d[i];
         p.yd[i] = fp.shared_rcp(d);
         const float q = fp.div_by(-p.R, d, p.yd[i]);         // -R/d, evaluated once for :31 and :32
-        p.C1[i] = 1.0f - rlm::expf_(q);
-        p.C2[i] = 1.0f - rlm::expf_(fp.div3(q));
+        p.C1[i] = 1.0f - rlm::expf_(fp, q);
+        p.C2[i] = 1.0f - rlm::expf_(fp, fp.div3(q));
     }
 }
 // src/rlSss.h:30-42 (thirds at 0.3333f / 0.6666f)
@@ -55,10 +55,10 @@ RLS_DEV float nd_get_radius(Fp &fp, const NdProfile &p, float rx, uint32_t &flag
     if (x > w) {
         flags |= 0x0400u;                            // RLS_FLAG_EXP_LOBE
         x = linearstep_m(fp, w, 1.0f, x);
-        r = rlm::logf_(1.0f - x * w2) * (-d * 3.0f);
+        r = rlm::logf_(fp, 1.0f - x * w2) * (-d * 3.0f);
     } else {
         x = linearstep_m(fp, 0.0f, w, x);
-        r = rlm::logf_(1.0f - x * w1) * (-d);
+        r = rlm::logf_(fp, 1.0f - x * w1) * (-d);
     }
     return r;
 }
@@ -71,8 +71,8 @@ RLS_DEV float nd_get_pdf(Fp &fp, const NdProfile &p, float r)
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         float d = max_m(p.d[i], kEps);
-        float p1 = rlm::expf_(fp.div(-r, d));
-        float p2 = rlm::expf_(fp.div(fp.div(-r, d), 3.0f));
+        float p1 = rlm::expf_(fp, fp.div(-r, d));
+        float p2 = rlm::expf_(fp, fp.div(fp.div(-r, d), 3.0f));
         pdf += fp.div(fp.div(p1 + p2, d), p.C1[i] + p.C2[i] * 3.0f);
     }
     return fp.div(pdf, kTwoPi * r * 3.0f);
@@ -89,7 +89,7 @@ RLS_DEV f3 nd_eval_profile(Fp &fp, const NdProfile &p, float r)
     for (int i = 0; i < 3; i++) {
         float d = p.d[i];
         o[i] = 1.0f;
-        if (!(d < kEps)) o[i] = fp.div(rlm::expf_(fp.div(-r, d)) + rlm::expf_(fp.div(-r, 3.0f * d)), denom * d);
+        if (!(d < kEps)) o[i] = fp.div(rlm::expf_(fp, fp.div(-r, d)) + rlm::expf_(fp, fp.div(-r, 3.0f * d)), denom * d);
     }
     return mk3(o[0], o[1], o[2]);
 }
@@ -109,17 +109,19 @@ RLS_DEV void nd_pdf_and_profile(Fp &fp, const NdProfile &p, float r, float &pdf_
     for (int i = 0; i < 3; i++) {
         const float d = p.d[i];
         const float dm = max_m(d, kEps);
-        // dm == d unless d < AI_EPSILON (or NaN): the quotients by dm then share setDistance's reciprocal of d
+        // dm == d unless d < AI_EPSILON (or NaN).  The fast policy sends those samples to the exact
+        // re-run (fp.require) and forms the quotients by dm with setDistance's reciprocal of d.
         const bool same = dm == d;
-        const float q1 = same ? fp.div_by(-r, d, p.yd[i]) : fp.div(-r, dm);
-        const float p1 = rlm::expf_(q1);
-        const float p2 = rlm::expf_(fp.div3(q1));
+        fp.require(same);
+        const float q1 = Fp::kFast ? fp.div_by(-r, d, p.yd[i]) : fp.div(-r, dm);
+        const float p1 = rlm::expf_(fp, q1);
+        const float p2 = rlm::expf_(fp, fp.div3(q1));
         const float s12 = p1 + p2;
-        pdf += fp.div(same ? fp.div_by(s12, d, p.yd[i]) : fp.div(s12, dm), p.C1[i] + p.C2[i] * 3.0f);
+        pdf += fp.div(Fp::kFast ? fp.div_by(s12, d, p.yd[i]) : fp.div(s12, dm), p.C1[i] + p.C2[i] * 3.0f);
         o[i] = 1.0f;
         if (!white && !(d < kEps)) {             // dm == d here (unless d is NaN): exp(-r/d) == p1
-            const float e1 = (dm == d) ? p1 : rlm::expf_(fp.div(-r, d));
-            o[i] = fp.div(e1 + rlm::expf_(fp.div(-r, 3.0f * d)), denom * d);
+            const float e1 = (Fp::kFast || same) ? p1 : rlm::expf_(fp, fp.div(-r, d));
+            o[i] = fp.div(e1 + rlm::expf_(fp, fp.div(-r, 3.0f * d)), denom * d);
         }
     }
     pdf_out = fp.div(pdf, kTwoPi * r * 3.0f);

@@ -63,6 +63,13 @@ int main(int argc, char **argv)
                 sincosf(x, &s0, &c0);
                 rlm::sincosf_(x, &s1, &c1);
                 ok = same(s0, s1) && same(c0, c1);
+            } else if (fn == "sincoslean") {            // fast-policy sincosf: main path only, for every |x| < 120
+                if (fabsf(x) < 120.0f) {
+                    float s0, c0, s1, c1;
+                    sincosf(x, &s0, &c0);
+                    rlm::sincosf_main_(x, &s1, &c1);
+                    ok = same(s0, s1) && same(c0, c1);
+                }
             } else if (fn == "cos") {                   // SampleWriter's cosf(theta) is served by sincosf_
                 float s1, c1;
                 rlm::sincosf_(x, &s1, &c1);
@@ -72,6 +79,12 @@ int main(int argc, char **argv)
             else if (fn == "acos") ok = same(acosf(x), rlm::acosf_(x));
             else if (fn == "exp") ok = same(expf(x), rlm::expf_(x));
             else if (fn == "log") ok = same(logf(x), rlm::logf_(x));
+            else if (fn == "loglean") {                 // fast-policy logf: main path only, every positive normal x
+                if ((uint32_t)u - 0x00800000u < 0x7f800000u - 0x00800000u) ok = same(logf(x), rlm::logf_main_((uint32_t)u));
+            }
+            else if (fn == "explean") {                 // fast-policy expf: clamp + main path, for every x < 88
+                if (x < 88.0f) ok = same(expf(x), rlm::expf_main_(x > -104.5f ? x : -104.5f));
+            }
             else if (fn == "pow5unit") {                // Schlick weights: every x in [0, 1] (subnormals too) and NaN
                 // (1 - c is never -0 in round-to-nearest, so the sign bit is clear on the path)
                 if ((x != x) || (x >= 0.0f && x <= 1.0f && !(fbits(x) >> 31))) ok = same(powf(x, 5.0f), rlm::pow5_unit_(x));

@@ -28,7 +28,7 @@ def checker():
     return EXE
 
 
-@pytest.mark.parametrize("fn", ["sincos", "cos", "tan", "atan", "acos", "exp", "log", "atan2", "pow", "pow5", "pow5unit"])
+@pytest.mark.parametrize("fn", ["sincos", "cos", "tan", "atan", "acos", "exp", "log", "atan2", "pow", "pow5", "pow5unit", "explean", "sincoslean", "loglean"])
 def test_device_libm_source_matches_host_libm(checker, fn):
     stride = "1" if os.environ.get("RLS_LIBM_EXHAUSTIVE") else ("61" if fn in ("atan2", "pow", "pow5") else "253")
     out = subprocess.run([checker, fn, stride], check=True, capture_output=True, text=True).stdout.split()
@@ -94,7 +94,7 @@ def test_fast_policy_equals_exact_policy_exhaustively():
     ctx = api.Context(0)
     try:
         full = 1 << 32
-        for name in ("sqrt", "rcp", "tanf", "acosf", "div3"):
+        for name in ("sqrt", "rcp", "tanf", "acosf", "div3", "expf", "sincosf"):
             ok, bad, rerun = ctx.debug_policy_check(name, 0, full)
             assert ok + rerun == full and bad == 0, (name, ok, bad, rerun)
             assert ok > (1 << 28), (name, ok)          # the window is not vacuous
