@@ -623,6 +623,7 @@ __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_disney_sample_eval_pdf(size_t n, ShadingSoA sg, DisneyParamsDev p, const float *rx_s, const float *ry_s,
                          const float *rx_d, const float *ry_d, DisneyOutDev o, unsigned long long *fallbacks)
 {
+    if (kFast) rlm::smem_tables_init();      // exp2 / log / log2 tables in shared memory (before the early exit below)
     RLS_INDEX();
     DisneyOut1 r;
     bool ok = false;
@@ -706,11 +707,12 @@ template <bool kFast>
 __global__ void __launch_bounds__(kBlockSkin, RLS_SKIN_MIN_BLOCKS)
 k_skin_profile(size_t n, SkinParamsDev sp, const float *rx, ProfileOutDev o, unsigned long long *fallbacks)
 {
+    if (kFast) rlm::smem_tables_init();      // exp2 / log tables in shared memory (before the early exit below)
     RLS_INDEX();
     Profile1 r;
     bool ok = false;
     if (kFast) {
-        FpFast fp;
+        FpFastSmemTab fp;
         r = skin_profile_unit(fp, skin_scatter_dist(sp, i), __ldg(rx + i));
         ok = fp.ok();
     }
@@ -1673,6 +1675,7 @@ extern "C" int rls_debug_libm(rls_context *ctx, int fn, size_t n, const float *a
 __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_debug_policy_check(int fn, uint32_t first, uint64_t count, uint32_t stride, float b, unsigned long long *counts)
 {
+    rlm::smem_tables_init();                 // FpFastLeanTrig reads its tables from shared memory
     unsigned long long okc = 0, bad = 0, rerun = 0;
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (uint64_t)gridDim.x * blockDim.x) {
         const float a = __uint_as_float(first + (uint32_t)k * stride);

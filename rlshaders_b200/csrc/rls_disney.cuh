@@ -92,8 +92,8 @@ RLS_DEV f3 disney_eval_diffuse(Fp &fp, const Disney &d, f3 L)
     float NdotH = dot(d.wo, H);   // sic: V.H (:210)
     if (NdotH < kEps || LdotH < kEps) return mk3(0.0f, 0.0f, 0.0f);
     float LdotH2 = sqr(LdotH);
-    float FL = rlm::pow5_unit_(clamp_m(1.0f - LdotN, 0.0f, 1.0f));
-    float FV = rlm::pow5_unit_(clamp_m(1.0f - VdotN, 0.0f, 1.0f));
+    float FL = rlm::pow5_unit_<Fp::kSmemTables>(clamp_m(1.0f - LdotN, 0.0f, 1.0f));
+    float FV = rlm::pow5_unit_<Fp::kSmemTables>(clamp_m(1.0f - VdotN, 0.0f, 1.0f));
     float F90 = 0.5f + 2.0f * d.roughness * LdotH2;
     float diffuseFactor = lerp_m(FL, 1.0f, F90) * lerp_m(FV, 1.0f, F90);
     float Fss90 = d.roughness * LdotH2;
@@ -115,7 +115,7 @@ RLS_DEV f3 disney_eval_specular(Fp &fp, const Disney &d, f3 L)
     if (NdotM < kEps || LdotM < kEps) return mk3(0.0f, 0.0f, 0.0f);
     float NdotM2 = sqr(NdotM);
     float Ds = D_GTR2Aniso(fp, d, M, NdotM2);
-    float FH = rlm::pow5_unit_(clamp_m(1.0f - LdotM, 0.0f, 1.0f));
+    float FH = rlm::pow5_unit_<Fp::kSmemTables>(clamp_m(1.0f - LdotM, 0.0f, 1.0f));
     f3 Fs = lerp_m(FH, d.F0, mk3(1.0f, 1.0f, 1.0f));
     float Gs = smithG_GGX(fp, LdotN, d.specRough) * smithG_GGX(fp, VdotN, d.specRough);
     float Dr = D_GTR1(fp, d, NdotM2);
@@ -150,7 +150,7 @@ RLS_DEV f3 disney_sample_gtr1(Fp &fp, const Disney &d, float rx, float ry)
     float phiH = kTwoPi * rx;
     float a2 = sqr(d.roughness);
     float cosThetaH = (a2 == 1.0f) ? fp.sqrt(1.0f - ry)
-                                   : fp.sqrt(fp.div(1.0f - rlm::powf_(a2, 1.0f - ry), 1.0f - a2));
+                                   : fp.sqrt(fp.div(1.0f - rlm::powf_<Fp::kSmemTables>(a2, 1.0f - ry), 1.0f - a2));
     f3 omega = spherical_direction(fp, cosThetaH, phiH);
     return normalize(fp, rotate_to_frame(omega, d.U, d.V, d.N));
 }

@@ -220,7 +220,7 @@ RLS_DEV DisneyOut1 disney_unit(Fp &fp, const Disney &d, float rx_s, float ry_s, 
             angle = kTwoPi * rx;                                  // sampleGTR1Direction (:393-404)
             float a2 = sqr(d.roughness);
             cosThetaH = (a2 == 1.0f) ? fp.sqrt(1.0f - ry_s)
-                                     : fp.sqrt(fp.div(1.0f - rlm::powf_(a2, 1.0f - ry_s), 1.0f - a2));
+                                     : fp.sqrt(fp.div(1.0f - rlm::powf_<Fp::kSmemTables>(a2, 1.0f - ry_s), 1.0f - a2));
         }
         float s, c;
         rlm::sincosf_(fp, angle, &s, &c);
@@ -268,7 +268,7 @@ RLS_DEV DisneyOut1 disney_unit(Fp &fp, const Disney &d, float rx_s, float ry_s, 
         if (LdotN < kEps || VdotN < kEps || NdotM < kEps || LdotM < kEps) {
             o.fs = mk3(0.0f, 0.0f, 0.0f) * LdotN;            // black * NdotL keeps the sign of zero
         } else {
-            const float FH = rlm::pow5_unit_(clamp_m(1.0f - LdotM, 0.0f, 1.0f));
+            const float FH = rlm::pow5_unit_<Fp::kSmemTables>(clamp_m(1.0f - LdotM, 0.0f, 1.0f));
             const f3 Fs = lerp_m(FH, d.F0, mk3(1.0f, 1.0f, 1.0f));
             const float Gs = smithG_GGX(fp, LdotN, d.specRough) * smithG_GGX(fp, VdotN, d.specRough);
             const float Fr = lerp_m(FH, 0.04f, 1.0f);

@@ -168,6 +168,46 @@ RLM_TABLE uint32_t kInvPio4[24] = {
     0x993c4390u, 0x3c439041u,
 };
 
+// The exp2 and log tables in SHARED memory, for kernels that call rlm::smem_tables_init() first
+// (policy types with kSmemTables): a lookup is SHL + LOP3 + LDS at an immediate base instead of
+// SHL + LOP3 + 64-bit add pair + LDG (15 lookups per skin-profile sample).
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint64_t *smem_tables()
+{
+    __shared__ uint64_t t[96];                 // [0, 32) kExp2Tab, [32, 64) kLogTab, [64, 96) kLog2Tab (bit patterns)
+    return t;
+}
+__device__ __forceinline__ void smem_tables_init()          // every thread of the CTA, before any early exit
+{
+    uint64_t *t = smem_tables();
+    if (threadIdx.x < 32) t[threadIdx.x] = kExp2Tab[threadIdx.x];
+    else if (threadIdx.x < 64) t[threadIdx.x] = d2u(kLogTab[threadIdx.x - 32]);
+    else if (threadIdx.x < 96) t[threadIdx.x] = d2u(kLog2Tab[threadIdx.x - 64]);
+    __syncthreads();
+}
+#endif
+template <bool kSmem> RLM_HD uint64_t exp2_tab(uint32_t i)
+{
+#if defined(__CUDA_ARCH__)
+    if (kSmem) return smem_tables()[i];
+#endif
+    return RLM_LD(kExp2Tab[i]);
+}
+template <bool kSmem> RLM_HD double log2_tab(int i)
+{
+#if defined(__CUDA_ARCH__)
+    if (kSmem) return u2d(smem_tables()[64 + i]);
+#endif
+    return RLM_LD(kLog2Tab[i]);
+}
+template <bool kSmem> RLM_HD double log_tab(int i)
+{
+#if defined(__CUDA_ARCH__)
+    if (kSmem) return u2d(smem_tables()[32 + i]);
+#endif
+    return RLM_LD(kLogTab[i]);
+}
+
 // ================================================================== sincosf
 // glibc 2.39 sysdeps/ieee754/flt-32/s_sincosf.{c,h} (ARM Optimized Routines), FMA build.
 // The cosine coefficients of quadrants 2,3 (__sincosf_table[1]) are the negated coefficients of
@@ -539,7 +579,7 @@ RLM_HD float acosf_(float x) { rls::FpExact fp; return acosf_(fp, x); }
 
 // ===================================================================== expf
 // glibc 2.39 e_expf.c (ARM Optimized Routines), FMA build
-RLM_HD float expf_main_(float x);
+template <bool kSmem> RLM_HD float expf_main_(float x);
 RLM_HD float expf_(float x)
 {
     if (!(fabsf_(x) < 88.0f)) {                // abstop12(x) >= 0x42b: |x| >= 88 or NaN
@@ -549,12 +589,13 @@ RLM_HD float expf_(float x)
         if (x < -0x1.9fe368p6f) return 0.0f;                        // underflow
         if (x < -0x1.9d1d9ep6f) return 0x1.4p-75f * 0x1.4p-75f;     // may-underflow value
     }
-    return expf_main_(x);
+    return expf_main_<false>(x);
 }
 // The main path of expf_ alone.  With the argument clamped from below at -104.5 it returns the host's
 // bits for EVERY x < 88 (tests/native/libm_check "explean", exhaustive): on [-103.97, -88) the host
 // itself falls through to this path, and below it both round to the values the host's underflow
 // returns produce (2^-149 down to -103.97, then 0).
+template <bool kSmem = false>
 RLM_HD float expf_main_(float x)
 {
     double xd = (double)x;
@@ -564,7 +605,7 @@ RLM_HD float expf_main_(float x)
     uint64_t ki = d2u(kd);
     kd -= Shift;
     double r = fma_(InvLn2N, xd, -kd);
-    uint64_t t = RLM_LD(kExp2Tab[(uint32_t)ki & 31u]);
+    uint64_t t = exp2_tab<kSmem>((uint32_t)ki & 31u);
     t += ki << 47;
     double s = u2d(t);
     double z = fma_(C0, r, C1);
@@ -582,16 +623,16 @@ RLM_HD float expf_(Fp &fp, float x)
     if (!Fp::kFast) return expf_(x);
     fp.require(x < 88.0f);
 #if defined(__CUDA_ARCH__)
-    return expf_main_(fmaxf(x, -104.5f));
+    return expf_main_<Fp::kSmemTables>(fmaxf(x, -104.5f));
 #else
-    return expf_main_(x > -104.5f ? x : -104.5f);
+    return expf_main_<false>(x > -104.5f ? x : -104.5f);
 #endif
 }
 
 
 // ===================================================================== logf
 // glibc 2.39 e_logf.c (ARM Optimized Routines), FMA build
-RLM_HD float logf_main_(uint32_t ix);
+template <bool kSmem> RLM_HD float logf_main_(uint32_t ix);
 RLM_HD float logf_(float x)
 {
     uint32_t ix = f2u(x);
@@ -603,11 +644,12 @@ RLM_HD float logf_(float x)
         ix = f2u(x * 0x1p23f);                              // subnormal: normalise
         ix -= 23u << 23;
     }
-    return logf_main_(ix);
+    return logf_main_<false>(ix);
 }
 // The main path of logf_ for the bits ix of a positive normal number.  It also returns the host's +0
 // for x == 1 (the host's shortcut is a speed-up, not a special value): tests/native/libm_check
 // "loglean" walks every positive normal binary32.
+template <bool kSmem = false>
 RLM_HD float logf_main_(uint32_t ix)
 {
     const double Ln2 = kLogC[0];
@@ -616,8 +658,8 @@ RLM_HD float logf_main_(uint32_t ix)
     int i = (int)((tmp >> 19) & 15u);
     int k = (int32_t)tmp >> 23;
     uint32_t iz = ix - (tmp & 0xff800000u);
-    double invc = RLM_LD(kLogTab[2 * i]);
-    double logc = RLM_LD(kLogTab[2 * i + 1]);
+    double invc = log_tab<kSmem>(2 * i);
+    double logc = log_tab<kSmem>(2 * i + 1);
     double z = (double)u2f(iz);
     double r = fma_(z, invc, -1.0);
     double y0 = fma_((double)k, Ln2, logc);
@@ -634,7 +676,7 @@ RLM_HD float logf_(Fp &fp, float x)
     if (!Fp::kFast) return logf_(x);
     const uint32_t ix = f2u(x);
     fp.require(ix - 0x00800000u < 0x7f800000u - 0x00800000u);
-    return logf_main_(ix);
+    return logf_main_<Fp::kSmemTables>(ix);
 }
 
 
@@ -642,6 +684,7 @@ RLM_HD float logf_(Fp &fp, float x)
 // glibc 2.39 e_powf.c (ARM Optimized Routines), FMA build.  Main path for x > 0; the
 // IEEE special cases the reference can reach (x == 0, x == 1, y == 0) are handled; negative
 // bases do not occur on the path (arguments are squares or clamped to [0, 1]).
+template <bool kSmem = false>
 RLM_HD float powf_(float x, float y)
 {
     uint32_t ix = f2u(x), iy = f2u(y);
@@ -673,8 +716,8 @@ RLM_HD float powf_(float x, float y)
     uint32_t top = tmp & 0xff800000u;
     uint32_t iz = ix - top;
     int k = (int32_t)top >> 23;
-    double invc = RLM_LD(kLog2Tab[2 * i]);
-    double logc = RLM_LD(kLog2Tab[2 * i + 1]);
+    double invc = log2_tab<kSmem>(2 * i);
+    double logc = log2_tab<kSmem>(2 * i + 1);
     double z = (double)u2f(iz);
     double r = fma_(z, invc, -1.0);
     double y0 = logc + (double)k;
@@ -699,7 +742,7 @@ RLM_HD float powf_(float x, float y)
     uint64_t ki = d2u(kd);
     kd -= ShiftScaled;
     double rr = ylogx - kd;
-    uint64_t t = RLM_LD(kExp2Tab[(uint32_t)ki & 31u]);
+    uint64_t t = exp2_tab<kSmem>((uint32_t)ki & 31u);
     t += ki << 47;
     double s = u2d(t);
     double zz = fma_(C0, rr, C1);
@@ -714,18 +757,19 @@ RLM_HD float powf_(float x, float y)
 // rlDisney (src/rlDisney.cpp:218-219,335).  The main path of powf_ without the tests that cannot
 // fire on this domain: x normal (1 - cos is 0 or >= 2^-24), 5 log2(x) in [-120, 0] (no overflow /
 // underflow range test).  x == 0 and NaN (and subnormals, for totality) go through powf_.
+template <bool kSmem = false>
 RLM_HD float pow5_unit_(float x)
 {
     uint32_t ix = f2u(x);
-    if (!(ix - 0x00800000u < 0x3f800000u - 0x00800000u + 1u)) return powf_(x, 5.0f);   // not a normal number in (0, 1]
+    if (!(ix - 0x00800000u < 0x3f800000u - 0x00800000u + 1u)) return powf_<kSmem>(x, 5.0f);   // not a normal number in (0, 1]
     const double A0 = kLog2C[0], A1 = kLog2C[1], A2 = kLog2C[2], A3 = kLog2C[3], A4 = kLog2C[4];
     uint32_t tmp = ix - 0x3f330000u;
     int i = (int)((tmp >> 19) & 15u);
     uint32_t top = tmp & 0xff800000u;
     uint32_t iz = ix - top;
     int k = (int32_t)top >> 23;
-    double invc = RLM_LD(kLog2Tab[2 * i]);
-    double logc = RLM_LD(kLog2Tab[2 * i + 1]);
+    double invc = log2_tab<kSmem>(2 * i);
+    double logc = log2_tab<kSmem>(2 * i + 1);
     double z = (double)u2f(iz);
     double r = fma_(z, invc, -1.0);
     double y0 = logc + (double)k;
@@ -743,7 +787,7 @@ RLM_HD float pow5_unit_(float x)
     uint64_t ki = d2u(kd);
     kd -= ShiftScaled;
     double rr = ylogx - kd;
-    uint64_t t = RLM_LD(kExp2Tab[(uint32_t)ki & 31u]);
+    uint64_t t = exp2_tab<kSmem>((uint32_t)ki & 31u);
     t += ki << 47;
     double s = u2d(t);
     double zz = fma_(C0, rr, C1);
