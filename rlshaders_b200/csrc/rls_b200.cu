@@ -63,6 +63,7 @@ static constexpr int kBlockGgx = RLS_GGX_BLOCK;
 #define RLS_SKIN_MIN_BLOCKS 9
 #endif
 static constexpr int kBlockSkin = RLS_SKIN_BLOCK;
+static_assert(kBlock >= 96 && kBlockSkin >= 96, "rlm::smem_tables_init() fills 96 table entries with one thread each");
 
 struct rls_context {
     int          device = 0;
