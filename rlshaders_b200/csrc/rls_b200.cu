@@ -32,7 +32,10 @@
 using namespace rls;
 
 // ============================================================== context
-static constexpr int kStages = 3;          // host-staging pipeline depth
+#ifndef RLS_STAGES
+#define RLS_STAGES 3
+#endif
+static constexpr int kStages = RLS_STAGES;  // host-staging pipeline depth
 // Launch shape: 256 threads x >= 4 resident CTAs per SM (<= 64 registers/thread).  Chosen from
 // sweeps on B200 (tools/sweep_variants.sh; profiles/r01_launch_sweep.txt): the kernels are
 // instruction-issue bound, so occupancy beyond ~50 % does not help and tighter register caps
@@ -82,9 +85,9 @@ struct rls_context {
                                                   // it is off unless RLS_PACKED=1 (kept for A/B runs and its test)
     unsigned long long *fallbacks = nullptr;      // device counter: samples re-run with FpExact
     // host-staging resources (lazily created by the *_host entry points)
-    cudaStream_t stage_stream[kStages] = { nullptr, nullptr, nullptr };
-    cudaEvent_t  stage_done[kStages] = { nullptr, nullptr, nullptr };
-    void        *stage_buf[kStages] = { nullptr, nullptr, nullptr };
+    cudaStream_t stage_stream[kStages] = {};
+    cudaEvent_t  stage_done[kStages] = {};
+    void        *stage_buf[kStages] = {};
     size_t       stage_bytes = 0;
 };
 
