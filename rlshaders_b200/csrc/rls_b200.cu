@@ -401,6 +401,7 @@ RLS_DEV void dielectric_sample(uint32_t i, const ShadingSoA &sg, const GgxParams
         const float ior = fetch_t<kArrays>(p.ior, i), rough = fetch_t<kArrays>(p.rough, i), aniso = fetch(p.aniso, i);
         const float u1 = __ldg(rx + i), u2 = __ldg(ry + i);
         FpFast fp;
+        // (dielectric_unit<kFlat = true>, the select form of the refraction branch, measured neutral: +-0.3 %)
         r = kPair ? pk::dielectric_unit_paired(fp, s, ior, rough, aniso, u1, u2, p.ndf != 0)
                   : dielectric_unit(fp, s, ior, rough, aniso, u1, u2, p.ndf != 0);
         ok = fp.ok();
