@@ -275,6 +275,15 @@ def run_product(args):
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     e2e_s = max_over_ranks(e2e_s * 1e3) * 1e-3
     clock_info = clocks.stop()
+    # The kernel is issue bound, not HBM bound: also report the fraction of the SM issue
+    # rate it sustains = executed warp instructions per launch (ncu count committed under profiles/)
+    # / launch time / (SMs x 4 schedulers x SM clock under load).
+    wi = measured_traffic("warp_instr_per_32_samples")
+    if isinstance(wi, dict) and wi.get("k_ggx_dielectric") and clock_info.get("sm_mhz"):
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        issued = wi["k_ggx_dielectric"] * (n / 32.0) / (ms * 1e-3)
+        roofline["issue"] = {"warp_instr_per_32_samples": wi["k_ggx_dielectric"],
+                             "frac_of_issue_peak": issued / (sms * 4 * clock_info["sm_mhz"] * 1e6)}
     e2e = {"value": world * ne / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "steps": e2e_steps, "ms_per_step": e2e_s * 1e3, "samples_per_gpu_per_step": ne,
            "host_cpus_bound_to_gpu_numa_node": numa}
