@@ -748,3 +748,43 @@ def test_tma_staged_kernels_match_plain_kernels(monkeypatch, n, adversarial):
             if a.dtype == np.float32:
                 bad &= ~(np.isnan(a) & np.isnan(b))
             assert not bad.any(), f"{case}.{k}: {int(bad.sum())} / {bad.size} elements differ (TMA vs plain), n={n}"
+
+
+def test_fast_policy_equals_exact_policy_on_nonfinite_inputs(ctx):
+    """NaN / Inf / huge / denormal values sprinkled over every input array: the fast policy must either
+    send the sample to the exact re-run or propagate the same (non-)values -- never a finite garbage
+    result where the guarded operators give NaN or Inf (NaN payloads and signs are not compared)."""
+    from rlshaders_b200 import api
+    n = 1 << 19
+    seed = 0xBADF00D
+    sg, kw, rx, ry = parity.ggx_dielectric_inputs(n, seed, aniso=True)
+    special = np.array([np.nan, np.inf, -np.inf, 3e38, -3e38, 1e-42, -1e-42, 1e30, 1e-30, 0.0, -0.0], np.float32)
+
+    def poison(a, stream):
+        a = np.array(a, dtype=np.float32, copy=True)
+        hit = ol.hash_uniform(a.size, seed, stream) < 0.01
+        pick = (ol.hash_uniform(a.size, seed, stream + 1) * len(special)).astype(np.int64) % len(special)
+        a[hit] = special[pick[hit]]
+        return a
+
+    sgp = {k: (poison(v, 200 + 2 * j) if v is not None and v.dtype == np.float32 else v) for j, (k, v) in enumerate(sg.items())}
+    rough, ior, aniso = poison(kw["specularRoughness"], 300), poison(kw["ior"], 302), poison(kw["anisotropic"], 304)
+    rxp, ryp = poison(rx, 306), poison(ry, 308)
+    dsg = api.ShadingBatch.from_numpy(sgp, ctx.device)
+    drx, dry = dev(rxp, ctx), dev(ryp, ctx)
+    g = api.GgxSampler(ctx, dsg, KsColor=(1.0, 0.5, 0.25), specularRoughness=dev(rough, ctx), ior=dev(ior, ctx),
+                       anisotropic=dev(aniso, ctx))
+    fb = {"dielectric": _run_both(ctx, lambda: g.dielectricSampleEvalPdf(drx, dry)),
+          "ggx": _run_both(ctx, lambda: g.sampleEvalPdf(drx, dry))}
+    _, dk, du = parity.disney_inputs(n, seed)
+    dk = {k: (tuple(poison(c, 400 + 7 * j + i) for i, c in enumerate(v)) if isinstance(v, tuple) else poison(v, 400 + 7 * j))
+          for j, (k, v) in enumerate(dk.items())}
+    d = api.DisneySampler(ctx, dsg, **parity.params_to_dev(dk, ctx.device))
+    ddu = [dev(poison(t, 500 + 2 * j), ctx) for j, t in enumerate(du)]
+    fb["disney"] = _run_both(ctx, lambda: d.sampleEvalPdf(*ddu))
+    sk, srx = parity.skin_inputs(n, seed)
+    sk["sss_scatter_dist"] = tuple(poison(c, 600 + 2 * j) for j, c in enumerate(sk["sss_scatter_dist"]))
+    s = api.SkinProfile(ctx, n, **parity.params_to_dev(sk, ctx.device))
+    dsrx = dev(poison(srx, 610), ctx)
+    fb["skin"] = _run_both(ctx, lambda: s.sampleEvalPdf(dsrx))
+    print(f"non-finite inputs: fast-policy fallbacks per {n} samples: {fb}")
