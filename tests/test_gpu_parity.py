@@ -788,3 +788,20 @@ def test_fast_policy_equals_exact_policy_on_nonfinite_inputs(ctx):
     dsrx = dev(poison(srx, 610), ctx)
     fb["skin"] = _run_both(ctx, lambda: s.sampleEvalPdf(dsrx))
     print(f"non-finite inputs: fast-policy fallbacks per {n} samples: {fb}")
+
+
+def test_dielectric_vs_oracle_on_adversarial_operands(ctx, orc):
+    """The shipped rough-dielectric kernel against the oracle on operands chosen to hit the special
+    cases: axis-aligned frames (exact-zero dot products, atan2(0, x)), exactly normal and grazing
+    views, views below the horizon, roughness 0, ior 1 (zero Fresnel numerator), ior < 1."""
+    from rlshaders_b200 import api
+    n = 1 << 18
+    sg = _adversarial_shading(n, 91)
+    rx, ry = ol.hash_uniform(n, 91, 0), ol.hash_uniform(n, 91, 1)
+    kw = dict(specularRoughness=_pick(n, 91, 2, [0.0, 1e-3, 0.05, 0.3, 1.0]), ior=_pick(n, 91, 3, [1.0, 0.47, 1.5, 2.5]))
+    cpu = orc.ggx_dielectric(sg, abi.ggx_params(**kw), rx, ry)
+    s = api.GgxSampler(ctx, api.ShadingBatch.from_numpy(sg, ctx.device), **parity.params_to_dev(kw, ctx.device))
+    gpu = s.dielectricSampleEvalPdf(dev(rx, ctx), dev(ry, ctx))
+    ctx.synchronize()
+    kinds = dict(fresnel="rel", wi_r="dir", f_r="rel", pdf_r="rel", wi_t="dir", f_t="rel", weight_t="rel", flags="flags")
+    check(parity.summarize(gpu, cpu, kinds), f"dielectric, adversarial operands, vs {orc.kind}")
