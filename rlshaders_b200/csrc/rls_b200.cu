@@ -79,11 +79,13 @@ struct rls_context {
                                                   // bit-exact, 5 % fewer issue slots, measured slower (RLS_PAIRED=1)
     bool         tma = false;                     // persistent TMA-staged fused kernels (rls_tile.cuh); RLS_TMA=1
     int          sm_count = 0;
+    unsigned     stagger_ns = 0;                  // persistent kernels: start delay between the CTAs of an SM (RLS_STAGGER_NS)
     int          persistent = 0;                  // CTAs per SM of the persistent grid-stride kernels; 0 = one CTA per tile (RLS_PERSISTENT)
     bool         packed = false;                  // two-samples-per-thread kernel (rls_packed.cuh): bit-exact but
                                                   // measured slower on B200 (latency bound at 128 registers), so
                                                   // it is off unless RLS_PACKED=1 (kept for A/B runs and its test)
     unsigned long long *fallbacks = nullptr;      // device counter: samples re-run with FpExact
+    unsigned    *chunk_counter = nullptr;         // device counter of the dynamically scheduled persistent kernel
     // host-staging resources (lazily created by the *_host entry points)
     cudaStream_t stage_stream[kStages] = {};
     cudaEvent_t  stage_done[kStages] = {};
@@ -144,6 +146,7 @@ extern "C" int rls_init(int device, void *stream, rls_context **out_ctx)
     if (const char *v = getenv("RLS_PAIRED")) ctx->paired = atoi(v) != 0;     // A/B switch for tuning runs
     if (const char *v = getenv("RLS_TMA")) ctx->tma = atoi(v) != 0;           // A/B switch for tuning runs
     if (const char *v = getenv("RLS_PERSISTENT")) ctx->persistent = atoi(v);  // A/B switch for tuning runs
+    if (const char *v = getenv("RLS_STAGGER_NS")) ctx->stagger_ns = (unsigned)atoi(v);
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     DeviceGuard guard(device);
@@ -163,6 +166,7 @@ extern "C" int rls_init(int device, void *stream, rls_context **out_ctx)
             return cuda_fail(nullptr, e, "cudaMemcpyToSymbol(c_negzero2)");
         }
     }
+    if (cudaMalloc((void **)&ctx->chunk_counter, sizeof(unsigned)) != cudaSuccess) ctx->chunk_counter = nullptr;
     e = cudaMalloc((void **)&ctx->fallbacks, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(ctx->fallbacks, 0, sizeof(unsigned long long));
     if (e != cudaSuccess) {
@@ -208,6 +212,7 @@ extern "C" int rls_shutdown(rls_context *ctx)
         if (ctx->stage_buf[b]) cudaFree(ctx->stage_buf[b]);
     }
     if (ctx->fallbacks) cudaFree(ctx->fallbacks);
+    if (ctx->chunk_counter) cudaFree(ctx->chunk_counter);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RLS_OK;
@@ -435,16 +440,44 @@ k_ggx_dielectric(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const
 }
 // Persistent form: grid = resident CTAs (a multiple of the SM count), every thread strides over the
 // batch.  No CTA turnover (a CTA slot of the plain kernel stays partly empty until its slowest warp
-// retires) and the warps of a CTA drift apart, so their load phases stop coinciding.
+// retires).  Measured SLOWER (static split, see k_ggx_dielectric_dynamic below); kept for A/B runs.
 template <bool kFast, bool kArrays, bool kPair>
 __global__ void __launch_bounds__(kBlockGgx, RLS_GGX_MIN_BLOCKS)
 k_ggx_dielectric_persistent(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, DielectricOutDev o,
-                            unsigned long long *fallbacks)
+                            unsigned long long *fallbacks, unsigned stagger_ns, unsigned sm_count)
 {
+    // phase-shift the CTAs that share an SM (the first wave is dealt round-robin: CTA b runs on SM b % sm_count)
+    if (stagger_ns) __nanosleep((blockIdx.x / sm_count) * stagger_ns);
     const uint32_t stride = gridDim.x * blockDim.x;
 #pragma unroll 1
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)n; i += stride)
         dielectric_sample<kFast, kArrays, kPair>(i, sg, p, rx, ry, o, fallbacks);
+}
+
+// Persistent form with DYNAMIC work distribution: every warp draws 128-sample chunks from a global counter
+// (the next index is fetched while the current chunk computes).  The static grid-stride form above loses
+// 13 %: the warp arbiter is unfair, CTAs in favoured slots finish their share early and the SM runs its tail at
+// low occupancy (ncu: 40.5 % average active warps with 9 resident CTAs per SM, 49.1 % for the plain kernel).
+template <bool kFast, bool kArrays, bool kPair>
+__global__ void __launch_bounds__(kBlockGgx, RLS_GGX_MIN_BLOCKS)
+k_ggx_dielectric_dynamic(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, DielectricOutDev o,
+                         unsigned long long *fallbacks, unsigned *counter)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_chunks = (uint32_t)((n + 127u) / 128u);
+    uint32_t c = 0;
+    if (lane == 0) c = atomicAdd(counter, 1u);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    while (c < n_chunks) {
+        uint32_t nxt = 0;
+        if (lane == 0) nxt = atomicAdd(counter, 1u);
+#pragma unroll 1
+        for (uint32_t j = 0; j < 4u; j++) {
+            const uint32_t i = c * 128u + j * 32u + lane;
+            if (i < (uint32_t)n) dielectric_sample<kFast, kArrays, kPair>(i, sg, p, rx, ry, o, fallbacks);
+        }
+        c = __shfl_sync(0xffffffffu, nxt, 0);
+    }
 }
 
 // Persistent, TMA-staged form of k_ggx_dielectric (rls_tile.cuh): grid = resident CTAs, every CTA
@@ -1172,8 +1205,11 @@ static int launch_ggx_dielectric(rls_context *ctx, cudaStream_t st, size_t n, co
         return RLS_OK;
     }
 #define RLS_DIELECTRIC_LAUNCH(F, A, P) \
-    do { if (ctx->persistent && grid_for(n, kBlockGgx) > (unsigned)(ctx->sm_count * ctx->persistent)) \
-             k_ggx_dielectric_persistent<F, A, P><<<ctx->sm_count * ctx->persistent, kBlockGgx, 0, st>>>(n, sh(*sg), pd, rx, ry, d, ctx->fallbacks); \
+    do { if (ctx->persistent < 0 && ctx->chunk_counter) { \
+             cudaMemsetAsync(ctx->chunk_counter, 0, sizeof(unsigned), st); \
+             k_ggx_dielectric_dynamic<F, A, P><<<ctx->sm_count * (-ctx->persistent), kBlockGgx, 0, st>>>(n, sh(*sg), pd, rx, ry, d, ctx->fallbacks, ctx->chunk_counter); } \
+         else if (ctx->persistent > 0 && grid_for(n, kBlockGgx) > (unsigned)(ctx->sm_count * ctx->persistent)) \
+             k_ggx_dielectric_persistent<F, A, P><<<ctx->sm_count * ctx->persistent, kBlockGgx, 0, st>>>(n, sh(*sg), pd, rx, ry, d, ctx->fallbacks, ctx->stagger_ns, (unsigned)ctx->sm_count); \
          else k_ggx_dielectric<F, A, P><<<grid_for(n, kBlockGgx), kBlockGgx, 0, st>>>(n, sh(*sg), pd, rx, ry, d, ctx->fallbacks); } while (0)
     if (fast && arrays && ctx->paired) RLS_DIELECTRIC_LAUNCH(true, true, true);
     else if (fast && arrays) RLS_DIELECTRIC_LAUNCH(true, true, false);
