@@ -66,6 +66,15 @@ static constexpr int kBlockGgx = RLS_GGX_BLOCK;
 #define RLS_SKIN_MIN_BLOCKS 9
 #endif
 static constexpr int kBlockSkin = RLS_SKIN_BLOCK;
+// ... and the albedo sweep (30.3 vs 29.5 G samples/s); its per-thread FP64 partial sums then cover other samples,
+// which changes the table in the last bits only (deterministic for a given build; tests: rtol 1e-12 across partitions).
+#ifndef RLS_SWEEP_BLOCK
+#define RLS_SWEEP_BLOCK 128
+#endif
+#ifndef RLS_SWEEP_MIN_BLOCKS
+#define RLS_SWEEP_MIN_BLOCKS 9
+#endif
+static constexpr int kBlockSweep = RLS_SWEEP_BLOCK;
 static_assert(kBlock >= 96 && kBlockSkin >= 96, "rlm::smem_tables_init() fills 96 table entries with one thread each");
 
 struct rls_context {
@@ -1029,7 +1038,7 @@ k_synth_shading(size_t n, uint64_t seed, uint64_t first, float cos_lo, float cos
 struct SweepGridDev { int n_rough, n_cos, n_ior; float rlo, rhi, ilo, ihi; };
 
 template <bool kFast>
-__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+__global__ void __launch_bounds__(kBlockSweep, RLS_SWEEP_MIN_BLOCKS)
 k_albedo_sweep(SweepGridDev g, uint64_t seed, uint32_t k0, uint32_t k1, double *table, unsigned long long *fallbacks)
 {
     const uint32_t cell = blockIdx.x;
@@ -1052,7 +1061,7 @@ k_albedo_sweep(SweepGridDev g, uint64_t seed, uint32_t k0, uint32_t k1, double *
     // (ior == 1: the refraction half vector is the zero vector; cos == 1) leaves the fast window
     // on every sample, so a thread that had to re-run one sample stays on the exact operators.
     bool fast = kFast;
-    for (uint32_t k = k0 + threadIdx.x; k < k1; k += kBlock) {
+    for (uint32_t k = k0 + threadIdx.x; k < k1; k += kBlockSweep) {
         uint64_t idx = ((uint64_t)cell << 32) | (uint64_t)k;
         float rx = uniform24(seed, 0u, idx);
         float ry = uniform24(seed, 1u, idx);
@@ -1072,7 +1081,7 @@ k_albedo_sweep(SweepGridDev g, uint64_t seed, uint32_t k0, uint32_t k1, double *
         if (r.flags & RLS_FLAG_TIR) acc[4] += 1.0; else acc[1] += (double)r.w_t;
         acc[2] += (double)r.F;
     }
-    __shared__ double red[RLS_SWEEP_VALUES_PER_CELL][kBlock / 32];
+    __shared__ double red[RLS_SWEEP_VALUES_PER_CELL][kBlockSweep / 32];
 #pragma unroll
     for (int j = 0; j < RLS_SWEEP_VALUES_PER_CELL; j++) {
         double v = acc[j];
@@ -1084,7 +1093,7 @@ k_albedo_sweep(SweepGridDev g, uint64_t seed, uint32_t k0, uint32_t k1, double *
     if (threadIdx.x < RLS_SWEEP_VALUES_PER_CELL) {
         double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < kBlock / 32; w++) v += red[threadIdx.x][w];
+        for (int w = 0; w < kBlockSweep / 32; w++) v += red[threadIdx.x][w];
         table[(size_t)cell * RLS_SWEEP_VALUES_PER_CELL + threadIdx.x] = v;
     }
 }
@@ -1506,9 +1515,9 @@ extern "C" int rls_albedo_sweep(rls_context *ctx, const rls_sweep_grid *grid, ui
     // instantiation stays reachable for A/B runs through RLS_SWEEP_FAST=1.
     static const bool sweep_fast = getenv("RLS_SWEEP_FAST") && atoi(getenv("RLS_SWEEP_FAST")) != 0;
     if (sweep_fast && ctx->arith == RLS_ARITH_FAST)
-        k_albedo_sweep<true><<<cells, kBlock, 0, ctx->stream>>>(g, seed, spp_begin, spp_end, table, ctx->fallbacks);
+        k_albedo_sweep<true><<<cells, kBlockSweep, 0, ctx->stream>>>(g, seed, spp_begin, spp_end, table, ctx->fallbacks);
     else
-        k_albedo_sweep<false><<<cells, kBlock, 0, ctx->stream>>>(g, seed, spp_begin, spp_end, table, ctx->fallbacks);
+        k_albedo_sweep<false><<<cells, kBlockSweep, 0, ctx->stream>>>(g, seed, spp_begin, spp_end, table, ctx->fallbacks);
     RLS_LAUNCH_CHECK(ctx);
     return RLS_OK;
 }
