@@ -1057,22 +1057,24 @@ k_albedo_sweep(SweepGridDev g, uint64_t seed, uint32_t k0, uint32_t k1, double *
     s.backfacing = false;
 
     double acc[RLS_SWEEP_VALUES_PER_CELL] = { 0.0, 0.0, 0.0, 0.0, 0.0 };
-    // All samples of a cell share (roughness, cos, ior): a cell whose parameters are degenerate
-    // (ior == 1: the refraction half vector is the zero vector; cos == 1) leaves the fast window
-    // on every sample, so a thread that had to re-run one sample stays on the exact operators.
-    bool fast = kFast;
+    // All samples of a cell share (roughness, cos, ior).  A cell whose parameters are degenerate (ior == 1: the
+    // refraction half vector is the zero vector; cos == 1: the view is the normal) leaves the fast window on every
+    // sample, so the WHOLE cell (a CTA-uniform decision) runs the exact operators; every other cell runs the fast
+    // policy with the usual per-sample exact re-run.
+    const bool cell_fast = kFast && ior != 1.0f && cosv != 1.0f;
     for (uint32_t k = k0 + threadIdx.x; k < k1; k += kBlockSweep) {
         uint64_t idx = ((uint64_t)cell << 32) | (uint64_t)k;
         float rx = uniform24(seed, 0u, idx);
         float ry = uniform24(seed, 1u, idx);
         Dielectric r;
-        if (fast) {
+        bool need_exact = !cell_fast;
+        if (cell_fast) {
             FpFast fp;
             r = dielectric_unit(fp, s, ior, rough, 0.0f, rx, ry);
-            fast = fp.ok();
-            if (!fast) atomicAdd(fallbacks, 1ull);
+            need_exact = !fp.ok();
+            if (need_exact) atomicAdd(fallbacks, 1ull);
         }
-        if (!fast) {
+        if (need_exact) {
             FpExact fp;
             r = dielectric_unit(fp, s, ior, rough, 0.0f, rx, ry);
         }
@@ -1508,11 +1510,12 @@ extern "C" int rls_albedo_sweep(rls_context *ctx, const rls_sweep_grid *grid, ui
     g.rlo = grid->roughness_lo; g.rhi = grid->roughness_hi; g.ilo = grid->ior_lo; g.ihi = grid->ior_hi;
     unsigned cells = (unsigned)(grid->n_rough * grid->n_cos * grid->n_ior);
     DeviceGuard guard(ctx->device);
-    // Measured on B200 (65536 cells x 4096 spp): the guarded operators run this kernel at 27.8 G
-    // samples/s, the fast policy at 23.9 -- the frame is a compile-time constant here, the
-    // accumulators and RNG leave no registers for a second code path, and 1/16 of the cells
-    // (ior == 1) are degenerate.  The sweep therefore always uses the exact policy; the fast
-    // instantiation stays reachable for A/B runs through RLS_SWEEP_FAST=1.
+    // Measured on B200 (65536 cells x 4096 spp): the guarded operators run this kernel at 30.3 G samples/s, the
+    // fast policy at 26.0 -- even with the policy chosen per CELL (degenerate cells, ior == 1 or cos == 1, run
+    // exact as a whole; 6.6e-5 of the other samples re-run).  Here everything that depends on the shading point
+    // only is loop invariant and hoisted by the compiler, the frame is a compile-time constant, and the FP64
+    // accumulators and the RNG leave no registers for a second code path.  The sweep therefore always uses the
+    // exact policy; the fast instantiation stays reachable for A/B runs through RLS_SWEEP_FAST=1.
     static const bool sweep_fast = getenv("RLS_SWEEP_FAST") && atoi(getenv("RLS_SWEEP_FAST")) != 0;
     if (sweep_fast && ctx->arith == RLS_ARITH_FAST)
         k_albedo_sweep<true><<<cells, kBlockSweep, 0, ctx->stream>>>(g, seed, spp_begin, spp_end, table, ctx->fallbacks);
