@@ -360,6 +360,34 @@ def run_product(args):
                                       "hbm_frac": n1 * B_ALG["ggx_conductor"] / (t1 * 1e-3) / 1e9 / peak,
                                       "exact_rerun_fraction": fb1,
                                       "l2": "flushed between iterations (512 MB memset, its time subtracted)"}
+        # The same 2^20-sample launch replayed from a CUDA graph: R x (L2 flush + kernel) captured once
+        # on a side stream through a context bound to that stream, minus a graph of the R flushes alone.
+        try:
+            R = 20
+            gs = torch.cuda.Stream()
+            gs.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(gs):
+                cg = api.Context(rank % torch.cuda.device_count())
+                s1g = api.GgxSampler(cg, s1.sg, KsColor=(1.0, 1.0, 1.0), specularRoughness=0.3, ior=0.47)
+                for _ in range(3):
+                    flush.zero_()
+                    s1g.sampleEvalPdf(rx1, ry1, out=o1)
+            gs.synchronize()
+            g_full, g_flush = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_flush, stream=gs):
+                for _ in range(R):
+                    flush.zero_()
+            with torch.cuda.graph(g_full, stream=gs):
+                for _ in range(R):
+                    flush.zero_()
+                    s1g.sampleEvalPdf(rx1, ry1, out=o1)
+            tg = (timed(g_full.replay, 3, 2) - timed(g_flush.replay, 3, 2)) / R
+            others["ggx_conductor_1M"]["cuda_graph"] = {"samples_per_s": world * n1 / (tg * 1e-3), "ms": tg,
+                                                        "launches_per_replay": R}
+            del g_full, g_flush, s1g
+            cg.close()
+        except Exception as exc:            # a capture problem must not cost the bench line
+            others["ggx_conductor_1M"]["cuda_graph"] = {"unavailable": repr(exc)[:200]}
         del flush, s1, o1
         del sampler, out, rough, ior
         torch.cuda.empty_cache()
