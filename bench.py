@@ -36,6 +36,10 @@ N_DIELECTRIC = 1 << 26          # configs[1]
 SEED = 0x5EED0002
 # Algorithmic bytes per sample (SURVEY.md 8(a) size table; DESIGN.md "Data layout"):
 B_ALG = {"ggx_conductor": 88, "ggx_dielectric": 113, "disney": 176, "skin_profile": 52}
+# Algorithmic FP32 work per sample (every add/mul/compare/select = 1, an FMA = 2, each
+# division, root and transcendental = 1, worst-case branch), and the nominal FP32 peak of one B200.
+F_ALG = {"ggx_conductor": 430, "ggx_dielectric": 680, "disney": 595, "skin_profile": 130}
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.4; FFMA-only microbenchmark on this pool: 67.5
 WORKLOAD = "ggx_dielectric_64M (BASELINE configs[1]: GGX rough dielectric reflection+refraction, " \
            "2^26 samples/GPU, per-sample roughness~U[0.05,1] ior~U[1.05,2.5], 25% back-facing)"
 
@@ -275,6 +279,18 @@ def run_product(args):
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     e2e_s = max_over_ranks(e2e_s * 1e3) * 1e-3
     clock_info = clocks.stop()
+    # FP32 roofline beside the HBM one: algorithmic flops, and the flops the kernel really issues
+    # (no FMA contraction, IEEE division / root sequences, the host libm's algorithms).
+    issued_flops = measured_traffic("fp32_flops_per_sample_issued")
+    per_gpu = n / (ms * 1e-3)
+    roofline["fp32"] = {"flops_per_sample_algorithmic": F_ALG["ggx_dielectric"],
+                        "achieved_tflops": per_gpu * F_ALG["ggx_dielectric"] / 1e12,
+                        "peak_tflops": FP32_PEAK_TFLOPS, "frac": per_gpu * F_ALG["ggx_dielectric"] / 1e12 / FP32_PEAK_TFLOPS,
+                        "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (FFMA-only microbenchmark: 67.5, "
+                                       "profiles/r01_ffma2_microbench.txt)"}
+    if isinstance(issued_flops, dict) and issued_flops.get("k_ggx_dielectric"):
+        roofline["fp32"]["flops_per_sample_issued"] = issued_flops["k_ggx_dielectric"]
+        roofline["fp32"]["issued_tflops"] = per_gpu * issued_flops["k_ggx_dielectric"] / 1e12
     # The kernel is issue bound, not HBM bound: also report the fraction of the SM issue
     # rate it sustains = executed warp instructions per launch (ncu count committed under profiles/)
     # / launch time / (SMs x 4 schedulers x SM clock under load).
