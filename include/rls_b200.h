@@ -205,6 +205,15 @@ typedef struct rls_ndprofile_soa {
     float   *max_radius;  /* mMaxRadius       */
 } rls_ndprofile_soa;
 
+/* GaussianProfile state produced by its setDistance (src/rlSss.h:71-76), one per sample.  The
+ * alternative `Profile` argument of SssSampler<Profile> (src/rlSss.h:63-97); rlSkin instantiates
+ * SssSampler<NDProfile> (src/rlSkin.cpp:236), this is the variant. */
+typedef struct rls_gaussprofile_soa {
+    float *variance;      /* mVariance  = maxRadius^2 / 12.46          */
+    float *max_radius;    /* mMaxRadius = dist.x                       */
+    float *norm;          /* mNorm      = 1 - exp(-maxRadius^2 / (2 v)) */
+} rls_gaussprofile_soa;
+
 /* Result of the fused skin-profile unit: setDistance + getRadius + getPdf + evalProfile. */
 typedef struct rls_profile_out {
     float    *r;      /* getRadius(rx), src/rlSss.cpp:36-66    */
@@ -306,6 +315,23 @@ int rls_skin_profile_sample_eval_pdf(rls_context *ctx, size_t n, const rls_skin_
 int rls_skin_layer_weights(rls_context *ctx, size_t n, const rls_skin_params *params,
                            const float *avg_fresnel_sheen, const float *avg_fresnel_specular,
                            float *out_specular_scale, float *out_sss_weight);
+
+/* GaussianProfile (src/rlSss.h:63-97), single channel.  Arnold's `fast_exp` is proprietary: the
+ * oracle shim defines it as expf (normative, oracle/shim/ai.h) and so does the library.
+ * set_distance reads dist.x only (src/rlSss.h:73); `albedo` is accepted and unused as in the reference.
+ * No guards, exactly as written: max_radius = 0 gives variance = 0 and NaN / Inf downstream. */
+int rls_gaussprofile_set_distance(rls_context *ctx, size_t n, rls_cvec3 dist, rls_cvec3 albedo,
+                                  const rls_gaussprofile_soa *out_profile);
+int rls_gaussprofile_get_radius(rls_context *ctx, size_t n, const rls_gaussprofile_soa *profile,
+                                const float *rx, float *out_r);
+int rls_gaussprofile_get_pdf(rls_context *ctx, size_t n, const rls_gaussprofile_soa *profile,
+                             const float *r, float *out_pdf);
+int rls_gaussprofile_eval_profile(rls_context *ctx, size_t n, const rls_gaussprofile_soa *profile,
+                                  const float *r, float *out_rd);
+/* Fused unit, the GaussianProfile counterpart of rls_skin_profile_sample_eval_pdf:
+ * setDistance((dist_x, ., .)), r = getRadius(rx), getPdf(r), evalProfile(r). */
+int rls_gaussprofile_sample_eval_pdf(rls_context *ctx, size_t n, const float *dist_x, const float *rx,
+                                     float *out_r, float *out_pdf, float *out_rd);
 
 /* Probe-ray geometry of SssSampler::getProbeRay (src/rlSss.h:487-533) for one (rx, ry) pair per
  * sample: axis pick 50/25/25 % N/U/V, r = getRadius(rx'), disc offset, chord length.  `sg`

@@ -62,6 +62,14 @@ void oracle_ndprofile_get_pdf(size_t n, const rls_ndprofile_soa *profile, const 
                               float *out_pdf);
 void oracle_ndprofile_eval_profile(size_t n, const rls_ndprofile_soa *profile, const float *r,
                                    rls_vec3 out_rd);
+/* GaussianProfile (src/rlSss.h:63-97) */
+void oracle_gaussprofile_set_distance(size_t n, rls_cvec3 dist, rls_cvec3 albedo,
+                                      const rls_gaussprofile_soa *out_profile);
+void oracle_gaussprofile_get_radius(size_t n, const rls_gaussprofile_soa *profile, const float *rx, float *out_r);
+void oracle_gaussprofile_get_pdf(size_t n, const rls_gaussprofile_soa *profile, const float *r, float *out_pdf);
+void oracle_gaussprofile_eval_profile(size_t n, const rls_gaussprofile_soa *profile, const float *r, float *out_rd);
+void oracle_gaussprofile_sample_eval_pdf(size_t n, const float *dist_x, const float *rx, float *out_r,
+                                         float *out_pdf, float *out_rd);
 void oracle_skin_profile_sample_eval_pdf(size_t n, const rls_skin_params *p, const float *rx,
                                          const rls_profile_out *out);
 void oracle_skin_layer_weights(size_t n, const rls_skin_params *p, const float *avg_f_sheen,

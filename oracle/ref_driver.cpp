@@ -453,6 +453,50 @@ void oracle_ndprofile_eval_profile(size_t n, const rls_ndprofile_soa *profile, c
     }
 }
 
+/* GaussianProfile: the reference class itself (src/rlSss.h:63-97). */
+static inline void loadGauss(const rls_gaussprofile_soa *s, size_t i, rls::GaussianProfile &p)
+{
+    p.mVariance = s->variance[i]; p.mMaxRadius = s->max_radius[i]; p.mNorm = s->norm[i];
+}
+void oracle_gaussprofile_set_distance(size_t n, rls_cvec3 dist, rls_cvec3 albedo, const rls_gaussprofile_soa *o)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        rls::GaussianProfile p;
+        AtVector d; AiV3Create(d, dist.x[i], dist.y ? dist.y[i] : 0.0f, dist.z ? dist.z[i] : 0.0f);
+        AtColor a = albedo.x ? rls_shim_rgb(albedo.x[i], albedo.y[i], albedo.z[i]) : rls_shim_rgb(1.0f, 1.0f, 1.0f);
+        p.setDistance(d, a);
+        o->variance[i] = p.mVariance; o->max_radius[i] = p.mMaxRadius; o->norm[i] = p.mNorm;
+    }
+}
+void oracle_gaussprofile_get_radius(size_t n, const rls_gaussprofile_soa *profile, const float *rx, float *out_r)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) { rls::GaussianProfile p; loadGauss(profile, i, p); out_r[i] = p.getRadius(rx[i]); }
+}
+void oracle_gaussprofile_get_pdf(size_t n, const rls_gaussprofile_soa *profile, const float *r, float *out_pdf)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) { rls::GaussianProfile p; loadGauss(profile, i, p); out_pdf[i] = p.getPdf(r[i]); }
+}
+void oracle_gaussprofile_eval_profile(size_t n, const rls_gaussprofile_soa *profile, const float *r, float *out_rd)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) { rls::GaussianProfile p; loadGauss(profile, i, p); out_rd[i] = p.evalProfile(r[i]); }
+}
+void oracle_gaussprofile_sample_eval_pdf(size_t n, const float *dist_x, const float *rx, float *out_r,
+                                         float *out_pdf, float *out_rd)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        rls::GaussianProfile p;
+        AtVector d; AiV3Create(d, dist_x[i], 0.0f, 0.0f);
+        p.setDistance(d, rls_shim_rgb(1.0f, 1.0f, 1.0f));
+        float r = p.getRadius(rx[i]);
+        out_r[i] = r; out_pdf[i] = p.getPdf(r); out_rd[i] = p.evalProfile(r);
+    }
+}
+
 void oracle_skin_profile_sample_eval_pdf(size_t n, const rls_skin_params *sp, const float *rx,
                                          const rls_profile_out *out)
 {

@@ -889,6 +889,67 @@ void oracle_ndprofile_eval_profile(size_t n, const rls_ndprofile_soa *profile, c
         st3(out_rd, i, nd_eval_profile(&p, r[i]));
     }
 }
+/* ------------------------------------------------------- GaussianProfile
+ * src/rlSss.h:63-97 (alternative Profile argument of SssSampler; fast_exp = expf per the shim). */
+typedef struct { float var, R, norm; } gaussprofile_t;
+/* :71-76 */
+static void gauss_set_distance(gaussprofile_t *p, float dist_x)
+{
+    p->R = dist_x;
+    p->var = (p->R * p->R) / 12.46f;
+    p->norm = 1.0f - expf(-(p->R * p->R) * 0.5f / p->var);
+}
+/* :78-81 */
+static float gauss_get_radius(const gaussprofile_t *p, float rx)
+{
+    return sqrtf(-2.0f * p->var * logf(1.0f - rx * p->norm));
+}
+/* :88-91 */
+static float gauss_eval_profile(const gaussprofile_t *p, float r)
+{
+    return 0.15915494309189533577f / p->var * expf(-r * r * 0.5f / p->var);
+}
+/* :83-86 */
+static float gauss_get_pdf(const gaussprofile_t *p, float r) { return gauss_eval_profile(p, r) / p->norm; }
+static inline void gauss_load(const rls_gaussprofile_soa *s, size_t i, gaussprofile_t *p)
+{
+    p->var = s->variance[i]; p->R = s->max_radius[i]; p->norm = s->norm[i];
+}
+void oracle_gaussprofile_set_distance(size_t n, rls_cvec3 dist, rls_cvec3 albedo, const rls_gaussprofile_soa *o)
+{
+    (void)albedo;
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        gaussprofile_t p; gauss_set_distance(&p, dist.x[i]);
+        o->variance[i] = p.var; o->max_radius[i] = p.R; o->norm[i] = p.norm;
+    }
+}
+void oracle_gaussprofile_get_radius(size_t n, const rls_gaussprofile_soa *profile, const float *rx, float *out_r)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) { gaussprofile_t p; gauss_load(profile, i, &p); out_r[i] = gauss_get_radius(&p, rx[i]); }
+}
+void oracle_gaussprofile_get_pdf(size_t n, const rls_gaussprofile_soa *profile, const float *r, float *out_pdf)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) { gaussprofile_t p; gauss_load(profile, i, &p); out_pdf[i] = gauss_get_pdf(&p, r[i]); }
+}
+void oracle_gaussprofile_eval_profile(size_t n, const rls_gaussprofile_soa *profile, const float *r, float *out_rd)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) { gaussprofile_t p; gauss_load(profile, i, &p); out_rd[i] = gauss_eval_profile(&p, r[i]); }
+}
+void oracle_gaussprofile_sample_eval_pdf(size_t n, const float *dist_x, const float *rx, float *out_r,
+                                         float *out_pdf, float *out_rd)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        gaussprofile_t p; gauss_set_distance(&p, dist_x[i]);
+        float r = gauss_get_radius(&p, rx[i]);
+        out_r[i] = r; out_pdf[i] = gauss_get_pdf(&p, r); out_rd[i] = gauss_eval_profile(&p, r);
+    }
+}
+
 void oracle_skin_profile_sample_eval_pdf(size_t n, const rls_skin_params *sp, const float *rx,
                                          const rls_profile_out *out)
 {

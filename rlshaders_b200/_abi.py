@@ -111,6 +111,10 @@ class NdProfileSoA(C.Structure):
     _fields_ = [("distance", Vec3), ("C1", Vec3), ("C2", Vec3), ("max_radius", C.c_void_p)]
 
 
+class GaussProfileSoA(C.Structure):
+    _fields_ = [("variance", C.c_void_p), ("max_radius", C.c_void_p), ("norm", C.c_void_p)]
+
+
 class ProfileOut(C.Structure):
     _fields_ = [("r", C.c_void_p), ("pdf", C.c_void_p), ("Rd", Vec3), ("flags", C.c_void_p)]
 

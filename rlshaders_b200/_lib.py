@@ -25,6 +25,8 @@ SYMBOLS = [
     "rls_ndprofile_set_distance", "rls_ndprofile_get_radius", "rls_ndprofile_get_pdf",
     "rls_ndprofile_eval_profile", "rls_skin_profile_sample_eval_pdf", "rls_skin_layer_weights",
     "rls_skin_probe_ray", "rls_skin_probe_mis_pdf",
+    "rls_gaussprofile_set_distance", "rls_gaussprofile_get_radius", "rls_gaussprofile_get_pdf",
+    "rls_gaussprofile_eval_profile", "rls_gaussprofile_sample_eval_pdf",
     "rls_ggx_sample_eval_pdf_host", "rls_ggx_dielectric_sample_eval_pdf_host",
     "rls_disney_sample_eval_pdf_host", "rls_skin_profile_sample_eval_pdf_host",
     "rls_host_alloc", "rls_host_free",
@@ -72,6 +74,11 @@ def load():
         "rls_skin_layer_weights": [vp, sz, P(abi.SkinParams), vp, vp, vp, vp],
         "rls_skin_probe_ray": [vp, sz, P(abi.ShadingSoA), P(abi.SkinParams), vp, vp, P(abi.ProbeOut)],
         "rls_skin_probe_mis_pdf": [vp, sz, P(abi.ShadingSoA), P(abi.SkinParams), abi.CVec3, abi.CVec3, vp],
+        "rls_gaussprofile_set_distance": [vp, sz, abi.CVec3, abi.CVec3, P(abi.GaussProfileSoA)],
+        "rls_gaussprofile_get_radius": [vp, sz, P(abi.GaussProfileSoA), vp, vp],
+        "rls_gaussprofile_get_pdf": [vp, sz, P(abi.GaussProfileSoA), vp, vp],
+        "rls_gaussprofile_eval_profile": [vp, sz, P(abi.GaussProfileSoA), vp, vp],
+        "rls_gaussprofile_sample_eval_pdf": [vp, sz, vp, vp, vp, vp, vp],
         "rls_ggx_sample_eval_pdf_host": [vp, sz, P(abi.ShadingSoA), P(abi.GgxParams), vp, vp,
                                          P(abi.BsdfOut), sz],
         "rls_ggx_dielectric_sample_eval_pdf_host": [vp, sz, P(abi.ShadingSoA), P(abi.GgxParams), vp, vp,

@@ -457,6 +457,55 @@ class NDProfile:
         return rd
 
 
+class GaussianProfile:
+    """`rls::GaussianProfile` (src/rlSss.h:63-97), the alternative `Profile` argument of SssSampler;
+    same method names as the reference class.  Single channel: setDistance reads dist.x only."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.state = None
+
+    def setDistance(self, dist, albedo):
+        n, c = dist.shape[1], self.ctx
+        self.n = n
+        self.state = dict(variance=c.empty(n), max_radius=c.empty(n), norm=c.empty(n))
+        self._struct = abi.GaussProfileSoA(self.state["variance"].data_ptr(), self.state["max_radius"].data_ptr(),
+                                           self.state["norm"].data_ptr())
+        _check(c.handle, c.lib.rls_gaussprofile_set_distance(c.handle, n, abi.vec3(_f32rows(dist, "dist")),
+                                                             abi.vec3(_f32rows(albedo, "albedo")),
+                                                             C.byref(self._struct)), c.lib)
+        return self.state
+
+    def maxRadius(self):
+        return self.state["max_radius"]
+
+    def _unary(self, fn, x, name):
+        c = self.ctx
+        out = c.empty(self.n)
+        _check(c.handle, fn(c.handle, self.n, C.byref(self._struct), _f32(x, name, self.n).data_ptr(),
+                            out.data_ptr()), c.lib)
+        return out
+
+    def getRadius(self, rx):
+        return self._unary(self.ctx.lib.rls_gaussprofile_get_radius, rx, "rx")
+
+    def getPdf(self, r):
+        return self._unary(self.ctx.lib.rls_gaussprofile_get_pdf, r, "r")
+
+    def evalProfile(self, r):
+        return self._unary(self.ctx.lib.rls_gaussprofile_eval_profile, r, "r")
+
+    @staticmethod
+    def sampleEvalPdf(ctx, dist_x, rx):
+        """Fused unit: setDistance + getRadius + getPdf + evalProfile, one launch."""
+        n = rx.shape[0]
+        out = dict(r=ctx.empty(n), pdf=ctx.empty(n), Rd=ctx.empty(n))
+        _check(ctx.handle, ctx.lib.rls_gaussprofile_sample_eval_pdf(
+            ctx.handle, n, _f32(dist_x, "dist_x", n).data_ptr(), _f32(rx, "rx", n).data_ptr(),
+            out["r"].data_ptr(), out["pdf"].data_ptr(), out["Rd"].data_ptr()), ctx.lib)
+        return out
+
+
 class SkinProfile:
     """The rlSkin diffusion-profile unit (src/rlSkin.cpp:234-241 + NDProfile): node
     parameters by name (src/rlSkin.cpp:109-131)."""

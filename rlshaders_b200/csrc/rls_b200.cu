@@ -739,6 +739,50 @@ k_nd_eval_profile(size_t n, NdProfileSoADev s, const float *r, V3 rd)
     FpExact fp;
     store3(rd, i, nd_eval_profile(fp, p, __ldg(r + i)));
 }
+// GaussianProfile (src/rlSss.h:63-97): 3 floats of state, 1 float per result; exact policy (variant row)
+struct GaussProfileSoADev { float *variance, *max_radius, *norm; };
+RLS_DEV GaussProfile gauss_load(const GaussProfileSoADev &s, uint32_t i)
+{
+    GaussProfile p; p.var = s.variance[i]; p.R = s.max_radius[i]; p.norm = s.norm[i]; return p;
+}
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+k_gauss_set_distance(size_t n, const float *dist_x, GaussProfileSoADev o)
+{
+    RLS_INDEX();
+    FpExact fp;
+    GaussProfile p; gauss_set_distance(fp, p, __ldg(dist_x + i));
+    o.variance[i] = p.var; o.max_radius[i] = p.R; o.norm[i] = p.norm;
+}
+template <int kOp>      // 0 getRadius(rx), 1 getPdf(r), 2 evalProfile(r)
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+k_gauss_unary(size_t n, GaussProfileSoADev s, const float *x, float *out)
+{
+    RLS_INDEX();
+    FpExact fp;
+    const GaussProfile p = gauss_load(s, i);
+    const float v = __ldg(x + i);
+    out[i] = kOp == 0 ? gauss_get_radius(fp, p, v) : (kOp == 1 ? gauss_get_pdf(fp, p, v) : gauss_eval_profile(fp, p, v));
+}
+template <bool kFast>
+__global__ void __launch_bounds__(kBlockSkin, RLS_SKIN_MIN_BLOCKS)
+k_gauss_profile(size_t n, const float *dist_x, const float *rx, float *r, float *pdf, float *rd, unsigned long long *fallbacks)
+{
+    if (kFast) rlm::smem_tables_init();
+    RLS_INDEX();
+    Gauss1 o;
+    bool ok = false;
+    if (kFast) {
+        FpFastSmemTab fp;
+        o = gauss_profile_unit(fp, __ldg(dist_x + i), __ldg(rx + i));
+        ok = fp.ok();
+    }
+    if (!ok) {
+        FpExact fp;
+        o = gauss_profile_unit(fp, __ldcg(dist_x + i), __ldcg(rx + i));
+        if (kFast) atomicAdd(fallbacks, 1ull);
+    }
+    r[i] = o.r; rd[i] = o.rd; pdf[i] = o.pdf;
+}
 struct ProfileOutDev { float *r, *pdf; V3 Rd; uint32_t *flags; };
 struct Profile1 { float r, pdf; f3 Rd; uint32_t flags; };
 template <class Fp>
@@ -1445,6 +1489,68 @@ extern "C" int rls_ndprofile_eval_profile(rls_context *ctx, size_t n, const rls_
     RLS_REQUIRE(ctx, ok_profile(profile) && r && has3(out_rd), "rls_ndprofile_eval_profile: NULL argument");
     DeviceGuard guard(ctx->device);
     k_nd_eval_profile<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, dev(*profile), r, mv(out_rd));
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+// ---- GaussianProfile (src/rlSss.h:63-97)
+static bool ok_gauss(const rls_gaussprofile_soa *s) { return s && s->variance && s->max_radius && s->norm; }
+static GaussProfileSoADev dev(const rls_gaussprofile_soa &s)
+{
+    GaussProfileSoADev o; o.variance = s.variance; o.max_radius = s.max_radius; o.norm = s.norm; return o;
+}
+extern "C" int rls_gaussprofile_set_distance(rls_context *ctx, size_t n, rls_cvec3 dist, rls_cvec3 albedo,
+                                             const rls_gaussprofile_soa *out)
+{
+    (void)albedo;   // unused by the reference too (src/rlSss.h:71-76)
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
+    RLS_REQUIRE(ctx, dist.x && ok_gauss(out), "rls_gaussprofile_set_distance: NULL argument");
+    DeviceGuard guard(ctx->device);
+    k_gauss_set_distance<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, dist.x, dev(*out));
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+template <int kOp>
+static int gauss_unary(rls_context *ctx, size_t n, const rls_gaussprofile_soa *profile, const float *x, float *out,
+                       const char *what)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
+    RLS_REQUIRE(ctx, ok_gauss(profile) && x && out, what);
+    DeviceGuard guard(ctx->device);
+    k_gauss_unary<kOp><<<grid_for(n), kBlock, 0, ctx->stream>>>(n, dev(*profile), x, out);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+extern "C" int rls_gaussprofile_get_radius(rls_context *ctx, size_t n, const rls_gaussprofile_soa *profile,
+                                           const float *rx, float *out_r)
+{
+    return gauss_unary<0>(ctx, n, profile, rx, out_r, "rls_gaussprofile_get_radius: NULL argument");
+}
+extern "C" int rls_gaussprofile_get_pdf(rls_context *ctx, size_t n, const rls_gaussprofile_soa *profile,
+                                        const float *r, float *out_pdf)
+{
+    return gauss_unary<1>(ctx, n, profile, r, out_pdf, "rls_gaussprofile_get_pdf: NULL argument");
+}
+extern "C" int rls_gaussprofile_eval_profile(rls_context *ctx, size_t n, const rls_gaussprofile_soa *profile,
+                                             const float *r, float *out_rd)
+{
+    return gauss_unary<2>(ctx, n, profile, r, out_rd, "rls_gaussprofile_eval_profile: NULL argument");
+}
+extern "C" int rls_gaussprofile_sample_eval_pdf(rls_context *ctx, size_t n, const float *dist_x, const float *rx,
+                                                float *out_r, float *out_pdf, float *out_rd)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
+    RLS_REQUIRE(ctx, dist_x && rx && out_r && out_pdf && out_rd, "rls_gaussprofile_sample_eval_pdf: NULL argument");
+    DeviceGuard guard(ctx->device);
+    if (ctx->arith == RLS_ARITH_FAST)
+        k_gauss_profile<true><<<grid_for(n, kBlockSkin), kBlockSkin, 0, ctx->stream>>>(n, dist_x, rx, out_r, out_pdf, out_rd, ctx->fallbacks);
+    else
+        k_gauss_profile<false><<<grid_for(n, kBlockSkin), kBlockSkin, 0, ctx->stream>>>(n, dist_x, rx, out_r, out_pdf, out_rd, ctx->fallbacks);
     RLS_LAUNCH_CHECK(ctx);
     return RLS_OK;
 }

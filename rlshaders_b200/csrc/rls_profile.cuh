@@ -128,6 +128,58 @@ RLS_DEV void nd_pdf_and_profile(Fp &fp, const NdProfile &p, float r, float &pdf_
     rd_out = mk3(o[0], o[1], o[2]);
 }
 
+// ------------------------------------------------------------------ GaussianProfile
+// src/rlSss.h:63-97, the alternative `Profile` argument of SssSampler (never instantiated by the
+// plugin: rlSkin uses SssSampler<NDProfile>).  `fast_exp` is Arnold's; the shim (normative) and this
+// restatement use expf.  No guards, as written: R = 0 -> variance 0 -> NaN / Inf downstream.
+struct GaussProfile { float var, R, norm; };
+constexpr float kInvTwoPi = 0.15915494309189533577f;   // AI_ONEOVER2PI
+
+// :71-76  (`albedo` unused; only dist.x is read)
+template <class Fp>
+RLS_DEV void gauss_set_distance(Fp &fp, GaussProfile &p, float dist_x)
+{
+    p.R = dist_x;
+    p.var = fp.div(p.R * p.R, 12.46f);
+    p.norm = 1.0f - rlm::expf_(fp, fp.div(-(p.R * p.R) * 0.5f, p.var));
+}
+// :78-81
+template <class Fp>
+RLS_DEV float gauss_get_radius(Fp &fp, const GaussProfile &p, float rx)
+{
+    return fp.sqrt(-2.0f * p.var * rlm::logf_(fp, 1.0f - rx * p.norm));
+}
+// :88-91
+template <class Fp>
+RLS_DEV float gauss_eval_profile(Fp &fp, const GaussProfile &p, float r)
+{
+    return fp.div(kInvTwoPi, p.var) * rlm::expf_(fp, fp.div(-r * r * 0.5f, p.var));
+}
+// :83-86
+template <class Fp>
+RLS_DEV float gauss_get_pdf(Fp &fp, const GaussProfile &p, float r)
+{
+    return fp.div(gauss_eval_profile(fp, p, r), p.norm);
+}
+
+// The fused unit: setDistance((dist_x, ., .)), r = getRadius(rx), evalProfile(r), getPdf(r).  The three
+// quotients by mVariance share one refined reciprocal under the fast policy (plain divisions under FpExact);
+// getPdf's evalProfile(r) is the same IEEE value as the evalProfile(r) result and is formed once.
+struct Gauss1 { float r, pdf, rd; };
+template <class Fp>
+RLS_DEV Gauss1 gauss_profile_unit(Fp &fp, float dist_x, float rx)
+{
+    Gauss1 o;
+    const float R2 = dist_x * dist_x;
+    const float var = fp.div(R2, 12.46f);
+    const float yv = fp.shared_rcp(var);
+    const float norm = 1.0f - rlm::expf_(fp, fp.div_by(-R2 * 0.5f, var, yv));
+    o.r = fp.sqrt(-2.0f * var * rlm::logf_(fp, 1.0f - rx * norm));
+    o.rd = fp.div_by(kInvTwoPi, var, yv) * rlm::expf_(fp, fp.div_by(-o.r * o.r * 0.5f, var, yv));
+    o.pdf = fp.div(o.rd, norm);
+    return o;
+}
+
 struct SkinParamsDev {
     P3 sss_color, sss_scatter_dist;
     P1 sss_weight, sss_dist_multiplier, specular_weight, sheen_weight;

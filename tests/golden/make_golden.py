@@ -24,10 +24,36 @@ def flat(prefix, d):
     return {f"{prefix}{k}": v for k, v in d.items() if v is not None}
 
 
-def main():
+def load_reference():
     ref = ol.load_ref()
     assert ref is not None and ref.kind == "reference", "reference library not built"
     ref.set_threads(1)
+    return ref
+
+
+def gaussian(ref):
+    """GaussianProfile (src/rlSss.h:63-97): varying radii incl. 0 (variance 0 -> NaN, as written) + the 0009 distance 1."""
+    rx = ol.hash_uniform(N, 106, 0)
+    dist_x = ol.hash_uniform(N, 106, 1, lo=0.05, hi=2.0)
+    dist_x[:8] = 0.0
+    dist_x[8:16] = 1.0
+    with np.errstate(all="ignore"):
+        out = dict(rx=rx, dist_x=dist_x)
+        out.update(flat("out_", ref.gaussprofile(dist_x, rx)))
+        dist = np.stack([dist_x, np.zeros_like(dist_x), np.zeros_like(dist_x)])
+        prof = ref.gaussprofile_set_distance(dist, np.ones_like(dist))
+        out.update(flat("state_", prof))
+        r = ol.hash_uniform(N, 106, 2, lo=0.0, hi=2.5)
+        out.update(r=r, pdf_at_r=ref.gaussprofile_get_pdf(prof, r), rd_at_r=ref.gaussprofile_eval_profile(prof, r),
+                   radius_at_rx=ref.gaussprofile_get_radius(prof, rx))
+    np.savez_compressed(os.path.join(HERE, "gaussian_profile.npz"), **out)
+
+
+def main():
+    ref = load_reference()
+    if sys.argv[1:] == ["gaussian"]:        # regenerate this one file only
+        gaussian(ref)
+        return
 
     # ---- rlGgx named fixtures: testsuite/mtoa/0001-0003 (roughness, ior, anisotropic)
     sg = ol.make_shading(N, 101)
@@ -82,6 +108,8 @@ def main():
     out["probe_ry"] = ryp
     out.update(flat("probe_", ref.skin_probe_ray(sgp, abi.skin_params(sss_color=color, sss_scatter_dist=dist), rx, ryp)))
     np.savez_compressed(os.path.join(HERE, "skin.npz"), **out)
+
+    gaussian(ref)
 
     # ---- albedo sweep on a reduced grid
     g = abi.SweepGrid(4, 4, 2, 0.05, 1.0, 1.0, 2.0)

@@ -261,6 +261,49 @@ class Oracle:
                                                abi.vec3(rd))
         return np.stack(rd)
 
+    # ---- GaussianProfile (src/rlSss.h:63-97)
+    @staticmethod
+    def _gauss_struct(prof):
+        keep = {k: np.ascontiguousarray(prof[k], dtype=f32) for k in ("variance", "max_radius", "norm")}
+        return keep, abi.GaussProfileSoA(keep["variance"].ctypes.data, keep["max_radius"].ctypes.data,
+                                         keep["norm"].ctypes.data)
+
+    def gaussprofile_set_distance(self, dist, albedo):
+        n = dist.shape[1]
+        out = dict(variance=_z(n), max_radius=_z(n), norm=_z(n))
+        _, s = self._gauss_struct(out)
+        s = abi.GaussProfileSoA(out["variance"].ctypes.data, out["max_radius"].ctypes.data, out["norm"].ctypes.data)
+        kd = [np.ascontiguousarray(dist[j], dtype=f32) for j in range(3)]
+        ka = [np.ascontiguousarray(albedo[j], dtype=f32) for j in range(3)]
+        self.lib.oracle_gaussprofile_set_distance(C.c_size_t(n), abi.vec3(kd), abi.vec3(ka), C.byref(s))
+        return out
+
+    def _gauss_unary(self, fn, prof, x):
+        n = len(x)
+        x = np.ascontiguousarray(x, dtype=f32)
+        out = _z(n)
+        keep, s = self._gauss_struct(prof)
+        fn(C.c_size_t(n), C.byref(s), C.c_void_p(x.ctypes.data), C.c_void_p(out.ctypes.data))
+        return out
+
+    def gaussprofile_get_radius(self, prof, rx):
+        return self._gauss_unary(self.lib.oracle_gaussprofile_get_radius, prof, rx)
+
+    def gaussprofile_get_pdf(self, prof, r):
+        return self._gauss_unary(self.lib.oracle_gaussprofile_get_pdf, prof, r)
+
+    def gaussprofile_eval_profile(self, prof, r):
+        return self._gauss_unary(self.lib.oracle_gaussprofile_eval_profile, prof, r)
+
+    def gaussprofile(self, dist_x, rx):
+        n = len(rx)
+        dist_x, rx = np.ascontiguousarray(dist_x, dtype=f32), np.ascontiguousarray(rx, dtype=f32)
+        out = dict(r=_z(n), pdf=_z(n), Rd=_z(n))
+        self.lib.oracle_gaussprofile_sample_eval_pdf(C.c_size_t(n), C.c_void_p(dist_x.ctypes.data),
+                                                     C.c_void_p(rx.ctypes.data), C.c_void_p(out["r"].ctypes.data),
+                                                     C.c_void_p(out["pdf"].ctypes.data), C.c_void_p(out["Rd"].ctypes.data))
+        return out
+
     def skin_profile(self, params, rx):
         n = len(rx)
         r, pdf, rd, fl = _z(n), _z(n), _v3(n), _z(n, np.uint32)

@@ -37,6 +37,7 @@ def test_struct_layouts_match_header():
                "rls_disney_params": abi.DisneyParams, "rls_skin_params": abi.SkinParams,
                "rls_bsdf_out": abi.BsdfOut, "rls_ggx_dielectric_out": abi.GgxDielectricOut,
                "rls_disney_out": abi.DisneyOut, "rls_ndprofile_soa": abi.NdProfileSoA,
+               "rls_gaussprofile_soa": abi.GaussProfileSoA,
                "rls_profile_out": abi.ProfileOut, "rls_probe_out": abi.ProbeOut,
                "rls_sweep_grid": abi.SweepGrid, "rls_skin_layers_out": abi.SkinLayersOut,
                "rls_light_sample": abi.LightSample}

@@ -176,6 +176,49 @@ def test_ndprofile_entry_points(ctx):
     assert parity.stat_rel(prof.evalProfile(dr).cpu().numpy(), crd)["within"] == 1.0
 
 
+def test_gaussian_profile_entry_points(ctx, orc):
+    """GaussianProfile (src/rlSss.h:63-97): every method and the fused unit, bit-exact
+    against both oracles incl. variance 0 / underflow / overflow, and against the golden fixture."""
+    from rlshaders_b200 import api
+    rx = ol.hash_uniform(N, 11, 0)
+    dist = np.stack([ol.hash_uniform(N, 11, 1 + j, lo=0.0, hi=3.0) for j in range(3)])
+    dist[0, :64] = 0.0
+    dist[0, 64:128] = 1e-30
+    dist[0, 128:192] = 1e20
+    r = ol.hash_uniform(N, 11, 5, lo=0.0, hi=4.0)
+    with np.errstate(all="ignore"):
+        cp = orc.gaussprofile_set_distance(dist, np.ones_like(dist))
+        want = dict(radius=orc.gaussprofile_get_radius(cp, rx), pdf=orc.gaussprofile_get_pdf(cp, r),
+                    rd=orc.gaussprofile_eval_profile(cp, r))
+        fused = orc.gaussprofile(dist[0], rx)
+    prof = api.GaussianProfile(ctx)
+    st = prof.setDistance(dev(dist, ctx), dev(np.ones_like(dist), ctx))
+    for k in ("variance", "max_radius", "norm"):
+        assert gio.bits_equal(st[k].cpu().numpy(), cp[k]), k
+    assert torch.equal(prof.maxRadius().cpu(), torch.from_numpy(dist[0]))
+    assert gio.bits_equal(prof.getRadius(dev(rx, ctx)).cpu().numpy(), want["radius"])
+    assert gio.bits_equal(prof.getPdf(dev(r, ctx)).cpu().numpy(), want["pdf"])
+    assert gio.bits_equal(prof.evalProfile(dev(r, ctx)).cpu().numpy(), want["rd"])
+    for policy in ("exact", "fast"):        # same bits either way; the fast policy re-runs the out-of-window samples
+        ctx.set_arith_policy(policy)
+        ctx.fallback_count(reset=True)
+        got = api.GaussianProfile.sampleEvalPdf(ctx, dev(np.ascontiguousarray(dist[0]), ctx), dev(rx, ctx))
+        for k in ("r", "pdf", "Rd"):
+            assert gio.bits_equal(got[k].cpu().numpy(), fused[k]), (policy, k)
+        fb = ctx.fallback_count(reset=True)
+        assert (fb == 0) if policy == "exact" else (192 <= fb < 192 + N // 1000), (policy, fb)
+    # finite, in-range results on the regular samples
+    reg = got["r"].cpu().numpy()[192:]
+    assert np.all(np.isfinite(reg)) and np.all(reg <= dist[0, 192:] * (1 + 1e-5))
+    g = gio.load("gaussian_profile")
+    got = api.GaussianProfile.sampleEvalPdf(ctx, dev(g["dist_x"], ctx), dev(g["rx"], ctx))
+    for k in ("r", "pdf", "Rd"):
+        assert gio.bits_equal(got[k].cpu().numpy(), g["out_" + k]), k
+    # empty batch and argument errors
+    assert ctx.lib.rls_gaussprofile_sample_eval_pdf(ctx.handle, 0, None, None, None, None, None) == abi.RLS_OK
+    assert ctx.lib.rls_gaussprofile_sample_eval_pdf(ctx.handle, 8, None, None, None, None, None) == abi.RLS_ERR_INVALID_ARGUMENT
+
+
 def test_skin_layer_weights_bit_exact(ctx):
     from rlshaders_b200 import api
     port = ol.load_port()

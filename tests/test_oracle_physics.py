@@ -102,6 +102,31 @@ def test_ndprofile_normalisation(orc):
         assert np.sum(rd[ch] * 2 * np.pi * r * dr) == pytest.approx(full, abs=3e-3)
 
 
+def test_gaussian_profile_normalisation_and_inverse_cdf(orc):
+    # GaussianProfile (src/rlSss.h:63-97): getPdf integrates to 1 over the disc r < maxRadius,
+    # getRadius inverts its radial CDF, getRadius(1) = maxRadius, variance = R^2 / 12.46.
+    n = 1 << 16
+    R = 1.7
+    dist = np.stack([np.full(n, R, f32), np.zeros(n, f32), np.zeros(n, f32)])
+    prof = orc.gaussprofile_set_distance(dist, np.ones((3, n), f32))
+    assert float(prof["max_radius"][0]) == np.float32(R)
+    v = float(prof["variance"][0])
+    assert v == pytest.approx(R * R / 12.46, rel=1e-6)
+    norm = float(prof["norm"][0])
+    assert norm == pytest.approx(1.0 - np.exp(-12.46 / 2.0), rel=1e-5)
+    r = ((np.arange(n, dtype=np.float64) + 0.5) / n * R).astype(f32)
+    pdf = orc.gaussprofile_get_pdf(prof, r).astype(np.float64)
+    assert np.sum(pdf * 2 * np.pi * r * (R / n)) == pytest.approx(1.0, abs=2e-4)
+    rd = orc.gaussprofile_eval_profile(prof, r).astype(np.float64)
+    assert np.allclose(rd, pdf * norm, rtol=1e-6)
+    rx = ((np.arange(n, dtype=np.float64) + 0.5) / n).astype(f32)
+    rad = orc.gaussprofile_get_radius(prof, rx).astype(np.float64)
+    cdf = (1.0 - np.exp(-rad * rad / (2 * v))) / norm
+    assert np.allclose(cdf, rx, atol=2e-5)
+    assert np.all(np.diff(rad) >= 0) and rad.max() <= R * (1 + 1e-5)
+    assert float(orc.gaussprofile_get_radius(prof, np.ones(n, f32))[0]) == pytest.approx(R, rel=1e-4)
+
+
 def test_ndprofile_radius_limits_and_thirds(orc):
     n = 6
     dist = np.ones((3, n), f32)

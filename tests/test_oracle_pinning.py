@@ -75,6 +75,18 @@ def test_port_vs_golden_skin(port):
     assert_same(want, got, "probe ray")
 
 
+def test_port_vs_golden_gaussian_profile(port):
+    g = gio.load("gaussian_profile")
+    with np.errstate(all="ignore"):
+        assert_same(gio.group(g, "out_"), port.gaussprofile(g["dist_x"], g["rx"]), "gaussian fused")
+        dist = np.stack([g["dist_x"], np.zeros_like(g["dist_x"]), np.zeros_like(g["dist_x"])])
+        prof = port.gaussprofile_set_distance(dist, np.ones_like(dist))
+        assert_same(gio.group(g, "state_"), prof, "gaussian setDistance")
+        assert gio.bits_equal(g["pdf_at_r"], port.gaussprofile_get_pdf(prof, g["r"]))
+        assert gio.bits_equal(g["rd_at_r"], port.gaussprofile_eval_profile(prof, g["r"]))
+        assert gio.bits_equal(g["radius_at_rx"], port.gaussprofile_get_radius(prof, g["rx"]))
+
+
 def test_port_vs_golden_sweep(port):
     g = gio.load("sweep")
     n = [int(x) for x in g["grid"]]
@@ -130,6 +142,25 @@ def test_port_vs_reference_profile(port, ref):
     sp = abi.skin_params(sheen_weight=ol.hash_uniform(N, 6, 3), specular_weight=ol.hash_uniform(N, 6, 4),
                          sss_weight=ol.hash_uniform(N, 6, 5))
     assert_same(ref.skin_layer_weights(sp, f1, f2), port.skin_layer_weights(sp, f1, f2), "layer weights")
+
+
+def test_port_vs_reference_gaussian_profile(port, ref):
+    """GaussianProfile (src/rlSss.h:63-97): the reference class itself vs the C restatement, every method."""
+    rx = ol.hash_uniform(N, 11, 0)
+    dist = np.stack([ol.hash_uniform(N, 11, 1 + j, lo=0.0, hi=3.0) for j in range(3)])
+    dist[0, :64] = 0.0            # variance 0: NaN / Inf exactly as the reference writes them
+    dist[0, 64:128] = 1e-30       # variance underflows to 0
+    dist[0, 128:192] = 1e20       # variance overflows
+    albedo = np.ones_like(dist)
+    with np.errstate(all="ignore"):
+        pa, pb = ref.gaussprofile_set_distance(dist, albedo), port.gaussprofile_set_distance(dist, albedo)
+        assert_same(pa, pb, "gaussian setDistance")
+        ra, rb = ref.gaussprofile_get_radius(pa, rx), port.gaussprofile_get_radius(pb, rx)
+        assert gio.bits_equal(ra, rb)
+        r = ol.hash_uniform(N, 11, 5, lo=0.0, hi=4.0)
+        assert gio.bits_equal(ref.gaussprofile_get_pdf(pa, r), port.gaussprofile_get_pdf(pb, r))
+        assert gio.bits_equal(ref.gaussprofile_eval_profile(pa, r), port.gaussprofile_eval_profile(pb, r))
+        assert_same(ref.gaussprofile(dist[0], rx), port.gaussprofile(dist[0], rx), "gaussian fused")
 
 
 def test_port_vs_reference_sweep(port, ref):
