@@ -454,6 +454,11 @@ def run_product(args):
                                              "exact_rerun_fraction": ctx.fallback_count(reset=True) /
                                              float(64 * 64 * 16 * (k1 - k0) * (max(2, steps_o // 2) + 1)),
                                              "collective": "nccl all_reduce(sum) of the 2.6 MB FP64 table" if world > 1 else "none (1 GPU)"}
+        # FP32 roofline of each (algorithmic flops per sample; the sweep has no per-sample memory
+        # traffic, so this is its governing roofline) -- per GPU, against the nominal FP32 peak
+        for key, unit in (("ggx_conductor_1M", "ggx_conductor"), ("skin_profile_256M", "skin_profile"),
+                          ("disney_256M", "disney"), ("albedo_sweep_65536x4096", "ggx_conductor")):
+            others[key]["fp32_frac"] = others[key]["samples_per_s"] / world * F_ALG[unit] / 1e12 / FP32_PEAK_TFLOPS
         line["other_workloads"] = others
 
     if rank == 0:

@@ -93,6 +93,7 @@ struct rls_context {
     bool         packed = false;                  // two-samples-per-thread kernel (rls_packed.cuh): bit-exact but
                                                   // measured slower on B200 (latency bound at 128 registers), so
                                                   // it is off unless RLS_PACKED=1 (kept for A/B runs and its test)
+    bool         gauss_scalar = false;            // GaussianProfile fused unit: one sample per thread instead of four (RLS_GAUSS_SCALAR=1, A/B)
     unsigned long long *fallbacks = nullptr;      // device counter: samples re-run with FpExact
     unsigned    *chunk_counter = nullptr;         // device counter of the dynamically scheduled persistent kernel
     // host-staging resources (lazily created by the *_host entry points)
@@ -156,6 +157,7 @@ extern "C" int rls_init(int device, void *stream, rls_context **out_ctx)
     if (const char *v = getenv("RLS_TMA")) ctx->tma = atoi(v) != 0;           // A/B switch for tuning runs
     if (const char *v = getenv("RLS_PERSISTENT")) ctx->persistent = atoi(v);  // A/B switch for tuning runs
     if (const char *v = getenv("RLS_STAGGER_NS")) ctx->stagger_ns = (unsigned)atoi(v);
+    if (const char *v = getenv("RLS_GAUSS_SCALAR")) ctx->gauss_scalar = atoi(v) != 0;   // A/B switch
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     DeviceGuard guard(device);
@@ -782,6 +784,38 @@ k_gauss_profile(size_t n, const float *dist_x, const float *rx, float *r, float 
         if (kFast) atomicAdd(fallbacks, 1ull);
     }
     r[i] = o.r; rd[i] = o.rd; pdf[i] = o.pdf;
+}
+// Four consecutive samples per thread, 128-bit loads and stores (all five arrays 16-byte aligned; the host picks this
+// form and runs the scalar kernel on the n % 4 tail): the unit is ~170 warp instructions per 32 samples, so with one
+// sample per thread the CTA turnover and the load-to-use latency bound it (ncu: 66 % issue slots, 65 % occupancy, DRAM 33 %).
+// One operand tracker for the quad; an out-of-window operand re-runs the four samples exactly.
+template <bool kFast>
+__global__ void __launch_bounds__(kBlockSkin, 4)
+k_gauss_profile_x4(size_t n4, const float4 *dist_x, const float4 *rx, float4 *r, float4 *pdf, float4 *rd,
+                   unsigned long long *fallbacks)
+{
+    if (kFast) rlm::smem_tables_init();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint32_t)n4) return;
+    Gauss1 o[4];
+    bool ok = false;
+    if (kFast) {
+        FpFastSmemTab fp;
+        const float4 d = __ldg(dist_x + i), x = __ldg(rx + i);
+        o[0] = gauss_profile_unit(fp, d.x, x.x); o[1] = gauss_profile_unit(fp, d.y, x.y);
+        o[2] = gauss_profile_unit(fp, d.z, x.z); o[3] = gauss_profile_unit(fp, d.w, x.w);
+        ok = fp.ok();
+    }
+    if (!ok) {
+        FpExact fp;
+        const float4 d = __ldcg(dist_x + i), x = __ldcg(rx + i);
+        o[0] = gauss_profile_unit(fp, d.x, x.x); o[1] = gauss_profile_unit(fp, d.y, x.y);
+        o[2] = gauss_profile_unit(fp, d.z, x.z); o[3] = gauss_profile_unit(fp, d.w, x.w);
+        if (kFast) atomicAdd(fallbacks, 4ull);
+    }
+    r[i] = make_float4(o[0].r, o[1].r, o[2].r, o[3].r);
+    rd[i] = make_float4(o[0].rd, o[1].rd, o[2].rd, o[3].rd);
+    pdf[i] = make_float4(o[0].pdf, o[1].pdf, o[2].pdf, o[3].pdf);
 }
 struct ProfileOutDev { float *r, *pdf; V3 Rd; uint32_t *flags; };
 struct Profile1 { float r, pdf; f3 Rd; uint32_t flags; };
@@ -1547,10 +1581,25 @@ extern "C" int rls_gaussprofile_sample_eval_pdf(rls_context *ctx, size_t n, cons
     if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, dist_x && rx && out_r && out_pdf && out_rd, "rls_gaussprofile_sample_eval_pdf: NULL argument");
     DeviceGuard guard(ctx->device);
-    if (ctx->arith == RLS_ARITH_FAST)
-        k_gauss_profile<true><<<grid_for(n, kBlockSkin), kBlockSkin, 0, ctx->stream>>>(n, dist_x, rx, out_r, out_pdf, out_rd, ctx->fallbacks);
+    const bool fast = ctx->arith == RLS_ARITH_FAST;
+    const bool aligned = ((((uintptr_t)dist_x | (uintptr_t)rx | (uintptr_t)out_r | (uintptr_t)out_pdf | (uintptr_t)out_rd) & 15u) == 0) &&
+                         !ctx->gauss_scalar;
+    const size_t n4 = aligned ? n / 4 : 0, done = n4 * 4;
+    if (n4) {
+        if (fast)
+            k_gauss_profile_x4<true><<<grid_for(n4, kBlockSkin), kBlockSkin, 0, ctx->stream>>>(
+                n4, (const float4 *)dist_x, (const float4 *)rx, (float4 *)out_r, (float4 *)out_pdf, (float4 *)out_rd, ctx->fallbacks);
+        else
+            k_gauss_profile_x4<false><<<grid_for(n4, kBlockSkin), kBlockSkin, 0, ctx->stream>>>(
+                n4, (const float4 *)dist_x, (const float4 *)rx, (float4 *)out_r, (float4 *)out_pdf, (float4 *)out_rd, ctx->fallbacks);
+        RLS_LAUNCH_CHECK(ctx);
+    }
+    if (done == n) return RLS_OK;
+    const size_t m = n - done;
+    if (fast)
+        k_gauss_profile<true><<<grid_for(m, kBlockSkin), kBlockSkin, 0, ctx->stream>>>(m, dist_x + done, rx + done, out_r + done, out_pdf + done, out_rd + done, ctx->fallbacks);
     else
-        k_gauss_profile<false><<<grid_for(n, kBlockSkin), kBlockSkin, 0, ctx->stream>>>(n, dist_x, rx, out_r, out_pdf, out_rd, ctx->fallbacks);
+        k_gauss_profile<false><<<grid_for(m, kBlockSkin), kBlockSkin, 0, ctx->stream>>>(m, dist_x + done, rx + done, out_r + done, out_pdf + done, out_rd + done, ctx->fallbacks);
     RLS_LAUNCH_CHECK(ctx);
     return RLS_OK;
 }

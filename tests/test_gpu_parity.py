@@ -207,7 +207,15 @@ def test_gaussian_profile_entry_points(ctx, orc):
             assert gio.bits_equal(got[k].cpu().numpy(), fused[k]), (policy, k)
         fb = ctx.fallback_count(reset=True)
         assert (fb == 0) if policy == "exact" else (192 <= fb < 192 + N // 1000), (policy, fb)
+    # the 128-bit form runs on 16-byte aligned arrays with the scalar kernel on the n % 4 tail; unaligned arrays
+    # take the scalar kernel throughout -- same bits
+    dd, dx = dev(np.ascontiguousarray(dist[0]), ctx), dev(rx, ctx)
+    for lo, hi in ((0, N - 5), (1, N - 2), (4, 4 + 3), (8, 8 + 4)):
+        got = api.GaussianProfile.sampleEvalPdf(ctx, dd[lo:hi], dx[lo:hi])
+        for k in ("r", "pdf", "Rd"):
+            assert gio.bits_equal(got[k].cpu().numpy(), fused[k][lo:hi]), (lo, hi, k)
     # finite, in-range results on the regular samples
+    got = api.GaussianProfile.sampleEvalPdf(ctx, dd, dx)
     reg = got["r"].cpu().numpy()[192:]
     assert np.all(np.isfinite(reg)) and np.all(reg <= dist[0, 192:] * (1 + 1e-5))
     g = gio.load("gaussian_profile")
