@@ -93,6 +93,8 @@ struct rls_context {
     bool         packed = false;                  // two-samples-per-thread kernel (rls_packed.cuh): bit-exact but
                                                   // measured slower on B200 (latency bound at 128 registers), so
                                                   // it is off unless RLS_PACKED=1 (kept for A/B runs and its test)
+    bool         disney_lobe_sort = false;        // CTA-level stable partition of the rlDisney samples by specular lobe: bit-identical,
+                                                  // measured 4 % SLOWER on B200 (16.02 vs 16.68 G samples/s), off unless RLS_DISNEY_LOBE_SORT=1
     bool         gauss_scalar = false;            // GaussianProfile fused unit: one sample per thread instead of four (RLS_GAUSS_SCALAR=1, A/B)
     unsigned long long *fallbacks = nullptr;      // device counter: samples re-run with FpExact
     unsigned    *chunk_counter = nullptr;         // device counter of the dynamically scheduled persistent kernel
@@ -157,6 +159,7 @@ extern "C" int rls_init(int device, void *stream, rls_context **out_ctx)
     if (const char *v = getenv("RLS_TMA")) ctx->tma = atoi(v) != 0;           // A/B switch for tuning runs
     if (const char *v = getenv("RLS_PERSISTENT")) ctx->persistent = atoi(v);  // A/B switch for tuning runs
     if (const char *v = getenv("RLS_STAGGER_NS")) ctx->stagger_ns = (unsigned)atoi(v);
+    if (const char *v = getenv("RLS_DISNEY_LOBE_SORT")) ctx->disney_lobe_sort = atoi(v) != 0;   // A/B switch
     if (const char *v = getenv("RLS_GAUSS_SCALAR")) ctx->gauss_scalar = atoi(v) != 0;   // A/B switch
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
@@ -667,13 +670,51 @@ RLS_DEV DisneyOut1 disney_unit_from(Fp &fp, const Shading &s, const DisneyParams
     Disney d; disney_init<kArrays, kReload>(fp, d, s, p, i);
     return disney_unit(fp, d, rx_s, ry_s, rx_d, ry_d);
 }
-template <bool kFast, bool kArrays>
+// Warp-uniform lobe selection (BASELINE north_star): a stable partition of the CTA's samples by specular lobe, so that
+// the ~10 % of samples that take the GTR1 (clearcoat) lobe sit together in the CTA's last warp(s) instead of making
+// almost every warp (1 - 0.9^32 = 97 %) run the GTR1-only code (general powf) for three lanes AND the GTR2-only code
+// (visible-normal sampling) for the rest.  Thread t then works on sample base + perm[t]; GTR2 samples keep their order,
+// so a warp's loads span ~36 consecutive samples instead of 32.  The predicate only steers the grouping (results do
+// not depend on it), so it is the approximate rx (c' + 1) < 1 rather than the unit's exact rx < 1 / (c' + 1).
+// MEASURED (tools/disney_ab.py, 2^26 samples, every parameter per sample): 16.02 G samples/s against 16.68 without it --
+// the GTR1-only code the other warps skip (~150 slots of ~1780) is worth less than the partition costs (two CTA barriers
+// before the first load of the unit can issue, ~50 slots, 29 loads and 15 stores per sample over two cache lines).
+// Kept behind RLS_DISNEY_LOBE_SORT=1 with its test (tests/test_gpu_parity.py::test_disney_lobe_partition_is_invisible).
+template <bool kArrays>
+RLS_DEV uint32_t disney_lobe_partition(size_t n, const DisneyParamsDev &p, const float *rx_s)
+{
+    __shared__ uint16_t perm[kBlock];
+    __shared__ uint32_t gtr1_in_warp[kBlock / 32];
+    const uint32_t t = threadIdx.x, lane = t & 31u, w = t >> 5, base = blockIdx.x * blockDim.x;
+    bool gtr1 = true;                                   // samples past the end are grouped with the last warp
+    if (base + t < (uint32_t)n) {
+        const float c = fetch_t<kArrays>(p.clearcoat, base + t) * 0.25f;
+        gtr1 = !(__ldg(rx_s + base + t) * (c + 1.0f) < 1.0f);
+    }
+    const uint32_t b = __ballot_sync(0xffffffffu, gtr1);
+    if (lane == 0) gtr1_in_warp[w] = __popc(b);
+    __syncthreads();
+    uint32_t before = 0, total = 0;                     // GTR1 samples in the warps before this one / in the CTA
+#pragma unroll
+    for (uint32_t k = 0; k < kBlock / 32; k++) {
+        const uint32_t c = gtr1_in_warp[k];
+        before += k < w ? c : 0u;
+        total += c;
+    }
+    const uint32_t mine = __popc(b & ((1u << lane) - 1u));
+    const uint32_t pos = gtr1 ? (kBlock - total) + before + mine : (t - before - mine);
+    perm[pos] = (uint16_t)t;
+    __syncthreads();
+    return base + perm[t];
+}
+template <bool kFast, bool kArrays, bool kLobeSort = false>
 __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_disney_sample_eval_pdf(size_t n, ShadingSoA sg, DisneyParamsDev p, const float *rx_s, const float *ry_s,
                          const float *rx_d, const float *ry_d, DisneyOutDev o, unsigned long long *fallbacks)
 {
     if (kFast) rlm::smem_tables_init();      // exp2 / log / log2 tables in shared memory (before the early exit below)
-    RLS_INDEX();
+    const uint32_t i = kLobeSort ? disney_lobe_partition<kArrays>(n, p, rx_s) : blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint32_t)n) return;
     DisneyOut1 r;
     bool ok = false;
     if (kFast) {
@@ -1322,9 +1363,13 @@ static int launch_disney_sample_eval_pdf(rls_context *ctx, cudaStream_t st, size
     bool arrays = pd.base_color.x && pd.base_color.y && pd.base_color.z;     // every parameter spatially varying?
     for (const P1 *q : scalars) arrays = arrays && q->array;
     const bool fast = ctx->arith == RLS_ARITH_FAST;
-#define RLS_DISNEY_LAUNCH(F, A) \
-    k_disney_sample_eval_pdf<F, A><<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), pd, rx_s, ry_s, rx_d, ry_d, d, ctx->fallbacks)
-    if (fast && arrays) RLS_DISNEY_LAUNCH(true, true);
+#define RLS_DISNEY_LAUNCH(F, A, ...) \
+    k_disney_sample_eval_pdf<F, A, ##__VA_ARGS__><<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), pd, rx_s, ry_s, rx_d, ry_d, d, ctx->fallbacks)
+    // the partition pays only when lobes are mixed inside a CTA, i.e. clearcoat varies per sample or is non-zero
+    const bool sort = ctx->disney_lobe_sort && fast && (pd.clearcoat.array || pd.clearcoat.value != 0.0f);
+    if (sort && arrays) RLS_DISNEY_LAUNCH(true, true, true);
+    else if (sort) RLS_DISNEY_LAUNCH(true, false, true);
+    else if (fast && arrays) RLS_DISNEY_LAUNCH(true, true);
     else if (fast) RLS_DISNEY_LAUNCH(true, false);
     else if (arrays) RLS_DISNEY_LAUNCH(false, true);
     else RLS_DISNEY_LAUNCH(false, false);

@@ -34,14 +34,12 @@ RLS_DEV f2 concentric_disk_sample(Fp &fp, float rx, float ry)
     ry = ry * 2.0f - 1.0f;
     f2 o; o.x = 0.0f; o.y = 0.0f;
     if (rx == 0.0f && ry == 0.0f) return o;
-    float r, phi;
-    if (abs_m(rx) > abs_m(ry)) {
-        r = rx;
-        phi = fp.div(kHalfPi * 0.5f * ry, rx);
-    } else {
-        r = ry;
-        phi = kHalfPi * (1.0f - fp.div(0.5f * rx, ry));
-    }
+    // rlUtil.cpp:16-22: the two sides divide different operands, so the operands are selected and ONE quotient is
+    // formed (a 50 / 50 branch would make every warp run both)
+    const bool wide = abs_m(rx) > abs_m(ry);
+    const float r = wide ? rx : ry;
+    const float q = fp.div(wide ? kHalfPi * 0.5f * ry : 0.5f * rx, r);
+    const float phi = wide ? q : kHalfPi * (1.0f - q);
     float s, c;
     rlm::sincosf_(fp, phi, &s, &c);
     o.x = r * c;

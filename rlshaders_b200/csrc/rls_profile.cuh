@@ -32,10 +32,13 @@ RLS_DEV void nd_set_distance(Fp &fp, NdProfile &p, f3 dist)
 template <class Fp>
 RLS_DEV int nd_select_dist_lobe(Fp &fp, float &x)
 {
-    if (x < 0.3333f) { x = linearstep_m(fp, 0.0f, 0.3333f, x); return 0; }
-    else if (x > 0.6666f) { x = linearstep_m(fp, 0.6666f, 1.0f, x); return 2; }
-    x = linearstep_m(fp, 0.3333f, 0.6666f, x);
-    return 1;
+    // one LINEARSTEP on selected bounds instead of three divergent ones (x - 0 is exact; hi - lo is the same
+    // binary32 difference whether the compiler or the FADD forms it)
+    const int ch = x < 0.3333f ? 0 : (x > 0.6666f ? 2 : 1);
+    const float lo = ch == 0 ? 0.0f : (ch == 2 ? 0.6666f : 0.3333f);
+    const float hi = ch == 0 ? 0.3333f : (ch == 2 ? 1.0f : 0.6666f);
+    x = linearstep_m(fp, lo, hi, x);
+    return ch;
 }
 RLS_DEV float pick3(const float (&a)[3], int i) { return i == 0 ? a[0] : (i == 1 ? a[1] : a[2]); }
 
@@ -51,16 +54,13 @@ RLS_DEV float nd_get_radius(Fp &fp, const NdProfile &p, float rx, uint32_t &flag
     float w1 = pick3(p.C1, ch);
     float w2 = pick3(p.C2, ch);
     float w = fp.div(w1, w1 + w2 * 3.0f);
-    float r;
-    if (x > w) {
-        flags |= 0x0400u;                            // RLS_FLAG_EXP_LOBE
-        x = linearstep_m(fp, w, 1.0f, x);
-        r = rlm::logf_(fp, 1.0f - x * w2) * (-d * 3.0f);
-    } else {
-        x = linearstep_m(fp, 0.0f, w, x);
-        r = rlm::logf_(fp, 1.0f - x * w1) * (-d);
-    }
-    return r;
+    // :52-65.  The two exponential lobes run the same operations on different operands, so the operands are
+    // selected and ONE linearstep + logf is evaluated (as a branch, almost every warp ran both sides: two quotients
+    // and two logf for one); x - 0 and w - 0 are exact, so LINEARSTEP(0, w, x) is unchanged.
+    const bool wide = x > w;                         // the exp(-r/3d) lobe
+    flags |= wide ? 0x0400u : 0u;                    // RLS_FLAG_EXP_LOBE
+    x = linearstep_m(fp, wide ? w : 0.0f, wide ? 1.0f : w, x);
+    return rlm::logf_(fp, 1.0f - x * (wide ? w2 : w1)) * (wide ? -d * 3.0f : -d);
 }
 // src/rlSss.cpp:68-84
 template <class Fp>

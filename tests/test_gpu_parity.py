@@ -78,6 +78,39 @@ def test_disney_parity(ctx, orc):
     check(parity.run_disney(ctx, orc, N)[0], f"config 3 vs {orc.kind}")
 
 
+def test_disney_lobe_partition_is_invisible(ctx, monkeypatch):
+    """The CTA-level partition by specular lobe (k_disney_sample_eval_pdf<.., kLobeSort>) only changes which thread
+    works on which sample: ragged sizes (partial last CTA, single sample), uniform and per-sample clearcoat, and the
+    same bits as the default context (partition off)."""
+    from rlshaders_b200 import api
+    port = ol.load_port()
+    monkeypatch.setenv("RLS_DISNEY_LOBE_SORT", "1")     # off by default (measured slower); read at rls_init
+    plain, ctx = ctx, api.Context(0)
+    plain_owner = ctx
+    monkeypatch.delenv("RLS_DISNEY_LOBE_SORT")
+    kinds = dict(wi_s="dir", f_s="rel", pdf_s="rel", wi_d="dir", f_d="rel", pdf_d="rel", flags="flags")
+    try:
+        for n in (1, 31, 255, 257, 1000, 65536 + 77):
+            sg, kw, u = parity.disney_inputs(n, seed=0x5EED0300 + n)
+            for uniform_clearcoat in (None, 0.0, 1.0):
+                if uniform_clearcoat is not None:
+                    kw = dict(kw, clearcoat=uniform_clearcoat)
+                cpu = port.disney_sample_eval_pdf(sg, abi.disney_params(**kw), *u)
+                outs = []
+                for c in (ctx, plain):
+                    smp = api.DisneySampler(c, api.ShadingBatch.from_numpy(sg, c.device), **parity.params_to_dev(kw, c.device))
+                    outs.append(smp.sampleEvalPdf(*[dev(t, c) for t in u]))
+                    c.synchronize()
+                for k in outs[0]:
+                    assert torch.equal(outs[0][k].view(torch.int32), outs[1][k].view(torch.int32)), (n, uniform_clearcoat, k)
+                st = parity.summarize(outs[0], cpu, kinds)
+                assert st["flags"]["mismatches"] == 0, (n, uniform_clearcoat)
+                for k in ("wi_s", "f_s", "pdf_s", "wi_d", "f_d", "pdf_d"):
+                    assert st[k]["bit_exact"] >= FRAC_EXACT, (n, uniform_clearcoat, k, st[k])
+    finally:
+        plain_owner.close()
+
+
 def test_skin_profile_parity(ctx, orc):
     stats = parity.run_skin(ctx, orc, N)[0]
     check(stats, f"config 4 vs {orc.kind}")
