@@ -677,7 +677,7 @@ RLS_DEV DisneyOut1 disney_unit_from(Fp &fp, const Shading &s, const DisneyParams
 // so a warp's loads span ~36 consecutive samples instead of 32.  The predicate only steers the grouping (results do
 // not depend on it), so it is the approximate rx (c' + 1) < 1 rather than the unit's exact rx < 1 / (c' + 1).
 // MEASURED (tools/disney_ab.py, 2^26 samples, every parameter per sample): 16.02 G samples/s against 16.68 without it --
-// the GTR1-only code the other warps skip (~150 slots of ~1780) is worth less than the partition costs (two CTA barriers
+// the GTR1-only code the other warps skip (98 slots of 1768 per warp, ncu) is worth less than the partition costs (two CTA barriers
 // before the first load of the unit can issue, ~50 slots, 29 loads and 15 stores per sample over two cache lines).
 // Kept behind RLS_DISNEY_LOBE_SORT=1 with its test (tests/test_gpu_parity.py::test_disney_lobe_partition_is_invisible).
 template <bool kArrays>
