@@ -459,6 +459,10 @@ def run_product(args):
         for key, unit in (("ggx_conductor_1M", "ggx_conductor"), ("skin_profile_256M", "skin_profile"),
                           ("disney_256M", "disney"), ("albedo_sweep_65536x4096", "ggx_conductor")):
             others[key]["fp32_frac"] = others[key]["samples_per_s"] / world * F_ALG[unit] / 1e12 / FP32_PEAK_TFLOPS
+        issued = measured_traffic("fp32_flops_per_sample_issued") or {}
+        for key, kern in (("skin_profile_256M", "k_skin_profile"), ("disney_256M", "k_disney_sample_eval_pdf")):
+            if isinstance(issued, dict) and issued.get(kern):
+                others[key]["fp32_issued_tflops"] = others[key]["samples_per_s"] / world * issued[kern] / 1e12
         line["other_workloads"] = others
 
     if rank == 0:
