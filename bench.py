@@ -497,8 +497,9 @@ def main():
     ap.add_argument("--e2e-samples", type=int, default=N_DIELECTRIC, help="samples per e2e step (per GPU)")
     ap.add_argument("--main-only", action="store_true", help="skip the other BASELINE configs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
-    ap.add_argument("--arith", choices=["fast", "exact"], default="fast",
-                    help="arithmetic policy of the fused kernels (same bits; csrc/rls_fp.cuh)")
+    ap.add_argument("--arith", choices=["fast", "exact", "tolerant"], default="fast",
+                    help="arithmetic policy of the fused kernels: fast / exact = same bits (csrc/rls_fp.cuh); "
+                         "tolerant = stated tolerance, bit-exact flags (csrc/rls_tol.cuh)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -68,6 +68,9 @@ extern "C" {
 #define RLS_FLAG_ENTERING       0x0010u /* dot(sg->N, sg->Rd) < 1e-4, src/rlGgx.h:137                */
 #define RLS_FLAG_TIR            0x0020u /* refraction failed, sample reflected, src/rlGgx.h:232-236  */
 #define RLS_FLAG_PDF_FLOORED    0x0040u /* pdf floor 1e-4 was taken, src/rlGgx.h:79, rlDisney.cpp:517 */
+#define RLS_FLAG_SLOPE_EARLY_OUT 0x0080u /* visible-normal sampling took the uniform-slope early-out: stretched view
+                                           along the normal (theta left 0) or |A^2 - 1| < 1e-4, src/rlGgx.cpp:27,38,82
+                                           (rlDisney.cpp:416-463,485): fused units and rls_disney_eval_sample        */
 #define RLS_FLAG_LOBE_SHIFT     8       /* bits 8-9: rlDisney 0 = GTR2, 1 = GTR1 (rlDisney.cpp:375); */
 #define RLS_FLAG_LOBE_MASK      0x0300u /*           profile: colour channel 0..2 (rlSss.h:30-42)    */
 #define RLS_FLAG_EXP_LOBE       0x0400u /* profile: second exponential (3d) chosen, rlSss.cpp:57     */
@@ -252,6 +255,19 @@ uint64_t rls_kernel_launch_count(const rls_context *ctx);
  * re-run since creation / the last reset (synchronises the context's streams). */
 #define RLS_ARITH_FAST  0
 #define RLS_ARITH_EXACT 1
+/* RLS_ARITH_TOLERANT (opt-in): the four fused *_sample_eval_pdf units computed to a stated TOLERANCE instead of to the
+ * bit (rlshaders_b200/csrc/rls_tol.cuh: fused multiply-adds, MUFU reciprocals / roots / exp2, polynomial log / sin /
+ * cos, visible-normal sampling without its angle round trips) -- about 1/3 of the instructions of the bit-exact
+ * kernels, which moves them from issue bound to HBM bound.  FLAGS, LOBE CHOICES AND DISCONTINUOUS BRANCHES STAY
+ * BIT-EXACT: a sample whose deciding comparand lies within a band of its threshold is re-evaluated by the bit-exact
+ * policy in a second kernel on the same stream (rls_fallback_count counts them, ~5e-4 of the samples).  Value
+ * contract, measured against the reference compiled on the host (tests/test_tolerant_policy.py):
+ * directions >= 95 % within 1e-6 absolute and >= 99.9 % within 1e-4; f / pdf / radii >= 90 % within 1e-5 relative and
+ * >= 99.9 % within 1e-3 -- the spread is the reference's own rounding noise (its angle round trips and cancellations
+ * amplify 1 ulp to more than 1e-6 in ~3 % of the samples), not an error of this policy: against an FP64
+ * evaluation of the same formulas the tolerance results are closer than the reference's.  The entry points without a
+ * tolerance form (triples with explicit wi, profiles, callers, sweep) run RLS_ARITH_FAST under this setting. */
+#define RLS_ARITH_TOLERANT 2
 int rls_set_arith_policy(rls_context *ctx, int policy);
 int rls_fallback_count(rls_context *ctx, uint64_t *out_count, int reset);
 /* The node names this library stands in for: "rlGgx", "rlDisney", "rlSkin"; NULL past

@@ -38,6 +38,36 @@ static inline float orc_uniform(uint64_t seed, uint32_t stream, uint64_t index)
     return (float)k * 5.9604644775390625e-8f;   /* 2^-24, exact */
 }
 
+/* RLS_FLAG_SLOPE_EARLY_OUT probe.  The reference's visible-normal sampler does not report which branch it took, so
+ * the flag is derived by re-evaluating the expressions that decide its two early-outs -- the float operations of
+ * src/rlGgx.cpp:66-84 (view -> stretched polar angle theta; theta is left 0 unless V.z < 1 - AI_EPSILON) and :27-38
+ * (theta < AI_EPSILON, or |A^2 - 1| < AI_EPSILON) -- on the same inputs.  src/rlDisney.cpp:467-489,416-438 is the same
+ * code.  view, U, V, N: 3 floats each; ax, ay: the sampler's alphas; rx: the first uniform as the sampler receives it. */
+#include <math.h>
+static inline int orc_vndf_early_out(const float *view, const float *U, const float *V, const float *N,
+                                     float ax, float ay, float rx)
+{
+    float d = N[0] * view[0] + N[1] * view[1] + N[2] * view[2];
+    float cosThetaV = d < -1.0f ? -1.0f : (d > 1.0f ? 1.0f : d);
+    float phiV = atan2f(V[0] * view[0] + V[1] * view[1] + V[2] * view[2], U[0] * view[0] + U[1] * view[1] + U[2] * view[2]);
+    float r = sqrtf(1.0f - cosThetaV * cosThetaV);
+    float x = r * cosf(phiV), y = r * sinf(phiV), z = cosThetaV;
+    x *= ax;
+    y *= ay;
+    float len = sqrtf(x * x + y * y + z * z);
+    if (len != 0.0f) { float inv = 1.0f / len; x *= inv; y *= inv; z *= inv; }
+    if (!(z < (1.0f - 1.0e-4f))) return 1;              /* theta = 0 -> sampleSlope's first early-out */
+    float theta = acosf(z);
+    if (theta < 1.0e-4f) return 1;
+    float B = tanf(theta);
+    float B2 = B * B;
+    float G1 = 2.0f / (1.0f + sqrtf(1.0f + B2));
+    float A = 2.0f * rx / G1 - 1.0f;
+    float A2 = A * A;
+    float dA = A2 - 1.0f;
+    return ((dA < 0) ? -dA : dA) < 1.0e-4f;
+}
+
 /* Sweep cell -> (roughness, cos theta_v, ior); see include/rls_b200.h rls_albedo_sweep. */
 static inline void orc_sweep_cell(const rls_sweep_grid *g, uint32_t cell, float *roughness, float *cosv, float *ior)
 {

@@ -90,6 +90,17 @@ inline uint32_t bsdfFlags(const AtVector &L, const AtVector &N, const AtColor &f
     return fl;
 }
 
+/* RLS_FLAG_SLOPE_EARLY_OUT: see orc_vndf_early_out (oracle_common.h).  Only VNDFKernel has the early-outs. */
+template <typename Sampler> struct UsesVndf { static const bool value = false; };
+template <> struct UsesVndf<rls::GgxSampler> { static const bool value = true; };
+inline uint32_t slopeEarlyOutFlag(const Shading &sh, float ax, float ay, float rx)
+{
+    const float view[3] = { -sh.sg.Rd.x, -sh.sg.Rd.y, -sh.sg.Rd.z };
+    const float U[3] = { sh.U.x, sh.U.y, sh.U.z }, V[3] = { sh.V.x, sh.V.y, sh.V.z };
+    const float N[3] = { sh.sg.Nf.x, sh.sg.Nf.y, sh.sg.Nf.z };
+    return orc_vndf_early_out(view, U, V, N, ax, ay, rx) ? RLS_FLAG_SLOPE_EARLY_OUT : 0u;
+}
+
 /* The dielectric unit of work, composed from the reference's own members. */
 struct DielectricResult {
     float F, f_r, pdf_r, f_t, w_t;
@@ -111,6 +122,7 @@ inline DielectricResult dielectricUnitT(Shading &sh, float ior, float rough, flo
     r.pdf_r = Sampler::evalPdf(&s, &r.wi_r);
     r.flags = bsdfFlags(r.wi_r, N, fr, r.pdf_r);
     if (AiV3Dot(sh.sg.N, sh.sg.Rd) < AI_EPSILON) r.flags |= RLS_FLAG_ENTERING;
+    if (UsesVndf<Sampler>::value) r.flags |= slopeEarlyOutFlag(sh, s.mAlphaX, s.mAlphaY, rx);
     AtVector t;
     if (s.getRefractDirection(m, V, t)) {
         r.wi_t = t;
@@ -154,6 +166,16 @@ inline uint32_t disneyLobe(const rls_disney_params *p, size_t i, float rx)
     float clearcoat = orc_p1(&p->clearcoat, i) * 0.25f;
     float gtr2Weight = 1.0f / (clearcoat + 1.0f);
     return rx < gtr2Weight ? 0u : 1u;
+}
+
+/* RLS_FLAG_SLOPE_EARLY_OUT of the rlDisney glossy sample: GTR2 lobe, visible-normal sampling, rx rescaled as
+ * src/rlDisney.cpp:376 before sampleGTR2AnisoDirectionFromSlope. */
+inline uint32_t disneySlopeEarlyOut(const rls_disney_params *p, size_t i, const Shading &sh, const DisneySampler &s, float rx)
+{
+    if (disneyLobe(p, i, rx) != 0u || !s.mSampleFromVisibleNormal) return 0u;
+    float clearcoat = orc_p1(&p->clearcoat, i) * 0.25f;
+    float gtr2Weight = 1.0f / (clearcoat + 1.0f);
+    return slopeEarlyOutFlag(sh, s.mAlphaX, s.mAlphaY, rx / gtr2Weight);
 }
 
 inline void loadProfile(const rls_ndprofile_soa *s, size_t i, rls::NDProfile &p)
@@ -239,6 +261,7 @@ void ggxSampleEvalPdfT(size_t n, const rls_shading_soa *sg, const rls_ggx_params
         if (out->fresnel) out->fresnel[i] = s.getAvgReflectWeight();
         uint32_t fl = bsdfFlags(L, sh.sg.Nf, f, pdf);
         if (AiV3Dot(sh.sg.N, sh.sg.Rd) < AI_EPSILON) fl |= RLS_FLAG_ENTERING;
+        if (UsesVndf<Sampler>::value) fl |= slopeEarlyOutFlag(sh, s.mAlphaX, s.mAlphaY, rx[i]);
         out->flags[i] = fl;
     }
 }
@@ -329,6 +352,7 @@ void oracle_disney_eval_sample(size_t n, const rls_shading_soa *sg, const rls_di
             if (AiV3IsZero(L)) fl |= RLS_FLAG_ZERO_L;
             if (AiV3Dot(L, sh.sg.Nf) <= 0.0f) fl |= RLS_FLAG_BELOW_HORIZON;
             if (sample_type != AI_RAY_DIFFUSE) fl |= disneyLobe(p, i, rx[i]) << RLS_FLAG_LOBE_SHIFT;
+            if (sample_type != AI_RAY_DIFFUSE) fl |= disneySlopeEarlyOut(p, i, sh, s, rx[i]);
             out_flags[i] = fl;
         }
     }
@@ -402,6 +426,7 @@ void oracle_disney_sample_eval_pdf(size_t n, const rls_shading_soa *sg,
 
         uint32_t fls = bsdfFlags(Ls, sh.sg.Nf, fs, ps) & ~RLS_FLAG_PDF_FLOORED;
         fls |= disneyLobe(p, i, rx_s[i]) << RLS_FLAG_LOBE_SHIFT;
+        fls |= disneySlopeEarlyOut(p, i, sh, s, rx_s[i]);
         uint32_t fld = bsdfFlags(Ld, sh.sg.Nf, fd, pd);
         out->flags[i] = fls | (fld << RLS_FLAG_DIFFUSE_SHIFT);
     }

@@ -124,9 +124,11 @@ static inline v2 uniform_slope(float rx, float ry)
     return s;
 }
 /* src/rlGgx.cpp:14-61 (VNDFKernel::sampleSlope) == src/rlDisney.cpp:416-463 */
+static _Thread_local int g_slope_early_out;    /* RLS_FLAG_SLOPE_EARLY_OUT of the last sample_slope call on this thread */
 static v2 sample_slope(float theta, float rx, float ry)
 {
     v2 slope;
+    g_slope_early_out = 1;
     if (theta < EPS) return uniform_slope(rx, ry);
 
     float B = tanf(theta);
@@ -136,6 +138,7 @@ static v2 sample_slope(float theta, float rx, float ry)
     float A = 2.0f * rx / G1 - 1.0f;
     float A2 = SQRF(A);
     if (ABSF(A2 - 1.0f) < EPS) return uniform_slope(rx, ry);
+    g_slope_early_out = 0;
 
     float tmp = 1.0f / (A2 - 1.0f);
     float D = sqrtf(MAXF(0.0f, B2 * SQRF(tmp) - (A2 - B2) * tmp));
@@ -231,6 +234,7 @@ static v3 sample_ndf_normal(v3 U, v3 Vax, v3 N, float ax, float ay, float rx, fl
 }
 static v3 ggx_sample_normal(const ggx_t *g, float rx, float ry)
 {
+    g_slope_early_out = 0;                       /* NDFKernel has no early-out */
     if (g->kernel == RLS_GGX_SAMPLER_NDF) return sample_ndf_normal(g->U, g->V, g->N, g->ax, g->ay, rx, ry);
     return sample_visible_normal(g->wo, g->U, g->V, g->N, g->ax, g->ay, rx, ry);
 }
@@ -389,6 +393,7 @@ static dielectric_t dielectric_unit(v3 U, v3 V, v3 N, v3 wo, int back, float ior
     r.pdf_r = ggx_eval_pdf(&g, r.wi_r);
     r.flags = bsdf_flags(r.wi_r, g.N, fr, r.pdf_r);
     if (g.entering) r.flags |= RLS_FLAG_ENTERING;
+    if (g_slope_early_out) r.flags |= RLS_FLAG_SLOPE_EARLY_OUT;
     v3 t;
     if (ggx_refract_direction(&g, m, g.wo, &t)) {
         r.wi_t = t;
@@ -552,6 +557,7 @@ static v3 disney_sample_gtr1(const disney_t *d, float rx, float ry)
 /* src/rlDisney.cpp:367-390; *lobe: 0 = GTR2, 1 = GTR1 */
 static v3 disney_sample_specular(const disney_t *d, float rx, float ry, uint32_t *lobe)
 {
+    g_slope_early_out = 0;                       /* set by the GTR2 visible-normal lobe only */
     v3 M;
     float gtr2Weight = 1.0f / (d->clearcoat + 1.0f);
     if (rx < gtr2Weight) {
@@ -762,6 +768,7 @@ void oracle_ggx_sample_eval_pdf(size_t n, const rls_shading_soa *sg, const rls_g
         if (out->fresnel) out->fresnel[i] = F;
         uint32_t fl = bsdf_flags(L, g.N, f, pdf);
         if (g.entering) fl |= RLS_FLAG_ENTERING;
+        if (g_slope_early_out) fl |= RLS_FLAG_SLOPE_EARLY_OUT;      /* set by ggx_eval_sample above */
         out->flags[i] = fl;
     }
 }
@@ -803,6 +810,7 @@ void oracle_disney_eval_sample(size_t n, const rls_shading_soa *sg, const rls_di
             if (iszero3(L)) fl |= RLS_FLAG_ZERO_L;
             if (dot3(L, d.N) <= 0.0f) fl |= RLS_FLAG_BELOW_HORIZON;
             fl |= lobe << RLS_FLAG_LOBE_SHIFT;
+            if (sample_type != RLS_RAY_DIFFUSE && g_slope_early_out) fl |= RLS_FLAG_SLOPE_EARLY_OUT;
             out_flags[i] = fl;
         }
     }
@@ -835,6 +843,7 @@ void oracle_disney_sample_eval_pdf(size_t n, const rls_shading_soa *sg,
         disney_t d; disney_init(&d, sg, p, i);
         uint32_t lobe = 0;
         v3 Ls = disney_sample_specular(&d, rx_s[i], ry_s[i], &lobe);
+        const int early = g_slope_early_out;
         v3 fs = disney_eval_brdf(&d, RLS_RAY_GLOSSY, Ls);
         float ps = disney_eval_pdf(&d, RLS_RAY_GLOSSY, Ls);
         v3 Ld = disney_sample_diffuse(&d, rx_d[i], ry_d[i]);
@@ -844,6 +853,7 @@ void oracle_disney_sample_eval_pdf(size_t n, const rls_shading_soa *sg,
         st3(out->wi_d, i, Ld); st3(out->f_d, i, fd); out->pdf_d[i] = pd;
         uint32_t fls = bsdf_flags(Ls, d.N, fs, ps) & ~RLS_FLAG_PDF_FLOORED;
         fls |= lobe << RLS_FLAG_LOBE_SHIFT;
+        if (early) fls |= RLS_FLAG_SLOPE_EARLY_OUT;
         uint32_t fld = bsdf_flags(Ld, d.N, fd, pd);
         out->flags[i] = fls | (fld << RLS_FLAG_DIFFUSE_SHIFT);
     }

@@ -35,20 +35,25 @@ SYMBOLS = [
     "rls_sample_writer_radiance", "rls_sample_writer_scatter",
 ]
 
-_lib = None
+# librls_b200_experiments.so: the same sources built with -DRLS_EXPERIMENTS (csrc/experiments/, kernels that
+# measured slower + their environment switches); only tests/test_experiments.py and the A/B tools load it.
+EXPERIMENTS_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "librls_b200_experiments.so")
+
+_libs = {}
 
 
-def load():
-    """Return the ctypes handle, loading it on first use.  Raises ImportError (never
-    falls back) when the CUDA library has not been built -- run __graft_entry__.build()."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def load(path=None):
+    """Return the ctypes handle of the product library (or of `path`, an alternative build of the SAME library),
+    loading it on first use.  Raises ImportError (never falls back) when the CUDA library has not been built --
+    run __graft_entry__.build()."""
+    path = path or LIB_PATH
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} is missing: the CUDA extension is not built "
+            f"{path} is missing: the CUDA extension is not built "
             "(python -c 'import __graft_entry__ as g; g.build()'). rlshaders_b200 has no CPU path.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, sz, u64, u32, i32, f = C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int, C.c_float
     P = C.POINTER
     sig = {
@@ -119,6 +124,6 @@ def load():
     lib.rls_node_name.argtypes = [i32]
     lib.rls_node_name.restype = C.c_char_p
     if lib.rls_abi_version() != abi.ABI_VERSION:
-        raise ImportError(f"{LIB_PATH}: ABI version {lib.rls_abi_version()} != {abi.ABI_VERSION}")
-    _lib = lib
+        raise ImportError(f"{path}: ABI version {lib.rls_abi_version()} != {abi.ABI_VERSION}")
+    _libs[path] = lib
     return lib

@@ -34,8 +34,8 @@ class Context:
     """Owns one rls_context bound to a CUDA device and a stream (default: torch's current
     stream on that device, so torch.cuda.Event timing sees the kernels)."""
 
-    def __init__(self, device=0, stream=None):
-        self.lib = load()
+    def __init__(self, device=0, stream=None, lib_path=None):
+        self.lib = load(lib_path)
         self.index = int(device if not isinstance(device, torch.device) else (device.index or 0))
         handle = C.c_void_p()
         if stream is None and torch.cuda.is_available():
@@ -71,9 +71,10 @@ class Context:
         return int(self.lib.rls_kernel_launch_count(self.handle))
 
     def set_arith_policy(self, policy):
-        """"fast" (default: guard-free IEEE sequences + exact re-run of out-of-window samples)
-        or "exact" (guarded operators only).  Same bits either way (csrc/rls_fp.cuh)."""
-        code = {"fast": 0, "exact": 1}[policy]
+        """"fast" (default: guard-free IEEE sequences + exact re-run of out-of-window samples) or "exact" (guarded
+        operators only): same bits either way (csrc/rls_fp.cuh).  "tolerant" (opt-in): the fused units to a stated
+        tolerance with bit-exact flags (csrc/rls_tol.cuh, include/rls_b200.h RLS_ARITH_TOLERANT)."""
+        code = {"fast": 0, "exact": 1, "tolerant": 2}[policy]
         _check(self.handle, self.lib.rls_set_arith_policy(self.handle, code), self.lib)
 
     def fallback_count(self, reset=False):

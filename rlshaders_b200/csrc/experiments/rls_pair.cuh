@@ -17,7 +17,7 @@
 // results are discarded, and anything they do to the operand tracker can only cause an exact
 // re-run.  tests/test_gpu_parity.py: paired == scalar exact policy == both oracles, bit for bit.
 #pragma once
-#include "rls_fused.cuh"
+#include "../rls_fused.cuh"
 #include "rls_f2.cuh"
 
 namespace rls {

@@ -25,9 +25,8 @@
 #include "rls_profile.cuh"
 #include "rls_fused.cuh"
 #include "rls_callers.cuh"
-#include "rls_pair.cuh"
-#include "rls_tile.cuh"
-#include "rls_packed.cuh"
+#include "rls_kernel_args.cuh"
+#include "rls_tol_launch.cuh"
 
 using namespace rls;
 
@@ -77,6 +76,15 @@ static constexpr int kBlockSkin = RLS_SKIN_BLOCK;
 static constexpr int kBlockSweep = RLS_SWEEP_BLOCK;
 static_assert(kBlock >= 96 && kBlockSkin >= 96, "rlm::smem_tables_init() fills 96 table entries with one thread each");
 
+#ifdef RLS_EXPERIMENTS
+// Only in librls_b200_experiments.so (tools/build_experiments.sh): A/B switches of kernels that measured slower.
+struct rls_experiments {
+    bool paired = false, tma = false, packed = false, disney_lobe_sort = false, gauss_scalar = false, sweep_fast = false;
+    int persistent = 0;              // CTAs per SM of the persistent dielectric kernel (negative: dynamic chunks)
+    unsigned stagger_ns = 0;
+    unsigned *chunk_counter = nullptr;
+};
+#endif
 struct rls_context {
     int          device = 0;
     cudaStream_t stream = nullptr;
@@ -84,20 +92,15 @@ struct rls_context {
     std::string  err;
     uint64_t     launches = 0;
     int          arith = RLS_ARITH_FAST;          // policy of the fused kernels (rls_fp.cuh)
-    bool         paired = false;                  // lane-paired evaluations inside one sample (rls_pair.cuh):
-                                                  // bit-exact, 5 % fewer issue slots, measured slower (RLS_PAIRED=1)
-    bool         tma = false;                     // persistent TMA-staged fused kernels (rls_tile.cuh); RLS_TMA=1
     int          sm_count = 0;
-    unsigned     stagger_ns = 0;                  // persistent kernels: start delay between the CTAs of an SM (RLS_STAGGER_NS)
-    int          persistent = 0;                  // CTAs per SM of the persistent grid-stride kernels; 0 = one CTA per tile (RLS_PERSISTENT)
-    bool         packed = false;                  // two-samples-per-thread kernel (rls_packed.cuh): bit-exact but
-                                                  // measured slower on B200 (latency bound at 128 registers), so
-                                                  // it is off unless RLS_PACKED=1 (kept for A/B runs and its test)
-    bool         disney_lobe_sort = false;        // CTA-level stable partition of the rlDisney samples by specular lobe: bit-identical,
-                                                  // measured 4 % SLOWER on B200 (16.02 vs 16.68 G samples/s), off unless RLS_DISNEY_LOBE_SORT=1
-    bool         gauss_scalar = false;            // GaussianProfile fused unit: one sample per thread instead of four (RLS_GAUSS_SCALAR=1, A/B)
-    unsigned long long *fallbacks = nullptr;      // device counter: samples re-run with FpExact
-    unsigned    *chunk_counter = nullptr;         // device counter of the dynamically scheduled persistent kernel
+    unsigned long long *fallbacks = nullptr;      // device counters: [0] samples re-run (FpFast -> FpExact; tolerance policy ->
+                                                  // bit-exact policy), [1] scratch (FpExact re-runs inside a tolerance re-run)
+    // RLS_ARITH_TOLERANT: one re-run list per stream the fused kernels are launched on (slot 0 = `stream`,
+    // 1.. = the host-staging streams), allocated on first use and grown when a larger batch arrives
+    tol::Worklist worklist[kStages + 1] = {};
+#ifdef RLS_EXPERIMENTS
+    rls_experiments exp;                          // switches of the measured-slower forms (experiments/rls_experiments.cuh)
+#endif
     // host-staging resources (lazily created by the *_host entry points)
     cudaStream_t stage_stream[kStages] = {};
     cudaEvent_t  stage_done[kStages] = {};
@@ -105,7 +108,14 @@ struct rls_context {
     size_t       stage_bytes = 0;
 };
 
+#ifdef RLS_EXPERIMENTS
+static int experiments_configure(rls_context *ctx);      // experiments/rls_experiments.cuh
+static void experiments_release(rls_context *ctx);
+#endif
+
 static thread_local std::string g_init_error;
+// The kernels that have no tolerance form run the fast (bit-exact) policy under RLS_ARITH_TOLERANT.
+static inline bool uses_fast_policy(const rls_context *ctx) { return ctx->arith != RLS_ARITH_EXACT; }
 
 static int fail(rls_context *ctx, int code, const std::string &msg)
 {
@@ -154,13 +164,6 @@ extern "C" int rls_init(int device, void *stream, rls_context **out_ctx)
                     "; kernels are built for sm_100a only");
     rls_context *ctx = new (std::nothrow) rls_context();
     if (!ctx) return fail(nullptr, RLS_ERR_OUT_OF_MEMORY, "rls_init: host allocation failed");
-    if (const char *v = getenv("RLS_PACKED")) ctx->packed = atoi(v) != 0;     // A/B switch for tuning runs
-    if (const char *v = getenv("RLS_PAIRED")) ctx->paired = atoi(v) != 0;     // A/B switch for tuning runs
-    if (const char *v = getenv("RLS_TMA")) ctx->tma = atoi(v) != 0;           // A/B switch for tuning runs
-    if (const char *v = getenv("RLS_PERSISTENT")) ctx->persistent = atoi(v);  // A/B switch for tuning runs
-    if (const char *v = getenv("RLS_STAGGER_NS")) ctx->stagger_ns = (unsigned)atoi(v);
-    if (const char *v = getenv("RLS_DISNEY_LOBE_SORT")) ctx->disney_lobe_sort = atoi(v) != 0;   // A/B switch
-    if (const char *v = getenv("RLS_GAUSS_SCALAR")) ctx->gauss_scalar = atoi(v) != 0;   // A/B switch
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     DeviceGuard guard(device);
@@ -171,18 +174,15 @@ extern "C" int rls_init(int device, void *stream, rls_context **out_ctx)
         if (e != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaStreamCreateWithFlags"); }
         ctx->own_stream = true;
     }
-    {   // {-0, -0} for the packed kernels' multiplies (rls_packed.cuh): a run-time value on purpose
-        const unsigned long long negzero2 = 0x8000000080000000ull;
-        e = cudaMemcpyToSymbol(pk::c_negzero2, &negzero2, sizeof(negzero2));
-        if (e != cudaSuccess) {
-            if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
-            delete ctx;
-            return cuda_fail(nullptr, e, "cudaMemcpyToSymbol(c_negzero2)");
-        }
+#ifdef RLS_EXPERIMENTS
+    if (experiments_configure(ctx) != RLS_OK) {
+        if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return RLS_ERR_CUDA;
     }
-    if (cudaMalloc((void **)&ctx->chunk_counter, sizeof(unsigned)) != cudaSuccess) ctx->chunk_counter = nullptr;
-    e = cudaMalloc((void **)&ctx->fallbacks, sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemset(ctx->fallbacks, 0, sizeof(unsigned long long));
+#endif
+    e = cudaMalloc((void **)&ctx->fallbacks, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ctx->fallbacks, 0, 2 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
         delete ctx;
@@ -195,8 +195,8 @@ extern "C" int rls_init(int device, void *stream, rls_context **out_ctx)
 extern "C" int rls_set_arith_policy(rls_context *ctx, int policy)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
-    if (policy != RLS_ARITH_FAST && policy != RLS_ARITH_EXACT)
-        return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "rls_set_arith_policy: policy must be RLS_ARITH_FAST or RLS_ARITH_EXACT");
+    if (policy != RLS_ARITH_FAST && policy != RLS_ARITH_EXACT && policy != RLS_ARITH_TOLERANT)
+        return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "rls_set_arith_policy: policy must be RLS_ARITH_FAST, RLS_ARITH_EXACT or RLS_ARITH_TOLERANT");
     ctx->arith = policy;
     return RLS_OK;
 }
@@ -226,7 +226,10 @@ extern "C" int rls_shutdown(rls_context *ctx)
         if (ctx->stage_buf[b]) cudaFree(ctx->stage_buf[b]);
     }
     if (ctx->fallbacks) cudaFree(ctx->fallbacks);
-    if (ctx->chunk_counter) cudaFree(ctx->chunk_counter);
+    for (tol::Worklist &w : ctx->worklist) { if (w.list) cudaFree(w.list); if (w.count) cudaFree(w.count); }
+#ifdef RLS_EXPERIMENTS
+    experiments_release(ctx);
+#endif
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RLS_OK;
@@ -280,7 +283,6 @@ static inline bool has3(const rls_vec3 &v) { return v.x && v.y && v.z; }
 static inline bool ok_shading(const rls_shading_soa *s) { return s && has3(s->U) && has3(s->V) && has3(s->N) && has3(s->wo); }
 static inline bool ok_p3(const rls_param3 &p) { return (!p.array.x && !p.array.y && !p.array.z) || has3(p.array); }
 
-struct GgxParamsDev { P3 ks; P1 rough, ior, aniso; int ndf; };
 static inline GgxParamsDev dev(const rls_ggx_params &p)
 {
     GgxParamsDev o; o.ks = p3(p.KsColor); o.rough = p1(p.specularRoughness); o.ior = p1(p.ior); o.aniso = p1(p.anisotropic);
@@ -305,12 +307,33 @@ static inline SkinParamsDev dev(const rls_skin_params &p)
     return o;
 }
 
+static inline BsdfOutDev dev(const rls_bsdf_out &o)
+{
+    BsdfOutDev d; d.wi = mv(o.wi); d.f = mv(o.f); d.pdf = o.pdf; d.fresnel = o.fresnel; d.flags = o.flags; return d;
+}
+static inline DielectricOutDev dev(const rls_ggx_dielectric_out &o)
+{
+    DielectricOutDev d; d.fresnel = o.fresnel; d.wi_r = mv(o.wi_r); d.f_r = o.f_r; d.pdf_r = o.pdf_r;
+    d.wi_t = mv(o.wi_t); d.f_t = o.f_t; d.weight_t = o.weight_t; d.flags = o.flags; return d;
+}
+static inline DisneyOutDev dev(const rls_disney_out &o)
+{
+    DisneyOutDev d; d.wi_s = mv(o.wi_s); d.f_s = mv(o.f_s); d.pdf_s = o.pdf_s;
+    d.wi_d = mv(o.wi_d); d.f_d = mv(o.f_d); d.pdf_d = o.pdf_d; d.flags = o.flags; return d;
+}
+static inline ProfileOutDev dev(const rls_profile_out &o)
+{
+    ProfileOutDev d; d.r = o.r; d.pdf = o.pdf; d.Rd = mv(o.Rd); d.flags = o.flags; return d;
+}
+
 static inline unsigned grid_for(size_t n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
+#ifdef RLS_EXPERIMENTS
 static inline bool aligned8(std::initializer_list<const void *> ptrs)
 {
     for (const void *q : ptrs) if ((uintptr_t)q & 7u) return false;
     return true;
 }
+#endif
 // 32-bit sample index: one IMAD.WIDE per array address instead of a 64-bit add pair; the entry
 // points reject n >= 2^32 (that many samples would not fit in HBM anyway).
 #define RLS_INDEX()                                                            \
@@ -379,11 +402,9 @@ RLS_DEV GgxBsdf ggx_unit_from(Fp &fp, const Shading &s, f3 ks, float ior, float 
     return ggx_unit(fp, g, rx, ry);
 }
 template <bool kFast>
-__global__ void __launch_bounds__(kBlockGgx, RLS_GGX_MIN_BLOCKS)
-k_ggx_sample_eval_pdf(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry,
-                      V3 wi, V3 f, float *pdf, float *fresnel, uint32_t *flags, unsigned long long *fallbacks)
+RLS_DEV void ggx_sample(uint32_t i, const ShadingSoA &sg, const GgxParamsDev &p, const float *rx, const float *ry,
+                        const V3 &wi, const V3 &f, float *pdf, float *fresnel, uint32_t *flags, unsigned long long *fallbacks)
 {
-    RLS_INDEX();
     GgxBsdf o;
     bool ok = false;
     if (kFast) {
@@ -406,23 +427,52 @@ k_ggx_sample_eval_pdf(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, 
     if (fresnel) fresnel[i] = o.fresnel;
     flags[i] = o.flags;
 }
+template <bool kFast>
+__global__ void __launch_bounds__(kBlockGgx, RLS_GGX_MIN_BLOCKS)
+k_ggx_sample_eval_pdf(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry,
+                      V3 wi, V3 f, float *pdf, float *fresnel, uint32_t *flags, unsigned long long *fallbacks)
+{
+    RLS_INDEX();
+    ggx_sample<kFast>(i, sg, p, rx, ry, wi, f, pdf, fresnel, flags, fallbacks);
+}
 
-struct DielectricOutDev { float *fresnel; V3 wi_r; float *f_r, *pdf_r; V3 wi_t; float *f_t, *weight_t; uint32_t *flags; };
+// ---- RLS_ARITH_TOLERANT: the bit-exact re-run of the samples a tolerance kernel listed (rls_tol_launch.cuh).
+// `body(i)` evaluates sample i with the fast policy (+ its own exact re-run) and overwrites its outputs.
+template <class Body>
+RLS_DEV void rerun_listed(uint32_t n, const tol::Worklist &wl, const uint32_t *flags, unsigned long long *fallbacks, Body body)
+{
+    const unsigned c = *wl.count;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    if (tid == 0 && c) atomicAdd(fallbacks, (unsigned long long)c);
+    const unsigned listed = c < wl.cap ? c : wl.cap;
+    for (uint32_t k = tid; k < listed; k += stride) body(wl.list[k]);
+    if (c > wl.cap)                      // list overflow: the remaining samples carry the sentinel in their flags word
+        for (uint32_t i = tid; i < n; i += stride)
+            if (flags[i] == tol::kRerunSentinel) body(i);
+}
+__global__ void __launch_bounds__(kBlockGgx, RLS_GGX_MIN_BLOCKS)
+k_ggx_sample_eval_pdf_rerun(uint32_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, BsdfOutDev o,
+                            tol::Worklist wl, unsigned long long *fallbacks)
+{
+    rerun_listed(n, wl, o.flags, fallbacks, [&](uint32_t i) {
+        ggx_sample<true>(i, sg, p, rx, ry, o.wi, o.f, o.pdf, o.fresnel, o.flags, fallbacks + 1);
+    });
+}
 
-template <bool kFast, bool kArrays, bool kPair>   // kArrays: ior and specularRoughness are per-sample arrays
+
+template <bool kFast, bool kArrays>   // kArrays: ior and specularRoughness are per-sample arrays
 RLS_DEV void dielectric_sample(uint32_t i, const ShadingSoA &sg, const GgxParamsDev &p, const float *rx, const float *ry,
                                const DielectricOutDev &o, unsigned long long *fallbacks)
 {
     Dielectric r;
     bool ok = false;
-    if (kFast) {        // kPair: reflection and refraction evaluations paired lane-wise (rls_pair.cuh)
+    if (kFast) {
         const Shading s = load_shading(sg, i);
         const float ior = fetch_t<kArrays>(p.ior, i), rough = fetch_t<kArrays>(p.rough, i), aniso = fetch(p.aniso, i);
         const float u1 = __ldg(rx + i), u2 = __ldg(ry + i);
         FpFast fp;
         // (dielectric_unit<kFlat = true>, the select form of the refraction branch, measured neutral: +-0.3 %)
-        r = kPair ? pk::dielectric_unit_paired(fp, s, ior, rough, aniso, u1, u2, p.ndf != 0)
-                  : dielectric_unit(fp, s, ior, rough, aniso, u1, u2, p.ndf != 0);
+        r = dielectric_unit(fp, s, ior, rough, aniso, u1, u2, p.ndf != 0);
         ok = fp.ok();
     }
     if (!ok) {
@@ -444,186 +494,22 @@ RLS_DEV void dielectric_sample(uint32_t i, const ShadingSoA &sg, const GgxParams
     o.weight_t[i] = r.w_t;
     o.flags[i] = r.flags;
 }
-template <bool kFast, bool kArrays, bool kPair>
+template <bool kFast, bool kArrays>
 __global__ void __launch_bounds__(kBlockGgx, RLS_GGX_MIN_BLOCKS)
 k_ggx_dielectric(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, DielectricOutDev o,
                  unsigned long long *fallbacks)
 {
     RLS_INDEX();
-    dielectric_sample<kFast, kArrays, kPair>(i, sg, p, rx, ry, o, fallbacks);
+    dielectric_sample<kFast, kArrays>(i, sg, p, rx, ry, o, fallbacks);
 }
-// Persistent form: grid = resident CTAs (a multiple of the SM count), every thread strides over the
-// batch.  No CTA turnover (a CTA slot of the plain kernel stays partly empty until its slowest warp
-// retires).  Measured SLOWER (static split, see k_ggx_dielectric_dynamic below); kept for A/B runs.
-template <bool kFast, bool kArrays, bool kPair>
-__global__ void __launch_bounds__(kBlockGgx, RLS_GGX_MIN_BLOCKS)
-k_ggx_dielectric_persistent(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, DielectricOutDev o,
-                            unsigned long long *fallbacks, unsigned stagger_ns, unsigned sm_count)
-{
-    // phase-shift the CTAs that share an SM (the first wave is dealt round-robin: CTA b runs on SM b % sm_count)
-    if (stagger_ns) __nanosleep((blockIdx.x / sm_count) * stagger_ns);
-    const uint32_t stride = gridDim.x * blockDim.x;
-#pragma unroll 1
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)n; i += stride)
-        dielectric_sample<kFast, kArrays, kPair>(i, sg, p, rx, ry, o, fallbacks);
-}
-
-// Persistent form with DYNAMIC work distribution: every warp draws 128-sample chunks from a global counter
-// (the next index is fetched while the current chunk computes).  The static grid-stride form above loses
-// 13 %: the warp arbiter is unfair, CTAs in favoured slots finish their share early and the SM runs its tail at
-// low occupancy (ncu: 40.5 % average active warps with 9 resident CTAs per SM, 49.1 % for the plain kernel).
-template <bool kFast, bool kArrays, bool kPair>
-__global__ void __launch_bounds__(kBlockGgx, RLS_GGX_MIN_BLOCKS)
-k_ggx_dielectric_dynamic(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, DielectricOutDev o,
-                         unsigned long long *fallbacks, unsigned *counter)
-{
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n_chunks = (uint32_t)((n + 127u) / 128u);
-    uint32_t c = 0;
-    if (lane == 0) c = atomicAdd(counter, 1u);
-    c = __shfl_sync(0xffffffffu, c, 0);
-    while (c < n_chunks) {
-        uint32_t nxt = 0;
-        if (lane == 0) nxt = atomicAdd(counter, 1u);
-#pragma unroll 1
-        for (uint32_t j = 0; j < 4u; j++) {
-            const uint32_t i = c * 128u + j * 32u + lane;
-            if (i < (uint32_t)n) dielectric_sample<kFast, kArrays, kPair>(i, sg, p, rx, ry, o, fallbacks);
-        }
-        c = __shfl_sync(0xffffffffu, nxt, 0);
-    }
-}
-
-// Persistent, TMA-staged form of k_ggx_dielectric (rls_tile.cuh): grid = resident CTAs, every CTA
-// walks whole 256-sample tiles; the inputs of the next tile are in flight while this one computes.
-// Fast policy only (the launch site keeps the plain kernel for the exact policy, unaligned arrays
-// and the ragged tail); a sample whose operands left the window reloads its inputs from global
-// memory and is re-run with FpExact, as in the plain kernel.
-namespace dielectric_slots {
-enum In { U = 0, V = 3, N = 6, WO = 9, RX = 12, RY = 13, ROUGH = 14, IOR = 15, ANISO = 16, BACK = 17, kIn = 18 };
-enum Out { FRESNEL = 0, WI_R = 1, F_R = 4, PDF_R = 5, WI_T = 6, F_T = 9, WEIGHT_T = 10, FLAGS = 11, kOut = 12 };
-}
-template <bool kArrays, bool kPair>
-__global__ void __launch_bounds__(tile::kTile, 4)
-k_ggx_dielectric_tma(uint32_t n_tiles, const __grid_constant__ tile::Arrays arr, ShadingSoA sg, GgxParamsDev p,
-                     const float *rx, const float *ry, unsigned long long *fallbacks)
-{
-    using namespace dielectric_slots;
-    __shared__ __align__(128) unsigned char smem[tile::Pipe<kIn, kOut>::kSmemBytes];
-    __shared__ uint64_t bar;
-    tile::Pipe<kIn, kOut> pipe;
-    pipe.init(&arr, smem, &bar);
-    const uint32_t tid = threadIdx.x;
-    uint32_t t = blockIdx.x;
-    if (t < n_tiles) pipe.issue_loads(t);
-#pragma unroll 1
-    for (; t < n_tiles; t += gridDim.x) {
-        pipe.wait_inputs();
-#define RLS_IN(k) pipe.in_slot(k)[tid]
-        Shading s;
-        s.U = mk3(RLS_IN(U), RLS_IN(U + 1), RLS_IN(U + 2));
-        s.V = mk3(RLS_IN(V), RLS_IN(V + 1), RLS_IN(V + 2));
-        s.N = mk3(RLS_IN(N), RLS_IN(N + 1), RLS_IN(N + 2));
-        s.wo = mk3(RLS_IN(WO), RLS_IN(WO + 1), RLS_IN(WO + 2));
-        s.backfacing = sg.backfacing ? (reinterpret_cast<const uint8_t *>(pipe.in_slot(BACK))[tid] != 0) : false;
-        const float ior = (kArrays || p.ior.array) ? RLS_IN(IOR) : p.ior.value;
-        const float rough = (kArrays || p.rough.array) ? RLS_IN(ROUGH) : p.rough.value;
-        const float aniso = p.aniso.array ? RLS_IN(ANISO) : p.aniso.value;
-        const float u1 = RLS_IN(RX), u2 = RLS_IN(RY);
-#undef RLS_IN
-        pipe.inputs_consumed(t + gridDim.x, n_tiles);
-        Dielectric r;
-        bool ok;
-        {
-            FpFast fp;
-            r = kPair ? pk::dielectric_unit_paired(fp, s, ior, rough, aniso, u1, u2, p.ndf != 0)
-                      : dielectric_unit(fp, s, ior, rough, aniso, u1, u2, p.ndf != 0);
-            ok = fp.ok();
-        }
-        if (!ok) {
-            const uint32_t i = t * tile::kTile + tid;
-            const Shading se = load_shading<true>(sg, i);
-            FpExact fp;
-            r = dielectric_unit(fp, se, fetch<true>(p.ior, i), fetch<true>(p.rough, i), fetch<true>(p.aniso, i),
-                                __ldcg(rx + i), __ldcg(ry + i), p.ndf != 0);
-            atomicAdd(fallbacks, 1ull);
-        }
-        pipe.begin_store();
-#define RLS_OUT(k) pipe.out_slot(k)[tid]
-        RLS_OUT(FRESNEL) = r.F;
-        RLS_OUT(WI_R) = r.wi_r.x; RLS_OUT(WI_R + 1) = r.wi_r.y; RLS_OUT(WI_R + 2) = r.wi_r.z;
-        RLS_OUT(F_R) = r.f_r;
-        RLS_OUT(PDF_R) = r.pdf_r;
-        RLS_OUT(WI_T) = r.wi_t.x; RLS_OUT(WI_T + 1) = r.wi_t.y; RLS_OUT(WI_T + 2) = r.wi_t.z;
-        RLS_OUT(F_T) = r.f_t;
-        RLS_OUT(WEIGHT_T) = r.w_t;
-        RLS_OUT(FLAGS) = __uint_as_float(r.flags);
-#undef RLS_OUT
-        pipe.end_store(t);
-    }
-    pipe.finish();
-}
-
-// Two samples per thread, packed f32x2 arithmetic (rls_packed.cuh): thread t owns samples 2t and
-// 2t + 1 of every SoA array (one 64-bit load / store each).  Fast policy only; a pair whose
-// tracker left the window is re-run lane by lane with the scalar FpExact unit.
-// EXPERIMENT, off by default (RLS_PACKED=1): 22 % fewer issue slots per sample (1092 vs 1396 per
-// 32 samples) but 128 registers/thread leave 4 warps per scheduler, issue utilisation drops from
-// 85 % to 48 % and the kernel runs at 16.2 instead of 22.6 G samples/s; capping registers at
-// 80 / 64 spills and is slower still (15.9 / 14.5).  profiles/r01_packed_experiment.md.
-#ifndef RLS_PACKED_MIN_BLOCKS
-#define RLS_PACKED_MIN_BLOCKS 2
-#endif
 template <bool kArrays>
-__global__ void __launch_bounds__(kBlock, RLS_PACKED_MIN_BLOCKS)
-k_ggx_dielectric2(size_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, DielectricOutDev o,
-                  unsigned long long *fallbacks)
+__global__ void __launch_bounds__(kBlockGgx, RLS_GGX_MIN_BLOCKS)
+k_ggx_dielectric_rerun(uint32_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, DielectricOutDev o,
+                       tol::Worklist wl, unsigned long long *fallbacks)
 {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (uint32_t)((n + 1) / 2)) return;
-    const bool tail = 2u * t + 1u >= (uint32_t)n;
-    const pk::V2 U = pk::ld2(sg.U, t, tail), V = pk::ld2(sg.V, t, tail), N = pk::ld2(sg.N, t, tail), wo = pk::ld2(sg.wo, t, tail);
-    pk::B2 back; back.a = false; back.b = false;
-    if (sg.backfacing) {
-        back.a = __ldg(sg.backfacing + 2u * t) != 0;
-        back.b = tail ? back.a : (__ldg(sg.backfacing + 2u * t + 1u) != 0);
-    }
-    const pk::F2 ior = kArrays ? pk::ld2(p.ior.array, t, tail) : pk::fetch2(p.ior, t, tail);
-    const pk::F2 rough = kArrays ? pk::ld2(p.rough.array, t, tail) : pk::fetch2(p.rough, t, tail);
-    const pk::F2 aniso = pk::fetch2(p.aniso, t, tail);
-    const pk::F2 u1 = pk::ld2(rx, t, tail), u2 = pk::ld2(ry, t, tail);
-    pk::Fp2 fp;
-    pk::Dielectric2 r = pk::dielectric_unit(fp, U, V, N, wo, back, ior, rough, aniso, u1, u2);
-    if (!fp.ok()) {
-        atomicAdd(fallbacks, tail ? 1ull : 2ull);
-#pragma unroll 1
-        for (int l = 0; l < 2; l++) {
-            Shading s;
-            s.U = l ? pk::lane1(U) : pk::lane0(U); s.V = l ? pk::lane1(V) : pk::lane0(V);
-            s.N = l ? pk::lane1(N) : pk::lane0(N); s.wo = l ? pk::lane1(wo) : pk::lane0(wo);
-            s.backfacing = l ? back.b : back.a;
-            FpExact fe;
-            const Dielectric e = dielectric_unit(fe, s, l ? pk::hi(ior) : pk::lo(ior), l ? pk::hi(rough) : pk::lo(rough),
-                                                 l ? pk::hi(aniso) : pk::lo(aniso), l ? pk::hi(u1) : pk::lo(u1),
-                                                 l ? pk::hi(u2) : pk::lo(u2), false);
-#define RLS_SET_LANE(dst, val) dst = l ? pk::mk(pk::lo(dst), (val)) : pk::mk((val), pk::hi(dst))
-            RLS_SET_LANE(r.F, e.F); RLS_SET_LANE(r.f_r, e.f_r); RLS_SET_LANE(r.pdf_r, e.pdf_r);
-            RLS_SET_LANE(r.f_t, e.f_t); RLS_SET_LANE(r.w_t, e.w_t);
-            RLS_SET_LANE(r.wi_r.x, e.wi_r.x); RLS_SET_LANE(r.wi_r.y, e.wi_r.y); RLS_SET_LANE(r.wi_r.z, e.wi_r.z);
-            RLS_SET_LANE(r.wi_t.x, e.wi_t.x); RLS_SET_LANE(r.wi_t.y, e.wi_t.y); RLS_SET_LANE(r.wi_t.z, e.wi_t.z);
-#undef RLS_SET_LANE
-            if (l) r.flags1 = e.flags; else r.flags0 = e.flags;
-        }
-    }
-    pk::st2(o.fresnel, t, tail, r.F);
-    pk::st2(o.wi_r, t, tail, r.wi_r);
-    pk::st2(o.f_r, t, tail, r.f_r);
-    pk::st2(o.pdf_r, t, tail, r.pdf_r);
-    pk::st2(o.wi_t, t, tail, r.wi_t);
-    pk::st2(o.f_t, t, tail, r.f_t);
-    pk::st2(o.weight_t, t, tail, r.w_t);
-    if (tail) o.flags[2u * t] = r.flags0;
-    else reinterpret_cast<uint2 *>(o.flags)[t] = make_uint2(r.flags0, r.flags1);
+    rerun_listed(n, wl, o.flags, fallbacks, [&](uint32_t i) {
+        dielectric_sample<true, kArrays>(i, sg, p, rx, ry, o, fallbacks + 1);
+    });
 }
 
 // ============================================================= rlDisney kernels
@@ -634,11 +520,12 @@ k_disney_eval_sample(size_t n, ShadingSoA sg, DisneyParamsDev p, int type, const
     FpExact fp;
     Disney d; disney_init(fp, d, load_shading(sg, i), p, i);
     uint32_t lobe = 0;
+    bool early = false;
     f3 L = (type == kRayDiffuse) ? disney_sample_diffuse(fp, d, __ldg(rx + i), __ldg(ry + i))
-                                 : disney_sample_specular(fp, d, __ldg(rx + i), __ldg(ry + i), lobe);
+                                 : disney_sample_specular(fp, d, __ldg(rx + i), __ldg(ry + i), lobe, &early);
     store3(wi, i, L);
     if (flags) {
-        uint32_t fl = lobe << RLS_FLAG_LOBE_SHIFT;
+        uint32_t fl = (lobe << RLS_FLAG_LOBE_SHIFT) | (early ? RLS_FLAG_SLOPE_EARLY_OUT : 0u);
         if (is_zero(L)) fl |= RLS_FLAG_ZERO_L;
         if (dot(L, d.N) <= 0.0f) fl |= RLS_FLAG_BELOW_HORIZON;
         flags[i] = fl;
@@ -661,7 +548,6 @@ k_disney_eval_pdf(size_t n, ShadingSoA sg, DisneyParamsDev p, int type, CV3 wi, 
     pdf[i] = disney_eval_pdf(fp, d, type, load3(wi, i));
 }
 
-struct DisneyOutDev { V3 wi_s, f_s; float *pdf_s; V3 wi_d, f_d; float *pdf_d; uint32_t *flags; };
 
 template <bool kArrays, bool kReload, class Fp>
 RLS_DEV DisneyOut1 disney_unit_from(Fp &fp, const Shading &s, const DisneyParamsDev &p, uint32_t i,
@@ -670,51 +556,11 @@ RLS_DEV DisneyOut1 disney_unit_from(Fp &fp, const Shading &s, const DisneyParams
     Disney d; disney_init<kArrays, kReload>(fp, d, s, p, i);
     return disney_unit(fp, d, rx_s, ry_s, rx_d, ry_d);
 }
-// Warp-uniform lobe selection (BASELINE north_star): a stable partition of the CTA's samples by specular lobe, so that
-// the ~10 % of samples that take the GTR1 (clearcoat) lobe sit together in the CTA's last warp(s) instead of making
-// almost every warp (1 - 0.9^32 = 97 %) run the GTR1-only code (general powf) for three lanes AND the GTR2-only code
-// (visible-normal sampling) for the rest.  Thread t then works on sample base + perm[t]; GTR2 samples keep their order,
-// so a warp's loads span ~36 consecutive samples instead of 32.  The predicate only steers the grouping (results do
-// not depend on it), so it is the approximate rx (c' + 1) < 1 rather than the unit's exact rx < 1 / (c' + 1).
-// MEASURED (tools/disney_ab.py, 2^26 samples, every parameter per sample): 16.02 G samples/s against 16.68 without it --
-// the GTR1-only code the other warps skip (98 slots of 1768 per warp, ncu) is worth less than the partition costs (two CTA barriers
-// before the first load of the unit can issue, ~50 slots, 29 loads and 15 stores per sample over two cache lines).
-// Kept behind RLS_DISNEY_LOBE_SORT=1 with its test (tests/test_gpu_parity.py::test_disney_lobe_partition_is_invisible).
-template <bool kArrays>
-RLS_DEV uint32_t disney_lobe_partition(size_t n, const DisneyParamsDev &p, const float *rx_s)
+// One rlDisney sample: fast policy, exact re-run when an operand left the window.
+template <bool kFast, bool kArrays>
+RLS_DEV void disney_sample(uint32_t i, const ShadingSoA &sg, const DisneyParamsDev &p, const float *rx_s, const float *ry_s,
+                           const float *rx_d, const float *ry_d, const DisneyOutDev &o, unsigned long long *fallbacks)
 {
-    __shared__ uint16_t perm[kBlock];
-    __shared__ uint32_t gtr1_in_warp[kBlock / 32];
-    const uint32_t t = threadIdx.x, lane = t & 31u, w = t >> 5, base = blockIdx.x * blockDim.x;
-    bool gtr1 = true;                                   // samples past the end are grouped with the last warp
-    if (base + t < (uint32_t)n) {
-        const float c = fetch_t<kArrays>(p.clearcoat, base + t) * 0.25f;
-        gtr1 = !(__ldg(rx_s + base + t) * (c + 1.0f) < 1.0f);
-    }
-    const uint32_t b = __ballot_sync(0xffffffffu, gtr1);
-    if (lane == 0) gtr1_in_warp[w] = __popc(b);
-    __syncthreads();
-    uint32_t before = 0, total = 0;                     // GTR1 samples in the warps before this one / in the CTA
-#pragma unroll
-    for (uint32_t k = 0; k < kBlock / 32; k++) {
-        const uint32_t c = gtr1_in_warp[k];
-        before += k < w ? c : 0u;
-        total += c;
-    }
-    const uint32_t mine = __popc(b & ((1u << lane) - 1u));
-    const uint32_t pos = gtr1 ? (kBlock - total) + before + mine : (t - before - mine);
-    perm[pos] = (uint16_t)t;
-    __syncthreads();
-    return base + perm[t];
-}
-template <bool kFast, bool kArrays, bool kLobeSort = false>
-__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
-k_disney_sample_eval_pdf(size_t n, ShadingSoA sg, DisneyParamsDev p, const float *rx_s, const float *ry_s,
-                         const float *rx_d, const float *ry_d, DisneyOutDev o, unsigned long long *fallbacks)
-{
-    if (kFast) rlm::smem_tables_init();      // exp2 / log / log2 tables in shared memory (before the early exit below)
-    const uint32_t i = kLobeSort ? disney_lobe_partition<kArrays>(n, p, rx_s) : blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (uint32_t)n) return;
     DisneyOut1 r;
     bool ok = false;
     if (kFast) {
@@ -732,6 +578,26 @@ k_disney_sample_eval_pdf(size_t n, ShadingSoA sg, DisneyParamsDev p, const float
     store3(o.wi_s, i, r.Ls); store3(o.f_s, i, r.fs); o.pdf_s[i] = r.ps;
     store3(o.wi_d, i, r.Ld); store3(o.f_d, i, r.fd); o.pdf_d[i] = r.pd;
     o.flags[i] = r.flags;
+}
+template <bool kFast, bool kArrays>
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+k_disney_sample_eval_pdf(size_t n, ShadingSoA sg, DisneyParamsDev p, const float *rx_s, const float *ry_s,
+                         const float *rx_d, const float *ry_d, DisneyOutDev o, unsigned long long *fallbacks)
+{
+    if (kFast) rlm::smem_tables_init();      // exp2 / log / log2 tables in shared memory (before the early exit below)
+    RLS_INDEX();
+    disney_sample<kFast, kArrays>(i, sg, p, rx_s, ry_s, rx_d, ry_d, o, fallbacks);
+}
+template <bool kArrays>
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+k_disney_sample_eval_pdf_rerun(uint32_t n, ShadingSoA sg, DisneyParamsDev p, const float *rx_s, const float *ry_s,
+                               const float *rx_d, const float *ry_d, DisneyOutDev o, tol::Worklist wl,
+                               unsigned long long *fallbacks)
+{
+    rlm::smem_tables_init();
+    rerun_listed(n, wl, o.flags, fallbacks, [&](uint32_t i) {
+        disney_sample<true, kArrays>(i, sg, p, rx_s, ry_s, rx_d, ry_d, o, fallbacks + 1);
+    });
 }
 
 // ================================================================ profile kernels
@@ -858,7 +724,6 @@ k_gauss_profile_x4(size_t n4, const float4 *dist_x, const float4 *rx, float4 *r,
     rd[i] = make_float4(o[0].rd, o[1].rd, o[2].rd, o[3].rd);
     pdf[i] = make_float4(o[0].pdf, o[1].pdf, o[2].pdf, o[3].pdf);
 }
-struct ProfileOutDev { float *r, *pdf; V3 Rd; uint32_t *flags; };
 struct Profile1 { float r, pdf; f3 Rd; uint32_t flags; };
 template <class Fp>
 RLS_DEV Profile1 skin_profile_unit(Fp &fp, f3 dist, float rx)
@@ -870,11 +735,8 @@ RLS_DEV Profile1 skin_profile_unit(Fp &fp, f3 dist, float rx)
     return o;
 }
 template <bool kFast>
-__global__ void __launch_bounds__(kBlockSkin, RLS_SKIN_MIN_BLOCKS)
-k_skin_profile(size_t n, SkinParamsDev sp, const float *rx, ProfileOutDev o, unsigned long long *fallbacks)
+RLS_DEV void skin_sample(uint32_t i, const SkinParamsDev &sp, const float *rx, const ProfileOutDev &o, unsigned long long *fallbacks)
 {
-    if (kFast) rlm::smem_tables_init();      // exp2 / log tables in shared memory (before the early exit below)
-    RLS_INDEX();
     Profile1 r;
     bool ok = false;
     if (kFast) {
@@ -891,6 +753,20 @@ k_skin_profile(size_t n, SkinParamsDev sp, const float *rx, ProfileOutDev o, uns
     o.pdf[i] = r.pdf;
     store3(o.Rd, i, r.Rd);
     o.flags[i] = r.flags;
+}
+template <bool kFast>
+__global__ void __launch_bounds__(kBlockSkin, RLS_SKIN_MIN_BLOCKS)
+k_skin_profile(size_t n, SkinParamsDev sp, const float *rx, ProfileOutDev o, unsigned long long *fallbacks)
+{
+    if (kFast) rlm::smem_tables_init();      // exp2 / log tables in shared memory (before the early exit below)
+    RLS_INDEX();
+    skin_sample<kFast>(i, sp, rx, o, fallbacks);
+}
+__global__ void __launch_bounds__(kBlockSkin, RLS_SKIN_MIN_BLOCKS)
+k_skin_profile_rerun(uint32_t n, SkinParamsDev sp, const float *rx, ProfileOutDev o, tol::Worklist wl, unsigned long long *fallbacks)
+{
+    rlm::smem_tables_init();
+    rerun_listed(n, wl, o.flags, fallbacks, [&](uint32_t i) { skin_sample<true>(i, sp, rx, o, fallbacks + 1); });
 }
 // src/rlSkin.cpp:191,204,214,228,231,238
 __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
@@ -1226,150 +1102,126 @@ k_albedo_sweep(SweepGridDev g, uint64_t seed, uint32_t k0, uint32_t k1, double *
 #define RLS_REQUIRE(ctx, cond, msg)                                              \
     do { if (!(cond)) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, msg); } while (0)
 
+// ---- RLS_ARITH_TOLERANT plumbing: the re-run list of the stream a fused kernel is launched on
+static int worklist_for(rls_context *ctx, cudaStream_t st, size_t n, tol::Worklist *out)
+{
+    int slot = 0;
+    for (int b = 0; b < kStages; b++) if (ctx->stage_stream[b] && st == ctx->stage_stream[b]) slot = b + 1;
+    tol::Worklist &w = ctx->worklist[slot];
+    // capacity: 1/16 of the batch (the bands list ~5e-4 of the samples), at least 64 Ki entries; a fuller list falls
+    // back to the sentinel scan (rls_tol_launch.cuh), so the capacity is a performance choice, not a correctness one
+    size_t want = n / 16 < 65536 ? 65536 : n / 16;
+    if (want > n) want = n;
+    if (!w.count) {
+        RLS_CUDA(ctx, cudaMalloc((void **)&w.count, sizeof(unsigned)));
+    }
+    if (w.cap < want) {
+        RLS_CUDA(ctx, cudaStreamSynchronize(st));        // an earlier launch on this stream may still use the old list
+        if (w.list) { RLS_CUDA(ctx, cudaFree(w.list)); w.list = nullptr; w.cap = 0; }
+        RLS_CUDA(ctx, cudaMalloc((void **)&w.list, want * sizeof(uint32_t)));
+        w.cap = (uint32_t)want;
+    }
+    RLS_CUDA(ctx, cudaMemsetAsync(w.count, 0, sizeof(unsigned), st));
+    *out = w;
+    return RLS_OK;
+}
+static inline unsigned rerun_grid(const rls_context *ctx) { return (unsigned)(ctx->sm_count * 2); }
+#define RLS_TOL_CHECK(ctx, call)                                        \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(ctx, e_, "tolerance-policy kernel launch"); \
+         (ctx)->launches++; } while (0)
+
 static int launch_ggx_sample_eval_pdf(rls_context *ctx, cudaStream_t st, size_t n, const rls_shading_soa *sg,
                                       const rls_ggx_params *p, const float *rx, const float *ry, const rls_bsdf_out *o)
 {
-    if (ctx->arith == RLS_ARITH_FAST)
+    if (ctx->arith == RLS_ARITH_TOLERANT && p->normal_sampler == RLS_GGX_SAMPLER_VNDF) {
+        tol::Worklist wl;
+        const int rc = worklist_for(ctx, st, n, &wl);
+        if (rc != RLS_OK) return rc;
+        RLS_TOL_CHECK(ctx, tol::launch_ggx_sample_eval_pdf(st, n, sh(*sg), dev(*p), rx, ry, dev(*o), wl));
+        k_ggx_sample_eval_pdf_rerun<<<rerun_grid(ctx), kBlockGgx, 0, st>>>((uint32_t)n, sh(*sg), dev(*p), rx, ry, dev(*o), wl, ctx->fallbacks);
+        RLS_LAUNCH_CHECK(ctx);
+        return RLS_OK;
+    }
+    if (uses_fast_policy(ctx))
         k_ggx_sample_eval_pdf<true><<<grid_for(n, kBlockGgx), kBlockGgx, 0, st>>>(n, sh(*sg), dev(*p), rx, ry, mv(o->wi), mv(o->f), o->pdf, o->fresnel, o->flags, ctx->fallbacks);
     else
         k_ggx_sample_eval_pdf<false><<<grid_for(n, kBlockGgx), kBlockGgx, 0, st>>>(n, sh(*sg), dev(*p), rx, ry, mv(o->wi), mv(o->f), o->pdf, o->fresnel, o->flags, ctx->fallbacks);
     RLS_LAUNCH_CHECK(ctx);
     return RLS_OK;
 }
-// ---- persistent TMA-staged launches (rls_tile.cuh): helpers shared by the fused entry points
-static inline rls_cvec3 adv(rls_cvec3 v, size_t k) { rls_cvec3 o = { v.x ? v.x + k : nullptr, v.y ? v.y + k : nullptr, v.z ? v.z + k : nullptr }; return o; }
-static inline rls_vec3 adv(rls_vec3 v, size_t k) { rls_vec3 o = { v.x ? v.x + k : nullptr, v.y ? v.y + k : nullptr, v.z ? v.z + k : nullptr }; return o; }
-template <typename T> static inline T *adv(T *q, size_t k) { return q ? q + k : nullptr; }
-static inline rls_param1 adv(rls_param1 q, size_t k) { q.array = adv(q.array, k); return q; }
-static inline rls_param3 adv(rls_param3 q, size_t k) { q.array = adv(q.array, k); return q; }
-static inline rls_shading_soa adv(const rls_shading_soa &s, size_t k)
-{
-    rls_shading_soa o; o.U = adv(s.U, k); o.V = adv(s.V, k); o.N = adv(s.N, k); o.wo = adv(s.wo, k);
-    o.backfacing = adv(s.backfacing, k); return o;
-}
-struct TileArrays {
-    tile::Arrays a;
-    bool aligned = true;
-    TileArrays() { memset(&a, 0, sizeof(a)); }
-    void in(int slot, const void *q, int elem = 4)
-    {
-        a.in[slot] = q; a.in_elem[slot] = (uint8_t)elem;
-        if (q) { a.in_bytes_per_tile += (uint32_t)(tile::kTile * elem); aligned = aligned && !((uintptr_t)q & 15u); }
-    }
-    void in3(int slot, const rls_cvec3 &v) { in(slot, v.x); in(slot + 1, v.y); in(slot + 2, v.z); }
-    void out(int slot, void *q) { a.out[slot] = q; if (q) aligned = aligned && !((uintptr_t)q & 15u); }
-    void out3(int slot, const rls_vec3 &v) { out(slot, v.x); out(slot + 1, v.y); out(slot + 2, v.z); }
-};
-// grid of a persistent kernel: every CTA resident at once (a multiple of the SM count), never more CTAs than tiles
-template <typename K> static unsigned persistent_grid(rls_context *ctx, K kernel, size_t n_tiles)
-{
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, tile::kTile, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-    const size_t resident = (size_t)per_sm * (size_t)ctx->sm_count;
-    return (unsigned)(n_tiles < resident ? n_tiles : resident);
-}
-
-static int launch_ggx_dielectric(rls_context *ctx, cudaStream_t st, size_t n, const rls_shading_soa *sg,
-                                 const rls_ggx_params *p, const float *rx, const float *ry, const rls_ggx_dielectric_out *o);
-static int launch_ggx_dielectric_tma(rls_context *ctx, cudaStream_t st, size_t n, const rls_shading_soa *sg,
-                                     const rls_ggx_params *p, const float *rx, const float *ry, const rls_ggx_dielectric_out *o,
-                                     bool *taken)
-{
-    using namespace dielectric_slots;
-    *taken = false;
-    if (!ctx->tma || ctx->arith != RLS_ARITH_FAST || n < (size_t)tile::kTile) return RLS_OK;
-    const GgxParamsDev pd = dev(*p);
-    TileArrays ta;
-    ta.in3(U, sg->U); ta.in3(V, sg->V); ta.in3(N, sg->N); ta.in3(WO, sg->wo);
-    ta.in(RX, rx); ta.in(RY, ry); ta.in(ROUGH, pd.rough.array); ta.in(IOR, pd.ior.array); ta.in(ANISO, pd.aniso.array);
-    ta.in(BACK, sg->backfacing, 1);
-    ta.out(FRESNEL, o->fresnel); ta.out3(WI_R, o->wi_r); ta.out(F_R, o->f_r); ta.out(PDF_R, o->pdf_r);
-    ta.out3(WI_T, o->wi_t); ta.out(F_T, o->f_t); ta.out(WEIGHT_T, o->weight_t); ta.out(FLAGS, o->flags);
-    if (!ta.aligned) return RLS_OK;
-    *taken = true;
-    const size_t n_tiles = n / tile::kTile;
-    const bool arrays = pd.ior.array && pd.rough.array;
-#define RLS_DIELECTRIC_TMA(A, P) \
-    k_ggx_dielectric_tma<A, P><<<persistent_grid(ctx, k_ggx_dielectric_tma<A, P>, n_tiles), tile::kTile, 0, st>>>( \
-        (uint32_t)n_tiles, ta.a, sh(*sg), pd, rx, ry, ctx->fallbacks)
-    if (arrays && ctx->paired) RLS_DIELECTRIC_TMA(true, true);
-    else if (arrays) RLS_DIELECTRIC_TMA(true, false);
-    else if (ctx->paired) RLS_DIELECTRIC_TMA(false, true);
-    else RLS_DIELECTRIC_TMA(false, false);
-#undef RLS_DIELECTRIC_TMA
-    RLS_LAUNCH_CHECK(ctx);
-    const size_t done = n_tiles * tile::kTile;
-    if (done == n) return RLS_OK;
-    // ragged tail: the plain kernel on the remaining n - done < 256 samples
-    const rls_shading_soa sg2 = adv(*sg, done);
-    rls_ggx_params p2 = *p;
-    p2.specularRoughness = adv(p->specularRoughness, done); p2.ior = adv(p->ior, done); p2.anisotropic = adv(p->anisotropic, done);
-    p2.KsColor = adv(p->KsColor, done);
-    rls_ggx_dielectric_out o2;
-    o2.fresnel = adv(o->fresnel, done); o2.wi_r = adv(o->wi_r, done); o2.f_r = adv(o->f_r, done); o2.pdf_r = adv(o->pdf_r, done);
-    o2.wi_t = adv(o->wi_t, done); o2.f_t = adv(o->f_t, done); o2.weight_t = adv(o->weight_t, done); o2.flags = adv(o->flags, done);
-    return launch_ggx_dielectric(ctx, st, n - done, &sg2, &p2, rx + done, ry + done, &o2);
-}
+#ifdef RLS_EXPERIMENTS
+#include "experiments/rls_experiments.cuh"
+#endif
 static int launch_ggx_dielectric(rls_context *ctx, cudaStream_t st, size_t n, const rls_shading_soa *sg,
                                  const rls_ggx_params *p, const float *rx, const float *ry, const rls_ggx_dielectric_out *o)
 {
+#ifdef RLS_EXPERIMENTS
     {
         bool taken = false;
-        const int rc = launch_ggx_dielectric_tma(ctx, st, n, sg, p, rx, ry, o, &taken);
+        const int rc = experiments_launch_ggx_dielectric(ctx, st, n, sg, p, rx, ry, o, &taken);
         if (taken || rc != RLS_OK) return rc;
     }
-    DielectricOutDev d; d.fresnel = o->fresnel; d.wi_r = mv(o->wi_r); d.f_r = o->f_r; d.pdf_r = o->pdf_r;
-    d.wi_t = mv(o->wi_t); d.f_t = o->f_t; d.weight_t = o->weight_t; d.flags = o->flags;
+#endif
+    const DielectricOutDev d = dev(*o);
     const GgxParamsDev pd = dev(*p);
     const bool arrays = pd.ior.array && pd.rough.array;
-    const bool fast = ctx->arith == RLS_ARITH_FAST;
-    // Packed two-samples-per-thread kernel: fast policy, shipped sampler, every array 8-byte aligned.
-    if (fast && !pd.ndf && ctx->packed &&
-        aligned8({ sg->U.x, sg->U.y, sg->U.z, sg->V.x, sg->V.y, sg->V.z, sg->N.x, sg->N.y, sg->N.z, sg->wo.x, sg->wo.y, sg->wo.z,
-                   pd.ior.array, pd.rough.array, pd.aniso.array, rx, ry, d.fresnel, d.wi_r.x, d.wi_r.y, d.wi_r.z, d.f_r, d.pdf_r,
-                   d.wi_t.x, d.wi_t.y, d.wi_t.z, d.f_t, d.weight_t, d.flags })) {
-        const unsigned grid = (unsigned)(((n + 1) / 2 + kBlock - 1) / kBlock);
-        if (arrays) k_ggx_dielectric2<true><<<grid, kBlock, 0, st>>>(n, sh(*sg), pd, rx, ry, d, ctx->fallbacks);
-        else k_ggx_dielectric2<false><<<grid, kBlock, 0, st>>>(n, sh(*sg), pd, rx, ry, d, ctx->fallbacks);
+    const bool fast = uses_fast_policy(ctx);
+    if (ctx->arith == RLS_ARITH_TOLERANT && !pd.ndf) {
+        tol::Worklist wl;
+        const int rc = worklist_for(ctx, st, n, &wl);
+        if (rc != RLS_OK) return rc;
+        RLS_TOL_CHECK(ctx, tol::launch_ggx_dielectric(st, n, sh(*sg), pd, rx, ry, d, wl));
+        if (arrays) k_ggx_dielectric_rerun<true><<<rerun_grid(ctx), kBlockGgx, 0, st>>>((uint32_t)n, sh(*sg), pd, rx, ry, d, wl, ctx->fallbacks);
+        else k_ggx_dielectric_rerun<false><<<rerun_grid(ctx), kBlockGgx, 0, st>>>((uint32_t)n, sh(*sg), pd, rx, ry, d, wl, ctx->fallbacks);
         RLS_LAUNCH_CHECK(ctx);
         return RLS_OK;
     }
-#define RLS_DIELECTRIC_LAUNCH(F, A, P) \
-    do { if (ctx->persistent < 0 && ctx->chunk_counter) { \
-             cudaMemsetAsync(ctx->chunk_counter, 0, sizeof(unsigned), st); \
-             k_ggx_dielectric_dynamic<F, A, P><<<ctx->sm_count * (-ctx->persistent), kBlockGgx, 0, st>>>(n, sh(*sg), pd, rx, ry, d, ctx->fallbacks, ctx->chunk_counter); } \
-         else if (ctx->persistent > 0 && grid_for(n, kBlockGgx) > (unsigned)(ctx->sm_count * ctx->persistent)) \
-             k_ggx_dielectric_persistent<F, A, P><<<ctx->sm_count * ctx->persistent, kBlockGgx, 0, st>>>(n, sh(*sg), pd, rx, ry, d, ctx->fallbacks, ctx->stagger_ns, (unsigned)ctx->sm_count); \
-         else k_ggx_dielectric<F, A, P><<<grid_for(n, kBlockGgx), kBlockGgx, 0, st>>>(n, sh(*sg), pd, rx, ry, d, ctx->fallbacks); } while (0)
-    if (fast && arrays && ctx->paired) RLS_DIELECTRIC_LAUNCH(true, true, true);
-    else if (fast && arrays) RLS_DIELECTRIC_LAUNCH(true, true, false);
-    else if (fast && ctx->paired) RLS_DIELECTRIC_LAUNCH(true, false, true);
-    else if (fast) RLS_DIELECTRIC_LAUNCH(true, false, false);
-    else if (arrays) RLS_DIELECTRIC_LAUNCH(false, true, false);
-    else RLS_DIELECTRIC_LAUNCH(false, false, false);
+#define RLS_DIELECTRIC_LAUNCH(F, A) \
+    k_ggx_dielectric<F, A><<<grid_for(n, kBlockGgx), kBlockGgx, 0, st>>>(n, sh(*sg), pd, rx, ry, d, ctx->fallbacks)
+    if (fast && arrays) RLS_DIELECTRIC_LAUNCH(true, true);
+    else if (fast) RLS_DIELECTRIC_LAUNCH(true, false);
+    else if (arrays) RLS_DIELECTRIC_LAUNCH(false, true);
+    else RLS_DIELECTRIC_LAUNCH(false, false);
 #undef RLS_DIELECTRIC_LAUNCH
     RLS_LAUNCH_CHECK(ctx);
     return RLS_OK;
+}
+static bool disney_all_arrays(const DisneyParamsDev &pd)       // every parameter spatially varying?
+{
+    const P1 *scalars[] = { &pd.subsurface, &pd.metallic, &pd.specular, &pd.specular_tint, &pd.roughness, &pd.anisotropic,
+                            &pd.sheen, &pd.sheen_tint, &pd.clearcoat, &pd.clearcoat_gloss };
+    bool arrays = pd.base_color.x && pd.base_color.y && pd.base_color.z;
+    for (const P1 *q : scalars) arrays = arrays && q->array;
+    return arrays;
 }
 static int launch_disney_sample_eval_pdf(rls_context *ctx, cudaStream_t st, size_t n, const rls_shading_soa *sg,
                                          const rls_disney_params *p, const float *rx_s, const float *ry_s,
                                          const float *rx_d, const float *ry_d, const rls_disney_out *o)
 {
-    DisneyOutDev d; d.wi_s = mv(o->wi_s); d.f_s = mv(o->f_s); d.pdf_s = o->pdf_s;
-    d.wi_d = mv(o->wi_d); d.f_d = mv(o->f_d); d.pdf_d = o->pdf_d; d.flags = o->flags;
+    const DisneyOutDev d = dev(*o);
     const DisneyParamsDev pd = dev(*p);
-    const P1 *scalars[] = { &pd.subsurface, &pd.metallic, &pd.specular, &pd.specular_tint, &pd.roughness, &pd.anisotropic,
-                            &pd.sheen, &pd.sheen_tint, &pd.clearcoat, &pd.clearcoat_gloss };
-    bool arrays = pd.base_color.x && pd.base_color.y && pd.base_color.z;     // every parameter spatially varying?
-    for (const P1 *q : scalars) arrays = arrays && q->array;
-    const bool fast = ctx->arith == RLS_ARITH_FAST;
-#define RLS_DISNEY_LAUNCH(F, A, ...) \
-    k_disney_sample_eval_pdf<F, A, ##__VA_ARGS__><<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), pd, rx_s, ry_s, rx_d, ry_d, d, ctx->fallbacks)
-    // the partition pays only when lobes are mixed inside a CTA, i.e. clearcoat varies per sample or is non-zero
-    const bool sort = ctx->disney_lobe_sort && fast && (pd.clearcoat.array || pd.clearcoat.value != 0.0f);
-    if (sort && arrays) RLS_DISNEY_LAUNCH(true, true, true);
-    else if (sort) RLS_DISNEY_LAUNCH(true, false, true);
-    else if (fast && arrays) RLS_DISNEY_LAUNCH(true, true);
+    const bool arrays = disney_all_arrays(pd);
+    const bool fast = uses_fast_policy(ctx);
+#ifdef RLS_EXPERIMENTS
+    {
+        bool taken = false;
+        const int rc = experiments_launch_disney(ctx, st, n, sg, pd, arrays, rx_s, ry_s, rx_d, ry_d, d, &taken);
+        if (taken || rc != RLS_OK) return rc;
+    }
+#endif
+    if (ctx->arith == RLS_ARITH_TOLERANT) {
+        tol::Worklist wl;
+        const int rc = worklist_for(ctx, st, n, &wl);
+        if (rc != RLS_OK) return rc;
+        RLS_TOL_CHECK(ctx, tol::launch_disney(st, n, sh(*sg), pd, arrays, rx_s, ry_s, rx_d, ry_d, d, wl));
+        if (arrays) k_disney_sample_eval_pdf_rerun<true><<<rerun_grid(ctx), kBlock, 0, st>>>((uint32_t)n, sh(*sg), pd, rx_s, ry_s, rx_d, ry_d, d, wl, ctx->fallbacks);
+        else k_disney_sample_eval_pdf_rerun<false><<<rerun_grid(ctx), kBlock, 0, st>>>((uint32_t)n, sh(*sg), pd, rx_s, ry_s, rx_d, ry_d, d, wl, ctx->fallbacks);
+        RLS_LAUNCH_CHECK(ctx);
+        return RLS_OK;
+    }
+#define RLS_DISNEY_LAUNCH(F, A) \
+    k_disney_sample_eval_pdf<F, A><<<grid_for(n), kBlock, 0, st>>>(n, sh(*sg), pd, rx_s, ry_s, rx_d, ry_d, d, ctx->fallbacks)
+    if (fast && arrays) RLS_DISNEY_LAUNCH(true, true);
     else if (fast) RLS_DISNEY_LAUNCH(true, false);
     else if (arrays) RLS_DISNEY_LAUNCH(false, true);
     else RLS_DISNEY_LAUNCH(false, false);
@@ -1380,8 +1232,17 @@ static int launch_disney_sample_eval_pdf(rls_context *ctx, cudaStream_t st, size
 static int launch_skin_profile(rls_context *ctx, cudaStream_t st, size_t n, const rls_skin_params *p,
                                const float *rx, const rls_profile_out *o)
 {
-    ProfileOutDev d; d.r = o->r; d.pdf = o->pdf; d.Rd = mv(o->Rd); d.flags = o->flags;
-    if (ctx->arith == RLS_ARITH_FAST)
+    const ProfileOutDev d = dev(*o);
+    if (ctx->arith == RLS_ARITH_TOLERANT) {
+        tol::Worklist wl;
+        const int rc = worklist_for(ctx, st, n, &wl);
+        if (rc != RLS_OK) return rc;
+        RLS_TOL_CHECK(ctx, tol::launch_skin_profile(st, n, dev(*p), rx, d, wl));
+        k_skin_profile_rerun<<<rerun_grid(ctx), kBlockSkin, 0, st>>>((uint32_t)n, dev(*p), rx, d, wl, ctx->fallbacks);
+        RLS_LAUNCH_CHECK(ctx);
+        return RLS_OK;
+    }
+    if (uses_fast_policy(ctx))
         k_skin_profile<true><<<grid_for(n, kBlockSkin), kBlockSkin, 0, st>>>(n, dev(*p), rx, d, ctx->fallbacks);
     else
         k_skin_profile<false><<<grid_for(n, kBlockSkin), kBlockSkin, 0, st>>>(n, dev(*p), rx, d, ctx->fallbacks);
@@ -1626,9 +1487,11 @@ extern "C" int rls_gaussprofile_sample_eval_pdf(rls_context *ctx, size_t n, cons
     if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
     RLS_REQUIRE(ctx, dist_x && rx && out_r && out_pdf && out_rd, "rls_gaussprofile_sample_eval_pdf: NULL argument");
     DeviceGuard guard(ctx->device);
-    const bool fast = ctx->arith == RLS_ARITH_FAST;
-    const bool aligned = ((((uintptr_t)dist_x | (uintptr_t)rx | (uintptr_t)out_r | (uintptr_t)out_pdf | (uintptr_t)out_rd) & 15u) == 0) &&
-                         !ctx->gauss_scalar;
+    const bool fast = uses_fast_policy(ctx);
+    bool aligned = (((uintptr_t)dist_x | (uintptr_t)rx | (uintptr_t)out_r | (uintptr_t)out_pdf | (uintptr_t)out_rd) & 15u) == 0;
+#ifdef RLS_EXPERIMENTS
+    aligned = aligned && !ctx->exp.gauss_scalar;      // A/B: one sample per thread
+#endif
     const size_t n4 = aligned ? n / 4 : 0, done = n4 * 4;
     if (n4) {
         if (fast)
@@ -1711,13 +1574,13 @@ extern "C" int rls_albedo_sweep(rls_context *ctx, const rls_sweep_grid *grid, ui
     unsigned cells = (unsigned)(grid->n_rough * grid->n_cos * grid->n_ior);
     DeviceGuard guard(ctx->device);
     // Measured on B200 (65536 cells x 4096 spp): the guarded operators run this kernel at 30.3 G samples/s, the
-    // fast policy at 26.0 -- even with the policy chosen per CELL (degenerate cells, ior == 1 or cos == 1, run
-    // exact as a whole; 6.6e-5 of the other samples re-run).  Here everything that depends on the shading point
-    // only is loop invariant and hoisted by the compiler, the frame is a compile-time constant, and the FP64
-    // accumulators and the RNG leave no registers for a second code path.  The sweep therefore always uses the
-    // exact policy; the fast instantiation stays reachable for A/B runs through RLS_SWEEP_FAST=1.
-    static const bool sweep_fast = getenv("RLS_SWEEP_FAST") && atoi(getenv("RLS_SWEEP_FAST")) != 0;
-    if (sweep_fast && ctx->arith == RLS_ARITH_FAST)
+    // fast policy at 26.0 (the FP64 accumulators and the RNG leave no registers for a second code path), so the
+    // bit-exact sweep always uses the exact policy.
+    bool sweep_fast = false;
+#ifdef RLS_EXPERIMENTS
+    sweep_fast = ctx->exp.sweep_fast && uses_fast_policy(ctx);
+#endif
+    if (sweep_fast)
         k_albedo_sweep<true><<<cells, kBlockSweep, 0, ctx->stream>>>(g, seed, spp_begin, spp_end, table, ctx->fallbacks);
     else
         k_albedo_sweep<false><<<cells, kBlockSweep, 0, ctx->stream>>>(g, seed, spp_begin, spp_end, table, ctx->fallbacks);
@@ -1783,7 +1646,7 @@ extern "C" int rls_skin_glossy_layers(rls_context *ctx, size_t n, uint32_t k, co
     sp.sss_weight = p1(p->sss_weight);
     SkinLayersOutDev o; o.sheen = mv(out->sheen); o.spec = mv(out->specular); o.sheenF = out->sheen_fresnel;
     o.specF = out->specular_fresnel; o.sssW = out->sss_weight; o.flags = out->flags;
-    if (ctx->arith == RLS_ARITH_FAST)
+    if (uses_fast_policy(ctx))
         k_skin_glossy_layers<true><<<grid_for(n), kBlock, 0, ctx->stream>>>(n, k, sh(*sg), sp, rx_a, ry_a, rx_b, ry_b, cv(li_a), cv(li_b), o, ctx->fallbacks);
     else
         k_skin_glossy_layers<false><<<grid_for(n), kBlock, 0, ctx->stream>>>(n, k, sh(*sg), sp, rx_a, ry_a, rx_b, ry_b, cv(li_a), cv(li_b), o, ctx->fallbacks);

@@ -156,14 +156,15 @@ RLS_DEV f3 disney_sample_gtr1(Fp &fp, const Disney &d, float rx, float ry)
 }
 // src/rlDisney.cpp:367-390; lobe: 0 = GTR2 (visible normals), 1 = GTR1 (clearcoat)
 template <class Fp>
-RLS_DEV f3 disney_sample_specular(Fp &fp, const Disney &d, float rx, float ry, uint32_t &lobe)
+RLS_DEV f3 disney_sample_specular(Fp &fp, const Disney &d, float rx, float ry, uint32_t &lobe, bool *early = nullptr)
 {
     f3 M;
+    if (early) *early = false;
     float gtr2Weight = fp.rcp(d.clearcoat + 1.0f);
     if (rx < gtr2Weight) {
         rx = fp.div(rx, gtr2Weight);
         // :377-379; sampleGTR2AnisoDirection (:406-414) is NDF sampling with (ry, rx)
-        M = d.visibleNormal ? sample_visible_normal(fp, d.wo, d.U, d.V, d.N, d.ax, d.ay, rx, ry)
+        M = d.visibleNormal ? sample_visible_normal(fp, d.wo, d.U, d.V, d.N, d.ax, d.ay, rx, ry, early)
                             : sample_ndf_normal(fp, d.U, d.V, d.N, d.ax, d.ay, ry, rx);
         lobe = 0;
     } else {

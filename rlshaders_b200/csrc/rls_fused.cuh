@@ -93,7 +93,8 @@ RLS_DEV Dielectric dielectric_unit(Fp &fp, const Shading &sh, float ior, float r
     ggx_init(fp, g, sh, mk3(1.0f, 1.0f, 1.0f), ior, rough, aniso);
     g.ndf = ndf;
     const GgxShared s = ggx_shared(fp, g);
-    f3 m = ggx_sample_normal(fp, g, rx, ry);
+    bool early;
+    f3 m = ggx_sample_normal(fp, g, rx, ry, &early);
     float Vm = dot(g.wo, m);
     // reflectDirection(V, m) = 2|V.m| m - V
     r.wi_r = m * (2.0f * fp.abs_nz(Vm)) - g.wo;       // Vm is the tracked numerator of w_t below
@@ -114,6 +115,7 @@ RLS_DEV Dielectric dielectric_unit(Fp &fp, const Shading &sh, float ior, float r
     if (r.f_r == 0.0f) fl |= 0x0008u;
     if (r.pdf_r == kEps) fl |= 0x0040u;
     if (g.entering) fl |= 0x0010u;
+    if (early) fl |= 0x0080u;                         // RLS_FLAG_SLOPE_EARLY_OUT
 
     // getRefractDirection(m, V): src/rlGgx.h:277-291
     const float eta = s.eta;
@@ -177,7 +179,8 @@ RLS_DEV GgxBsdf ggx_unit(Fp &fp, const Ggx &g, float rx, float ry)
 {
     GgxBsdf o;
     const GgxShared s = ggx_shared(fp, g);
-    f3 m = ggx_sample_normal(fp, g, rx, ry);
+    bool early;
+    f3 m = ggx_sample_normal(fp, g, rx, ry, &early);
     o.L = m * (2.0f * abs_m(dot(g.wo, m))) - g.wo;
     o.fresnel = ggx_fresnel_c(fp, s.ratio2, fabsf(dot(o.L, m)));
     const float LdotN = dot(o.L, g.N);
@@ -187,6 +190,7 @@ RLS_DEV GgxBsdf ggx_unit(Fp &fp, const Ggx &g, float rx, float ry)
     o.f = black ? mk3(0.0f, 0.0f, 0.0f) : g.ks * refl * LdotN;
     o.flags = bsdf_flags(o.L, g.N, o.f, o.pdf);
     if (g.entering) o.flags |= 0x0010u;
+    if (early) o.flags |= 0x0080u;                    // RLS_FLAG_SLOPE_EARLY_OUT
     return o;
 }
 
@@ -222,6 +226,7 @@ RLS_DEV DisneyOut1 disney_unit(Fp &fp, const Disney &d, float rx_s, float ry_s, 
     // one rotate/normalize tail: GTR2 (visible normals) needs sincosf(phi or 2 pi ry), GTR1
     // sincosf(2 pi rx'), plain GTR2 sincosf(2 pi rx) -- the angle is selected per lane.
     uint32_t lobe;
+    bool early = false;                                           // GTR2 visible-normal lobe only
     f3 M;
     {
         float gtr2Weight = fp.rcp(d.clearcoat + 1.0f);
@@ -249,7 +254,7 @@ RLS_DEV DisneyOut1 disney_unit(Fp &fp, const Disney &d, float rx_s, float ry_s, 
         rlm::sincosf_(fp, angle, &s, &c);
         f3 omega;
         if (lobe == 0) {
-            omega = d.visibleNormal ? vndf_omega(fp, st, s, c, d.ax, d.ay, rx, ry_s)
+            omega = d.visibleNormal ? vndf_omega(fp, st, s, c, d.ax, d.ay, rx, ry_s, &early)
                                     : mk3(g * d.ax * c, g * d.ay * s, 1.0f);
         } else {                                                  // sphericalDirection(cosThetaH, phiH)
             float r = fp.sqrt(1.0f - sqr(cosThetaH));
@@ -308,7 +313,7 @@ RLS_DEV DisneyOut1 disney_unit(Fp &fp, const Disney &d, float rx_s, float ry_s, 
     o.fd = disney_eval_brdf(fp, d, kRayDiffuse, o.Ld);
     o.pd = disney_eval_pdf(fp, d, kRayDiffuse, o.Ld);
 
-    const uint32_t fls = (bsdf_flags(o.Ls, d.N, o.fs, o.ps) & ~0x0040u) | (lobe << 8);
+    const uint32_t fls = (bsdf_flags(o.Ls, d.N, o.fs, o.ps) & ~0x0040u) | (lobe << 8) | (early ? 0x0080u : 0u);
     const uint32_t fld = bsdf_flags(o.Ld, d.N, o.fd, o.pd);
     o.flags = fls | (fld << 16);
     return o;

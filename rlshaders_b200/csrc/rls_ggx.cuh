@@ -61,8 +61,9 @@ RLS_DEV f2 uniform_slope(Fp &fp, float rx, float ry)
 }
 // src/rlGgx.cpp:14-61 (VNDFKernel::sampleSlope) for theta >= AI_EPSILON; rlDisney.cpp:416-463 is
 // the same code.  The theta < AI_EPSILON early-out (:27) is taken by the caller.
+// *early (optional) = the |A^2 - 1| < AI_EPSILON early-out (:38) was taken (RLS_FLAG_SLOPE_EARLY_OUT).
 template <class Fp>
-RLS_DEV f2 sample_slope(Fp &fp, float theta, float rx, float ry)
+RLS_DEV f2 sample_slope(Fp &fp, float theta, float rx, float ry, bool *early = nullptr)
 {
     float B = rlm::tanf_(fp, theta);
     float B2 = sqr(B);
@@ -71,7 +72,10 @@ RLS_DEV f2 sample_slope(Fp &fp, float theta, float rx, float ry)
 
     float A = fp.div(2.0f * rx, G1) - 1.0f;
     float A2 = sqr(A);
-    if (abs_m(A2 - 1.0f) < kEps) return uniform_slope(fp, rx, ry);
+    if (abs_m(A2 - 1.0f) < kEps) {
+        if (early) *early = true;
+        return uniform_slope(fp, rx, ry);
+    }
 
     float tmp = fp.rcp(A2 - 1.0f);
     float D = fp.sqrt(max_m(0.0f, B2 * sqr(tmp) - (A2 - B2) * tmp));
@@ -129,8 +133,10 @@ RLS_DEV VndfState vndf_prepare(Fp &fp, f3 view, f3 U, f3 Vax, f3 N, float ax, fl
 RLS_DEV float vndf_angle(const VndfState &st, float ry) { return st.along_normal ? kTwoPi * ry : st.phi; }
 
 template <class Fp>
-RLS_DEV f3 vndf_omega(Fp &fp, const VndfState &st, float s, float c, float ax, float ay, float rx, float ry)
+RLS_DEV f3 vndf_omega(Fp &fp, const VndfState &st, float s, float c, float ax, float ay, float rx, float ry,
+                      bool *early = nullptr)
 {
+    if (early) *early = st.along_normal;         // theta left 0: the :27 early-out
     f2 slope;
     float sinPhi, cosPhi;
     if (st.along_normal) {                       // uniform_slope(rx, ry), then a rotation by phi = 0
@@ -140,7 +146,7 @@ RLS_DEV f3 vndf_omega(Fp &fp, const VndfState &st, float s, float c, float ax, f
         sinPhi = 0.0f;
         cosPhi = 1.0f;
     } else {
-        slope = sample_slope(fp, st.theta, rx, ry);
+        slope = sample_slope(fp, st.theta, rx, ry, early);
         sinPhi = s;
         cosPhi = c;
     }
@@ -152,12 +158,13 @@ RLS_DEV f3 vndf_omega(Fp &fp, const VndfState &st, float s, float c, float ax, f
 }
 
 template <class Fp>
-RLS_DEV f3 sample_visible_normal(Fp &fp, f3 view, f3 U, f3 Vax, f3 N, float ax, float ay, float rx, float ry)
+RLS_DEV f3 sample_visible_normal(Fp &fp, f3 view, f3 U, f3 Vax, f3 N, float ax, float ay, float rx, float ry,
+                                 bool *early = nullptr)
 {
     const VndfState st = vndf_prepare(fp, view, U, Vax, N, ax, ay);
     float s, c;
     rlm::sincosf_(fp, vndf_angle(st, ry), &s, &c);
-    return normalize(fp, rotate_to_frame(vndf_omega(fp, st, s, c, ax, ay, rx, ry), U, Vax, N));
+    return normalize(fp, rotate_to_frame(vndf_omega(fp, st, s, c, ax, ay, rx, ry, early), U, Vax, N));
 }
 
 // src/rlGgx.h:33-41 (NDFKernel::evalSample, Burley Eq.14): plain NDF sampling; also
@@ -182,10 +189,11 @@ struct Ggx {
     bool ndf;        // GgxSamplerT<NDFKernel> instead of the shipped GgxSamplerT<VNDFKernel>
 };
 template <class Fp>
-RLS_DEV f3 ggx_sample_normal(Fp &fp, const Ggx &g, float rx, float ry)
+RLS_DEV f3 ggx_sample_normal(Fp &fp, const Ggx &g, float rx, float ry, bool *early = nullptr)
 {
+    if (early) *early = false;                   // NDFKernel has no early-out
     if (g.ndf) return sample_ndf_normal(fp, g.U, g.V, g.N, g.ax, g.ay, rx, ry);
-    return sample_visible_normal(fp, g.wo, g.U, g.V, g.N, g.ax, g.ay, rx, ry);
+    return sample_visible_normal(fp, g.wo, g.U, g.V, g.N, g.ax, g.ay, rx, ry, early);
 }
 
 // src/rlGgx.h:130-156 (GgxSamplerT ctor)

@@ -1,0 +1,146 @@
+// rls_tol.cu -- the fused kernels of the TOLERANCE arithmetic policy (RLS_ARITH_TOLERANT, rls_tol.cuh).
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=true -c rls_tol.cu   (FMA contraction ON:
+// this is the one translation unit of the library that is not bit-exact by construction; see __graft_entry__.build).
+//
+// One thread = one sample, SoA loads / stores exactly as the bit-exact kernels (rls_b200.cu).  Per 32 samples the
+// dielectric unit is ~1/4 of the bit-exact kernel's instructions, so these kernels are bound by HBM, not by issue.
+// A sample whose band tracker fired is appended to the re-run list (rls_tol_launch.cuh) and evaluated again by the
+// bit-exact policy in a second kernel: flags, lobes and discontinuous choices are therefore the reference's, bit for bit.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "rls_tol.cuh"
+#include "rls_tol_launch.cuh"
+
+namespace rls {
+namespace tol {
+
+#ifndef RLS_TOL_BLOCK
+#define RLS_TOL_BLOCK 256
+#endif
+#ifndef RLS_TOL_MIN_BLOCKS
+#define RLS_TOL_MIN_BLOCKS 4
+#endif
+static constexpr int kBlockTol = RLS_TOL_BLOCK;
+
+static __device__ __forceinline__ v3 tv(f3 a) { return mk(a.x, a.y, a.z); }
+static __device__ __forceinline__ void st3(const V3 &v, uint32_t i, v3 a) { v.x[i] = a.x; v.y[i] = a.y; v.z[i] = a.z; }
+
+// Returns the flags word to store: the sample's own, or the sentinel when the list is full.
+static __device__ __forceinline__ uint32_t enlist(bool rerun, uint32_t i, uint32_t flags, const Worklist &wl)
+{
+    if (rerun) {
+        const unsigned k = atomicAdd(wl.count, 1u);
+        if (k < wl.cap) wl.list[k] = i; else flags = kRerunSentinel;
+    }
+    return flags;
+}
+
+#define RLS_TOL_INDEX()                                                        \
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;                  \
+    if (i >= n) return;
+
+__global__ void __launch_bounds__(kBlockTol, RLS_TOL_MIN_BLOCKS)
+k_ggx_sample_eval_pdf_tol(uint32_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, BsdfOutDev o, Worklist wl)
+{
+    RLS_TOL_INDEX();
+    const Shading s = load_shading(sg, i);
+    Bands bd;
+    const GgxBsdfT r = ggx_unit(bd, tv(s.U), tv(s.V), tv(s.N), tv(s.wo), s.backfacing, tv(fetch(p.ks, i)), fetch(p.ior, i),
+                                fetch(p.rough, i), fetch(p.aniso, i), __ldg(rx + i), __ldg(ry + i));
+    st3(o.wi, i, r.L);
+    st3(o.f, i, r.f);
+    o.pdf[i] = r.pdf;
+    if (o.fresnel) o.fresnel[i] = r.fresnel;
+    o.flags[i] = enlist(bd.rerun, i, r.flags, wl);
+}
+
+template <bool kArrays>       // kArrays: ior and specularRoughness are per-sample arrays
+__global__ void __launch_bounds__(kBlockTol, RLS_TOL_MIN_BLOCKS)
+k_ggx_dielectric_tol(uint32_t n, ShadingSoA sg, GgxParamsDev p, const float *rx, const float *ry, DielectricOutDev o, Worklist wl)
+{
+    RLS_TOL_INDEX();
+    const Shading s = load_shading(sg, i);
+    const float ior = fetch_t<kArrays>(p.ior, i), rough = fetch_t<kArrays>(p.rough, i), aniso = fetch(p.aniso, i);
+    Bands bd;
+    const DielectricT r = dielectric_unit(bd, tv(s.U), tv(s.V), tv(s.N), tv(s.wo), s.backfacing, ior, rough, aniso,
+                                          __ldg(rx + i), __ldg(ry + i));
+    o.fresnel[i] = r.F;
+    st3(o.wi_r, i, r.wi_r);
+    o.f_r[i] = r.f_r;
+    o.pdf_r[i] = r.pdf_r;
+    st3(o.wi_t, i, r.wi_t);
+    o.f_t[i] = r.f_t;
+    o.weight_t[i] = r.w_t;
+    o.flags[i] = enlist(bd.rerun, i, r.flags, wl);
+}
+
+template <bool kArrays>       // kArrays: every rlDisney parameter is a per-sample array
+__global__ void __launch_bounds__(kBlockTol, RLS_TOL_MIN_BLOCKS)
+k_disney_sample_eval_pdf_tol(uint32_t n, ShadingSoA sg, DisneyParamsDev p, const float *rx_s, const float *ry_s,
+                             const float *rx_d, const float *ry_d, DisneyOutDev o, Worklist wl)
+{
+    RLS_TOL_INDEX();
+    const Shading s = load_shading(sg, i);
+    DisneyIn in;
+    in.base = tv(fetch_t<kArrays>(p.base_color, i));
+    in.subsurface = fetch_t<kArrays>(p.subsurface, i); in.metallic = fetch_t<kArrays>(p.metallic, i);
+    in.specular = fetch_t<kArrays>(p.specular, i); in.specular_tint = fetch_t<kArrays>(p.specular_tint, i);
+    in.roughness = fetch_t<kArrays>(p.roughness, i); in.anisotropic = fetch_t<kArrays>(p.anisotropic, i);
+    in.sheen = fetch_t<kArrays>(p.sheen, i); in.sheen_tint = fetch_t<kArrays>(p.sheen_tint, i);
+    in.clearcoat = fetch_t<kArrays>(p.clearcoat, i); in.clearcoat_gloss = fetch_t<kArrays>(p.clearcoat_gloss, i);
+    Bands bd;
+    const DisneyT r = disney_unit(bd, tv(s.U), tv(s.V), tv(s.N), tv(s.wo), in, p.sample_from_visible_normal != 0,
+                                  __ldg(rx_s + i), __ldg(ry_s + i), __ldg(rx_d + i), __ldg(ry_d + i));
+    st3(o.wi_s, i, r.Ls); st3(o.f_s, i, r.fs); o.pdf_s[i] = r.ps;
+    st3(o.wi_d, i, r.Ld); st3(o.f_d, i, r.fd); o.pdf_d[i] = r.pd;
+    o.flags[i] = enlist(bd.rerun, i, r.flags, wl);
+}
+
+__global__ void __launch_bounds__(kBlockTol, RLS_TOL_MIN_BLOCKS)
+k_skin_profile_tol(uint32_t n, SkinParamsDev sp, const float *rx, ProfileOutDev o, Worklist wl)
+{
+    RLS_TOL_INDEX();
+    const f3 d = fetch(sp.sss_scatter_dist, i);
+    const float mult = fetch(sp.sss_dist_multiplier, i);
+    Bands bd;
+    // src/rlSkin.cpp:236: scatterDist = sss_scatter_dist * sss_dist_multiplier (one rounding each, as the reference)
+    const ProfileT r = skin_profile_unit(bd, mk(mul_rn(d.x, mult), mul_rn(d.y, mult), mul_rn(d.z, mult)), __ldg(rx + i));
+    o.r[i] = r.r;
+    o.pdf[i] = r.pdf;
+    st3(o.Rd, i, r.Rd);
+    o.flags[i] = enlist(bd.rerun, i, r.flags, wl);
+}
+
+static inline unsigned grid_for(size_t n) { return (unsigned)((n + kBlockTol - 1) / kBlockTol); }
+
+cudaError_t launch_ggx_sample_eval_pdf(cudaStream_t st, size_t n, const ShadingSoA &sg, const GgxParamsDev &p, const float *rx,
+                                       const float *ry, const BsdfOutDev &o, const Worklist &wl)
+{
+    k_ggx_sample_eval_pdf_tol<<<grid_for(n), kBlockTol, 0, st>>>((uint32_t)n, sg, p, rx, ry, o, wl);
+    return cudaGetLastError();
+}
+cudaError_t launch_ggx_dielectric(cudaStream_t st, size_t n, const ShadingSoA &sg, const GgxParamsDev &p, const float *rx,
+                                  const float *ry, const DielectricOutDev &o, const Worklist &wl)
+{
+    if (p.ior.array && p.rough.array) k_ggx_dielectric_tol<true><<<grid_for(n), kBlockTol, 0, st>>>((uint32_t)n, sg, p, rx, ry, o, wl);
+    else k_ggx_dielectric_tol<false><<<grid_for(n), kBlockTol, 0, st>>>((uint32_t)n, sg, p, rx, ry, o, wl);
+    return cudaGetLastError();
+}
+cudaError_t launch_disney(cudaStream_t st, size_t n, const ShadingSoA &sg, const DisneyParamsDev &p, bool all_arrays,
+                          const float *rx_s, const float *ry_s, const float *rx_d, const float *ry_d, const DisneyOutDev &o,
+                          const Worklist &wl)
+{
+    if (all_arrays) k_disney_sample_eval_pdf_tol<true><<<grid_for(n), kBlockTol, 0, st>>>((uint32_t)n, sg, p, rx_s, ry_s, rx_d, ry_d, o, wl);
+    else k_disney_sample_eval_pdf_tol<false><<<grid_for(n), kBlockTol, 0, st>>>((uint32_t)n, sg, p, rx_s, ry_s, rx_d, ry_d, o, wl);
+    return cudaGetLastError();
+}
+cudaError_t launch_skin_profile(cudaStream_t st, size_t n, const SkinParamsDev &p, const float *rx, const ProfileOutDev &o,
+                                const Worklist &wl)
+{
+    k_skin_profile_tol<<<grid_for(n), kBlockTol, 0, st>>>((uint32_t)n, p, rx, o, wl);
+    return cudaGetLastError();
+}
+
+} // namespace tol
+} // namespace rls

@@ -1,0 +1,199 @@
+"""RLS_ARITH_TOLERANT (include/rls_b200.h, rlshaders_b200/csrc/rls_tol.cuh): the opt-in tolerance policy of the four
+fused units.  Contract checked here, against the reference compiled on the host (and its pinned C port):
+
+  * flags -- lobe, invalid / zero-pdf / black / floored / entering / TIR / early-out bits -- BIT-EXACT, every sample
+    (the samples whose deciding comparand is near its threshold are re-run by the bit-exact policy);
+  * values by percentile (the spread is the reference's own rounding noise):
+        directions  >= 95 % within 1e-6 absolute,  >= 99.5 % within 1e-5,  >= 99.9 % within 1e-4
+        f/pdf/radii >= 90 % within 1e-5 relative,  >= 99 %  within 1e-4,  >= 99.9 % within 1e-3
+  * re-run fraction below 0.5 %.
+
+The CPU part runs the very same unit functions compiled for the host (tests/native/tol_host.cpp; the header is
+__host__ __device__), once with correctly rounded stand-ins for the MUFU approximations and once with every stand-in
+moved by a pseudo-random ulp, so the bands are exercised without a GPU; the -m gpu part runs the CUDA kernels through
+the C ABI and additionally checks the device results against the host build of the same code.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import parity
+import tol_host as th
+from rlshaders_b200 import _abi as abi
+
+DIR_FRACS = {1e-6: 0.95, 1e-5: 0.995, 1e-4: 0.999}
+REL_FRACS = {1e-5: 0.90, 1e-4: 0.99, 1e-3: 0.999}
+MAX_RERUN = 5e-3
+
+
+def check(st, title):
+    print(th.report(title, st))
+    assert st["rerun_fraction"] <= MAX_RERUN, (title, st["rerun_fraction"])
+    for name, s in st.items():
+        if not isinstance(s, dict):
+            continue
+        if "mismatches" in s:
+            assert s["mismatches"] == 0, (title, name, s, st.get("_bad_index"))
+        else:
+            fr = DIR_FRACS if 1e-6 in s["within"] else REL_FRACS
+            for tol, need in fr.items():
+                assert s["within"][tol] >= need, (title, name, tol, s)
+
+
+@pytest.fixture(scope="module")
+def orc():
+    o = ol.load_ref() or ol.load_port()
+    o.set_threads(0)
+    return o
+
+
+# ----------------------------------------------------------------- CPU: the units compiled for the host
+@pytest.mark.parametrize("ulp", [False, True])
+@pytest.mark.parametrize("workload", ["dielectric", "aniso", "conductor", "disney", "skin"])
+def test_host_build_of_the_units(orc, workload, ulp):
+    lib = th.load(ulp=ulp)
+    n = 1 << 19
+    fn = dict(dielectric=lambda: th.run_dielectric(lib, orc, n), aniso=lambda: th.run_dielectric(lib, orc, n, aniso=True),
+              conductor=lambda: th.run_conductor(lib, orc, n), disney=lambda: th.run_disney(lib, orc, n),
+              skin=lambda: th.run_skin(lib, orc, n))[workload]
+    check(fn(), f"host build, {workload}, ulp perturbation={ulp}")
+
+
+def test_bands_catch_adversarial_inputs(orc):
+    """Operands ON the thresholds: grazing / normal views, ior 1, roughness 0 and 1, uniforms at the lobe bounds.
+    Every such sample must either be flagged for the exact re-run or agree on its flags."""
+    lib = th.load()
+    n = 1 << 14
+    sg = ol.make_shading(n, 0xBAD5EED, cos_lo=0.0, cos_hi=1.0, backfacing_fraction=0.5)
+    rng = np.random.default_rng(7)
+    pick = lambda vals: rng.choice(np.asarray(vals, np.float32), n).astype(np.float32)   # noqa: E731
+    kw = dict(specularRoughness=pick([0.0, 1e-3, 0.05, 0.3, 1.0]), ior=pick([1.0, 1.0001, 1.5, 0.47, 1e-5]),
+              anisotropic=pick([0.0, 0.5, 1.0]))
+    rx, ry = pick([2.0 ** -24, 0.25, 0.5, 0.75, 1 - 2.0 ** -24]), pick([2.0 ** -24, 0.5, 0.5 + 2.0 ** -24, 1 - 2.0 ** -24])
+    # a few views exactly along / orthogonal to the normal
+    for c in "xyz":
+        sg["wo" + c][:64] = sg["N" + c][:64]
+        sg["wo" + c][64:128] = sg["U" + c][64:128]
+    p = abi.ggx_params(**kw)
+    t, rerun = th.ggx_dielectric(lib, sg, p, rx, ry)
+    o = orc.ggx_dielectric(sg, p, rx, ry)
+    bad = (t["flags"] != o["flags"]) & (rerun == 0)
+    assert int(bad.sum()) == 0, np.nonzero(bad)[0][:8]
+
+
+# ----------------------------------------------------------------- GPU: the CUDA kernels through the C ABI
+@pytest.fixture(scope="module")
+def tctx():
+    from rlshaders_b200 import api
+    c = api.Context(0)
+    c.set_arith_policy("tolerant")
+    yield c
+    c.close()
+
+
+def _gpu_stats(gpu, cpu, kinds):
+    g = {k: v.cpu().numpy().view(np.uint32) if kinds[k] == "flags" else v.cpu().numpy() for k, v in gpu.items() if k in kinds}
+    return th.compare(g, np.zeros(len(cpu["flags"]), np.uint8), cpu, kinds)
+
+
+N_GPU = 1 << 22
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("aniso", [False, True])
+def test_gpu_dielectric(tctx, orc, aniso):
+    tctx.fallback_count(reset=True)
+    _, gpu, cpu, _ = parity.run_ggx_dielectric(tctx, orc, N_GPU, aniso=aniso)
+    st = _gpu_stats(gpu, cpu, th.KINDS_DIELECTRIC)
+    st["rerun_fraction"] = tctx.fallback_count(reset=True) / N_GPU
+    check(st, f"GPU tolerant policy, config 2 aniso={aniso}")
+
+
+@pytest.mark.gpu
+def test_gpu_conductor(tctx, orc):
+    tctx.fallback_count(reset=True)
+    _, gpu, cpu, _ = parity.run_ggx_conductor(tctx, orc, N_GPU)
+    st = _gpu_stats(gpu, cpu, th.KINDS_GGX)
+    st["rerun_fraction"] = tctx.fallback_count(reset=True) / N_GPU
+    check(st, "GPU tolerant policy, config 1")
+
+
+@pytest.mark.gpu
+def test_gpu_disney(tctx, orc):
+    tctx.fallback_count(reset=True)
+    _, gpu, cpu, _ = parity.run_disney(tctx, orc, N_GPU)
+    st = _gpu_stats(gpu, cpu, th.KINDS_DISNEY)
+    st["rerun_fraction"] = tctx.fallback_count(reset=True) / N_GPU
+    check(st, "GPU tolerant policy, config 3")
+
+
+@pytest.mark.gpu
+def test_gpu_skin(tctx, orc):
+    tctx.fallback_count(reset=True)
+    _, gpu, cpu, _ = parity.run_skin(tctx, orc, N_GPU)
+    st = _gpu_stats(gpu, cpu, th.KINDS_SKIN)
+    st["rerun_fraction"] = tctx.fallback_count(reset=True) / N_GPU
+    check(st, "GPU tolerant policy, config 4")
+
+
+@pytest.mark.gpu
+def test_gpu_flags_equal_the_bit_exact_policy_on_16M_samples(tctx):
+    """Flags of RLS_ARITH_TOLERANT == flags of the default policy on 2^24 device-generated samples per config (the
+    oracle-free form of the flag contract; the bit-exact policy equals the reference on every bit, test_gpu_parity)."""
+    import torch
+    from rlshaders_b200 import api
+    n = 1 << 24
+    ectx = api.Context(0)
+    try:
+        sg = ectx.synth_shading(n, 0x5EED0002, 0, 0.02, 1.0, 0.25)
+        u = [ectx.synth_uniform(n, 0x5EED0002, s) for s in range(4)]
+        rough, ior = ectx.synth_uniform(n, 0x5EED0002, 2, 0, 0.05, 1.0), ectx.synth_uniform(n, 0x5EED0002, 3, 0, 1.05, 2.5)
+        for ctx_kw in (dict(specularRoughness=rough, ior=ior),):
+            a = api.GgxSampler(ectx, sg, **ctx_kw).dielectricSampleEvalPdf(u[0], u[1])
+            b = api.GgxSampler(tctx, sg, **ctx_kw).dielectricSampleEvalPdf(u[0], u[1])
+            torch.cuda.synchronize()
+            assert int((a["flags"] != b["flags"]).sum()) == 0
+            # and the values agree to the contract
+            for k, tol in (("wi_r", 1e-4), ("wi_t", 1e-4)):
+                assert float(((a[k] - b[k]).abs().amax(0) <= tol).float().mean()) >= 0.999
+        del a, b
+        names = ["subsurface", "metallic", "specular", "specular_tint", "roughness", "anisotropic",
+                 "sheen", "sheen_tint", "clearcoat", "clearcoat_gloss"]
+        kw = {nm: ectx.synth_uniform(n, 0x5EED0003, 20 + j) for j, nm in enumerate(names)}
+        kw["base_color"] = tuple(ectx.synth_uniform(n, 0x5EED0003, 30 + j) for j in range(3))
+        sg3 = api.ShadingBatch(sg.U, sg.V, sg.N, sg.wo)
+        a = api.DisneySampler(ectx, sg3, **kw).sampleEvalPdf(*u)
+        b = api.DisneySampler(tctx, sg3, **kw).sampleEvalPdf(*u)
+        torch.cuda.synchronize()
+        assert int((a["flags"] != b["flags"]).sum()) == 0
+        del a, b
+        dist = tuple(ectx.synth_uniform(n, 0x5EED0004, 50 + j, 0, 0.05, 2.0) for j in range(3))
+        a = api.SkinProfile(ectx, n, sss_scatter_dist=dist).sampleEvalPdf(u[0])
+        b = api.SkinProfile(tctx, n, sss_scatter_dist=dist).sampleEvalPdf(u[0])
+        torch.cuda.synchronize()
+        assert int((a["flags"] != b["flags"]).sum()) == 0
+    finally:
+        ectx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_rerun_list_overflow_uses_the_sentinel_scan(orc):
+    """A batch in which EVERY sample is flagged (ior = 1 is inside a band): the list (n / 16 entries) overflows, the
+    rest carries the sentinel, and the result must equal the bit-exact policy on every sample and every output."""
+    import torch
+    from rlshaders_b200 import api
+    n = 1 << 21
+    t, e = api.Context(0), api.Context(0)
+    try:
+        t.set_arith_policy("tolerant")
+        sg = e.synth_shading(n, 0x5EED0BAD, 0, 0.02, 1.0, 0.25)
+        rx, ry = e.synth_uniform(n, 0x5EED0BAD, 0), e.synth_uniform(n, 0x5EED0BAD, 1)
+        a = api.GgxSampler(e, sg, specularRoughness=0.4, ior=1.0).dielectricSampleEvalPdf(rx, ry)
+        b = api.GgxSampler(t, sg, specularRoughness=0.4, ior=1.0).dielectricSampleEvalPdf(rx, ry)
+        torch.cuda.synchronize()
+        assert t.fallback_count() == n
+        for k in a:
+            x, y = a[k].view(torch.int32), b[k].view(torch.int32)
+            assert bool((x == y).all()), k
+    finally:
+        t.close(); e.close()
