@@ -29,6 +29,9 @@ extern "C" {
 const char *oracle_kind(void);             /* "reference" or "port"            */
 int  oracle_max_threads(void);             /* OpenMP threads available          */
 void oracle_set_threads(int n);            /* 0 = all                           */
+/* RLS_FLAG_SLOPE_EARLY_OUT costs the reference library a partial re-evaluation of the sampler (oracle_common.h
+ * orc_vndf_early_out): 0 switches that probe off for timed runs (the bit is then absent), 1 (default) on. */
+void oracle_set_flag_probe(int on);
 
 void oracle_ggx_eval_sample(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
                             const float *rx, const float *ry, rls_vec3 out_wi, float *out_fresnel);

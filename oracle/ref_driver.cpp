@@ -93,8 +93,12 @@ inline uint32_t bsdfFlags(const AtVector &L, const AtVector &N, const AtColor &f
 /* RLS_FLAG_SLOPE_EARLY_OUT: see orc_vndf_early_out (oracle_common.h).  Only VNDFKernel has the early-outs. */
 template <typename Sampler> struct UsesVndf { static const bool value = false; };
 template <> struct UsesVndf<rls::GgxSampler> { static const bool value = true; };
+/* The probe re-evaluates part of the sampler: it is builder code, so a TIMED run of the reference (bench.py
+ * --impl reference, cpu_baseline) switches it off with oracle_set_flag_probe(0) and the bit is then simply absent. */
+static int g_flag_probe = 1;
 inline uint32_t slopeEarlyOutFlag(const Shading &sh, float ax, float ay, float rx)
 {
+    if (!g_flag_probe) return 0u;
     const float view[3] = { -sh.sg.Rd.x, -sh.sg.Rd.y, -sh.sg.Rd.z };
     const float U[3] = { sh.U.x, sh.U.y, sh.U.z }, V[3] = { sh.V.x, sh.V.y, sh.V.z };
     const float N[3] = { sh.sg.Nf.x, sh.sg.Nf.y, sh.sg.Nf.z };
@@ -279,6 +283,7 @@ int oracle_max_threads(void)
     return 1;
 #endif
 }
+void oracle_set_flag_probe(int on) { g_flag_probe = on; }
 void oracle_set_threads(int n)
 {
 #ifdef _OPENMP

@@ -711,6 +711,7 @@ int oracle_max_threads(void)
     return 1;
 #endif
 }
+void oracle_set_flag_probe(int on) { (void)on; }   /* the port derives the flag from its own code path: free */
 void oracle_set_threads(int n)
 {
 #ifdef _OPENMP

@@ -9,6 +9,7 @@ import ctypes as C
 ABI_VERSION = 1
 
 RLS_OK = 0
+ARITH_FAST, ARITH_EXACT, ARITH_TOLERANT = 0, 1, 2
 RLS_ERR_INVALID_ARGUMENT = -1
 RLS_ERR_CUDA = -2
 RLS_ERR_NO_DEVICE = -3
@@ -27,6 +28,7 @@ FLAG_F_BLACK = 0x0008
 FLAG_ENTERING = 0x0010
 FLAG_TIR = 0x0020
 FLAG_PDF_FLOORED = 0x0040
+FLAG_SLOPE_EARLY_OUT = 0x0080
 FLAG_LOBE_SHIFT = 8
 FLAG_LOBE_MASK = 0x0300
 FLAG_EXP_LOBE = 0x0400

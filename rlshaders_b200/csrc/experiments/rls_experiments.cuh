@@ -24,7 +24,6 @@ static int experiments_configure(rls_context *ctx)
     if (const char *v = getenv("RLS_STAGGER_NS")) { int k = atoi(v); x.stagger_ns = (unsigned)(k < 0 ? 0 : (k > 1000000 ? 1000000 : k)); }
     x.disney_lobe_sort = flag("RLS_DISNEY_LOBE_SORT");
     x.gauss_scalar = flag("RLS_GAUSS_SCALAR");
-    x.sweep_fast = flag("RLS_SWEEP_FAST");
     const unsigned long long negzero2 = 0x8000000080000000ull;   // {-0, -0} for the packed multiplies: a run-time value on purpose
     cudaError_t e = cudaMemcpyToSymbol(pk::c_negzero2, &negzero2, sizeof(negzero2));
     if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaMemcpyToSymbol(c_negzero2)");

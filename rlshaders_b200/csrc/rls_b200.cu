@@ -27,6 +27,7 @@
 #include "rls_callers.cuh"
 #include "rls_kernel_args.cuh"
 #include "rls_tol_launch.cuh"
+#include "rls_sweep.cuh"
 
 using namespace rls;
 
@@ -65,21 +66,16 @@ static constexpr int kBlockGgx = RLS_GGX_BLOCK;
 #define RLS_SKIN_MIN_BLOCKS 9
 #endif
 static constexpr int kBlockSkin = RLS_SKIN_BLOCK;
-// ... and the albedo sweep (30.3 vs 29.5 G samples/s); its per-thread FP64 partial sums then cover other samples,
-// which changes the table in the last bits only (deterministic for a given build; tests: rtol 1e-12 across partitions).
-#ifndef RLS_SWEEP_BLOCK
-#define RLS_SWEEP_BLOCK 128
-#endif
+// ... and the albedo sweep (128 threads = 4 warps = 4 cells per CTA, rls_sweep.cuh).
 #ifndef RLS_SWEEP_MIN_BLOCKS
 #define RLS_SWEEP_MIN_BLOCKS 9
 #endif
-static constexpr int kBlockSweep = RLS_SWEEP_BLOCK;
 static_assert(kBlock >= 96 && kBlockSkin >= 96, "rlm::smem_tables_init() fills 96 table entries with one thread each");
 
 #ifdef RLS_EXPERIMENTS
 // Only in librls_b200_experiments.so (tools/build_experiments.sh): A/B switches of kernels that measured slower.
 struct rls_experiments {
-    bool paired = false, tma = false, packed = false, disney_lobe_sort = false, gauss_scalar = false, sweep_fast = false;
+    bool paired = false, tma = false, packed = false, disney_lobe_sort = false, gauss_scalar = false;
     int persistent = 0;              // CTAs per SM of the persistent dielectric kernel (negative: dynamic chunks)
     unsigned stagger_ns = 0;
     unsigned *chunk_counter = nullptr;
@@ -98,6 +94,7 @@ struct rls_context {
     // RLS_ARITH_TOLERANT: one re-run list per stream the fused kernels are launched on (slot 0 = `stream`,
     // 1.. = the host-staging streams), allocated on first use and grown when a larger batch arrives
     tol::Worklist worklist[kStages + 1] = {};
+    tol::SweepWorklist sweep_worklist = {};       // RLS_ARITH_TOLERANT sweep: (cell, k) of the band samples
 #ifdef RLS_EXPERIMENTS
     rls_experiments exp;                          // switches of the measured-slower forms (experiments/rls_experiments.cuh)
 #endif
@@ -227,6 +224,8 @@ extern "C" int rls_shutdown(rls_context *ctx)
     }
     if (ctx->fallbacks) cudaFree(ctx->fallbacks);
     for (tol::Worklist &w : ctx->worklist) { if (w.list) cudaFree(w.list); if (w.count) cudaFree(w.count); }
+    if (ctx->sweep_worklist.list) cudaFree(ctx->sweep_worklist.list);
+    if (ctx->sweep_worklist.count) cudaFree(ctx->sweep_worklist.count);
 #ifdef RLS_EXPERIMENTS
     experiments_release(ctx);
 #endif
@@ -983,19 +982,7 @@ k_writer_scatter_paint(size_t n, int W, int H, const uint32_t *scratch, float *i
 }
 
 // ============================================================ synthetic generators
-RLS_DEV uint64_t hash64(uint64_t seed, uint32_t stream, uint64_t index)
-{
-    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (index + 1ull) + 0xD1B54A32D192ED03ull * (uint64_t)stream;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
-RLS_DEV float uniform24(uint64_t seed, uint32_t stream, uint64_t index)
-{
-    uint32_t k = (uint32_t)(hash64(seed, stream, index) >> 40);
-    if (k == 0u) k = 1u;
-    return (float)k * 5.9604644775390625e-8f;
-}
+RLS_DEV float uniform24(uint64_t seed, uint32_t stream, uint64_t index) { return sweep_uniform24(seed, stream, index); }
 __global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
 k_synth_uniform(size_t n, uint64_t seed, uint32_t stream, uint64_t first, float lo, float hi, float *out)
 {
@@ -1030,68 +1017,56 @@ k_synth_shading(size_t n, uint64_t seed, uint64_t first, float cos_lo, float cos
 }
 
 // ================================================================= albedo sweep
-struct SweepGridDev { int n_rough, n_cos, n_ior; float rlo, rhi, ilo, ihi; };
-
-template <bool kFast>
-__global__ void __launch_bounds__(kBlockSweep, RLS_SWEEP_MIN_BLOCKS)
-k_albedo_sweep(SweepGridDev g, uint64_t seed, uint32_t k0, uint32_t k1, double *table, unsigned long long *fallbacks)
+// Bit-exact policy: one warp per cell (rls_sweep.cuh), the rough-dielectric unit on the canonical frame.  All samples of
+// a cell share (roughness, cos, ior), so everything that depends on the shading point only is loop invariant and is
+// hoisted by the compiler.  The guarded operators run this kernel FASTER than the fast policy (30.3 vs 26.0 G samples/s
+// on B200: the FP64 accumulators and the counter hash leave no registers for a second code path), so the bit-exact sweep
+// uses FpExact throughout; RLS_ARITH_TOLERANT has its own kernel (rls_tol.cu).
+__global__ void __launch_bounds__(kSweepBlock, RLS_SWEEP_MIN_BLOCKS)
+k_albedo_sweep(SweepGridDev g, uint32_t n_cells, uint64_t seed, uint32_t k0, uint32_t k1, double *table)
 {
-    const uint32_t cell = blockIdx.x;
-    uint32_t ie = cell % (uint32_t)g.n_ior;
-    uint32_t ic = (cell / (uint32_t)g.n_ior) % (uint32_t)g.n_cos;
-    uint32_t ir = cell / (uint32_t)(g.n_ior * g.n_cos);
-    float tr = g.n_rough > 1 ? (float)ir / (float)(g.n_rough - 1) : 0.0f;
-    float te = g.n_ior > 1 ? (float)ie / (float)(g.n_ior - 1) : 0.0f;
-    float rough = g.rlo + (g.rhi - g.rlo) * tr;
-    float ior = g.ilo + (g.ihi - g.ilo) * te;
-    float cosv = (float)(ic + 1u) / (float)g.n_cos;
-
+    const uint32_t cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (cell >= n_cells) return;                         // whole warps
+    float rough, cosv, ior;
+    sweep_cell(g, cell, rough, cosv, ior);
     Shading s;
     s.U = mk3(1.0f, 0.0f, 0.0f); s.V = mk3(0.0f, 1.0f, 0.0f); s.N = mk3(0.0f, 0.0f, 1.0f);
     s.wo = mk3(sqrtf(1.0f - cosv * cosv), 0.0f, cosv);
     s.backfacing = false;
-
-    double acc[RLS_SWEEP_VALUES_PER_CELL] = { 0.0, 0.0, 0.0, 0.0, 0.0 };
-    // All samples of a cell share (roughness, cos, ior).  A cell whose parameters are degenerate (ior == 1: the
-    // refraction half vector is the zero vector; cos == 1: the view is the normal) leaves the fast window on every
-    // sample, so the WHOLE cell (a CTA-uniform decision) runs the exact operators; every other cell runs the fast
-    // policy with the usual per-sample exact re-run.
-    const bool cell_fast = kFast && ior != 1.0f && cosv != 1.0f;
-    for (uint32_t k = k0 + threadIdx.x; k < k1; k += kBlockSweep) {
-        uint64_t idx = ((uint64_t)cell << 32) | (uint64_t)k;
-        float rx = uniform24(seed, 0u, idx);
-        float ry = uniform24(seed, 1u, idx);
-        Dielectric r;
-        bool need_exact = !cell_fast;
-        if (cell_fast) {
-            FpFast fp;
-            r = dielectric_unit(fp, s, ior, rough, 0.0f, rx, ry);
-            need_exact = !fp.ok();
-            if (need_exact) atomicAdd(fallbacks, 1ull);
-        }
-        if (need_exact) {
-            FpExact fp;
-            r = dielectric_unit(fp, s, ior, rough, 0.0f, rx, ry);
-        }
-        bool valid = !(r.flags & (RLS_FLAG_ZERO_L | RLS_FLAG_BELOW_HORIZON));
-        if (valid) { acc[0] += (double)(r.f_r / r.pdf_r); acc[3] += 1.0; }
-        if (r.flags & RLS_FLAG_TIR) acc[4] += 1.0; else acc[1] += (double)r.w_t;
-        acc[2] += (double)r.F;
+    double acc[kSweepValues] = { 0.0, 0.0, 0.0, 0.0, 0.0 };
+    for (uint32_t k = k0 + (threadIdx.x & 31u); k < k1; k += 32u) {      // the entry point rejects k1 > 2^32 - 32
+        const uint64_t idx = ((uint64_t)cell << 32) | (uint64_t)k;
+        FpExact fp;
+        const Dielectric r = dielectric_unit(fp, s, ior, rough, 0.0f, sweep_uniform24(seed, 0u, idx), sweep_uniform24(seed, 1u, idx));
+        sweep_accumulate(acc, r.flags, r.f_r, r.pdf_r, r.w_t, r.F);
     }
-    __shared__ double red[RLS_SWEEP_VALUES_PER_CELL][kBlockSweep / 32];
+    sweep_store(acc, cell, table);
+}
+// RLS_ARITH_TOLERANT: the samples the tolerance sweep kernel listed (cell, k) evaluated exactly and ADDED to the table
+// (FP64 atomics: the table then differs from run to run in the last bits of the sums, never in the counts).
+__global__ void __launch_bounds__(kSweepBlock, RLS_SWEEP_MIN_BLOCKS)
+k_albedo_sweep_rerun(SweepGridDev g, uint64_t seed, tol::SweepWorklist wl, double *table, unsigned long long *fallbacks)
+{
+    const unsigned c = *wl.count;
+    const unsigned listed = c < wl.cap ? c : wl.cap;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    if (tid == 0 && listed) atomicAdd(fallbacks, (unsigned long long)listed);
+    for (uint32_t j = tid; j < listed; j += stride) {
+        const uint2 e = wl.list[j];
+        float rough, cosv, ior;
+        sweep_cell(g, e.x, rough, cosv, ior);
+        Shading s;
+        s.U = mk3(1.0f, 0.0f, 0.0f); s.V = mk3(0.0f, 1.0f, 0.0f); s.N = mk3(0.0f, 0.0f, 1.0f);
+        s.wo = mk3(sqrtf(1.0f - cosv * cosv), 0.0f, cosv);
+        s.backfacing = false;
+        const uint64_t idx = ((uint64_t)e.x << 32) | (uint64_t)e.y;
+        FpExact fp;
+        const Dielectric r = dielectric_unit(fp, s, ior, rough, 0.0f, sweep_uniform24(seed, 0u, idx), sweep_uniform24(seed, 1u, idx));
+        double acc[kSweepValues] = { 0.0, 0.0, 0.0, 0.0, 0.0 };
+        sweep_accumulate(acc, r.flags, r.f_r, r.pdf_r, r.w_t, r.F);
 #pragma unroll
-    for (int j = 0; j < RLS_SWEEP_VALUES_PER_CELL; j++) {
-        double v = acc[j];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0) red[j][threadIdx.x >> 5] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < RLS_SWEEP_VALUES_PER_CELL) {
-        double v = 0.0;
-#pragma unroll
-        for (int w = 0; w < kBlockSweep / 32; w++) v += red[threadIdx.x][w];
-        table[(size_t)cell * RLS_SWEEP_VALUES_PER_CELL + threadIdx.x] = v;
+        for (int v = 0; v < kSweepValues; v++)
+            if (acc[v] != 0.0) atomicAdd(table + (size_t)e.x * kSweepValues + v, acc[v]);
     }
 }
 
@@ -1563,29 +1538,42 @@ extern "C" int rls_skin_probe_mis_pdf(rls_context *ctx, size_t n, const rls_shad
 }
 
 // ================================================================= C ABI: sweep
+// Validates the grid and enqueues the sweep of samples [spp_begin, spp_end) of every cell on `st` (the entry point below
+// and the multi-device form rls_multi_albedo_sweep share it).  `slot` names the re-run list (RLS_ARITH_TOLERANT).
+static int launch_albedo_sweep(rls_context *ctx, cudaStream_t st, const rls_sweep_grid *grid, uint64_t seed,
+                               uint32_t spp_begin, uint32_t spp_end, double *table)
+{
+    RLS_REQUIRE(ctx, grid && table, "rls_albedo_sweep: NULL argument");
+    RLS_REQUIRE(ctx, grid->n_rough > 0 && grid->n_cos > 0 && grid->n_ior > 0 && spp_end >= spp_begin, "rls_albedo_sweep: bad grid");
+    const uint64_t cells64 = (uint64_t)grid->n_rough * (uint64_t)grid->n_cos * (uint64_t)grid->n_ior;
+    RLS_REQUIRE(ctx, cells64 <= 0x7fffffffull / 32ull, "rls_albedo_sweep: more than 2^26 - 1 cells (one warp per cell)");
+    RLS_REQUIRE(ctx, spp_end <= 0xffffffffu - 32u, "rls_albedo_sweep: spp_end must be at most 2^32 - 33");
+    SweepGridDev g; g.n_rough = grid->n_rough; g.n_cos = grid->n_cos; g.n_ior = grid->n_ior;
+    g.rlo = grid->roughness_lo; g.rhi = grid->roughness_hi; g.ilo = grid->ior_lo; g.ihi = grid->ior_hi;
+    const uint32_t cells = (uint32_t)cells64;
+    const unsigned blocks = (unsigned)((cells64 * 32ull + kSweepBlock - 1) / kSweepBlock);
+    if (ctx->arith == RLS_ARITH_TOLERANT) {
+        // the band samples go to a (cell, k) list and are added to the table by the exact policy afterwards
+        tol::SweepWorklist &w = ctx->sweep_worklist;
+        const uint32_t want = 1u << 22;
+        if (!w.count) RLS_CUDA(ctx, cudaMalloc((void **)&w.count, sizeof(unsigned)));
+        if (!w.list) { RLS_CUDA(ctx, cudaMalloc((void **)&w.list, (size_t)want * sizeof(uint2))); w.cap = want; }
+        RLS_CUDA(ctx, cudaMemsetAsync(w.count, 0, sizeof(unsigned), st));
+        RLS_TOL_CHECK(ctx, tol::launch_albedo_sweep(st, g, cells, seed, spp_begin, spp_end, table, w));
+        k_albedo_sweep_rerun<<<rerun_grid(ctx), kSweepBlock, 0, st>>>(g, seed, w, table, ctx->fallbacks);
+        RLS_LAUNCH_CHECK(ctx);
+        return RLS_OK;
+    }
+    k_albedo_sweep<<<blocks, kSweepBlock, 0, st>>>(g, cells, seed, spp_begin, spp_end, table);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
 extern "C" int rls_albedo_sweep(rls_context *ctx, const rls_sweep_grid *grid, uint64_t seed, uint32_t spp_begin,
                                 uint32_t spp_end, double *table)
 {
     if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
-    RLS_REQUIRE(ctx, grid && table, "rls_albedo_sweep: NULL argument");
-    RLS_REQUIRE(ctx, grid->n_rough > 0 && grid->n_cos > 0 && grid->n_ior > 0 && spp_end >= spp_begin, "rls_albedo_sweep: bad grid");
-    SweepGridDev g; g.n_rough = grid->n_rough; g.n_cos = grid->n_cos; g.n_ior = grid->n_ior;
-    g.rlo = grid->roughness_lo; g.rhi = grid->roughness_hi; g.ilo = grid->ior_lo; g.ihi = grid->ior_hi;
-    unsigned cells = (unsigned)(grid->n_rough * grid->n_cos * grid->n_ior);
     DeviceGuard guard(ctx->device);
-    // Measured on B200 (65536 cells x 4096 spp): the guarded operators run this kernel at 30.3 G samples/s, the
-    // fast policy at 26.0 (the FP64 accumulators and the RNG leave no registers for a second code path), so the
-    // bit-exact sweep always uses the exact policy.
-    bool sweep_fast = false;
-#ifdef RLS_EXPERIMENTS
-    sweep_fast = ctx->exp.sweep_fast && uses_fast_policy(ctx);
-#endif
-    if (sweep_fast)
-        k_albedo_sweep<true><<<cells, kBlockSweep, 0, ctx->stream>>>(g, seed, spp_begin, spp_end, table, ctx->fallbacks);
-    else
-        k_albedo_sweep<false><<<cells, kBlockSweep, 0, ctx->stream>>>(g, seed, spp_begin, spp_end, table, ctx->fallbacks);
-    RLS_LAUNCH_CHECK(ctx);
-    return RLS_OK;
+    return launch_albedo_sweep(ctx, ctx->stream, grid, seed, spp_begin, spp_end, table);
 }
 
 // ================================================================= C ABI: synth

@@ -112,6 +112,33 @@ k_skin_profile_tol(uint32_t n, SkinParamsDev sp, const float *rx, ProfileOutDev 
     o.flags[i] = enlist(bd.rerun, i, r.flags, wl);
 }
 
+// The albedo sweep (rls_sweep.cuh: one warp per cell) on the tolerance-policy unit.  Band samples are listed for the
+// exact re-run and left out of the sums.
+__global__ void __launch_bounds__(kSweepBlock, 8)
+k_albedo_sweep_tol(SweepGridDev g, uint32_t n_cells, uint64_t seed, uint32_t k0, uint32_t k1, double *table, SweepWorklist wl)
+{
+    const uint32_t cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (cell >= n_cells) return;
+    float rough, cosv, ior;
+    sweep_cell(g, cell, rough, cosv, ior);
+    const v3 U = mk(1.0f, 0.0f, 0.0f), V = mk(0.0f, 1.0f, 0.0f), N = mk(0.0f, 0.0f, 1.0f);
+    const v3 wo = mk(sqrtf(1.0f - cosv * cosv), 0.0f, cosv);
+    double acc[kSweepValues] = { 0.0, 0.0, 0.0, 0.0, 0.0 };
+    for (uint32_t k = k0 + (threadIdx.x & 31u); k < k1; k += 32u) {
+        const uint64_t idx = ((uint64_t)cell << 32) | (uint64_t)k;
+        Bands bd;
+        const DielectricT r = dielectric_unit(bd, U, V, N, wo, false, ior, rough, 0.0f, sweep_uniform24(seed, 0u, idx),
+                                              sweep_uniform24(seed, 1u, idx));
+        bool mine = true;
+        if (bd.rerun) {
+            const unsigned j = atomicAdd(wl.count, 1u);
+            if (j < wl.cap) { wl.list[j] = make_uint2(cell, k); mine = false; }
+        }
+        if (mine) sweep_accumulate(acc, r.flags, r.f_r, r.pdf_r, r.w_t, r.F);
+    }
+    sweep_store(acc, cell, table);
+}
+
 static inline unsigned grid_for(size_t n) { return (unsigned)((n + kBlockTol - 1) / kBlockTol); }
 
 cudaError_t launch_ggx_sample_eval_pdf(cudaStream_t st, size_t n, const ShadingSoA &sg, const GgxParamsDev &p, const float *rx,
@@ -133,6 +160,13 @@ cudaError_t launch_disney(cudaStream_t st, size_t n, const ShadingSoA &sg, const
 {
     if (all_arrays) k_disney_sample_eval_pdf_tol<true><<<grid_for(n), kBlockTol, 0, st>>>((uint32_t)n, sg, p, rx_s, ry_s, rx_d, ry_d, o, wl);
     else k_disney_sample_eval_pdf_tol<false><<<grid_for(n), kBlockTol, 0, st>>>((uint32_t)n, sg, p, rx_s, ry_s, rx_d, ry_d, o, wl);
+    return cudaGetLastError();
+}
+cudaError_t launch_albedo_sweep(cudaStream_t st, const SweepGridDev &g, uint32_t n_cells, uint64_t seed, uint32_t k0, uint32_t k1,
+                                double *table, const SweepWorklist &wl)
+{
+    const unsigned blocks = (unsigned)(((uint64_t)n_cells * 32ull + kSweepBlock - 1) / kSweepBlock);
+    k_albedo_sweep_tol<<<blocks, kSweepBlock, 0, st>>>(g, n_cells, seed, k0, k1, table, wl);
     return cudaGetLastError();
 }
 cudaError_t launch_skin_profile(cudaStream_t st, size_t n, const SkinParamsDev &p, const float *rx, const ProfileOutDev &o,

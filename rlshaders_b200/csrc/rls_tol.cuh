@@ -222,10 +222,13 @@ constexpr uint32_t kFlagZeroL = 0x0001u, kFlagBelowHorizon = 0x0002u, kFlagPdfZe
 // ================================================================== visible-normal sampling
 // VNDFKernel::evalSample + sampleSlope (src/rlGgx.cpp:14-99; src/rlDisney.cpp:416-502 is the same code).
 // vz = N.wo in the reference's operation order.  Returns the world-space microfacet normal; `early` = the
-// uniform-slope early-out was taken (src/rlGgx.cpp:27,38).
+// uniform-slope early-out was taken (src/rlGgx.cpp:27,38); `noise` = an estimate of the REFERENCE's own rounding noise
+// in the sampled direction (its two roots of :42-46 are differences of terms ~ 1 / (A^2 - 1): 1 ulp becomes
+// ~1e-7 / |A^2 - 1|), which the bands on direction-derived comparands add to their width.
 RLT_HD v3 sample_visible_normal(Bands &bd, v3 wo, v3 U, v3 Vax, v3 N, float vz, float ax, float ay, float rx, float ry,
-                                bool &early)
+                                bool &early, float &noise)
 {
+    noise = 0.0f;
     // :66-75  view -> local polar -> sphericalDirection: (r cos phiV, r sin phiV, cz), r = sqrt(1 - cz^2)
     const float vx = dot(U, wo), vy = dot(Vax, wo);
     const float cz = clampf(vz, -1.0f, 1.0f);
@@ -268,15 +271,17 @@ RLT_HD v3 sample_visible_normal(Bands &bd, v3 wo, v3 U, v3 Vax, v3 N, float vz, 
         sincos_(kTwoPi * ry, &s, &c);
         slx = ru * c; sly = ru * s;
     } else {
-        // :40-46.  D = sqrt(B^2 tmp^2 - (A^2 - B^2) tmp) = |A| sqrt(1 + B^2 - A^2) |tmp| without the cancellation;
-        // slopeX2 > 1/B  <=>  A > 1 (for 0 <= A < 1 the second root stays below 1/B, for A > 1 above it; they
-        // meet only where D = 0).
+        // :40-46.  With tmp = 1 / (A^2 - 1), u = sqrt(1 + B^2 - A^2): D = sqrt(B^2 tmp^2 - (A^2 - B^2) tmp) = |A| u |tmp|,
+        // and slopeX2 > 1/B  <=>  A > 1 (for 0 <= A < 1 the second root stays below 1/B, for A > 1 above it; they meet
+        // only where D = 0).  The root the reference picks is therefore tmp (B - A u) for every A -- for A >= 0 a
+        // difference that cancels as A -> 1, evaluated here in its conjugate form (A^2 - B^2) / (B + A u), which is
+        // smooth through A = 1.
         const float tmp = rcp(A2 - 1.0f);
         const float u2 = fma_(B, B, 1.0f - A2);                 // 1 + B^2 - A^2 >= 0; cancels as rx -> 1 (A -> S)
         bd.require(u2 > 1e-3f * (S * S));
-        const float Dq = fabsf(A * tmp) * sqrt_(fmaxf(0.0f, u2));
-        const float Bt = B * tmp;
-        slx = (A < 0.0f || A > 1.0f) ? Bt - Dq : Bt + Dq;
+        const float Au = A * sqrt_(fmaxf(0.0f, u2));
+        slx = (A < 0.0f) ? (B - Au) * tmp : (A2 - B * B) * rcp(B + Au);
+        noise = 4e-7f * fabsf(tmp) * (1.0f + B);
         // :48-58  slope_y: the rational fit on the reference's own operations (its denominator cancels to 5e-4)
         const bool up = ry > 0.5f;
         const float t = up ? 2.0f * (ry - 0.5f) : 2.0f * (0.5f - ry);
@@ -360,16 +365,18 @@ RLT_HD DielectricT dielectric_unit(Bands &bd, v3 U, v3 V, v3 N, v3 wo, bool back
     bd.near(g.b, 1.0f, 1e-4f);                                  // ior == 1: F == 0 and the zero half vector are rounding-decided
 
     bool early;
-    const v3 m = sample_visible_normal(bd, wo, U, V, N, g.vz, g.ax, g.ay, rx, ry, early);
+    float noise;
+    const v3 m = sample_visible_normal(bd, wo, U, V, N, g.vz, g.ax, g.ay, rx, ry, early, noise);
     const float Vm = dot(wo, m), aVm = fabsf(Vm);
     const float mN = dot(m, N);
-    bd.near(Vm, 0.0f, 1e-3f);                                   // sign of V.m decides the masking terms
+    const float band = 1e-3f + noise;                           // on comparands that follow the sampled direction
+    bd.near(Vm, 0.0f, band);                                    // sign of V.m decides the masking terms
     // reflectDirection(V, m) = 2|V.m| m - V; its half vector with V is m, V.H = V.m, L.H = 2|V.m| - V.m
     r.wi_r = m * (2.0f * aVm) - wo;
     const float LH = 2.0f * aVm - Vm;
     r.F = fresnel_c(ratio2, fabsf(LH));                         // fresnel(L, m), c = |L.m|
     const float LdotN = dot(r.wi_r, N);
-    bd.near(LdotN, 0.0f, 2e-5f);
+    bd.near(LdotN, 0.0f, band);
     const float Dm = ggx_D(g, m, mN);
     const float G1v = G1_value(g.a2g, VdotN), G1l = G1_value(g.a2g, LdotN);
     // evalPdf (src/rlGgx.h:121-127, :72-80): max(D G1(V, H) / (4 |V.N|), eps)
@@ -393,7 +400,7 @@ RLT_HD DielectricT dielectric_unit(Bands &bd, v3 U, v3 V, v3 N, v3 wo, bool back
 
     // getRefractDirection(m, V) (src/rlGgx.h:277-291; eta is not squared, as in the reference)
     const float cT2 = fma_(eta, fma_(Vm, Vm, -1.0f), 1.0f);
-    bd.near(cT2, 0.0f, 3e-5f * (1.0f + eta));
+    bd.near(cT2, 0.0f, band * (1.0f + eta));
     float TdotN, G1t, Tm;
     if (cT2 < 0.0f) {                                           // total internal reflection: reflect about m
         fl |= kFlagTir;
@@ -414,7 +421,7 @@ RLT_HD DielectricT dielectric_unit(Bands &bd, v3 U, v3 V, v3 N, v3 wo, bool back
         const float w = fma_(iorIn, IdotH, iorOut * OdotH);
         const float G1ti = (IdotH * VdotN < 0.0f) ? 0.0f : G1v;
         const float G1to = (OdotH * TdotN < 0.0f) ? 0.0f : G1t;
-        bd.near(TdotN, 0.0f, 2e-5f);
+        bd.near(TdotN, 0.0f, band);
         r.f_t = fabsf(OdotH * IdotH) * (iorOut * iorOut) * (1.0f - Fh) * (G1ti * G1to) * Dm *
                 rcp(fabsf(TdotN) * absVN * (w * w));
     }
@@ -441,14 +448,16 @@ RLT_HD GgxBsdfT ggx_unit(Bands &bd, v3 U, v3 V, v3 N, v3 wo, bool backfacing, v3
     const float ratio2 = ratio * ratio;
     bd.near(g.b, 1.0f, 1e-4f);
     bool early;
-    const v3 m = sample_visible_normal(bd, wo, U, V, N, g.vz, g.ax, g.ay, rx, ry, early);   // requires V.N > eps
+    float noise;
+    const v3 m = sample_visible_normal(bd, wo, U, V, N, g.vz, g.ax, g.ay, rx, ry, early, noise);   // requires V.N > eps
     const float Vm = dot(wo, m), aVm = fabsf(Vm);
-    bd.near(Vm, 0.0f, 1e-3f);
+    const float band = 1e-3f + noise;
+    bd.near(Vm, 0.0f, band);
     o.L = m * (2.0f * aVm) - wo;
     const float LH = 2.0f * aVm - Vm;
     o.fresnel = fresnel_c(ratio2, fabsf(LH));
     const float LdotN = dot(o.L, N);
-    bd.near(LdotN, 0.0f, 2e-5f);
+    bd.near(LdotN, 0.0f, band);
     const float Dm = ggx_D(g, m, dot(m, N));
     const float G1v = G1_value(g.a2g, VdotN), G1l = G1_value(g.a2g, LdotN);
     const float i4vn = 0.25f * rcp(absVN);
@@ -519,11 +528,12 @@ RLT_HD DisneyT disney_unit(Bands &bd, v3 U, v3 V, v3 N, v3 wo, const DisneyIn &p
 #endif
     const uint32_t lobe = rx_s < gtr2Weight ? 0u : 1u;
     bool early = false;
+    float noise = 0.0f;
     v3 M;
     if (lobe == 0u) {
         const float rx = div(rx_s, gtr2Weight);
         if (visible) {
-            M = sample_visible_normal(bd, wo, U, V, N, VdotN, ax, ay, rx, ry_s, early);
+            M = sample_visible_normal(bd, wo, U, V, N, VdotN, ax, ay, rx, ry_s, early, noise);
         } else {                                                  // sampleGTR2AnisoDirection (:406-414)
             const float g = sqrt_(div(ry_s, 1.0f - ry_s));
             float s, c;
@@ -539,11 +549,12 @@ RLT_HD DisneyT disney_unit(Bands &bd, v3 U, v3 V, v3 N, v3 wo, const DisneyIn &p
         const float ct = sqrt_(fmaxf(ct2, 0.0f)), st = sqrt_(fmaxf(1.0f - ct2, 0.0f));
         M = normalize(to_frame(st * c, st * s, ct, U, V, N));
     }
+    const float band = 1e-3f + noise;                             // on comparands that follow the sampled direction
     const float NM = dot(N, M);
-    bd.near(NM, 0.0f, 2e-6f);
+    bd.near(NM, 0.5f * kEps, 0.5f * kEps + band);                 // N.M < 0 and N.M < eps
     const bool zeroS = NM < 0.0f;
     const float VM = dot(wo, M), aVM = fabsf(VM);
-    bd.near(VM, 0.0f, 1e-3f);       // L ~ -V: the reference's half vector normalize(L + V) is rounding noise
+    bd.near(VM, 0.5f * kEps, 0.5f * kEps + band);   // L ~ -V: the reference's half vector normalize(L + V) is rounding noise; L.M < eps
     uint32_t fls = lobe << 8;
     if (early) fls |= kFlagSlopeEarlyOut;
     if (zeroS) {
@@ -569,9 +580,7 @@ RLT_HD DisneyT disney_unit(Bands &bd, v3 U, v3 V, v3 N, v3 wo, const DisneyIn &p
             o.ps = fma_(Dr, cw, (1.0f - cw) * Ds) * NM * 0.25f * rcp(LdotM);
         }
         // eval (:318-356) x N.L (:136)
-        bd.near(LdotN, 0.5f * kEps, 0.9f * kEps);                 // L.N <= 0 and L.N < eps
-        bd.near(NM, kEps, 2e-5f);
-        bd.near(LdotM, kEps, 2e-5f);
+        bd.near(LdotN, 0.5f * kEps, 0.5f * kEps + band);          // L.N <= 0 and L.N < eps
         if (LdotN < kEps || VdotN < kEps || NM < kEps || LdotM < kEps) {
             o.fs = zero;
         } else {

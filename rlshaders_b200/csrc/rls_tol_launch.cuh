@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "rls_kernel_args.cuh"
+#include "rls_sweep.cuh"
 
 namespace rls {
 namespace tol {
@@ -29,6 +30,12 @@ cudaError_t launch_ggx_dielectric(cudaStream_t st, size_t n, const ShadingSoA &s
 cudaError_t launch_disney(cudaStream_t st, size_t n, const ShadingSoA &sg, const DisneyParamsDev &p, bool all_arrays,
                           const float *rx_s, const float *ry_s, const float *rx_d, const float *ry_d, const DisneyOutDev &o,
                           const Worklist &wl);
+// The sweep's re-run list: (cell, k) of every band sample.  The tolerance kernel leaves such a sample OUT of its sums and
+// k_albedo_sweep_rerun (rls_b200.cu) adds its bit-exact contribution; when the list is full the kernel keeps its own
+// tolerance-policy value for the sample instead (nothing is lost, the counts may then differ on a band sample).
+struct SweepWorklist { uint2 *list; unsigned *count; uint32_t cap; };
+cudaError_t launch_albedo_sweep(cudaStream_t st, const SweepGridDev &g, uint32_t n_cells, uint64_t seed, uint32_t k0, uint32_t k1,
+                                double *table, const SweepWorklist &wl);
 cudaError_t launch_skin_profile(cudaStream_t st, size_t n, const SkinParamsDev &p, const float *rx, const ProfileOutDev &o,
                                 const Worklist &wl);
 

@@ -130,6 +130,10 @@ class Oracle:
     def max_threads(self):
         return self.lib.oracle_max_threads()
 
+    def set_flag_probe(self, on):
+        """Timed runs switch the RLS_FLAG_SLOPE_EARLY_OUT probe of the reference library off (oracle_api.h)."""
+        self.lib.oracle_set_flag_probe(C.c_int(1 if on else 0))
+
     # ---- rlGgx
     def ggx_eval_sample(self, sg, params, rx, ry):
         n = len(rx)
@@ -174,6 +178,44 @@ class Oracle:
             C.c_void_p(rx.ctypes.data), C.c_void_p(ry.ctypes.data), C.byref(out))
         return dict(fresnel=F, wi_r=np.stack(wir), f_r=fr, pdf_r=pr, wi_t=np.stack(wit), f_t=ft,
                     weight_t=wt, flags=fl)
+
+    def prepare_ggx_dielectric(self, sg, params, rx, ry):
+        """For timing: outputs allocated AND touched once, ctypes arguments built once.  Returns (call, outputs) where
+        call() is nothing but the library's oracle_ggx_dielectric_sample_eval_pdf on those buffers."""
+        n = len(rx)
+        F, wir, fr, pr, wit, ft, wt, fl = _z(n), _v3(n), _z(n), _z(n), _v3(n), _z(n), _z(n), _z(n, np.uint32)
+        out = abi.GgxDielectricOut(F.ctypes.data, abi.vec3(wir), fr.ctypes.data, pr.ctypes.data,
+                                   abi.vec3(wit), ft.ctypes.data, wt.ctypes.data, fl.ctypes.data)
+        for a in (F, fr, pr, ft, wt, fl) + wir + wit:
+            a.fill(0)
+        args = (C.c_size_t(n), C.byref(shading_struct(sg)), C.byref(params), C.c_void_p(rx.ctypes.data),
+                C.c_void_p(ry.ctypes.data), C.byref(out))
+        keep = (sg, params, rx, ry, out)
+        fn = self.lib.oracle_ggx_dielectric_sample_eval_pdf
+
+        def call():
+            fn(*args)
+            return keep is None
+        outs = dict(fresnel=F, wi_r=wir, f_r=fr, pdf_r=pr, wi_t=wit, f_t=ft, weight_t=wt, flags=fl)
+        return call, outs
+
+    def prepare_disney(self, sg, params, rx_s, ry_s, rx_d, ry_d):
+        """As prepare_ggx_dielectric, for oracle_disney_sample_eval_pdf."""
+        n = len(rx_s)
+        wis, fs, ps, wid, fd, pd, fl = _v3(n), _v3(n), _z(n), _v3(n), _v3(n), _z(n), _z(n, np.uint32)
+        out = abi.DisneyOut(abi.vec3(wis), abi.vec3(fs), ps.ctypes.data, abi.vec3(wid), abi.vec3(fd),
+                            pd.ctypes.data, fl.ctypes.data)
+        for a in (ps, pd, fl) + wis + fs + wid + fd:
+            a.fill(0)
+        args = (C.c_size_t(n), C.byref(shading_struct(sg)), C.byref(params), C.c_void_p(rx_s.ctypes.data),
+                C.c_void_p(ry_s.ctypes.data), C.c_void_p(rx_d.ctypes.data), C.c_void_p(ry_d.ctypes.data), C.byref(out))
+        keep = (sg, params, rx_s, ry_s, rx_d, ry_d, out)
+        fn = self.lib.oracle_disney_sample_eval_pdf
+
+        def call():
+            fn(*args)
+            return keep is None
+        return call, dict(wi_s=wis, f_s=fs, pdf_s=ps, wi_d=wid, f_d=fd, pdf_d=pd, flags=fl)
 
     # ---- rlDisney
     def disney_eval_sample(self, sg, params, sample_type, rx, ry):

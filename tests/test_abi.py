@@ -64,11 +64,13 @@ def test_flag_constants_match_header():
     for cname, val in (("RLS_FLAG_ZERO_L", abi.FLAG_ZERO_L), ("RLS_FLAG_BELOW_HORIZON", abi.FLAG_BELOW_HORIZON),
                        ("RLS_FLAG_PDF_ZERO", abi.FLAG_PDF_ZERO), ("RLS_FLAG_F_BLACK", abi.FLAG_F_BLACK),
                        ("RLS_FLAG_ENTERING", abi.FLAG_ENTERING), ("RLS_FLAG_TIR", abi.FLAG_TIR),
-                       ("RLS_FLAG_PDF_FLOORED", abi.FLAG_PDF_FLOORED), ("RLS_FLAG_EXP_LOBE", abi.FLAG_EXP_LOBE),
+                       ("RLS_FLAG_PDF_FLOORED", abi.FLAG_PDF_FLOORED), ("RLS_FLAG_SLOPE_EARLY_OUT", abi.FLAG_SLOPE_EARLY_OUT),
+                       ("RLS_ARITH_FAST", abi.ARITH_FAST), ("RLS_ARITH_EXACT", abi.ARITH_EXACT), ("RLS_ARITH_TOLERANT", abi.ARITH_TOLERANT),
+                       ("RLS_FLAG_EXP_LOBE", abi.FLAG_EXP_LOBE),
                        ("RLS_FLAG_DEGENERATE", abi.FLAG_DEGENERATE), ("RLS_FLAG_LOBE_MASK", abi.FLAG_LOBE_MASK),
                        ("RLS_RAY_DIFFUSE", abi.RLS_RAY_DIFFUSE), ("RLS_RAY_GLOSSY", abi.RLS_RAY_GLOSSY)):
-        m = re.search(rf"#define\s+{cname}\s+(0x[0-9a-fA-F]+)", text)
-        assert m and int(m.group(1), 16) == val, cname
+        m = re.search(rf"#define\s+{cname}\s+(0x[0-9a-fA-F]+|\d+)", text)
+        assert m and int(m.group(1), 0) == val, cname
 
 
 def test_node_names_and_version():
