@@ -51,6 +51,7 @@ extern "C" {
 #define RLS_ERR_CUDA             (-2)
 #define RLS_ERR_NO_DEVICE        (-3)
 #define RLS_ERR_OUT_OF_MEMORY    (-4)
+#define RLS_ERR_NCCL             (-5)   /* rls_multi_*: libnccl.so.2 missing or an NCCL call failed */
 
 /* Sample type of the rlDisney triple; values mirror AI_RAY_DIFFUSE / AI_RAY_GLOSSY as
  * passed to DisneySampler::setSampleType (src/rlDisney.cpp:194,242,268,275,281). */
@@ -245,6 +246,13 @@ int  rls_shutdown(rls_context *ctx);                      /* node_finish analogu
 int  rls_synchronize(rls_context *ctx);                   /* waits for the context stream  */
 const char *rls_last_error_string(const rls_context *ctx);/* ctx may be NULL: init errors  */
 int  rls_abi_version(void);
+/* The cudaStream_t (as void*) this context enqueues on. */
+void *rls_stream(const rls_context *ctx);
+/* Device memory on the context's device for a host driver that links against this C ABI only
+ * (rlshaders_b200/host/rls_driver.cpp); rls_memcpy_to_host waits for the context's stream first. */
+int rls_device_alloc(rls_context *ctx, size_t bytes, void **out_ptr);
+int rls_device_free(rls_context *ctx, void *ptr);
+int rls_memcpy_to_host(rls_context *ctx, void *host_dst, const void *device_src, size_t bytes);
 /* Number of kernels this context has launched since creation (bench bookkeeping). */
 uint64_t rls_kernel_launch_count(const rls_context *ctx);
 /* Arithmetic policy of the fused *_sample_eval_pdf kernels (rlshaders_b200/csrc/rls_fp.cuh).
@@ -269,6 +277,7 @@ uint64_t rls_kernel_launch_count(const rls_context *ctx);
  * tolerance form (triples with explicit wi, profiles, callers, sweep) run RLS_ARITH_FAST under this setting. */
 #define RLS_ARITH_TOLERANT 2
 int rls_set_arith_policy(rls_context *ctx, int policy);
+int rls_get_arith_policy(const rls_context *ctx);
 int rls_fallback_count(rls_context *ctx, uint64_t *out_count, int reset);
 /* The node names this library stands in for: "rlGgx", "rlDisney", "rlSkin"; NULL past
  * the end -- same enumeration contract as NodeLoader(i, ...). */
@@ -398,6 +407,33 @@ typedef struct rls_sweep_grid {
 #define RLS_SWEEP_VALUES_PER_CELL 5
 int rls_albedo_sweep(rls_context *ctx, const rls_sweep_grid *grid, uint64_t seed,
                      uint32_t spp_begin, uint32_t spp_end, double *table);
+
+/* ---------------------------------------------- several devices, one process */
+/* The multi-GPU half of the host driver that stands where Arnold's bucket / thread parallelism around shader_evaluate
+ * stood (src/rlGgx.cpp:248-327).  rls_multi owns one context (own stream) per device.
+ *   configs 1-4: samples are independent -- the caller gives every device a contiguous index range through the ordinary
+ *     entry points on rls_multi_context(m, k) and times the slowest device with rls_multi_timer_begin / _end; no collective.
+ *   config 5:    rls_multi_albedo_sweep splits the spp range [0, spp) of every cell over the devices (device k takes
+ *     [spp k / G, spp (k+1) / G)), every device writes its partial table into tables[k] (a device pointer ON device k), and one
+ *     ncclAllReduce(sum, FP64) per device leaves the full table in every tables[k].  Single process (ncclCommInitAll), one
+ *     stream per device; from the second call with the same arguments on, kernel(s) + all-reduce are replayed from one
+ *     CUDA graph per device.  libnccl.so.2 is loaded at the first such call (no link-time dependency).
+ * n_devices = 0: every visible device; devices = NULL: 0 .. n_devices - 1. */
+typedef struct rls_multi rls_multi;
+#define RLS_MULTI_NO_GRAPH  1   /* flags of rls_multi_albedo_sweep: enqueue kernel + collective every call, no CUDA graph */
+#define RLS_MULTI_NO_REDUCE 2   /*                                  leave the partial tables (no collective)              */
+int  rls_multi_init(int n_devices, const int *devices, rls_multi **out);
+int  rls_multi_shutdown(rls_multi *m);
+int  rls_multi_device_count(const rls_multi *m);
+rls_context *rls_multi_context(rls_multi *m, int k);
+int  rls_multi_synchronize(rls_multi *m);
+const char *rls_multi_last_error_string(const rls_multi *m);   /* m may be NULL: init errors */
+int  rls_multi_timer_begin(rls_multi *m);
+int  rls_multi_timer_end(rls_multi *m, float *out_ms_slowest_device, float *out_ms_per_device /* n floats, may be NULL */);
+int  rls_multi_albedo_sweep(rls_multi *m, const rls_sweep_grid *grid, uint64_t seed, uint32_t spp,
+                            double *const *tables, int flags);
+uint64_t rls_multi_graph_replays(const rls_multi *m);           /* how many sweeps ran from the captured graphs */
+int  rls_multi_set_nccl_library(const char *path);              /* optional: where libnccl.so.2 is (process-wide) */
 
 /* ------------------------- callers of the triple */
 /* f2 -- rlSkin's two glossy layers for P shading points with K BRDF samples each

@@ -33,6 +33,10 @@ SYMBOLS = [
     "rls_albedo_sweep", "rls_synth_uniform", "rls_synth_shading", "rls_debug_libm", "rls_debug_policy_check",
     "rls_skin_glossy_layers", "rls_ggx_evaluate_light_sample", "rls_disney_evaluate_light_sample",
     "rls_sample_writer_radiance", "rls_sample_writer_scatter",
+    "rls_get_arith_policy", "rls_stream", "rls_device_alloc", "rls_device_free", "rls_memcpy_to_host",
+    "rls_multi_init", "rls_multi_shutdown", "rls_multi_device_count", "rls_multi_context", "rls_multi_synchronize",
+    "rls_multi_last_error_string", "rls_multi_timer_begin", "rls_multi_timer_end", "rls_multi_albedo_sweep",
+    "rls_multi_graph_replays", "rls_multi_set_nccl_library",
 ]
 
 # librls_b200_experiments.so: the same sources built with -DRLS_EXPERIMENTS (csrc/experiments/, kernels that
@@ -123,6 +127,26 @@ def load(path=None):
     lib.rls_fallback_count.restype = C.c_int
     lib.rls_node_name.argtypes = [i32]
     lib.rls_node_name.restype = C.c_char_p
+    lib.rls_get_arith_policy.argtypes = [vp]
+    lib.rls_get_arith_policy.restype = C.c_int
+    lib.rls_stream.argtypes = [vp]
+    lib.rls_stream.restype = vp
+    for name, argtypes in {"rls_device_alloc": [vp, sz, P(vp)], "rls_device_free": [vp, vp], "rls_memcpy_to_host": [vp, vp, vp, sz],
+                           "rls_multi_init": [i32, P(i32), P(vp)], "rls_multi_shutdown": [vp], "rls_multi_synchronize": [vp],
+                           "rls_multi_timer_begin": [vp], "rls_multi_timer_end": [vp, P(f), P(f)],
+                           "rls_multi_albedo_sweep": [vp, P(abi.SweepGrid), u64, u32, P(vp), i32],
+                           "rls_multi_set_nccl_library": [C.c_char_p]}.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.rls_multi_device_count.argtypes = [vp]
+    lib.rls_multi_device_count.restype = C.c_int
+    lib.rls_multi_context.argtypes = [vp, i32]
+    lib.rls_multi_context.restype = vp
+    lib.rls_multi_last_error_string.argtypes = [vp]
+    lib.rls_multi_last_error_string.restype = C.c_char_p
+    lib.rls_multi_graph_replays.argtypes = [vp]
+    lib.rls_multi_graph_replays.restype = C.c_uint64
     if lib.rls_abi_version() != abi.ABI_VERSION:
         raise ImportError(f"{path}: ABI version {lib.rls_abi_version()} != {abi.ABI_VERSION}")
     _libs[path] = lib

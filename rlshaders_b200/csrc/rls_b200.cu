@@ -198,6 +198,31 @@ extern "C" int rls_set_arith_policy(rls_context *ctx, int policy)
     return RLS_OK;
 }
 
+extern "C" int rls_get_arith_policy(const rls_context *ctx) { return ctx ? ctx->arith : RLS_ERR_INVALID_ARGUMENT; }
+extern "C" void *rls_stream(const rls_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" int rls_device_alloc(rls_context *ctx, size_t bytes, void **out_ptr)
+{
+    if (!ctx || !out_ptr) return RLS_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    RLS_CUDA(ctx, cudaMalloc(out_ptr, bytes));
+    return RLS_OK;
+}
+extern "C" int rls_device_free(rls_context *ctx, void *ptr)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    RLS_CUDA(ctx, cudaFree(ptr));
+    return RLS_OK;
+}
+extern "C" int rls_memcpy_to_host(rls_context *ctx, void *host_dst, const void *device_src, size_t bytes)
+{
+    if (!ctx || (bytes && (!host_dst || !device_src))) return RLS_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    RLS_CUDA(ctx, cudaMemcpyAsync(host_dst, device_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    RLS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RLS_OK;
+}
+
 extern "C" int rls_fallback_count(rls_context *ctx, uint64_t *out_count, int reset)
 {
     if (!ctx || !out_count) return RLS_ERR_INVALID_ARGUMENT;
@@ -1100,7 +1125,16 @@ static int worklist_for(rls_context *ctx, cudaStream_t st, size_t n, tol::Workli
     *out = w;
     return RLS_OK;
 }
-static inline unsigned rerun_grid(const rls_context *ctx) { return (unsigned)(ctx->sm_count * 2); }
+// Grid of a re-run kernel: the list length is only known on the device, so the grid is sized for 1/64 of the batch (one
+// listed sample per thread up to a re-run fraction of 1.5 %; a thread strides over the list beyond that).  CTAs past the
+// end of the list exit at once.  A grid of 2 CTAs per SM made every thread walk ~4 exact samples one after the other
+// (0.1 ms of latency per 2^26-sample launch, 8 % of the tolerance kernel's time).
+static inline unsigned rerun_grid(const rls_context *ctx, size_t n, int block)
+{
+    size_t blocks = (n / 64 + block - 1) / block;
+    const size_t lo = (size_t)ctx->sm_count * 2, hi = (size_t)1 << 20;
+    return (unsigned)(blocks < lo ? lo : (blocks > hi ? hi : blocks));
+}
 #define RLS_TOL_CHECK(ctx, call)                                        \
     do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(ctx, e_, "tolerance-policy kernel launch"); \
          (ctx)->launches++; } while (0)
@@ -1113,7 +1147,7 @@ static int launch_ggx_sample_eval_pdf(rls_context *ctx, cudaStream_t st, size_t 
         const int rc = worklist_for(ctx, st, n, &wl);
         if (rc != RLS_OK) return rc;
         RLS_TOL_CHECK(ctx, tol::launch_ggx_sample_eval_pdf(st, n, sh(*sg), dev(*p), rx, ry, dev(*o), wl));
-        k_ggx_sample_eval_pdf_rerun<<<rerun_grid(ctx), kBlockGgx, 0, st>>>((uint32_t)n, sh(*sg), dev(*p), rx, ry, dev(*o), wl, ctx->fallbacks);
+        k_ggx_sample_eval_pdf_rerun<<<rerun_grid(ctx, n, kBlockGgx), kBlockGgx, 0, st>>>((uint32_t)n, sh(*sg), dev(*p), rx, ry, dev(*o), wl, ctx->fallbacks);
         RLS_LAUNCH_CHECK(ctx);
         return RLS_OK;
     }
@@ -1146,8 +1180,8 @@ static int launch_ggx_dielectric(rls_context *ctx, cudaStream_t st, size_t n, co
         const int rc = worklist_for(ctx, st, n, &wl);
         if (rc != RLS_OK) return rc;
         RLS_TOL_CHECK(ctx, tol::launch_ggx_dielectric(st, n, sh(*sg), pd, rx, ry, d, wl));
-        if (arrays) k_ggx_dielectric_rerun<true><<<rerun_grid(ctx), kBlockGgx, 0, st>>>((uint32_t)n, sh(*sg), pd, rx, ry, d, wl, ctx->fallbacks);
-        else k_ggx_dielectric_rerun<false><<<rerun_grid(ctx), kBlockGgx, 0, st>>>((uint32_t)n, sh(*sg), pd, rx, ry, d, wl, ctx->fallbacks);
+        if (arrays) k_ggx_dielectric_rerun<true><<<rerun_grid(ctx, n, kBlockGgx), kBlockGgx, 0, st>>>((uint32_t)n, sh(*sg), pd, rx, ry, d, wl, ctx->fallbacks);
+        else k_ggx_dielectric_rerun<false><<<rerun_grid(ctx, n, kBlockGgx), kBlockGgx, 0, st>>>((uint32_t)n, sh(*sg), pd, rx, ry, d, wl, ctx->fallbacks);
         RLS_LAUNCH_CHECK(ctx);
         return RLS_OK;
     }
@@ -1189,8 +1223,8 @@ static int launch_disney_sample_eval_pdf(rls_context *ctx, cudaStream_t st, size
         const int rc = worklist_for(ctx, st, n, &wl);
         if (rc != RLS_OK) return rc;
         RLS_TOL_CHECK(ctx, tol::launch_disney(st, n, sh(*sg), pd, arrays, rx_s, ry_s, rx_d, ry_d, d, wl));
-        if (arrays) k_disney_sample_eval_pdf_rerun<true><<<rerun_grid(ctx), kBlock, 0, st>>>((uint32_t)n, sh(*sg), pd, rx_s, ry_s, rx_d, ry_d, d, wl, ctx->fallbacks);
-        else k_disney_sample_eval_pdf_rerun<false><<<rerun_grid(ctx), kBlock, 0, st>>>((uint32_t)n, sh(*sg), pd, rx_s, ry_s, rx_d, ry_d, d, wl, ctx->fallbacks);
+        if (arrays) k_disney_sample_eval_pdf_rerun<true><<<rerun_grid(ctx, n, kBlock), kBlock, 0, st>>>((uint32_t)n, sh(*sg), pd, rx_s, ry_s, rx_d, ry_d, d, wl, ctx->fallbacks);
+        else k_disney_sample_eval_pdf_rerun<false><<<rerun_grid(ctx, n, kBlock), kBlock, 0, st>>>((uint32_t)n, sh(*sg), pd, rx_s, ry_s, rx_d, ry_d, d, wl, ctx->fallbacks);
         RLS_LAUNCH_CHECK(ctx);
         return RLS_OK;
     }
@@ -1213,7 +1247,7 @@ static int launch_skin_profile(rls_context *ctx, cudaStream_t st, size_t n, cons
         const int rc = worklist_for(ctx, st, n, &wl);
         if (rc != RLS_OK) return rc;
         RLS_TOL_CHECK(ctx, tol::launch_skin_profile(st, n, dev(*p), rx, d, wl));
-        k_skin_profile_rerun<<<rerun_grid(ctx), kBlockSkin, 0, st>>>((uint32_t)n, dev(*p), rx, d, wl, ctx->fallbacks);
+        k_skin_profile_rerun<<<rerun_grid(ctx, n, kBlockSkin), kBlockSkin, 0, st>>>((uint32_t)n, dev(*p), rx, d, wl, ctx->fallbacks);
         RLS_LAUNCH_CHECK(ctx);
         return RLS_OK;
     }
@@ -1560,7 +1594,7 @@ static int launch_albedo_sweep(rls_context *ctx, cudaStream_t st, const rls_swee
         if (!w.list) { RLS_CUDA(ctx, cudaMalloc((void **)&w.list, (size_t)want * sizeof(uint2))); w.cap = want; }
         RLS_CUDA(ctx, cudaMemsetAsync(w.count, 0, sizeof(unsigned), st));
         RLS_TOL_CHECK(ctx, tol::launch_albedo_sweep(st, g, cells, seed, spp_begin, spp_end, table, w));
-        k_albedo_sweep_rerun<<<rerun_grid(ctx), kSweepBlock, 0, st>>>(g, seed, w, table, ctx->fallbacks);
+        k_albedo_sweep_rerun<<<rerun_grid(ctx, (size_t)cells * (spp_end - spp_begin), kSweepBlock), kSweepBlock, 0, st>>>(g, seed, w, table, ctx->fallbacks);
         RLS_LAUNCH_CHECK(ctx);
         return RLS_OK;
     }

@@ -128,7 +128,7 @@ k_albedo_sweep_tol(SweepGridDev g, uint32_t n_cells, uint64_t seed, uint32_t k0,
         const uint64_t idx = ((uint64_t)cell << 32) | (uint64_t)k;
         Bands bd;
         const DielectricT r = dielectric_unit(bd, U, V, N, wo, false, ior, rough, 0.0f, sweep_uniform24(seed, 0u, idx),
-                                              sweep_uniform24(seed, 1u, idx));
+                                              sweep_uniform24(seed, 1u, idx), /* ior_band = */ false);
         bool mine = true;
         if (bd.rerun) {
             const unsigned j = atomicAdd(wl.count, 1u);

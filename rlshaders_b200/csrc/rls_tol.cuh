@@ -349,8 +349,9 @@ RLT_HD float ggx_D(const GgxT &g, v3 m, float mN)
 struct DielectricT { float F, f_r, pdf_r, f_t, w_t; v3 wi_r, wi_t; uint32_t flags; };
 
 // The rough-dielectric unit (same composition as rls_fused.cuh dielectric_unit / both oracles).
+// ior_band = false (the albedo sweep, whose table reads neither F_BLACK nor f_t): no band around ior = 1.
 RLT_HD DielectricT dielectric_unit(Bands &bd, v3 U, v3 V, v3 N, v3 wo, bool backfacing, float ior, float roughness,
-                                   float aniso, float rx, float ry)
+                                   float aniso, float rx, float ry, bool ior_band = true)
 {
     DielectricT r;
     GgxT g;
@@ -362,7 +363,7 @@ RLT_HD DielectricT dielectric_unit(Bands &bd, v3 U, v3 V, v3 N, v3 wo, bool back
     const float eta = g.entering ? invB : g.b;                  // mIorIn / mIorOut
     const float iorIn = g.entering ? 1.0f : g.b, iorOut = g.entering ? g.b : 1.0f;
     const float ratio2 = ratio * ratio;
-    bd.near(g.b, 1.0f, 1e-4f);                                  // ior == 1: F == 0 and the zero half vector are rounding-decided
+    if (ior_band) bd.near(g.b, 1.0f, 1e-4f);                    // ior == 1: F == 0 and the zero half vector are rounding-decided
 
     bool early;
     float noise;
@@ -415,7 +416,7 @@ RLT_HD DielectricT dielectric_unit(Bands &bd, v3 U, v3 V, v3 N, v3 wo, bool back
         G1t = G1_value(g.a2g, TdotN);
         Tm = sc - eta * Vm;                                     // T.m = -sgn(V.N) sqrt(cT2)
         // refraction(V, T, N) (src/rlGgx.h:316-328): ht = -normalize(eta_i V + eta_o T) = -sgn(sc) m
-        bd.near(sc, 0.0f, 1e-3f);                               // ht is the reference's rounding residue when sc -> 0
+        if (ior_band) bd.near(sc, 0.0f, 1e-3f);                 // ht is the reference's rounding residue when sc -> 0
         const float sh = sc < 0.0f ? 1.0f : -1.0f;
         const float IdotH = sh * Vm, OdotH = sh * Tm;
         const float w = fma_(iorIn, IdotH, iorOut * OdotH);
