@@ -138,18 +138,51 @@ class Context:
         return out
 
 
-def _f32rows(t, name):
+def _placed(t, name, ctx, host):
+    """Every pointer handed to the C ABI must live where the entry point reads it: on the context's device for the
+    device forms, in host memory for the *_host forms (a wrong placement is an illegal-address fault, i.e. a dead CUDA
+    context, not an exception)."""
+    if ctx is None:
+        return
+    if host:
+        if t.device.type != "cpu":
+            raise ValueError(f"{name}: the host-buffer form needs a CPU (pinned) tensor, got {t.device}")
+    elif t.device != ctx.device:
+        raise ValueError(f"{name}: expected a tensor on {ctx.device}, got {t.device} "
+                         "(only the fused *SampleEvalPdf calls have a host-buffer form)")
+
+
+def _f32rows(t, name, n=None, ctx=None, host=False):
     if t.dtype != torch.float32 or t.dim() != 2 or t.shape[0] != 3 or not t.is_contiguous():
         raise ValueError(f"{name}: expected a contiguous float32 tensor of shape [3, n]")
+    if n is not None and t.shape[1] != n:
+        raise ValueError(f"{name}: expected {n} samples, got {t.shape[1]}")
+    _placed(t, name, ctx, host)
     return (t[0], t[1], t[2])
 
 
-def _f32(t, name, n=None):
+def _f32(t, name, n=None, ctx=None, host=False):
     if t.dtype != torch.float32 or t.dim() != 1 or not t.is_contiguous():
         raise ValueError(f"{name}: expected a contiguous float32 tensor of shape [n]")
     if n is not None and t.shape[0] != n:
         raise ValueError(f"{name}: expected {n} samples, got {t.shape[0]}")
+    _placed(t, name, ctx, host)
     return t
+
+
+def _i32(t, name, n, ctx=None, host=False):
+    if t.dtype != torch.int32 or t.dim() != 1 or not t.is_contiguous() or t.shape[0] != n:
+        raise ValueError(f"{name}: expected a contiguous int32 tensor of shape [{n}]")
+    _placed(t, name, ctx, host)
+    return t
+
+
+def _params_placed(params_kw, n, ctx, host):
+    """Node-parameter tensors (per-sample arrays) of a sampler: length n, float32, placed like the shading batch."""
+    for k, v in params_kw.items():
+        for j, t in enumerate(v if isinstance(v, (tuple, list)) else (v,)):
+            if isinstance(t, torch.Tensor):
+                _f32(t, f"{k}[{j}]" if isinstance(v, (tuple, list)) else k, n, ctx, host)
 
 
 class ShadingBatch:
@@ -158,10 +191,21 @@ class ShadingBatch:
 
     def __init__(self, U, V, N, wo, backfacing=None):
         self.U, self.V, self.N, self.wo, self.backfacing = U, V, N, wo, backfacing
-        self.n = U.shape[1]
+        self.n = n = U.shape[1] if U.dim() == 2 else -1
         self.on_host = U.device.type == "cpu"
-        self.struct = abi.shading(_f32rows(U, "U"), _f32rows(V, "V"), _f32rows(N, "N"),
-                                  _f32rows(wo, "wo"), backfacing)
+        for name, t in (("V", V), ("N", N), ("wo", wo), ("backfacing", backfacing)):
+            if t is not None and t.device != U.device:
+                raise ValueError(f"ShadingBatch: {name} is on {t.device}, U on {U.device}")
+        if backfacing is not None and (backfacing.dtype != torch.uint8 or backfacing.dim() != 1 or backfacing.shape[0] != n
+                                       or not backfacing.is_contiguous()):
+            raise ValueError(f"backfacing: expected a contiguous uint8 tensor of shape [{n}]")
+        self.struct = abi.shading(_f32rows(U, "U", n), _f32rows(V, "V", n), _f32rows(N, "N", n),
+                                  _f32rows(wo, "wo", n), backfacing)
+
+    def placed(self, ctx, host=False):
+        """Raises unless the batch lives where the entry point reads it (see _placed)."""
+        _placed(self.U, "ShadingBatch", ctx, host)
+        return self
 
     @classmethod
     def from_numpy(cls, sg, device=None, pin=False):
@@ -193,17 +237,20 @@ class GgxSampler:
     def __init__(self, ctx, sg, KsColor=(1.0, 1.0, 1.0), ior=1.0, specularRoughness=0.0, anisotropic=0.0,
                  normal_sampler=abi.GGX_SAMPLER_VNDF, **ignored_node_params):
         self.ctx, self.sg = ctx, sg
+        _params_placed(dict(KsColor=KsColor, ior=ior, specularRoughness=specularRoughness, anisotropic=anisotropic,
+                            **ignored_node_params), sg.n, ctx, sg.on_host)
         self.params = abi.ggx_params(KsColor=KsColor, ior=ior, specularRoughness=specularRoughness,
                                      anisotropic=anisotropic, normal_sampler=normal_sampler,
                                      **ignored_node_params)
 
     def evalSample(self, rx, ry, want_fresnel=True):
         n, c = self.sg.n, self.ctx
-        wi = c.empty(3, n, like=rx)
-        F = c.empty(n, like=rx) if want_fresnel else None
+        self.sg.placed(c)
+        wi = c.empty(3, n)
+        F = c.empty(n) if want_fresnel else None
         _check(c.handle, c.lib.rls_ggx_eval_sample(
-            c.handle, n, C.byref(self.sg.struct), C.byref(self.params), _f32(rx, "rx", n).data_ptr(),
-            _f32(ry, "ry", n).data_ptr(), abi.vec3(_f32rows(wi, "wi")), F.data_ptr() if F is not None else None), c.lib)
+            c.handle, n, C.byref(self.sg.struct), C.byref(self.params), _f32(rx, "rx", n, c).data_ptr(),
+            _f32(ry, "ry", n, c).data_ptr(), abi.vec3(_f32rows(wi, "wi")), F.data_ptr() if F is not None else None), c.lib)
         return wi, F
 
     def evalLightSample(self, Ld, Li, light_pdf, rx=None, ry=None, Li_at_l=None, pdf_at_l=None):
@@ -214,16 +261,18 @@ class GgxSampler:
 
     def evalBrdf(self, wi):
         n, c = self.sg.n, self.ctx
-        f = c.empty(3, n, like=wi)
+        self.sg.placed(c)
+        f = c.empty(3, n)
         _check(c.handle, c.lib.rls_ggx_eval_brdf(c.handle, n, C.byref(self.sg.struct), C.byref(self.params),
-                                                 abi.vec3(_f32rows(wi, "wi")), abi.vec3(_f32rows(f, "f"))), c.lib)
+                                                 abi.vec3(_f32rows(wi, "wi", n, c)), abi.vec3(_f32rows(f, "f"))), c.lib)
         return f
 
     def evalPdf(self, wi):
         n, c = self.sg.n, self.ctx
-        pdf = c.empty(n, like=wi)
+        self.sg.placed(c)
+        pdf = c.empty(n)
         _check(c.handle, c.lib.rls_ggx_eval_pdf(c.handle, n, C.byref(self.sg.struct), C.byref(self.params),
-                                                abi.vec3(_f32rows(wi, "wi")), pdf.data_ptr()), c.lib)
+                                                abi.vec3(_f32rows(wi, "wi", n, c)), pdf.data_ptr()), c.lib)
         return pdf
 
     def alloc_out(self, like, want_fresnel=True):
@@ -236,11 +285,14 @@ class GgxSampler:
         """The fused unit of work: ctor + evalSample + evalBrdf(L) + evalPdf(L)."""
         n, c = self.sg.n, self.ctx
         out = self.alloc_out(rx, want_fresnel) if out is None else out
-        o = abi.BsdfOut(abi.vec3(_f32rows(out["wi"], "wi")), abi.vec3(_f32rows(out["f"], "f")),
-                        out["pdf"].data_ptr(), out["fresnel"].data_ptr() if out.get("fresnel") is not None else None,
-                        out["flags"].data_ptr())
-        args = (c.handle, n, C.byref(self.sg.struct), C.byref(self.params), _f32(rx, "rx", n).data_ptr(),
-                _f32(ry, "ry", n).data_ptr(), C.byref(o))
+        h = self.sg.on_host
+        self.sg.placed(c, h)
+        o = abi.BsdfOut(abi.vec3(_f32rows(out["wi"], "wi", n, c, h)), abi.vec3(_f32rows(out["f"], "f", n, c, h)),
+                        _f32(out["pdf"], "pdf", n, c, h).data_ptr(),
+                        _f32(out["fresnel"], "fresnel", n, c, h).data_ptr() if out.get("fresnel") is not None else None,
+                        _i32(out["flags"], "flags", n, c, h).data_ptr())
+        args = (c.handle, n, C.byref(self.sg.struct), C.byref(self.params), _f32(rx, "rx", n, c, h).data_ptr(),
+                _f32(ry, "ry", n, c, h).data_ptr(), C.byref(o))
         if self.sg.on_host:
             _check(c.handle, c.lib.rls_ggx_sample_eval_pdf_host(*args, chunk), c.lib)
         else:
@@ -258,12 +310,14 @@ class GgxSampler:
         refraction branches (src/rlGgx.h:228-243, 277-328)."""
         n, c = self.sg.n, self.ctx
         out = self.alloc_dielectric_out(rx) if out is None else out
-        o = abi.GgxDielectricOut(out["fresnel"].data_ptr(), abi.vec3(_f32rows(out["wi_r"], "wi_r")),
-                                 out["f_r"].data_ptr(), out["pdf_r"].data_ptr(),
-                                 abi.vec3(_f32rows(out["wi_t"], "wi_t")), out["f_t"].data_ptr(),
-                                 out["weight_t"].data_ptr(), out["flags"].data_ptr())
-        args = (c.handle, n, C.byref(self.sg.struct), C.byref(self.params), _f32(rx, "rx", n).data_ptr(),
-                _f32(ry, "ry", n).data_ptr(), C.byref(o))
+        h = self.sg.on_host
+        self.sg.placed(c, h)
+        sc = lambda k: _f32(out[k], k, n, c, h).data_ptr()   # noqa: E731
+        o = abi.GgxDielectricOut(sc("fresnel"), abi.vec3(_f32rows(out["wi_r"], "wi_r", n, c, h)), sc("f_r"), sc("pdf_r"),
+                                 abi.vec3(_f32rows(out["wi_t"], "wi_t", n, c, h)), sc("f_t"), sc("weight_t"),
+                                 _i32(out["flags"], "flags", n, c, h).data_ptr())
+        args = (c.handle, n, C.byref(self.sg.struct), C.byref(self.params), _f32(rx, "rx", n, c, h).data_ptr(),
+                _f32(ry, "ry", n, c, h).data_ptr(), C.byref(o))
         if self.sg.on_host:
             _check(c.handle, c.lib.rls_ggx_dielectric_sample_eval_pdf_host(*args, chunk), c.lib)
         else:
@@ -271,23 +325,24 @@ class GgxSampler:
         return out
 
 
-def _light(direction, radiance, pdf, n):
-    d = _f32rows(direction, "Ld") if direction is not None else None
-    return abi.light_sample(d, _f32rows(radiance, "Li"), _f32(pdf, "light pdf", n))
+def _light(direction, radiance, pdf, n, ctx):
+    d = _f32rows(direction, "Ld", n, ctx) if direction is not None else None
+    return abi.light_sample(d, _f32rows(radiance, "Li", n, ctx), _f32(pdf, "light pdf", n, ctx))
 
 
 def _eval_light_sample(fn, sampler, head_args, Ld, Li, light_pdf, rx, ry, Li_at_l, pdf_at_l):
     """Shared body of {GgxSampler,DisneySampler}.evalLightSample (include/rls_b200.h, f3)."""
     n, c = sampler.sg.n, sampler.ctx
-    light = _light(Ld, Li, light_pdf, n)
+    sampler.sg.placed(c)
+    light = _light(Ld, Li, light_pdf, n, c)
     at_l = None
     if Li_at_l is not None:
-        at_l = _light(None, Li_at_l, pdf_at_l, n)
-    rgb = c.empty(3, n, like=light_pdf)
-    wl, wb = c.empty(n, like=light_pdf), c.empty(n, like=light_pdf)
+        at_l = _light(None, Li_at_l, pdf_at_l, n, c)
+    rgb = c.empty(3, n)
+    wl, wb = c.empty(n), c.empty(n)
     _check(c.handle, fn(c.handle, n, C.byref(sampler.sg.struct), C.byref(sampler.params), *head_args, C.byref(light),
-                        _f32(rx, "rx", n).data_ptr() if rx is not None else None,
-                        _f32(ry, "ry", n).data_ptr() if ry is not None else None,
+                        _f32(rx, "rx", n, c).data_ptr() if rx is not None else None,
+                        _f32(ry, "ry", n, c).data_ptr() if ry is not None else None,
                         C.byref(at_l) if at_l is not None else None,
                         abi.vec3(_f32rows(rgb, "rgb")), wl.data_ptr(), wb.data_ptr()), c.lib)
     return dict(rgb=rgb, w_light=wl, w_brdf=wb)
@@ -314,6 +369,9 @@ class SampleWriter:
     def writeRadiance(self, brdf, point=0):
         c = self.ctx
         node, st = self._node(brdf)
+        brdf.sg.placed(c)
+        if not 0 <= int(point) < brdf.sg.n:
+            raise ValueError("point index out of range")
         _check(c.handle, c.lib.rls_sample_writer_radiance(c.handle, node, C.byref(brdf.sg.struct),
                                                           C.cast(C.byref(brdf.params), C.c_void_p), point, st,
                                                           self.width, self.height, self.image.data_ptr()), c.lib)
@@ -323,9 +381,10 @@ class SampleWriter:
         c = self.ctx
         node, st = self._node(brdf)
         n = rx.shape[0]
+        brdf.sg.placed(c)
         _check(c.handle, c.lib.rls_sample_writer_scatter(c.handle, node, C.byref(brdf.sg.struct),
                                                          C.cast(C.byref(brdf.params), C.c_void_p), point, st, n,
-                                                         _f32(rx, "rx", n).data_ptr(), _f32(ry, "ry", n).data_ptr(),
+                                                         _f32(rx, "rx", n, c).data_ptr(), _f32(ry, "ry", n, c).data_ptr(),
                                                          self.width, self.height, self.image.data_ptr(),
                                                          self._scratch.data_ptr(), self.missing.data_ptr()), c.lib)
         return self.image
@@ -348,6 +407,7 @@ class DisneySampler:
 
     def __init__(self, ctx, sg, **node_params):
         self.ctx, self.sg = ctx, sg
+        _params_placed(node_params, sg.n, ctx, sg.on_host)
         self.params = abi.disney_params(**node_params)
         self.sample_type = abi.RLS_RAY_GLOSSY
 
@@ -364,27 +424,30 @@ class DisneySampler:
 
     def evalSample(self, rx, ry):
         n, c = self.sg.n, self.ctx
-        wi = c.empty(3, n, like=rx)
-        flags = c.empty(n, dtype=torch.int32, like=rx)
+        self.sg.placed(c)
+        wi = c.empty(3, n)
+        flags = c.empty(n, dtype=torch.int32)
         _check(c.handle, c.lib.rls_disney_eval_sample(
             c.handle, n, C.byref(self.sg.struct), C.byref(self.params), self.sample_type,
-            _f32(rx, "rx", n).data_ptr(), _f32(ry, "ry", n).data_ptr(), abi.vec3(_f32rows(wi, "wi")),
+            _f32(rx, "rx", n, c).data_ptr(), _f32(ry, "ry", n, c).data_ptr(), abi.vec3(_f32rows(wi, "wi")),
             flags.data_ptr()), c.lib)
         return wi, flags
 
     def evalBrdf(self, wi):
         n, c = self.sg.n, self.ctx
-        f = c.empty(3, n, like=wi)
+        self.sg.placed(c)
+        f = c.empty(3, n)
         _check(c.handle, c.lib.rls_disney_eval_brdf(c.handle, n, C.byref(self.sg.struct), C.byref(self.params),
-                                                    self.sample_type, abi.vec3(_f32rows(wi, "wi")),
+                                                    self.sample_type, abi.vec3(_f32rows(wi, "wi", n, c)),
                                                     abi.vec3(_f32rows(f, "f"))), c.lib)
         return f
 
     def evalPdf(self, wi):
         n, c = self.sg.n, self.ctx
-        pdf = c.empty(n, like=wi)
+        self.sg.placed(c)
+        pdf = c.empty(n)
         _check(c.handle, c.lib.rls_disney_eval_pdf(c.handle, n, C.byref(self.sg.struct), C.byref(self.params),
-                                                   self.sample_type, abi.vec3(_f32rows(wi, "wi")),
+                                                   self.sample_type, abi.vec3(_f32rows(wi, "wi", n, c)),
                                                    pdf.data_ptr()), c.lib)
         return pdf
 
@@ -398,12 +461,14 @@ class DisneySampler:
         """Fused: ctor + glossy triple on (rx_s, ry_s) + diffuse triple on (rx_d, ry_d)."""
         n, c = self.sg.n, self.ctx
         out = self.alloc_out(rx_s) if out is None else out
-        o = abi.DisneyOut(abi.vec3(_f32rows(out["wi_s"], "wi_s")), abi.vec3(_f32rows(out["f_s"], "f_s")),
-                          out["pdf_s"].data_ptr(), abi.vec3(_f32rows(out["wi_d"], "wi_d")),
-                          abi.vec3(_f32rows(out["f_d"], "f_d")), out["pdf_d"].data_ptr(), out["flags"].data_ptr())
-        args = (c.handle, n, C.byref(self.sg.struct), C.byref(self.params), _f32(rx_s, "rx_s", n).data_ptr(),
-                _f32(ry_s, "ry_s", n).data_ptr(), _f32(rx_d, "rx_d", n).data_ptr(),
-                _f32(ry_d, "ry_d", n).data_ptr(), C.byref(o))
+        h = self.sg.on_host
+        self.sg.placed(c, h)
+        v3 = lambda k: abi.vec3(_f32rows(out[k], k, n, c, h))   # noqa: E731
+        o = abi.DisneyOut(v3("wi_s"), v3("f_s"), _f32(out["pdf_s"], "pdf_s", n, c, h).data_ptr(), v3("wi_d"), v3("f_d"),
+                          _f32(out["pdf_d"], "pdf_d", n, c, h).data_ptr(), _i32(out["flags"], "flags", n, c, h).data_ptr())
+        args = (c.handle, n, C.byref(self.sg.struct), C.byref(self.params), _f32(rx_s, "rx_s", n, c, h).data_ptr(),
+                _f32(ry_s, "ry_s", n, c, h).data_ptr(), _f32(rx_d, "rx_d", n, c, h).data_ptr(),
+                _f32(ry_d, "ry_d", n, c, h).data_ptr(), C.byref(o))
         if self.sg.on_host:
             _check(c.handle, c.lib.rls_disney_sample_eval_pdf_host(*args, chunk), c.lib)
         else:
@@ -426,8 +491,8 @@ class NDProfile:
                                         abi.vec3(_f32rows(self.state["C1"], "C1")),
                                         abi.vec3(_f32rows(self.state["C2"], "C2")),
                                         self.state["max_radius"].data_ptr())
-        _check(c.handle, c.lib.rls_ndprofile_set_distance(c.handle, n, abi.vec3(_f32rows(dist, "dist")),
-                                                          abi.vec3(_f32rows(albedo, "albedo")),
+        _check(c.handle, c.lib.rls_ndprofile_set_distance(c.handle, n, abi.vec3(_f32rows(dist, "dist", n, c)),
+                                                          abi.vec3(_f32rows(albedo, "albedo", n, c)),
                                                           C.byref(self._struct)), c.lib)
         return self.state
 
@@ -438,7 +503,7 @@ class NDProfile:
         c = self.ctx
         r, fl = c.empty(self.n), c.empty(self.n, dtype=torch.int32)
         _check(c.handle, c.lib.rls_ndprofile_get_radius(c.handle, self.n, C.byref(self._struct),
-                                                        _f32(rx, "rx", self.n).data_ptr(), r.data_ptr(),
+                                                        _f32(rx, "rx", self.n, c).data_ptr(), r.data_ptr(),
                                                         fl.data_ptr()), c.lib)
         return r, fl
 
@@ -446,14 +511,14 @@ class NDProfile:
         c = self.ctx
         pdf = c.empty(self.n)
         _check(c.handle, c.lib.rls_ndprofile_get_pdf(c.handle, self.n, C.byref(self._struct),
-                                                     _f32(r, "r", self.n).data_ptr(), pdf.data_ptr()), c.lib)
+                                                     _f32(r, "r", self.n, c).data_ptr(), pdf.data_ptr()), c.lib)
         return pdf
 
     def evalProfile(self, r):
         c = self.ctx
         rd = c.empty(3, self.n)
         _check(c.handle, c.lib.rls_ndprofile_eval_profile(c.handle, self.n, C.byref(self._struct),
-                                                          _f32(r, "r", self.n).data_ptr(),
+                                                          _f32(r, "r", self.n, c).data_ptr(),
                                                           abi.vec3(_f32rows(rd, "rd"))), c.lib)
         return rd
 
@@ -472,8 +537,8 @@ class GaussianProfile:
         self.state = dict(variance=c.empty(n), max_radius=c.empty(n), norm=c.empty(n))
         self._struct = abi.GaussProfileSoA(self.state["variance"].data_ptr(), self.state["max_radius"].data_ptr(),
                                            self.state["norm"].data_ptr())
-        _check(c.handle, c.lib.rls_gaussprofile_set_distance(c.handle, n, abi.vec3(_f32rows(dist, "dist")),
-                                                             abi.vec3(_f32rows(albedo, "albedo")),
+        _check(c.handle, c.lib.rls_gaussprofile_set_distance(c.handle, n, abi.vec3(_f32rows(dist, "dist", n, c)),
+                                                             abi.vec3(_f32rows(albedo, "albedo", n, c)),
                                                              C.byref(self._struct)), c.lib)
         return self.state
 
@@ -483,7 +548,7 @@ class GaussianProfile:
     def _unary(self, fn, x, name):
         c = self.ctx
         out = c.empty(self.n)
-        _check(c.handle, fn(c.handle, self.n, C.byref(self._struct), _f32(x, name, self.n).data_ptr(),
+        _check(c.handle, fn(c.handle, self.n, C.byref(self._struct), _f32(x, name, self.n, c).data_ptr(),
                             out.data_ptr()), c.lib)
         return out
 
@@ -502,7 +567,7 @@ class GaussianProfile:
         n = rx.shape[0]
         out = dict(r=ctx.empty(n), pdf=ctx.empty(n), Rd=ctx.empty(n))
         _check(ctx.handle, ctx.lib.rls_gaussprofile_sample_eval_pdf(
-            ctx.handle, n, _f32(dist_x, "dist_x", n).data_ptr(), _f32(rx, "rx", n).data_ptr(),
+            ctx.handle, n, _f32(dist_x, "dist_x", n, ctx).data_ptr(), _f32(rx, "rx", n, ctx).data_ptr(),
             out["r"].data_ptr(), out["pdf"].data_ptr(), out["Rd"].data_ptr()), ctx.lib)
         return out
 
@@ -513,6 +578,7 @@ class SkinProfile:
 
     def __init__(self, ctx, n, **node_params):
         self.ctx, self.n = ctx, n
+        self._node_params = node_params
         self.params = abi.skin_params(**node_params)
 
     def alloc_out(self, like):
@@ -523,10 +589,12 @@ class SkinProfile:
     def sampleEvalPdf(self, rx, out=None, chunk=0):
         c, n = self.ctx, self.n
         out = self.alloc_out(rx) if out is None else out
-        o = abi.ProfileOut(out["r"].data_ptr(), out["pdf"].data_ptr(), abi.vec3(_f32rows(out["Rd"], "Rd")),
-                           out["flags"].data_ptr())
-        args = (c.handle, n, C.byref(self.params), _f32(rx, "rx", n).data_ptr(), C.byref(o))
-        if rx.device.type == "cpu":
+        h = rx.device.type == "cpu"
+        _params_placed(self._node_params, n, c, h)
+        o = abi.ProfileOut(_f32(out["r"], "r", n, c, h).data_ptr(), _f32(out["pdf"], "pdf", n, c, h).data_ptr(),
+                           abi.vec3(_f32rows(out["Rd"], "Rd", n, c, h)), _i32(out["flags"], "flags", n, c, h).data_ptr())
+        args = (c.handle, n, C.byref(self.params), _f32(rx, "rx", n, c, h).data_ptr(), C.byref(o))
+        if h:
             _check(c.handle, c.lib.rls_skin_profile_sample_eval_pdf_host(*args, chunk), c.lib)
         else:
             _check(c.handle, c.lib.rls_skin_profile_sample_eval_pdf(*args), c.lib)
@@ -540,8 +608,12 @@ class SkinProfile:
                    flags=c.empty(n, dtype=torch.int32))
         o = abi.ProbeOut(out["r"].data_ptr(), abi.vec3(_f32rows(out["origin"], "origin")),
                          abi.vec3(_f32rows(out["dir"], "dir")), out["maxdist"].data_ptr(), out["flags"].data_ptr())
+        if sg.n != n:
+            raise ValueError(f"ShadingBatch has {sg.n} samples, the profile {n}")
+        sg.placed(c)
+        _params_placed(self._node_params, n, c, False)
         _check(c.handle, c.lib.rls_skin_probe_ray(c.handle, n, C.byref(sg.struct), C.byref(self.params),
-                                                  _f32(rx, "rx", n).data_ptr(), _f32(ry, "ry", n).data_ptr(),
+                                                  _f32(rx, "rx", n, c).data_ptr(), _f32(ry, "ry", n, c).data_ptr(),
                                                   C.byref(o)), c.lib)
         return out
 
@@ -549,9 +621,13 @@ class SkinProfile:
         """The 3-axis MIS pdf of a probe hit (src/rlSss.h:252-263)."""
         c, n = self.ctx, self.n
         pdf = c.empty(n)
+        if sg.n != n:
+            raise ValueError(f"ShadingBatch has {sg.n} samples, the profile {n}")
+        sg.placed(c)
+        _params_placed(self._node_params, n, c, False)
         _check(c.handle, c.lib.rls_skin_probe_mis_pdf(c.handle, n, C.byref(sg.struct), C.byref(self.params),
-                                                      abi.vec3(_f32rows(disp, "disp")),
-                                                      abi.vec3(_f32rows(hit_normal, "hit_normal")),
+                                                      abi.vec3(_f32rows(disp, "disp", n, c)),
+                                                      abi.vec3(_f32rows(hit_normal, "hit_normal", n, c)),
                                                       pdf.data_ptr()), c.lib)
         return pdf
 
@@ -560,16 +636,19 @@ class SkinProfile:
         average-Fresnel hand-off to the SSS weight (src/rlSkin.cpp:184-238).  Sample arrays are
         sample-major [k * n]; li_* are optional [3, k * n] incoming radiances."""
         c, n = self.ctx, self.n
+        if int(k) < 1 or sg.n != n:
+            raise ValueError("glossyLayers: k must be at least 1 and the ShadingBatch must hold one entry per shading point")
+        sg.placed(c)
+        _params_placed(self._node_params, n, c, False)
         for nm, t in (("rx_sheen", rx_sheen), ("ry_sheen", ry_sheen), ("rx_specular", rx_specular), ("ry_specular", ry_specular)):
-            _f32(t, nm, n * k)
-        out = dict(sheen=c.empty(3, n, like=rx_sheen), specular=c.empty(3, n, like=rx_sheen),
-                   sheen_fresnel=c.empty(n, like=rx_sheen), specular_fresnel=c.empty(n, like=rx_sheen),
-                   sss_weight=c.empty(n, like=rx_sheen), flags=c.empty(n, dtype=torch.int32, like=rx_sheen))
+            _f32(t, nm, n * k, c)
+        out = dict(sheen=c.empty(3, n), specular=c.empty(3, n), sheen_fresnel=c.empty(n), specular_fresnel=c.empty(n),
+                   sss_weight=c.empty(n), flags=c.empty(n, dtype=torch.int32))
         o = abi.SkinLayersOut(abi.vec3(_f32rows(out["sheen"], "sheen")), abi.vec3(_f32rows(out["specular"], "specular")),
                               out["sheen_fresnel"].data_ptr(), out["specular_fresnel"].data_ptr(),
                               out["sss_weight"].data_ptr(), out["flags"].data_ptr())
-        la = abi.vec3(_f32rows(li_sheen, "li_sheen")) if li_sheen is not None else abi.vec3(None)
-        lb = abi.vec3(_f32rows(li_specular, "li_specular")) if li_specular is not None else abi.vec3(None)
+        la = abi.vec3(_f32rows(li_sheen, "li_sheen", n * k, c)) if li_sheen is not None else abi.vec3(None)
+        lb = abi.vec3(_f32rows(li_specular, "li_specular", n * k, c)) if li_specular is not None else abi.vec3(None)
         _check(c.handle, c.lib.rls_skin_glossy_layers(c.handle, n, k, C.byref(sg.struct), C.byref(self.params),
                                                       rx_sheen.data_ptr(), ry_sheen.data_ptr(), rx_specular.data_ptr(),
                                                       ry_specular.data_ptr(), la, lb, C.byref(o)), c.lib)
@@ -578,7 +657,9 @@ class SkinProfile:
     def layerWeights(self, avg_fresnel_sheen, avg_fresnel_specular):
         c, n = self.ctx, self.n
         a, b = c.empty(n), c.empty(n)
+        _params_placed(self._node_params, n, c, False)
         _check(c.handle, c.lib.rls_skin_layer_weights(c.handle, n, C.byref(self.params),
-                                                      avg_fresnel_sheen.data_ptr(), avg_fresnel_specular.data_ptr(),
+                                                      _f32(avg_fresnel_sheen, "avg_fresnel_sheen", n, c).data_ptr(),
+                                                      _f32(avg_fresnel_specular, "avg_fresnel_specular", n, c).data_ptr(),
                                                       a.data_ptr(), b.data_ptr()), c.lib)
         return a, b

@@ -95,3 +95,38 @@ def test_reduce_table_is_identity_without_a_group():
     t = torch.arange(10, dtype=torch.float64)
     assert torch.equal(shard.reduce_table(t.clone(), None), t)
     assert torch.equal(shard.reduce_table(t.clone(), dist), t)
+
+
+# ------------------------------------------------------------------ argument validation of the Python mirror
+def test_api_rejects_wrong_lengths_dtypes_and_placement():
+    """Every pointer the mirror hands to the C ABI is checked first: a wrong length or a tensor in the wrong memory would
+    be an out-of-bounds read / illegal address on the device (a dead CUDA context), not an exception."""
+    import pytest
+    import torch
+    from rlshaders_b200 import api
+
+    n = 8
+    f = lambda *s: torch.zeros(*s, dtype=torch.float32)   # noqa: E731
+    with pytest.raises(ValueError):
+        api.ShadingBatch(f(3, n), f(3, n), f(3, n + 1), f(3, n))                       # N has another sample count
+    with pytest.raises(ValueError):
+        api.ShadingBatch(f(3, n), f(3, n), f(3, n), f(3, n), torch.zeros(n, dtype=torch.int32))   # backfacing must be uint8
+    with pytest.raises(ValueError):
+        api.ShadingBatch(f(3, n), f(3, n), f(3, n), f(3, n), torch.zeros(n + 1, dtype=torch.uint8))
+    with pytest.raises(ValueError):
+        api._f32rows(f(3, n), "wi", n + 1)
+    with pytest.raises(ValueError):
+        api._f32(f(n).double(), "rx", n)
+    with pytest.raises(ValueError):
+        api._i32(torch.zeros(n, dtype=torch.int64), "flags", n)
+
+    class FakeCtx:                               # placement rules need only the context's device
+        device = torch.device("cuda", 0)
+    with pytest.raises(ValueError):
+        api._f32(f(n), "rx", n, FakeCtx, host=False)                                   # CPU tensor to a device entry point
+    api._f32(f(n), "rx", n, FakeCtx, host=True)                                        # ... fine for a *_host form
+    sg = api.ShadingBatch(f(3, n), f(3, n), f(3, n), f(3, n))
+    with pytest.raises(ValueError):
+        sg.placed(FakeCtx, host=False)
+    with pytest.raises(ValueError):
+        api._params_placed(dict(ior=f(n + 1)), n, FakeCtx, True)                       # per-sample parameter of the wrong length
