@@ -294,6 +294,18 @@ int rls_ggx_eval_brdf(rls_context *ctx, size_t n, const rls_shading_soa *sg,
 /* GgxSampler ctor + evalPdf at a caller-supplied indir (src/rlGgx.h:121-127,72-80). */
 int rls_ggx_eval_pdf(rls_context *ctx, size_t n, const rls_shading_soa *sg,
                      const rls_ggx_params *params, rls_cvec3 wi, float *out_pdf);
+/* The refraction half at caller-supplied directions (the pieces the rough-dielectric unit below composes):
+ *   rls_ggx_refract_direction  getRefractDirection(m, V) (src/rlGgx.h:277-291; eta not squared, as written) for a
+ *                              microfacet normal m: out_wi = the refracted direction, or the zero vector with
+ *                              RLS_FLAG_TIR in out_flags (may be NULL) when it fails; RLS_FLAG_ENTERING as the ctor decides;
+ *   rls_ggx_eval_btdf          refraction(V, wi, N) (src/rlGgx.h:316-328, Walter Eq.21) at a transmitted direction wi;
+ *   rls_ggx_sample_weight      getSampleWeight(V, wi, m) (src/rlGgx.h:294-301, Walter Eq.41). */
+int rls_ggx_refract_direction(rls_context *ctx, size_t n, const rls_shading_soa *sg,
+                              const rls_ggx_params *params, rls_cvec3 m, rls_vec3 out_wi, uint32_t *out_flags);
+int rls_ggx_eval_btdf(rls_context *ctx, size_t n, const rls_shading_soa *sg,
+                      const rls_ggx_params *params, rls_cvec3 wi, float *out_ft);
+int rls_ggx_sample_weight(rls_context *ctx, size_t n, const rls_shading_soa *sg,
+                          const rls_ggx_params *params, rls_cvec3 wi, rls_cvec3 m, float *out_weight);
 /* The fused unit of work: ctor + evalSample + evalBrdf(L) + evalPdf(L). */
 int rls_ggx_sample_eval_pdf(rls_context *ctx, size_t n, const rls_shading_soa *sg,
                             const rls_ggx_params *params, const float *rx, const float *ry,
@@ -371,7 +383,11 @@ int rls_skin_probe_mis_pdf(rls_context *ctx, size_t n, const rls_shading_soa *sg
 
 /* -------------------------------------------- host-buffer (end-to-end) forms */
 /* Same contracts as the device forms above but every array pointer is a HOST pointer.
- * `chunk` = samples per staged chunk (0 = library default).  Synchronous. */
+ * `chunk` = samples per staged chunk (0 = library default).  Synchronous: the call returns when every output is in the
+ * host buffers (on an error, too: the library's copy streams are drained first).  The work runs on the context's own
+ * staging streams, ordered AFTER whatever was queued on the context's stream when the call was made.  A context allocates
+ * its staging buffers (3 x chunk x the entry point's bytes per sample, e.g. 3 x 2^21 x 144 B = 0.9 GB for the dielectric
+ * unit) at the first such call and keeps them: use one context per device for the host forms, not one per thread. */
 int rls_ggx_sample_eval_pdf_host(rls_context *ctx, size_t n, const rls_shading_soa *sg,
                                  const rls_ggx_params *params, const float *rx, const float *ry,
                                  const rls_bsdf_out *out, size_t chunk);

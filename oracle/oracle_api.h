@@ -39,6 +39,11 @@ void oracle_ggx_eval_brdf(size_t n, const rls_shading_soa *sg, const rls_ggx_par
                           rls_cvec3 wi, rls_vec3 out_f);
 void oracle_ggx_eval_pdf(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
                          rls_cvec3 wi, float *out_pdf);
+void oracle_ggx_refract_direction(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
+                                  rls_cvec3 m, rls_vec3 out_wi, uint32_t *out_flags);
+void oracle_ggx_eval_btdf(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p, rls_cvec3 wi, float *out_ft);
+void oracle_ggx_sample_weight(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
+                              rls_cvec3 wi, rls_cvec3 m, float *out_weight);
 void oracle_ggx_sample_eval_pdf(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
                                 const float *rx, const float *ry, const rls_bsdf_out *out);
 void oracle_ggx_dielectric_sample_eval_pdf(size_t n, const rls_shading_soa *sg,

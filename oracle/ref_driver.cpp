@@ -269,6 +269,46 @@ void ggxSampleEvalPdfT(size_t n, const rls_shading_soa *sg, const rls_ggx_params
         out->flags[i] = fl;
     }
 }
+/* The refraction half at caller-supplied directions: the reference's own members (src/rlGgx.h:277-328). */
+template <typename Sampler>
+void ggxRefractDirectionT(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p, rls_cvec3 m, rls_vec3 out_wi, uint32_t *out_flags)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        Shading sh; loadShading(sg, i, sh);
+        GgxArgs a = ggxArgs(p, i);
+        Sampler s(&sh.sg, a.ks, a.ior, a.rough, a.aniso);
+        AtVector mm, t = AI_V3_ZERO; AiV3Create(mm, m.x[i], m.y[i], m.z[i]);
+        bool ok = s.getRefractDirection(mm, s.mViewDir, t);
+        if (!ok) t = AI_V3_ZERO;
+        store3(out_wi, i, t.x, t.y, t.z);
+        if (out_flags) out_flags[i] = (ok ? 0u : RLS_FLAG_TIR) | (AiV3Dot(sh.sg.N, sh.sg.Rd) < AI_EPSILON ? RLS_FLAG_ENTERING : 0u);
+    }
+}
+template <typename Sampler>
+void ggxEvalBtdfT(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p, rls_cvec3 wi, float *out_ft)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        Shading sh; loadShading(sg, i, sh);
+        GgxArgs a = ggxArgs(p, i);
+        Sampler s(&sh.sg, a.ks, a.ior, a.rough, a.aniso);
+        AtVector o; AiV3Create(o, wi.x[i], wi.y[i], wi.z[i]);
+        out_ft[i] = s.refraction(s.mViewDir, o, s.mAxisN);
+    }
+}
+template <typename Sampler>
+void ggxSampleWeightT(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p, rls_cvec3 wi, rls_cvec3 m, float *out_w)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        Shading sh; loadShading(sg, i, sh);
+        GgxArgs a = ggxArgs(p, i);
+        Sampler s(&sh.sg, a.ks, a.ior, a.rough, a.aniso);
+        AtVector o, mm; AiV3Create(o, wi.x[i], wi.y[i], wi.z[i]); AiV3Create(mm, m.x[i], m.y[i], m.z[i]);
+        out_w[i] = s.getSampleWeight(s.mViewDir, o, mm);
+    }
+}
 #define GGX_DISPATCH(p, fn, ...) \
     do { if ((p)->normal_sampler == RLS_GGX_SAMPLER_NDF) fn<GgxNdfSampler>(__VA_ARGS__); else fn<rls::GgxSampler>(__VA_ARGS__); } while (0)
 
@@ -309,6 +349,21 @@ void oracle_ggx_eval_pdf(size_t n, const rls_shading_soa *sg, const rls_ggx_para
                          rls_cvec3 wi, float *out_pdf)
 {
     GGX_DISPATCH(p, ggxEvalPdfT, n, sg, p, wi, out_pdf);
+}
+
+void oracle_ggx_refract_direction(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
+                                  rls_cvec3 m, rls_vec3 out_wi, uint32_t *out_flags)
+{
+    GGX_DISPATCH(p, ggxRefractDirectionT, n, sg, p, m, out_wi, out_flags);
+}
+void oracle_ggx_eval_btdf(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p, rls_cvec3 wi, float *out_ft)
+{
+    GGX_DISPATCH(p, ggxEvalBtdfT, n, sg, p, wi, out_ft);
+}
+void oracle_ggx_sample_weight(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
+                              rls_cvec3 wi, rls_cvec3 m, float *out_weight)
+{
+    GGX_DISPATCH(p, ggxSampleWeightT, n, sg, p, wi, m, out_weight);
 }
 
 void oracle_ggx_sample_eval_pdf(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,

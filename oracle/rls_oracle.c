@@ -753,6 +753,36 @@ void oracle_ggx_eval_pdf(size_t n, const rls_shading_soa *sg, const rls_ggx_para
         out_pdf[i] = ggx_eval_pdf(&g, mk3(wi.x[i], wi.y[i], wi.z[i]));
     }
 }
+/* src/rlGgx.h:277-291, :316-328, :294-301 at caller-supplied directions */
+void oracle_ggx_refract_direction(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
+                                  rls_cvec3 m, rls_vec3 out_wi, uint32_t *out_flags)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        ggx_t g; ggx_from_params(&g, sg, p, i);
+        v3 t = mk3(0.0f, 0.0f, 0.0f);
+        int ok = ggx_refract_direction(&g, mk3(m.x[i], m.y[i], m.z[i]), g.wo, &t);
+        st3(out_wi, i, ok ? t : mk3(0.0f, 0.0f, 0.0f));
+        if (out_flags) out_flags[i] = (ok ? 0u : RLS_FLAG_TIR) | (g.entering ? RLS_FLAG_ENTERING : 0u);
+    }
+}
+void oracle_ggx_eval_btdf(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p, rls_cvec3 wi, float *out_ft)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        ggx_t g; ggx_from_params(&g, sg, p, i);
+        out_ft[i] = ggx_refraction(&g, g.wo, mk3(wi.x[i], wi.y[i], wi.z[i]), g.N);
+    }
+}
+void oracle_ggx_sample_weight(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
+                              rls_cvec3 wi, rls_cvec3 m, float *out_weight)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        ggx_t g; ggx_from_params(&g, sg, p, i);
+        out_weight[i] = ggx_sample_weight(&g, g.wo, mk3(wi.x[i], wi.y[i], wi.z[i]), mk3(m.x[i], m.y[i], m.z[i]));
+    }
+}
 void oracle_ggx_sample_eval_pdf(size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
                                 const float *rx, const float *ry, const rls_bsdf_out *out)
 {

@@ -19,7 +19,7 @@ SYMBOLS = [
     "rls_init", "rls_shutdown", "rls_synchronize", "rls_last_error_string", "rls_abi_version",
     "rls_kernel_launch_count", "rls_node_name", "rls_set_arith_policy", "rls_fallback_count",
     "rls_ggx_eval_sample", "rls_ggx_eval_brdf", "rls_ggx_eval_pdf", "rls_ggx_sample_eval_pdf",
-    "rls_ggx_dielectric_sample_eval_pdf",
+    "rls_ggx_dielectric_sample_eval_pdf", "rls_ggx_refract_direction", "rls_ggx_eval_btdf", "rls_ggx_sample_weight",
     "rls_disney_eval_sample", "rls_disney_eval_brdf", "rls_disney_eval_pdf",
     "rls_disney_sample_eval_pdf",
     "rls_ndprofile_set_distance", "rls_ndprofile_get_radius", "rls_ndprofile_get_pdf",
@@ -67,6 +67,9 @@ def load(path=None):
         "rls_ggx_eval_sample": [vp, sz, P(abi.ShadingSoA), P(abi.GgxParams), vp, vp, abi.Vec3, vp],
         "rls_ggx_eval_brdf": [vp, sz, P(abi.ShadingSoA), P(abi.GgxParams), abi.CVec3, abi.Vec3],
         "rls_ggx_eval_pdf": [vp, sz, P(abi.ShadingSoA), P(abi.GgxParams), abi.CVec3, vp],
+        "rls_ggx_refract_direction": [vp, sz, P(abi.ShadingSoA), P(abi.GgxParams), abi.CVec3, abi.Vec3, vp],
+        "rls_ggx_eval_btdf": [vp, sz, P(abi.ShadingSoA), P(abi.GgxParams), abi.CVec3, vp],
+        "rls_ggx_sample_weight": [vp, sz, P(abi.ShadingSoA), P(abi.GgxParams), abi.CVec3, abi.CVec3, vp],
         "rls_ggx_sample_eval_pdf": [vp, sz, P(abi.ShadingSoA), P(abi.GgxParams), vp, vp, P(abi.BsdfOut)],
         "rls_ggx_dielectric_sample_eval_pdf": [vp, sz, P(abi.ShadingSoA), P(abi.GgxParams), vp, vp,
                                                P(abi.GgxDielectricOut)],

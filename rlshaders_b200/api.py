@@ -275,6 +275,36 @@ class GgxSampler:
                                                 abi.vec3(_f32rows(wi, "wi", n, c)), pdf.data_ptr()), c.lib)
         return pdf
 
+    def getRefractDirection(self, m):
+        """getRefractDirection(m, V) (src/rlGgx.h:277-291) for a microfacet normal m: (wi, flags); wi is the zero
+        vector and flags carries RLS_FLAG_TIR where refraction fails."""
+        n, c = self.sg.n, self.ctx
+        self.sg.placed(c)
+        wi, fl = c.empty(3, n), c.empty(n, dtype=torch.int32)
+        _check(c.handle, c.lib.rls_ggx_refract_direction(c.handle, n, C.byref(self.sg.struct), C.byref(self.params),
+                                                         abi.vec3(_f32rows(m, "m", n, c)), abi.vec3(_f32rows(wi, "wi")),
+                                                         fl.data_ptr()), c.lib)
+        return wi, fl
+
+    def refraction(self, wi):
+        """refraction(V, wi, N) (src/rlGgx.h:316-328): the BTDF at a transmitted direction."""
+        n, c = self.sg.n, self.ctx
+        self.sg.placed(c)
+        ft = c.empty(n)
+        _check(c.handle, c.lib.rls_ggx_eval_btdf(c.handle, n, C.byref(self.sg.struct), C.byref(self.params),
+                                                 abi.vec3(_f32rows(wi, "wi", n, c)), ft.data_ptr()), c.lib)
+        return ft
+
+    def getSampleWeight(self, wi, m):
+        """getSampleWeight(V, wi, m) (src/rlGgx.h:294-301)."""
+        n, c = self.sg.n, self.ctx
+        self.sg.placed(c)
+        w = c.empty(n)
+        _check(c.handle, c.lib.rls_ggx_sample_weight(c.handle, n, C.byref(self.sg.struct), C.byref(self.params),
+                                                     abi.vec3(_f32rows(wi, "wi", n, c)), abi.vec3(_f32rows(m, "m", n, c)),
+                                                     w.data_ptr()), c.lib)
+        return w
+
     def alloc_out(self, like, want_fresnel=True):
         n, c = self.sg.n, self.ctx
         return dict(wi=c.empty(3, n, like=like), f=c.empty(3, n, like=like), pdf=c.empty(n, like=like),

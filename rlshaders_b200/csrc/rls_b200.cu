@@ -417,6 +417,36 @@ k_ggx_eval_pdf(size_t n, ShadingSoA sg, GgxParamsDev p, CV3 wi, float *pdf)
     pdf[i] = ggx_eval_pdf(fp, g, load3(wi, i));
 }
 
+// The refraction half of the path at caller-supplied directions (src/rlGgx.h:277-328): the pieces the fused dielectric
+// unit composes, as entry points of their own so that each can be checked at the oracle's direction bits.
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+k_ggx_refract_direction(size_t n, ShadingSoA sg, GgxParamsDev p, CV3 m, V3 wi, uint32_t *flags)
+{
+    RLS_INDEX();
+    FpExact fp;
+    Ggx g = ggx_make(fp, sg, p, i);
+    f3 dir = mk3(0.0f, 0.0f, 0.0f);
+    const bool ok = ggx_refract_direction(fp, g, load3(m, i), g.wo, dir);      // getRefractDirection(m, V, dir)
+    store3(wi, i, ok ? dir : mk3(0.0f, 0.0f, 0.0f));
+    if (flags) flags[i] = (ok ? 0u : RLS_FLAG_TIR) | (g.entering ? RLS_FLAG_ENTERING : 0u);
+}
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+k_ggx_eval_btdf(size_t n, ShadingSoA sg, GgxParamsDev p, CV3 wi, float *ft)
+{
+    RLS_INDEX();
+    FpExact fp;
+    Ggx g = ggx_make(fp, sg, p, i);
+    ft[i] = ggx_refraction(fp, g, g.wo, load3(wi, i), g.N);                     // refraction(V, wi, N)
+}
+__global__ void __launch_bounds__(kBlock, RLS_MIN_BLOCKS)
+k_ggx_sample_weight(size_t n, ShadingSoA sg, GgxParamsDev p, CV3 wi, CV3 m, float *w)
+{
+    RLS_INDEX();
+    FpExact fp;
+    Ggx g = ggx_make(fp, sg, p, i);
+    w[i] = ggx_sample_weight(fp, g, g.wo, load3(wi, i), load3(m, i));          // getSampleWeight(V, wi, m)
+}
+
 template <class Fp>
 RLS_DEV GgxBsdf ggx_unit_from(Fp &fp, const Shading &s, f3 ks, float ior, float rough, float aniso, bool ndf, float rx, float ry)
 {
@@ -1309,6 +1339,42 @@ extern "C" int rls_ggx_eval_pdf(rls_context *ctx, size_t n, const rls_shading_so
     RLS_LAUNCH_CHECK(ctx);
     return RLS_OK;
 }
+extern "C" int rls_ggx_refract_direction(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
+                                         rls_cvec3 m, rls_vec3 out_wi, uint32_t *out_flags)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && has3(m) && has3(out_wi), "rls_ggx_refract_direction: NULL argument");
+    DeviceGuard guard(ctx->device);
+    k_ggx_refract_direction<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), cv(m), mv(out_wi), out_flags);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+extern "C" int rls_ggx_eval_btdf(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
+                                 rls_cvec3 wi, float *out_ft)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && has3(wi) && out_ft, "rls_ggx_eval_btdf: NULL argument");
+    DeviceGuard guard(ctx->device);
+    k_ggx_eval_btdf<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), cv(wi), out_ft);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+extern "C" int rls_ggx_sample_weight(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
+                                     rls_cvec3 wi, rls_cvec3 m, float *out_weight)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
+    RLS_REQUIRE(ctx, ok_shading(sg) && ok_ggx_params(p) && has3(wi) && has3(m) && out_weight, "rls_ggx_sample_weight: NULL argument");
+    DeviceGuard guard(ctx->device);
+    k_ggx_sample_weight<<<grid_for(n), kBlock, 0, ctx->stream>>>(n, sh(*sg), dev(*p), cv(wi), cv(m), out_weight);
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
 extern "C" int rls_ggx_sample_eval_pdf(rls_context *ctx, size_t n, const rls_shading_soa *sg, const rls_ggx_params *p,
                                        const float *rx, const float *ry, const rls_bsdf_out *out)
 {
@@ -1959,20 +2025,36 @@ int run_staged(rls_context *ctx, size_t n, size_t chunk, size_t slots, Body body
     DeviceGuard guard(ctx->device);
     int rc = stage_prepare(ctx, slots * Stager::align256(chunk * sizeof(float)));
     if (rc != RLS_OK) return rc;
+    // The staging streams are private: order them after whatever the caller already queued on the context's stream.
+    cudaEvent_t entry = nullptr;
+    RLS_CUDA(ctx, cudaEventCreateWithFlags(&entry, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(entry, ctx->stream);
+    for (int b = 0; b < kStages && e == cudaSuccess; b++) e = cudaStreamWaitEvent(ctx->stage_stream[b], entry, 0);
+    cudaEventDestroy(entry);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "host staging: ordering after the context stream");
     Stager st{ ctx, chunk };
     size_t c = 0;
+    // On ANY failure every staging stream is drained before returning: copies of earlier chunks may still be reading
+    // or writing the caller's host buffers.
+    auto drain = [&]() { for (int b = 0; b < kStages; b++) if (ctx->stage_stream[b]) cudaStreamSynchronize(ctx->stage_stream[b]); };
     for (size_t first = 0; first < n; first += chunk, c++) {
         st.stage = (int)(c % kStages);
         st.first = first;
         st.count = (n - first < chunk) ? (n - first) : chunk;
         st.offset = 0;
-        if (c >= (size_t)kStages) RLS_CUDA(ctx, cudaEventSynchronize(ctx->stage_done[st.stage]));
+        if (c >= (size_t)kStages) {
+            e = cudaEventSynchronize(ctx->stage_done[st.stage]);
+            if (e != cudaSuccess) { drain(); return cuda_fail(ctx, e, "host staging: waiting for a stage"); }
+        }
         rc = body(st);
-        if (rc != RLS_OK) return rc;
-        st.finish();
-        if (st.err != cudaSuccess) return cuda_fail(ctx, st.err, "host staging copy");
+        st.finish();                   // the downloads of this chunk are queued even when its launch failed: nothing is dropped
+        if (rc != RLS_OK) { drain(); return rc; }
+        if (st.err != cudaSuccess) { drain(); return cuda_fail(ctx, st.err, "host staging copy"); }
     }
-    for (int b = 0; b < kStages; b++) RLS_CUDA(ctx, cudaStreamSynchronize(ctx->stage_stream[b]));
+    for (int b = 0; b < kStages; b++) {
+        e = cudaStreamSynchronize(ctx->stage_stream[b]);
+        if (e != cudaSuccess) { drain(); return cuda_fail(ctx, e, "host staging: final synchronisation"); }
+    }
     return RLS_OK;
 }
 
@@ -2049,7 +2131,10 @@ extern "C" int rls_skin_profile_sample_eval_pdf_host(rls_context *ctx, size_t n,
     RLS_REQUIRE(ctx, ok_skin_params(p) && rx && ok_profile_out(out), "rls_skin_profile_sample_eval_pdf_host: NULL argument");
     return run_staged(ctx, n, chunk, 16, [&](Stager &st) {
         rls_skin_params q = *p;
-        q.sss_color = st.inp3(p->sss_color); q.sss_scatter_dist = st.inp3(p->sss_scatter_dist);
+        // sss_color is NOT uploaded: the profile maths never reads it (it only feeds the dead `s` of src/rlSss.cpp:22-23),
+        // and it was 12 of the 28 input bytes per sample
+        q.sss_color.array.x = q.sss_color.array.y = q.sss_color.array.z = nullptr;
+        q.sss_scatter_dist = st.inp3(p->sss_scatter_dist);
         q.sss_dist_multiplier = st.in1(p->sss_dist_multiplier);
         const float *drx = st.in(rx);
         rls_profile_out o; o.r = st.out(out->r); o.pdf = st.out(out->pdf); o.Rd = st.out3(out->Rd); o.flags = st.out(out->flags);

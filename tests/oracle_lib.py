@@ -179,6 +179,31 @@ class Oracle:
         return dict(fresnel=F, wi_r=np.stack(wir), f_r=fr, pdf_r=pr, wi_t=np.stack(wit), f_t=ft,
                     weight_t=wt, flags=fl)
 
+    def ggx_refract_direction(self, sg, params, m):
+        n = m.shape[1]
+        wi, fl = _v3(n), _z(n, np.uint32)
+        keep = [np.ascontiguousarray(m[j], dtype=f32) for j in range(3)]
+        self.lib.oracle_ggx_refract_direction(C.c_size_t(n), C.byref(shading_struct(sg)), C.byref(params),
+                                              abi.vec3(keep), abi.vec3(wi), C.c_void_p(fl.ctypes.data))
+        return np.stack(wi), fl
+
+    def ggx_eval_btdf(self, sg, params, wi):
+        n = wi.shape[1]
+        ft = _z(n)
+        keep = [np.ascontiguousarray(wi[j], dtype=f32) for j in range(3)]
+        self.lib.oracle_ggx_eval_btdf(C.c_size_t(n), C.byref(shading_struct(sg)), C.byref(params), abi.vec3(keep),
+                                      C.c_void_p(ft.ctypes.data))
+        return ft
+
+    def ggx_sample_weight(self, sg, params, wi, m):
+        n = wi.shape[1]
+        w = _z(n)
+        k1 = [np.ascontiguousarray(wi[j], dtype=f32) for j in range(3)]
+        k2 = [np.ascontiguousarray(m[j], dtype=f32) for j in range(3)]
+        self.lib.oracle_ggx_sample_weight(C.c_size_t(n), C.byref(shading_struct(sg)), C.byref(params), abi.vec3(k1),
+                                          abi.vec3(k2), C.c_void_p(w.ctypes.data))
+        return w
+
     def prepare_ggx_dielectric(self, sg, params, rx, ry):
         """For timing: outputs allocated AND touched once, ctypes arguments built once.  Returns (call, outputs) where
         call() is nothing but the library's oracle_ggx_dielectric_sample_eval_pdf on those buffers."""

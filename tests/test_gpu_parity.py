@@ -104,6 +104,27 @@ def test_ggx_eval_brdf_pdf_bit_exact_at_oracle_directions(ctx):
     assert np.all(f[:, :16] == 0) and np.all(pdf[:16] >= 1e-4)
 
 
+def test_ggx_refraction_half_bit_exact_at_oracle_directions(ctx, orc):
+    """rls_ggx_refract_direction / rls_ggx_eval_btdf / rls_ggx_sample_weight (src/rlGgx.h:277-328) fed the ORACLE's
+    direction bits: only + - * / sqrt, so bit-exact for every sample, TIR and back-facing samples included."""
+    from rlshaders_b200 import api
+    sg, kw, rx, ry = parity.ggx_dielectric_inputs(N, aniso=True)
+    p = abi.ggx_params(**kw)
+    d = orc.ggx_dielectric(sg, p, rx, ry)
+    wo = np.stack([sg["wo" + c] for c in "xyz"])
+    m = d["wi_r"] + wo
+    m = (m / np.linalg.norm(m, axis=0)).astype(np.float32)
+    s = api.GgxSampler(ctx, api.ShadingBatch.from_numpy(sg, ctx.device), **parity.params_to_dev(kw, ctx.device))
+    dm, dwt = dev(np.ascontiguousarray(m), ctx), dev(np.ascontiguousarray(d["wi_t"]), ctx)
+    wi, fl = s.getRefractDirection(dm)
+    ft, w = s.refraction(dwt), s.getSampleWeight(dwt, dm)
+    ctx.synchronize()
+    cw, cf = orc.ggx_refract_direction(sg, p, m)
+    assert gio.bits_equal(wi.cpu().numpy(), cw) and np.array_equal(fl.cpu().numpy().view(np.uint32), cf)
+    assert gio.bits_equal(ft.cpu().numpy(), orc.ggx_eval_btdf(sg, p, d["wi_t"]))
+    assert gio.bits_equal(w.cpu().numpy(), orc.ggx_sample_weight(sg, p, d["wi_t"], m))
+
+
 def test_ggx_eval_sample_matches_oracle_and_fused(ctx):
     from rlshaders_b200 import api
     port = ol.load_port()

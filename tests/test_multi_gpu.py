@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 def run(*args):
     r = subprocess.run([EXE] + [str(a) for a in args], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    return json.loads(r.stdout)
+    return json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])     # NCCL prints its version banner first
 
 
 def n_gpus():

@@ -111,6 +111,32 @@ def test_port_vs_reference_ggx(port, ref):
     assert gio.bits_equal(ref.ggx_eval_pdf(sg, p, d["wi_t"]), port.ggx_eval_pdf(sg, p, d["wi_t"]))
 
 
+def test_port_vs_reference_refraction_half(port, ref):
+    """getRefractDirection / refraction / getSampleWeight at given directions (src/rlGgx.h:277-328): the port equals
+    the reference's own members bit for bit, including TIR, back-facing samples and a microfacet normal that is not
+    the one the sampler drew."""
+    n = 1 << 16
+    sg = ol.make_shading(n, 0x5EED0002, backfacing_fraction=0.25)
+    kw = dict(specularRoughness=ol.hash_uniform(n, 0x5EED0002, 2, lo=0.05, hi=1.0), ior=ol.hash_uniform(n, 0x5EED0002, 3, lo=1.05, hi=2.5),
+              anisotropic=ol.hash_uniform(n, 0x5EED0002, 4))
+    rx, ry = ol.hash_uniform(n, 0x5EED0002, 0), ol.hash_uniform(n, 0x5EED0002, 1)
+    p = abi.ggx_params(**kw)
+    d = ref.ggx_dielectric(sg, p, rx, ry)
+    wo = np.stack([sg["wo" + c] for c in "xyz"])
+    m = d["wi_r"] + wo                                 # reflection about m: m ~ (wi_r + wo) / |.|
+    m = (m / np.linalg.norm(m, axis=0)).astype(np.float32)
+    m[:, :64] = np.stack([sg["N" + c] for c in "xyz"])[:, :64]
+    for o in (port, ref):
+        o.set_flag_probe(True)
+    wr, fr = ref.ggx_refract_direction(sg, p, m)
+    wp, fp = port.ggx_refract_direction(sg, p, m)
+    assert gio.bits_equal(wr, wp) and np.array_equal(fr, fp)
+    assert 0 < int((fr & abi.FLAG_TIR != 0).sum()) < n
+    wt = d["wi_t"]
+    assert gio.bits_equal(ref.ggx_eval_btdf(sg, p, wt), port.ggx_eval_btdf(sg, p, wt))
+    assert gio.bits_equal(ref.ggx_sample_weight(sg, p, wt, m), port.ggx_sample_weight(sg, p, wt, m))
+
+
 def test_port_vs_reference_disney(port, ref):
     sg, p, u = ol.workload_disney(N)
     a = ref.disney_sample_eval_pdf(sg, p, *u)
