@@ -21,6 +21,7 @@ from rlshaders_b200 import _abi as abi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PORT_SO = os.path.join(ROOT, "oracle", "librls_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "librls_ref.so")
+F64_SO = os.path.join(ROOT, "oracle", "librls_oracle_f64.so")
 REFERENCE_SRC = "/root/reference/src"
 
 f32 = np.float32
@@ -476,6 +477,52 @@ def load_port():
     if not os.path.exists(PORT_SO):
         build_oracles()
     return Oracle(PORT_SO)
+
+
+class _PrefixedLib:
+    """oracle_X -> f64_oracle_X (oracle/rls_oracle_f64.c renames its exports)."""
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        return getattr(self._lib, "f64_" + name)
+
+
+class F64Oracle(Oracle):
+    """oracle/librls_oracle_f64.so: the port re-typed to binary64 -- a yardstick for the reference's own rounding noise,
+    NOT an oracle of its bits.  The ABI structs keep binary32 arrays; bare `float *` arguments are `double *` there, so
+    the four fused calls below hand the uniforms over as float64."""
+
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.path = path
+        self.lib = _PrefixedLib(C.CDLL(path))
+        self.lib.oracle_max_threads.restype = C.c_int
+        self.kind = "port-f64"
+
+    @staticmethod
+    def _d(a):
+        return np.ascontiguousarray(a, dtype=np.float64)
+
+    def ggx_sample_eval_pdf(self, sg, params, rx, ry):
+        return Oracle.ggx_sample_eval_pdf(self, sg, params, self._d(rx), self._d(ry))
+
+    def ggx_dielectric(self, sg, params, rx, ry):
+        return Oracle.ggx_dielectric(self, sg, params, self._d(rx), self._d(ry))
+
+    def disney_sample_eval_pdf(self, sg, params, rx_s, ry_s, rx_d, ry_d):
+        return Oracle.disney_sample_eval_pdf(self, sg, params, self._d(rx_s), self._d(ry_s), self._d(rx_d), self._d(ry_d))
+
+    def skin_profile(self, params, rx):
+        return Oracle.skin_profile(self, params, self._d(rx))
+
+
+def load_f64():
+    if not os.path.exists(F64_SO):
+        build_oracles()
+    return F64Oracle(F64_SO)
 
 
 def load_ref():
