@@ -401,6 +401,38 @@ int rls_disney_sample_eval_pdf_host(rls_context *ctx, size_t n, const rls_shadin
                                     const rls_disney_out *out, size_t chunk);
 int rls_skin_profile_sample_eval_pdf_host(rls_context *ctx, size_t n, const rls_skin_params *params,
                                           const float *rx, const rls_profile_out *out, size_t chunk);
+
+/* Compact shading frames for the host forms (PCIe is what bounds them: 65 -> 45 B uploaded per rlGgx sample).
+ * An orthonormal frame has three degrees of freedom; shipping U, V, N costs nine floats.  `rls_shading_quat_soa` carries
+ * a unit quaternion q = (x, y, z, w) per sample instead, and the frame is DEFINED as the columns of q's rotation matrix,
+ * every entry evaluated in binary32 with one rounding per operation, in exactly this order (x2 = x + x etc.):
+ *     x2 = x + x, y2 = y + y, z2 = z + z
+ *     xx = x * x2, yy = y * y2, zz = z * z2, xy = x * y2, xz = x * z2, yz = y * z2, wx = w * x2, wy = w * y2, wz = w * z2
+ *     U = (1 - (yy + zz),  xy + wz,        xz - wy)
+ *     V = (xy - wz,        1 - (xx + zz),  yz + wx)
+ *     N = (xz + wy,        yz - wx,        1 - (xx + yy))
+ * (tests/oracle_lib.py frame_from_quaternion restates it in numpy; the decoded U, V, N then feed the reference's own
+ * constructors, src/rlGgx.h:145-146, src/rlDisney.cpp:173-174, so parity is checked on identical frame bits).
+ * rls_frame_from_quaternion is the decode as a device entry point; the *_hostq forms upload q, wo, backfacing, decode
+ * on the device into the staging buffers and run the same fused kernels as the *_host forms. */
+typedef struct rls_shading_quat_soa {
+    const float   *qx, *qy, *qz, *qw;
+    rls_cvec3      wo;
+    const uint8_t *backfacing;          /* optional, as in rls_shading_soa */
+} rls_shading_quat_soa;
+int rls_frame_from_quaternion(rls_context *ctx, size_t n, const float *qx, const float *qy, const float *qz,
+                              const float *qw, rls_vec3 out_U, rls_vec3 out_V, rls_vec3 out_N);
+int rls_ggx_sample_eval_pdf_hostq(rls_context *ctx, size_t n, const rls_shading_quat_soa *sq,
+                                  const rls_ggx_params *params, const float *rx, const float *ry,
+                                  const rls_bsdf_out *out, size_t chunk);
+int rls_ggx_dielectric_sample_eval_pdf_hostq(rls_context *ctx, size_t n, const rls_shading_quat_soa *sq,
+                                             const rls_ggx_params *params, const float *rx,
+                                             const float *ry, const rls_ggx_dielectric_out *out,
+                                             size_t chunk);
+int rls_disney_sample_eval_pdf_hostq(rls_context *ctx, size_t n, const rls_shading_quat_soa *sq,
+                                     const rls_disney_params *params, const float *rx_s,
+                                     const float *ry_s, const float *rx_d, const float *ry_d,
+                                     const rls_disney_out *out, size_t chunk);
 /* Pinned host allocation helpers for the _host forms. */
 int rls_host_alloc(rls_context *ctx, size_t bytes, void **out_ptr);
 int rls_host_free(rls_context *ctx, void *ptr);

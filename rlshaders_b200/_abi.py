@@ -62,6 +62,12 @@ class ShadingSoA(C.Structure):
                 ("backfacing", C.c_void_p)]
 
 
+class ShadingQuatSoA(C.Structure):
+    # rls_shading_quat_soa: unit quaternion (x, y, z, w) in place of U, V, N (include/rls_b200.h)
+    _fields_ = [("qx", C.c_void_p), ("qy", C.c_void_p), ("qz", C.c_void_p), ("qw", C.c_void_p), ("wo", CVec3),
+                ("backfacing", C.c_void_p)]
+
+
 class GgxParams(C.Structure):
     # names = rlGgx node parameters, reference src/rlGgx.cpp:172-186
     _fields_ = [("KsColor", Param3), ("Ks", Param1), ("specularRoughness", Param1),
@@ -237,6 +243,13 @@ def disney_params(**kw):
 
 def skin_params(**kw):
     return _fill_params(SkinParams, SKIN_DEFAULTS, kw)
+
+
+def shading_quat(q, wo, backfacing=None):
+    """q: four arrays (x, y, z, w)."""
+    s = ShadingQuatSoA(_addr(q[0]), _addr(q[1]), _addr(q[2]), _addr(q[3]), vec3(wo), _addr(backfacing))
+    s._keepalive = (q, wo, backfacing)
+    return s
 
 
 def shading(U, V, N, wo, backfacing=None):

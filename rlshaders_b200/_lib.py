@@ -29,6 +29,8 @@ SYMBOLS = [
     "rls_gaussprofile_eval_profile", "rls_gaussprofile_sample_eval_pdf",
     "rls_ggx_sample_eval_pdf_host", "rls_ggx_dielectric_sample_eval_pdf_host",
     "rls_disney_sample_eval_pdf_host", "rls_skin_profile_sample_eval_pdf_host",
+    "rls_frame_from_quaternion", "rls_ggx_sample_eval_pdf_hostq", "rls_ggx_dielectric_sample_eval_pdf_hostq",
+    "rls_disney_sample_eval_pdf_hostq",
     "rls_host_alloc", "rls_host_free",
     "rls_albedo_sweep", "rls_synth_uniform", "rls_synth_shading", "rls_debug_libm", "rls_debug_policy_check",
     "rls_skin_glossy_layers", "rls_ggx_evaluate_light_sample", "rls_disney_evaluate_light_sample",
@@ -98,6 +100,12 @@ def load(path=None):
         "rls_disney_sample_eval_pdf_host": [vp, sz, P(abi.ShadingSoA), P(abi.DisneyParams), vp, vp, vp, vp,
                                             P(abi.DisneyOut), sz],
         "rls_skin_profile_sample_eval_pdf_host": [vp, sz, P(abi.SkinParams), vp, P(abi.ProfileOut), sz],
+        "rls_frame_from_quaternion": [vp, sz, vp, vp, vp, vp, abi.Vec3, abi.Vec3, abi.Vec3],
+        "rls_ggx_sample_eval_pdf_hostq": [vp, sz, P(abi.ShadingQuatSoA), P(abi.GgxParams), vp, vp, P(abi.BsdfOut), sz],
+        "rls_ggx_dielectric_sample_eval_pdf_hostq": [vp, sz, P(abi.ShadingQuatSoA), P(abi.GgxParams), vp, vp,
+                                                     P(abi.GgxDielectricOut), sz],
+        "rls_disney_sample_eval_pdf_hostq": [vp, sz, P(abi.ShadingQuatSoA), P(abi.DisneyParams), vp, vp, vp, vp,
+                                             P(abi.DisneyOut), sz],
         "rls_host_alloc": [vp, sz, P(vp)],
         "rls_host_free": [vp, vp],
         "rls_albedo_sweep": [vp, P(abi.SweepGrid), u64, u32, u32, vp],

@@ -224,6 +224,49 @@ class ShadingBatch:
         return cls(mk("U"), mk("V"), mk("N"), mk("wo"), bf)
 
 
+class QuatShadingBatch:
+    """Compact shading batch for the host-buffer forms (include/rls_b200.h rls_shading_quat_soa): a unit quaternion
+    q = (x, y, z, w) [4, n] in place of the nine floats of U, V, N -- PCIe bounds those forms, and this cuts the upload
+    from 65 to 45 B per rlGgx sample.  The frame is DEFINED by the header's binary32 decode (`decode(ctx)` runs it on
+    the device; the test suite restates it in numpy).  CPU (pinned) tensors only."""
+
+    def __init__(self, q, wo, backfacing=None):
+        self.q, self.wo, self.backfacing = q, wo, backfacing
+        if q.dtype != torch.float32 or q.dim() != 2 or q.shape[0] != 4 or not q.is_contiguous():
+            raise ValueError("q: expected a contiguous float32 tensor of shape [4, n]")
+        self.n = n = q.shape[1]
+        self.on_host = True
+        self.quat = True
+        for name, t in (("q", q), ("wo", wo), ("backfacing", backfacing)):
+            if t is not None and t.device.type != "cpu":
+                raise ValueError(f"QuatShadingBatch: {name} must be a CPU (pinned) tensor; decode(ctx) gives the device frame")
+        if backfacing is not None and (backfacing.dtype != torch.uint8 or backfacing.dim() != 1 or backfacing.shape[0] != n
+                                       or not backfacing.is_contiguous()):
+            raise ValueError(f"backfacing: expected a contiguous uint8 tensor of shape [{n}]")
+        self.struct = abi.shading_quat((q[0], q[1], q[2], q[3]), _f32rows(wo, "wo", n), backfacing)
+
+    def placed(self, ctx, host=False):
+        if not host:
+            raise ValueError("QuatShadingBatch: only the fused *SampleEvalPdf calls (host-buffer form) take compact frames")
+        return self
+
+    def decode(self, ctx):
+        """-> ShadingBatch on ctx.device with U, V, N decoded by rls_frame_from_quaternion."""
+        q = self.q.to(ctx.device)
+        U, V, N = ctx.empty(3, self.n), ctx.empty(3, self.n), ctx.empty(3, self.n)
+        _check(ctx.handle, ctx.lib.rls_frame_from_quaternion(ctx.handle, self.n, q[0].data_ptr(), q[1].data_ptr(),
+                                                             q[2].data_ptr(), q[3].data_ptr(), abi.vec3((U[0], U[1], U[2])),
+                                                             abi.vec3((V[0], V[1], V[2])), abi.vec3((N[0], N[1], N[2]))), ctx.lib)
+        ctx.synchronize()
+        return ShadingBatch(U, V, N, self.wo.to(ctx.device),
+                            self.backfacing.to(ctx.device) if self.backfacing is not None else None)
+
+
+def _host_form(lib, name, sg):
+    """The host-buffer entry point of a fused unit: *_hostq for compact frames, *_host otherwise."""
+    return getattr(lib, name + ("_hostq" if getattr(sg, "quat", False) else "_host"))
+
+
 def _param(v):
     """Node-parameter value -> what _abi.param1/param3 accept (scalars stay uniform)."""
     return v
@@ -324,7 +367,7 @@ class GgxSampler:
         args = (c.handle, n, C.byref(self.sg.struct), C.byref(self.params), _f32(rx, "rx", n, c, h).data_ptr(),
                 _f32(ry, "ry", n, c, h).data_ptr(), C.byref(o))
         if self.sg.on_host:
-            _check(c.handle, c.lib.rls_ggx_sample_eval_pdf_host(*args, chunk), c.lib)
+            _check(c.handle, _host_form(c.lib, "rls_ggx_sample_eval_pdf", self.sg)(*args, chunk), c.lib)
         else:
             _check(c.handle, c.lib.rls_ggx_sample_eval_pdf(*args), c.lib)
         return out
@@ -349,7 +392,7 @@ class GgxSampler:
         args = (c.handle, n, C.byref(self.sg.struct), C.byref(self.params), _f32(rx, "rx", n, c, h).data_ptr(),
                 _f32(ry, "ry", n, c, h).data_ptr(), C.byref(o))
         if self.sg.on_host:
-            _check(c.handle, c.lib.rls_ggx_dielectric_sample_eval_pdf_host(*args, chunk), c.lib)
+            _check(c.handle, _host_form(c.lib, "rls_ggx_dielectric_sample_eval_pdf", self.sg)(*args, chunk), c.lib)
         else:
             _check(c.handle, c.lib.rls_ggx_dielectric_sample_eval_pdf(*args), c.lib)
         return out
@@ -500,7 +543,7 @@ class DisneySampler:
                 _f32(ry_s, "ry_s", n, c, h).data_ptr(), _f32(rx_d, "rx_d", n, c, h).data_ptr(),
                 _f32(ry_d, "ry_d", n, c, h).data_ptr(), C.byref(o))
         if self.sg.on_host:
-            _check(c.handle, c.lib.rls_disney_sample_eval_pdf_host(*args, chunk), c.lib)
+            _check(c.handle, _host_form(c.lib, "rls_disney_sample_eval_pdf", self.sg)(*args, chunk), c.lib)
         else:
             _check(c.handle, c.lib.rls_disney_sample_eval_pdf(*args), c.lib)
         return out

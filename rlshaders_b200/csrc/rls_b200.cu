@@ -1938,6 +1938,41 @@ extern "C" int rls_debug_policy_check(rls_context *ctx, int fn, uint32_t first_b
     return RLS_OK;
 }
 
+// ===================================================== compact frames (include/rls_b200.h rls_shading_quat_soa)
+// One rounding per written operation (this translation unit is compiled -fmad=false): the frame bits are a function of
+// the quaternion bits alone, the same on the host (the test suite restates the decode in numpy).
+__global__ void __launch_bounds__(256)
+k_frame_from_quat(uint32_t n, const float *qx, const float *qy, const float *qz, const float *qw, V3 U, V3 V, V3 N)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = __ldg(qx + i), y = __ldg(qy + i), z = __ldg(qz + i), w = __ldg(qw + i);
+    const float x2 = x + x, y2 = y + y, z2 = z + z;
+    const float xx = x * x2, yy = y * y2, zz = z * z2, xy = x * y2, xz = x * z2, yz = y * z2;
+    const float wx = w * x2, wy = w * y2, wz = w * z2;
+    U.x[i] = 1.0f - (yy + zz); U.y[i] = xy + wz;          U.z[i] = xz - wy;
+    V.x[i] = xy - wz;          V.y[i] = 1.0f - (xx + zz); V.z[i] = yz + wx;
+    N.x[i] = xz + wy;          N.y[i] = yz - wx;          N.z[i] = 1.0f - (xx + yy);
+}
+static int launch_frame_from_quat(rls_context *ctx, cudaStream_t st, size_t n, const float *qx, const float *qy, const float *qz,
+                                  const float *qw, const rls_vec3 &U, const rls_vec3 &V, const rls_vec3 &N)
+{
+    k_frame_from_quat<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((uint32_t)n, qx, qy, qz, qw, mv(U), mv(V), mv(N));
+    RLS_LAUNCH_CHECK(ctx);
+    return RLS_OK;
+}
+extern "C" int rls_frame_from_quaternion(rls_context *ctx, size_t n, const float *qx, const float *qy, const float *qz,
+                                         const float *qw, rls_vec3 out_U, rls_vec3 out_V, rls_vec3 out_N)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
+    RLS_REQUIRE(ctx, qx && qy && qz && qw && out_U.x && out_U.y && out_U.z && out_V.x && out_V.y && out_V.z &&
+                out_N.x && out_N.y && out_N.z, "rls_frame_from_quaternion: NULL argument");
+    DeviceGuard guard(ctx->device);
+    return launch_frame_from_quat(ctx, ctx->stream, n, qx, qy, qz, qw, out_U, out_V, out_N);
+}
+
 // ===================================================== host-buffer (end-to-end) forms
 // A chunk of samples is staged through one of kStages device buffers: H2D of every input
 // slice, the kernel, D2H of every output slice, all on that stage's stream, so that chunk
@@ -1985,6 +2020,18 @@ struct Stager {
     rls_shading_soa shading(const rls_shading_soa &s)
     {
         rls_shading_soa o; o.U = in3(s.U); o.V = in3(s.V); o.N = in3(s.N); o.wo = in3(s.wo); o.backfacing = in(s.backfacing); return o;
+    }
+    template <typename T> T *scratch() { return (T *)slot(sizeof(T)); }
+    // Compact frame: q, wo, backfacing are uploaded; U, V, N are decoded into this stage's scratch on the stage's stream.
+    int shading_from_quat(const rls_shading_quat_soa &q, rls_shading_soa *o)
+    {
+        const float *x = in(q.qx), *y = in(q.qy), *z = in(q.qz), *w = in(q.qw);
+        rls_vec3 U = { scratch<float>(), scratch<float>(), scratch<float>() };
+        rls_vec3 V = { scratch<float>(), scratch<float>(), scratch<float>() };
+        rls_vec3 N = { scratch<float>(), scratch<float>(), scratch<float>() };
+        o->U = { U.x, U.y, U.z }; o->V = { V.x, V.y, V.z }; o->N = { N.x, N.y, N.z };
+        o->wo = in3(q.wo); o->backfacing = in(q.backfacing);
+        return launch_frame_from_quat(ctx, ctx->stage_stream[stage], count, x, y, z, w, U, V, N);
     }
     void finish()
     {
@@ -2139,5 +2186,76 @@ extern "C" int rls_skin_profile_sample_eval_pdf_host(rls_context *ctx, size_t n,
         const float *drx = st.in(rx);
         rls_profile_out o; o.r = st.out(out->r); o.pdf = st.out(out->pdf); o.Rd = st.out3(out->Rd); o.flags = st.out(out->flags);
         return launch_skin_profile(ctx, ctx->stage_stream[st.stage], st.count, &q, drx, &o);
+    });
+}
+
+// ---- the same three fused units with compact frames (rls_shading_quat_soa): 4 + 3 floats (+ 1 byte) of shading per sample
+static inline bool ok_shading_quat(const rls_shading_quat_soa *s) { return s && s->qx && s->qy && s->qz && s->qw && has3(s->wo); }
+extern "C" int rls_ggx_sample_eval_pdf_hostq(rls_context *ctx, size_t n, const rls_shading_quat_soa *sq, const rls_ggx_params *p,
+                                             const float *rx, const float *ry, const rls_bsdf_out *out, size_t chunk)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
+    RLS_REQUIRE(ctx, ok_shading_quat(sq) && ok_ggx_params(p) && rx && ry && ok_bsdf_out(out), "rls_ggx_sample_eval_pdf_hostq: NULL argument");
+    return run_staged(ctx, n, chunk, 36, [&](Stager &st) {
+        rls_shading_soa s;
+        int rc = st.shading_from_quat(*sq, &s);
+        if (rc != RLS_OK) return rc;
+        rls_ggx_params q = *p;
+        q.KsColor = st.inp3(p->KsColor); q.specularRoughness = st.in1(p->specularRoughness);
+        q.ior = st.in1(p->ior); q.anisotropic = st.in1(p->anisotropic);
+        const float *drx = st.in(rx), *dry = st.in(ry);
+        rls_bsdf_out o; o.wi = st.out3(out->wi); o.f = st.out3(out->f); o.pdf = st.out(out->pdf);
+        o.fresnel = st.out(out->fresnel); o.flags = st.out(out->flags);
+        return launch_ggx_sample_eval_pdf(ctx, ctx->stage_stream[st.stage], st.count, &s, &q, drx, dry, &o);
+    });
+}
+extern "C" int rls_ggx_dielectric_sample_eval_pdf_hostq(rls_context *ctx, size_t n, const rls_shading_quat_soa *sq,
+                                                        const rls_ggx_params *p, const float *rx, const float *ry,
+                                                        const rls_ggx_dielectric_out *out, size_t chunk)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
+    RLS_REQUIRE(ctx, ok_shading_quat(sq) && ok_ggx_params(p) && rx && ry && ok_dielectric_out(out),
+                "rls_ggx_dielectric_sample_eval_pdf_hostq: NULL argument");
+    return run_staged(ctx, n, chunk, 40, [&](Stager &st) {
+        rls_shading_soa s;
+        int rc = st.shading_from_quat(*sq, &s);
+        if (rc != RLS_OK) return rc;
+        rls_ggx_params q = *p;
+        q.KsColor = st.inp3(p->KsColor); q.specularRoughness = st.in1(p->specularRoughness);
+        q.ior = st.in1(p->ior); q.anisotropic = st.in1(p->anisotropic);
+        const float *drx = st.in(rx), *dry = st.in(ry);
+        rls_ggx_dielectric_out o;
+        o.fresnel = st.out(out->fresnel); o.wi_r = st.out3(out->wi_r); o.f_r = st.out(out->f_r); o.pdf_r = st.out(out->pdf_r);
+        o.wi_t = st.out3(out->wi_t); o.f_t = st.out(out->f_t); o.weight_t = st.out(out->weight_t); o.flags = st.out(out->flags);
+        return launch_ggx_dielectric(ctx, ctx->stage_stream[st.stage], st.count, &s, &q, drx, dry, &o);
+    });
+}
+extern "C" int rls_disney_sample_eval_pdf_hostq(rls_context *ctx, size_t n, const rls_shading_quat_soa *sq, const rls_disney_params *p,
+                                                const float *rx_s, const float *ry_s, const float *rx_d, const float *ry_d,
+                                                const rls_disney_out *out, size_t chunk)
+{
+    if (!ctx) return RLS_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RLS_OK;
+    if (n >> 32) return fail(ctx, RLS_ERR_INVALID_ARGUMENT, "n must be below 2^32 samples per call");
+    RLS_REQUIRE(ctx, ok_shading_quat(sq) && ok_disney_params(p) && rx_s && ry_s && rx_d && ry_d && ok_disney_out(out),
+                "rls_disney_sample_eval_pdf_hostq: NULL argument");
+    return run_staged(ctx, n, chunk, 52, [&](Stager &st) {
+        rls_shading_soa s;
+        int rc = st.shading_from_quat(*sq, &s);
+        if (rc != RLS_OK) return rc;
+        rls_disney_params q = *p;
+        q.base_color = st.inp3(p->base_color); q.subsurface = st.in1(p->subsurface); q.metallic = st.in1(p->metallic);
+        q.specular = st.in1(p->specular); q.specular_tint = st.in1(p->specular_tint); q.roughness = st.in1(p->roughness);
+        q.anisotropic = st.in1(p->anisotropic); q.sheen = st.in1(p->sheen); q.sheen_tint = st.in1(p->sheen_tint);
+        q.clearcoat = st.in1(p->clearcoat); q.clearcoat_gloss = st.in1(p->clearcoat_gloss);
+        const float *a = st.in(rx_s), *b = st.in(ry_s), *c = st.in(rx_d), *d = st.in(ry_d);
+        rls_disney_out o;
+        o.wi_s = st.out3(out->wi_s); o.f_s = st.out3(out->f_s); o.pdf_s = st.out(out->pdf_s);
+        o.wi_d = st.out3(out->wi_d); o.f_d = st.out3(out->f_d); o.pdf_d = st.out(out->pdf_d); o.flags = st.out(out->flags);
+        return launch_disney_sample_eval_pdf(ctx, ctx->stage_stream[st.stage], st.count, &s, &q, a, b, c, d, &o);
     });
 }

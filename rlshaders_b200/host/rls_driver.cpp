@@ -9,7 +9,8 @@
 //   ./rls_driver --gpus N [--policy fast|exact|tolerant] [--reps R] dielectric|disney|skin|sweep [log2(samples per GPU)]
 //       ONE process, N devices (rls_multi): device-resident slices of the index-addressed synthetic stream, every device
 //       launched then synchronised, throughput = samples / slowest device's time; `sweep` = config 5 with the spp range
-//       sharded over the devices and the NCCL all-reduce (+ CUDA graph) behind rls_multi_albedo_sweep.
+//       sharded over the devices and the NCCL all-reduce (+ CUDA graph) behind rls_multi_albedo_sweep; its optional
+//       argument is log2(spp) (default 12; below 10 the grid shrinks to 16 x 16 x 4 cells: sanitizer runs).
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -134,8 +135,12 @@ int multi_main(int gpus, const std::string &policy, int reps, const std::string 
         std::vector<double> check(G, 0.0);
         double total = 0.0;
         if (what == "sweep") {
+            // optional argument: log2(spp), default 12 (BASELINE configs[4]: 65 536 cells x 4096 spp); below 2^10 spp the
+            // grid shrinks to 16 x 16 x 4 cells as well (sanitizer runs, tools/sanitize.sh)
+            const int log2spp = (log2n >= 1 && log2n <= 16) ? log2n : 12;
+            const uint32_t spp = 1u << log2spp;
             rls_sweep_grid grid = { 64, 64, 16, 0.02f, 1.0f, 1.0f, 2.5f };
-            const uint32_t spp = 4096;
+            if (log2spp < 10) { grid.n_rough = 16; grid.n_cos = 16; grid.n_ior = 4; }
             const size_t cells = (size_t)grid.n_rough * grid.n_cos * grid.n_ior, count = cells * RLS_SWEEP_VALUES_PER_CELL;
             std::vector<double *> tables(G);
             for (int k = 0; k < G; k++) tables[k] = (double *)arena[k]->raw(count * sizeof(double));

@@ -21,6 +21,9 @@ from rlshaders_b200 import _abi as abi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PORT_SO = os.path.join(ROOT, "oracle", "librls_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "librls_ref.so")
+if os.environ.get("RLS_ORACLE_DIR"):        # tools/sanitize.sh host: ASan / UBSan builds of the same two libraries
+    PORT_SO = os.path.join(os.environ["RLS_ORACLE_DIR"], "librls_oracle.so")
+    REF_SO = os.path.join(os.environ["RLS_ORACLE_DIR"], "librls_ref.so")
 F64_SO = os.path.join(ROOT, "oracle", "librls_oracle_f64.so")
 REFERENCE_SRC = "/root/reference/src"
 
@@ -531,6 +534,48 @@ def load_ref():
     if not os.path.exists(REF_SO) and os.path.exists(os.path.join(REFERENCE_SRC, "rlGgx.h")):
         build_oracles()
     return Oracle(REF_SO) if os.path.exists(REF_SO) else None
+
+
+# ------------------------------------------------ compact frames (include/rls_b200.h rls_shading_quat_soa)
+def frame_from_quaternion(q):
+    """numpy restatement of the header's DEFINITION of the frame of a unit quaternion q = (x, y, z, w) [4, n]: every
+    operation below is one binary32 operation (numpy float32 arithmetic rounds each), in the header's order.  Returns
+    the dict-of-arrays shading form's U*, V*, N* entries."""
+    x, y, z, w = (np.ascontiguousarray(c, dtype=f32) for c in q)
+    one = f32(1.0)
+    x2, y2, z2 = x + x, y + y, z + z
+    xx, yy, zz, xy, xz, yz = x * x2, y * y2, z * z2, x * y2, x * z2, y * z2
+    wx, wy, wz = w * x2, w * y2, w * z2
+    out = {"Ux": one - (yy + zz), "Uy": xy + wz, "Uz": xz - wy,
+           "Vx": xy - wz, "Vy": one - (xx + zz), "Vz": yz + wx,
+           "Nx": xz + wy, "Ny": yz - wx, "Nz": one - (xx + yy)}
+    return {k: np.ascontiguousarray(v, dtype=f32) for k, v in out.items()}
+
+
+def quaternion_from_frame(sg):
+    """A unit quaternion [4, n] (float32) whose rotation matrix has columns ~ U, V, N of the dict-of-arrays shading form
+    (computed in float64, largest-component branch; how a renderer would encode its frames)."""
+    m = np.array([[sg["Ux"], sg["Vx"], sg["Nx"]], [sg["Uy"], sg["Vy"], sg["Ny"]], [sg["Uz"], sg["Vz"], sg["Nz"]]], dtype=np.float64)
+    m00, m01, m02, m10, m11, m12, m20, m21, m22 = (m[i, j] for i in range(3) for j in range(3))
+    cand = np.stack([
+        np.stack([1 + m00 - m11 - m22, m01 + m10, m02 + m20, m21 - m12]),      # x largest
+        np.stack([m01 + m10, 1 - m00 + m11 - m22, m12 + m21, m02 - m20]),      # y largest
+        np.stack([m02 + m20, m12 + m21, 1 - m00 - m11 + m22, m10 - m01]),      # z largest
+        np.stack([m21 - m12, m02 - m20, m10 - m01, 1 + m00 + m11 + m22]),      # w largest
+    ])                                                                           # [4 candidates, 4 comps, n]
+    pick = np.argmax(np.stack([cand[0, 0], cand[1, 1], cand[2, 2], cand[3, 3]]), axis=0)
+    q = np.take_along_axis(cand, pick[None, None, :], axis=0)[0]
+    q = q / np.sqrt(np.sum(q * q, axis=0))
+    return np.ascontiguousarray(q, dtype=f32)
+
+
+def shading_from_quaternion(q, sg):
+    """The shading dict the oracle sees for a compact batch: decoded frame + the batch's own wo / backfacing."""
+    out = frame_from_quaternion(q)
+    for k in ("wox", "woy", "woz"):
+        out[k] = sg[k]
+    out["backfacing"] = sg.get("backfacing")
+    return out
 
 
 # ------------------------------------------------ BASELINE.json workload recipes

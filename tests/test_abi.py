@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     """Compile a C probe against the real header and compare sizeof/offsetof."""
     structs = {"rls_cvec3": abi.CVec3, "rls_param1": abi.Param1, "rls_param3": abi.Param3,
-               "rls_shading_soa": abi.ShadingSoA, "rls_ggx_params": abi.GgxParams,
+               "rls_shading_soa": abi.ShadingSoA, "rls_shading_quat_soa": abi.ShadingQuatSoA, "rls_ggx_params": abi.GgxParams,
                "rls_disney_params": abi.DisneyParams, "rls_skin_params": abi.SkinParams,
                "rls_bsdf_out": abi.BsdfOut, "rls_ggx_dielectric_out": abi.GgxDielectricOut,
                "rls_disney_out": abi.DisneyOut, "rls_ndprofile_soa": abi.NdProfileSoA,

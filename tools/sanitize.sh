@@ -1,0 +1,63 @@
+#!/bin/bash
+# Sanitizer evidence.
+#   GPU box:   tools/sanitize.sh gpu [tag]   compute-sanitizer memcheck / racecheck / initcheck / synccheck over the C++ host
+#              driver (every fused kernel under the three arithmetic policies, the host-staged pipeline with its
+#              three copy streams, the compact-frame decode, the sweep + re-run lists) and over the experiments library's
+#              shared-memory kernels (TMA / mbarrier pipe, CTA-level lobe partition) through pytest at reduced sizes.
+#   anywhere:  tools/sanitize.sh host [tag]  -fsanitize=address,undefined builds of both oracles + the oracle pinning and
+#              physics tests on them (CPU only).
+# Logs: gpurun_out/<tag>_sanitizer_*.txt (copy the summaries to profiles/).
+MODE=${1:-gpu}
+TAG=${2:-r02}
+ROOT=$(cd "$(dirname "$0")/.." && pwd)
+cd "$ROOT"
+mkdir -p gpurun_out
+if [ "$MODE" = gpu ]; then
+  D=rlshaders_b200/host/rls_driver
+  CS="compute-sanitizer --error-exitcode 9 --print-limit 20"
+  for TOOL in memcheck racecheck initcheck synccheck; do
+    LOG=gpurun_out/${TAG}_sanitizer_${TOOL}.txt
+    : > $LOG
+    run() { echo "### $*" >> $LOG; timeout 900 $CS --tool $TOOL "$@" >> $LOG 2>&1; echo "rc=$?" >> $LOG; }
+    for W in ggx dielectric disney skin; do run $D $W 17; done                      # host-staged path, default policy
+    for P in fast exact tolerant; do
+      for W in dielectric disney skin; do run $D --gpus 1 --policy $P --reps 1 $W 17; done
+      run $D --gpus 1 --policy $P --reps 1 sweep 6
+    done
+    # the experiments library (shared-memory permutation with two barriers, TMA bulk copies + mbarrier) and the compact
+    # frames, through pytest at reduced sizes
+    echo "### pytest experiments + compact frames" >> $LOG
+    RLS_TEST_N=16384 timeout 1500 $CS --tool $TOOL --target-processes all python -m pytest -q -x tests/test_experiments.py \
+        "tests/test_gpu_parity.py::test_compact_frame_host_forms" -k "not packed" >> $LOG 2>&1; echo "rc=$?" >> $LOG
+    echo "$TOOL: $(grep -c '^rc=0' $LOG) runs clean, $(grep -c '^rc=[1-9]' $LOG) with findings; $(grep -h 'ERROR SUMMARY' $LOG | sort | uniq -c | tr '\n' ';')"
+  done
+  # the C++ host driver itself under ASan + UBSan (host side of the staging pipeline, arenas, multi-device bookkeeping)
+  LOG=gpurun_out/${TAG}_sanitizer_driver_asan_ubsan.txt
+  : > $LOG
+  g++ -O1 -g -std=c++14 -fsanitize=address,undefined -fno-omit-frame-pointer -o build/rls_driver_asan rlshaders_b200/host/rls_driver.cpp \
+      -Lrlshaders_b200 -lrls_b200 -Wl,-rpath,$ROOT/rlshaders_b200 >> $LOG 2>&1
+  export ASAN_OPTIONS=protect_shadow_gap=0:detect_leaks=0:halt_on_error=0 UBSAN_OPTIONS=print_stacktrace=1
+  for W in ggx dielectric disney skin; do echo "### $W 18" >> $LOG; timeout 600 build/rls_driver_asan $W 18 >> $LOG 2>&1; echo "rc=$?" >> $LOG; done
+  for P in fast tolerant; do
+    for W in dielectric disney skin "sweep 6"; do echo "### --gpus 1 --policy $P $W" >> $LOG; timeout 600 build/rls_driver_asan --gpus 1 --policy $P --reps 2 $W 18 >> $LOG 2>&1; echo "rc=$?" >> $LOG; done
+  done
+  echo "driver asan/ubsan: $(grep -c 'runtime error' $LOG) UBSan reports, $(grep -c 'ERROR: AddressSanitizer' $LOG) ASan reports, $(grep -c '^rc=0' $LOG) runs clean, $(grep -c '^rc=[1-9]' $LOG) failed"
+else
+  LOG=gpurun_out/${TAG}_sanitizer_host_asan_ubsan.txt
+  : > $LOG
+  SAN="-fsanitize=address,undefined -fno-omit-frame-pointer -g"
+  mkdir -p build/san
+  # same sources, same pinned FP flags (oracle/Makefile), into build/san/ (the normal libraries are left alone)
+  FP="-O1 -ffp-contract=off -fno-fast-math -fopenmp -fPIC -DNDEBUG"
+  gcc -std=c11 $FP $SAN -shared -o build/san/librls_oracle.so oracle/rls_oracle.c -lm >> $LOG 2>&1
+  if [ -f /root/reference/src/rlGgx.h ]; then
+    g++ -std=c++14 -D_LINUX $FP $SAN -Ioracle/shim -I/root/reference/src -Ioracle -w -shared -o build/san/librls_ref.so \
+        oracle/ref_driver.cpp oracle/shim/shim_stubs.cpp /root/reference/src/rlUtil.cpp /root/reference/src/rlGgx.cpp \
+        /root/reference/src/rlSss.cpp -lm >> $LOG 2>&1
+  fi
+  ASAN_LIB=$(gcc -print-file-name=libasan.so)
+  echo "### pytest tests/test_oracle_pinning.py tests/test_oracle_physics.py on the sanitized oracles" >> $LOG
+  RLS_ORACLE_DIR=$ROOT/build/san LD_PRELOAD=$ASAN_LIB ASAN_OPTIONS=detect_leaks=0:halt_on_error=0 UBSAN_OPTIONS=print_stacktrace=1 \
+      python -m pytest -q tests/test_oracle_pinning.py tests/test_oracle_physics.py >> $LOG 2>&1; echo "rc=$?" >> $LOG
+  echo "asan/ubsan: $(grep -c 'runtime error' $LOG) UBSan reports, $(grep -c 'ERROR: AddressSanitizer' $LOG) ASan reports; $(tail -3 $LOG | tr '\n' ' ')"
+fi
