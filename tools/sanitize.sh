@@ -26,9 +26,12 @@ if [ "$MODE" = gpu ]; then
     done
     # the experiments library (shared-memory permutation with two barriers, TMA bulk copies + mbarrier) and the compact
     # frames, through pytest at reduced sizes
-    echo "### pytest experiments + compact frames" >> $LOG
-    RLS_TEST_N=16384 timeout 1500 $CS --tool $TOOL --target-processes all python -m pytest -q -x tests/test_experiments.py \
-        "tests/test_gpu_parity.py::test_compact_frame_host_forms" -k "not packed" >> $LOG 2>&1; echo "rc=$?" >> $LOG
+    # (initcheck: without the TMA-staged kernel -- it reports that kernel's cp.async.bulk shared->global stores as never
+    #  having initialised the output arrays, 20 reports per array, and then crawls; memcheck covers that kernel)
+    SKIP="not packed"; [ $TOOL = initcheck ] && SKIP="not packed and not tma"
+    echo "### pytest experiments + compact frames ($SKIP)" >> $LOG
+    RLS_TEST_N=16384 timeout 900 $CS --tool $TOOL --target-processes all python -m pytest -q -x tests/test_experiments.py \
+        "tests/test_gpu_parity.py::test_compact_frame_host_forms" -k "$SKIP" >> $LOG 2>&1; echo "rc=$?" >> $LOG
     echo "$TOOL: $(grep -c '^rc=0' $LOG) runs clean, $(grep -c '^rc=[1-9]' $LOG) with findings; $(grep -h 'ERROR SUMMARY' $LOG | sort | uniq -c | tr '\n' ';')"
   done
   # the C++ host driver itself under ASan + UBSan (host side of the staging pipeline, arenas, multi-device bookkeeping)
