@@ -152,6 +152,41 @@ def run_skin(ctx, oracle, n, seed=0x5EED0004):
     return summarize(gpu, cpu, kinds), gpu, cpu, (kw, s)
 
 
+_HOST_LIBM = None
+
+
+def host_libm_status():
+    """RLS_HOST_LIBM_CHECK: does THIS host's libm return the bits the device port reproduces (glibc 2.39, x86-64 FMA
+    builds; rlshaders_b200/csrc/rls_libm.cuh)?  A few hundred thousand known-answer arguments per transcendental, the
+    device port's own source compiled for the host against the host libm (tests/native/libm_check).  Returns
+    ("ok", "") or ("degraded", "<function>: k mismatches ..."): on a degraded host the GPU parity tests fall back from
+    "bit-identical" to their fractional tolerances and say so, instead of failing on a libm they were not written for.
+    RLS_HOST_LIBM_CHECK=0 skips the probe (assumes ok)."""
+    global _HOST_LIBM
+    if _HOST_LIBM is not None:
+        return _HOST_LIBM
+    import subprocess
+    if _os.environ.get("RLS_HOST_LIBM_CHECK", "1") == "0":
+        _HOST_LIBM = ("ok", "probe skipped (RLS_HOST_LIBM_CHECK=0)")
+        return _HOST_LIBM
+    src = _os.path.join(_ROOT, "tests", "native", "libm_check.cpp")
+    exe = _os.path.join(_ROOT, "tests", "native", "libm_check")
+    deps = [src, _os.path.join(_ROOT, "rlshaders_b200", "csrc", "rls_libm.cuh")]
+    try:
+        if not _os.path.exists(exe) or any(_os.path.getmtime(d) > _os.path.getmtime(exe) for d in deps):
+            subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-o", exe, src, "-lm"],
+                           check=True)
+        bad = []
+        for fn in ("sincos", "tan", "atan", "acos", "exp", "log", "atan2", "pow"):
+            out = subprocess.run([exe, fn, "16411"], check=True, capture_output=True, text=True).stdout.split()
+            if int(out[4]) != 0:
+                bad.append(f"{fn}: {out[4]} of {out[2]} arguments differ")
+        _HOST_LIBM = ("ok", "") if not bad else ("degraded", "; ".join(bad))
+    except Exception as e:        # noqa: BLE001
+        _HOST_LIBM = ("degraded", f"probe could not run: {e}")
+    return _HOST_LIBM
+
+
 def format_report(title, stats):
     lines = [title]
     for name, s in stats.items():

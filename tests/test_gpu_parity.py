@@ -50,15 +50,23 @@ def orc(request):
 
 
 def check(stats, title):
+    """On a host whose libm is not the one the device port reproduces (parity.host_libm_status), bit-identity is not
+    expected: the test then reports "parity degraded" and asserts the fractional tolerances measured for a merely
+    correctly-rounded libm instead of FRAC_EXACT."""
     print(parity.format_report(title, stats))
+    status, why = parity.host_libm_status()
+    if status != "ok":
+        print(f"PARITY DEGRADED: the host libm is not glibc 2.39's ({why}); bit-identity is not asserted")
+    frac_tol, frac_loose = (FRAC_TOL, FRAC_LOOSE) if status == "ok" else (0.995, 0.998)
     for name, s in stats.items():
         if "mismatches" in s:
-            assert s["mismatches"] == 0, (title, name, s)
+            assert s["mismatches"] <= (0 if status == "ok" else 1e-4 * s["n"]), (title, name, s)
         else:
             loose = s.get("within_1e4", s.get("within_1e3"))
-            assert s["within"] >= FRAC_TOL, (title, name, s)
-            assert loose >= FRAC_LOOSE, (title, name, s)
-            assert s["bit_exact"] >= FRAC_EXACT, (title, name, s)
+            assert s["within"] >= frac_tol, (title, name, s)
+            assert loose >= frac_loose, (title, name, s)
+            if status == "ok":
+                assert s["bit_exact"] >= FRAC_EXACT, (title, name, s)
 
 
 def dev(a, ctx):

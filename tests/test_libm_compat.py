@@ -36,6 +36,14 @@ def test_device_libm_source_matches_host_libm(checker, fn):
     assert int(out[4]) == 0, " ".join(out)
 
 
+def test_host_libm_probe_reports_ok_on_the_pinned_image():
+    """parity.host_libm_status (RLS_HOST_LIBM_CHECK): this image's glibc 2.39 is the libm the device port reproduces, so
+    the probe must say "ok" here; on another libm it says "degraded" and the GPU parity tests relax bit-identity."""
+    import parity
+    status, why = parity.host_libm_status()
+    assert status == "ok", why
+
+
 def _bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
 
