@@ -112,6 +112,41 @@ k_skin_profile_tol(uint32_t n, SkinParamsDev sp, const float *rx, ProfileOutDev 
     o.flags[i] = enlist(bd.rerun, i, r.flags, wl);
 }
 
+// Two consecutive samples per thread with 64-bit loads / stores: the skin unit is ~100 FP instructions under ~130 of
+// address arithmetic, constant loads and pointer tests for its ten arrays -- at one sample per thread it is ISSUE bound
+// (239 instructions per 32 samples, 83 % issue slots, DRAM 62 %) although it moves only 40 B per sample.  A pair shares
+// the address arithmetic, and the launch site guarantees what the pointer tests asked (sss_scatter_dist is three
+// per-sample arrays, the multiplier is uniform, every pointer is 8-byte aligned).  The odd last sample takes scalar
+// accesses in the same kernel.
+__global__ void __launch_bounds__(kBlockTol, RLS_TOL_MIN_BLOCKS)
+k_skin_profile_tol_x2(uint32_t n, const float *dx, const float *dy, const float *dz, float mult, const float *rx,
+                      ProfileOutDev o, Worklist wl)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = 2u * t;
+    if (i >= n) return;
+    if (i + 1u < n) {
+        const float2 ax = __ldg((const float2 *)(dx + i)), ay = __ldg((const float2 *)(dy + i)), az = __ldg((const float2 *)(dz + i));
+        const float2 u = __ldg((const float2 *)(rx + i));
+        Bands b0, b1;
+        const ProfileT r0 = skin_profile_unit(b0, mk(mul_rn(ax.x, mult), mul_rn(ay.x, mult), mul_rn(az.x, mult)), u.x);
+        const ProfileT r1 = skin_profile_unit(b1, mk(mul_rn(ax.y, mult), mul_rn(ay.y, mult), mul_rn(az.y, mult)), u.y);
+        *(float2 *)(o.r + i) = make_float2(r0.r, r1.r);
+        *(float2 *)(o.pdf + i) = make_float2(r0.pdf, r1.pdf);
+        *(float2 *)(o.Rd.x + i) = make_float2(r0.Rd.x, r1.Rd.x);
+        *(float2 *)(o.Rd.y + i) = make_float2(r0.Rd.y, r1.Rd.y);
+        *(float2 *)(o.Rd.z + i) = make_float2(r0.Rd.z, r1.Rd.z);
+        const uint32_t f0 = enlist(b0.rerun, i, r0.flags, wl), f1 = enlist(b1.rerun, i + 1u, r1.flags, wl);
+        *(uint2 *)(o.flags + i) = make_uint2(f0, f1);
+    } else {
+        Bands bd;
+        const ProfileT r = skin_profile_unit(bd, mk(mul_rn(__ldg(dx + i), mult), mul_rn(__ldg(dy + i), mult), mul_rn(__ldg(dz + i), mult)),
+                                             __ldg(rx + i));
+        o.r[i] = r.r; o.pdf[i] = r.pdf; st3(o.Rd, i, r.Rd);
+        o.flags[i] = enlist(bd.rerun, i, r.flags, wl);
+    }
+}
+
 // The albedo sweep (rls_sweep.cuh: one warp per cell) on the tolerance-policy unit.  Band samples are listed for the
 // exact re-run and left out of the sums.
 __global__ void __launch_bounds__(kSweepBlock, 8)
@@ -172,7 +207,15 @@ cudaError_t launch_albedo_sweep(cudaStream_t st, const SweepGridDev &g, uint32_t
 cudaError_t launch_skin_profile(cudaStream_t st, size_t n, const SkinParamsDev &p, const float *rx, const ProfileOutDev &o,
                                 const Worklist &wl)
 {
-    k_skin_profile_tol<<<grid_for(n), kBlockTol, 0, st>>>((uint32_t)n, p, rx, o, wl);
+    const auto al8 = [](const void *q) { return ((uintptr_t)q & 7u) == 0; };
+    const bool pairs = n >= 2 && p.sss_scatter_dist.x && p.sss_scatter_dist.y && p.sss_scatter_dist.z && !p.sss_dist_multiplier.array &&
+                       al8(p.sss_scatter_dist.x) && al8(p.sss_scatter_dist.y) && al8(p.sss_scatter_dist.z) && al8(rx) && al8(o.r) &&
+                       al8(o.pdf) && al8(o.Rd.x) && al8(o.Rd.y) && al8(o.Rd.z) && al8(o.flags);
+    if (pairs)
+        k_skin_profile_tol_x2<<<grid_for((n + 1) / 2), kBlockTol, 0, st>>>((uint32_t)n, p.sss_scatter_dist.x, p.sss_scatter_dist.y,
+                                                                          p.sss_scatter_dist.z, p.sss_dist_multiplier.value, rx, o, wl);
+    else
+        k_skin_profile_tol<<<grid_for(n), kBlockTol, 0, st>>>((uint32_t)n, p, rx, o, wl);
     return cudaGetLastError();
 }
 

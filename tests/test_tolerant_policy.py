@@ -156,6 +156,39 @@ def test_gpu_skin(tctx, orc):
 
 
 @pytest.mark.gpu
+def test_gpu_skin_pair_kernel_equals_the_scalar_kernel(tctx, orc):
+    """k_skin_profile_tol_x2 (two samples per thread, 64-bit accesses) is taken when sss_scatter_dist is three 8-byte
+    aligned per-sample arrays and the multiplier is uniform; an odd n ends in a scalar tail inside the same kernel; a
+    view that starts at an odd element, a per-sample multiplier or a uniform distance take the one-sample kernel.  Same
+    unit function: the two kernels must agree (to the policy's own tolerance where the compiler contracted differently),
+    and both agree with the oracle on every flag."""
+    import torch
+    from rlshaders_b200 import api
+    n = (1 << 18) + 1                                              # odd: exercises the tail
+    kw, rx = parity.skin_inputs(n + 1)
+    dist = tuple(parity.to_dev(c, tctx.device) for c in kw["sss_scatter_dist"])
+    drx = parity.to_dev(rx, tctx.device)
+    cut = lambda t, a: t[a:a + n]                                  # noqa: E731  (a = 1: 4-byte aligned only)
+    outs = {}
+    for a in (0, 1):
+        s = api.SkinProfile(tctx, n, sss_scatter_dist=tuple(cut(c, a) for c in dist), sss_dist_multiplier=1.0)
+        outs[a] = s.sampleEvalPdf(cut(drx, a))
+    tctx.synchronize()
+    # the same samples through both kernels: elements 1 .. n-1 of the aligned run are elements 0 .. n-2 of the shifted one
+    for k in outs[0]:
+        x, y = outs[0][k][..., 1:], outs[1][k][..., :-1]
+        if k == "flags":
+            assert torch.equal(x, y)
+        else:
+            assert bool(((x - y).abs() <= 1e-5 * y.abs().clamp_min(1e-30)).all()), k
+    hkw = dict(sss_scatter_dist=tuple(np.ascontiguousarray(c[:n]) for c in kw["sss_scatter_dist"]), sss_dist_multiplier=1.0)
+    cpu = orc.skin_profile(abi.skin_params(**hkw), np.ascontiguousarray(rx[:n]))
+    st = _gpu_stats(outs[0], cpu, th.KINDS_SKIN)
+    st["rerun_fraction"] = 0.0
+    check(st, "GPU tolerant policy, skin pair kernel, odd n")
+
+
+@pytest.mark.gpu
 def test_gpu_flags_equal_the_bit_exact_policy_on_16M_samples(tctx):
     """Flags of RLS_ARITH_TOLERANT == flags of the default policy on 2^24 device-generated samples per config (the
     oracle-free form of the flag contract; the bit-exact policy equals the reference on every bit, test_gpu_parity)."""
