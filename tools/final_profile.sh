@@ -34,7 +34,7 @@ if [ "$STAGE" = all ] || [ "$STAGE" = ncu ]; then
     rm -f gpurun_out/${TAG}_prof_disney_$P.ncu-rep
   done
   # the other configs run under both policies inside the default line: anchored names, first timed launch of each
-  for K in k_ggx_sample_eval_pdf k_ggx_sample_eval_pdf_tol k_skin_profile k_skin_profile_tol k_albedo_sweep k_albedo_sweep_tol; do
+  for K in k_ggx_sample_eval_pdf k_ggx_sample_eval_pdf_tol k_skin_profile k_skin_profile_tol_x2 k_albedo_sweep k_albedo_sweep_tol; do
     timeout 400 ncu --set full --clock-control none -k "regex:^${K}\$" -s 1 -c 1 -f -o gpurun_out/${TAG}_prof_$K \
         python bench.py $SMALL > /dev/null 2>&1
     ncu -i gpurun_out/${TAG}_prof_$K.ncu-rep --page raw --csv > gpurun_out/${TAG}_prof_$K.raw.csv 2>/dev/null

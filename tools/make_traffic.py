@@ -6,8 +6,8 @@ launch shape, duration under ncu, and the hash of the kernel's SASS in the libra
 equals the running library's, so a capture never describes a kernel that has since changed.
 
 Usage: make_traffic.py TAG raw.csv [raw.csv ...]      (run where the library of the capture is the one in the tree)
-Samples per launch: grid x block for the one-thread-per-sample kernels; the sweep kernels take theirs from
---sweep-samples (cells x spp, default 65536 x 4096)."""
+Samples per launch: grid x block for the one-thread-per-sample kernels (x 2 / x 4 for kernels named *_x2 / *_x4); the
+sweep kernels take theirs from --sweep-samples (cells x spp, default 65536 x 4096)."""
 import argparse
 import csv
 import json
@@ -56,7 +56,8 @@ def main():
             name = m.group(1)
             grid = num(r, hdr, units, "launch__grid_size")
             block = num(r, hdr, units, "launch__block_size")
-            n = a.sweep_samples if "sweep" in name else grid * block * a.samples_per_thread
+            per_thread = 2.0 if name.endswith("_x2") else (4.0 if name.endswith("_x4") else a.samples_per_thread)
+            n = a.sweep_samples if "sweep" in name else grid * block * per_thread
             rd, wr = num(r, hdr, units, "dram__bytes_read.sum"), num(r, hdr, units, "dram__bytes_write.sum")
             inst = num(r, hdr, units, "smsp__inst_executed.sum")
             e = {"sass_sha16": hashes.get(name), "samples_per_launch": n, "grid": grid, "block": block,
