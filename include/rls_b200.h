@@ -482,6 +482,10 @@ int  rls_multi_albedo_sweep(rls_multi *m, const rls_sweep_grid *grid, uint64_t s
                             double *const *tables, int flags);
 uint64_t rls_multi_graph_replays(const rls_multi *m);           /* how many sweeps ran from the captured graphs */
 int  rls_multi_set_nccl_library(const char *path);              /* optional: where libnccl.so.2 is (process-wide) */
+/* The partition every multi-device path of this library uses (and the one process-per-GPU harnesses reuse, so that both
+ * forms shard identically): part k of `parts` owns the contiguous items [k * total / parts, (k + 1) * total / parts) --
+ * index ranges of the sample stream for configs 1-4, the spp range of every cell for the sweep.  Needs no device. */
+int  rls_multi_partition(uint64_t total, int parts, int k, uint64_t *out_begin, uint64_t *out_end);
 
 /* ------------------------- callers of the triple */
 /* f2 -- rlSkin's two glossy layers for P shading points with K BRDF samples each

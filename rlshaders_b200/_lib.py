@@ -38,7 +38,7 @@ SYMBOLS = [
     "rls_get_arith_policy", "rls_stream", "rls_device_alloc", "rls_device_free", "rls_memcpy_to_host",
     "rls_multi_init", "rls_multi_shutdown", "rls_multi_device_count", "rls_multi_context", "rls_multi_synchronize",
     "rls_multi_last_error_string", "rls_multi_timer_begin", "rls_multi_timer_end", "rls_multi_albedo_sweep",
-    "rls_multi_graph_replays", "rls_multi_set_nccl_library",
+    "rls_multi_graph_replays", "rls_multi_set_nccl_library", "rls_multi_partition",
 ]
 
 # librls_b200_experiments.so: the same sources built with -DRLS_EXPERIMENTS (csrc/experiments/, kernels that
@@ -146,7 +146,8 @@ def load(path=None):
                            "rls_multi_init": [i32, P(i32), P(vp)], "rls_multi_shutdown": [vp], "rls_multi_synchronize": [vp],
                            "rls_multi_timer_begin": [vp], "rls_multi_timer_end": [vp, P(f), P(f)],
                            "rls_multi_albedo_sweep": [vp, P(abi.SweepGrid), u64, u32, P(vp), i32],
-                           "rls_multi_set_nccl_library": [C.c_char_p]}.items():
+                           "rls_multi_set_nccl_library": [C.c_char_p],
+                           "rls_multi_partition": [u64, i32, i32, P(u64), P(u64)]}.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int

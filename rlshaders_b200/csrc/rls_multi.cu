@@ -213,14 +213,25 @@ static int ensure_nccl(rls_multi *m)
     return RLS_OK;
 }
 
+extern "C" int rls_multi_partition(uint64_t total, int parts, int k, uint64_t *out_begin, uint64_t *out_end)
+{
+    if (parts <= 0 || k < 0 || k >= parts || !out_begin || !out_end) return RLS_ERR_INVALID_ARGUMENT;
+    // total * k can exceed 64 bits for totals near 2^64: split into quotient and remainder of total / parts
+    const uint64_t q = total / (uint64_t)parts, r = total % (uint64_t)parts;
+    *out_begin = q * (uint64_t)k + r * (uint64_t)k / (uint64_t)parts;
+    *out_end = q * (uint64_t)(k + 1) + r * (uint64_t)(k + 1) / (uint64_t)parts;
+    return RLS_OK;
+}
+
 // Enqueues, on every device's stream: its share of the sweep, then (unless RLS_MULTI_NO_REDUCE) the all-reduce.
 static int enqueue_sweep(rls_multi *m, const rls_sweep_grid *grid, uint64_t seed, uint32_t spp, double *const *tables, int flags)
 {
     const int G = (int)m->ctx.size();
     const size_t count = (size_t)grid->n_rough * grid->n_cos * grid->n_ior * RLS_SWEEP_VALUES_PER_CELL;
     for (int k = 0; k < G; k++) {
-        const uint32_t k0 = (uint32_t)((uint64_t)spp * k / G), k1 = (uint32_t)((uint64_t)spp * (k + 1) / G);
-        const int rc = rls_albedo_sweep(m->ctx[k], grid, seed, k0, k1, tables[k]);
+        uint64_t k0 = 0, k1 = 0;
+        rls_multi_partition(spp, G, k, &k0, &k1);
+        const int rc = rls_albedo_sweep(m->ctx[k], grid, seed, (uint32_t)k0, (uint32_t)k1, tables[k]);
         if (rc != RLS_OK) return mfail(m, rc, rls_last_error_string(m->ctx[k]));
     }
     if (G > 1 && !(flags & RLS_MULTI_NO_REDUCE)) {
