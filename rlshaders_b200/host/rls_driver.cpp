@@ -6,6 +6,7 @@
 //
 //   g++ -O2 -std=c++14 -o rls_driver rls_driver.cpp -L.. -lrls_b200 -Wl,-rpath,'$ORIGIN/..'
 //   ./rls_driver [ggx|dielectric|disney|skin] [log2(samples)] [device]          host buffers, one device
+//   ./rls_driver [ggx_q|dielectric_q|disney_q] ...                              the same with compact frames (quaternions)
 //   ./rls_driver --gpus N [--policy fast|exact|tolerant] [--reps R] dielectric|disney|skin|sweep [log2(samples per GPU)]
 //       ONE process, N devices (rls_multi): device-resident slices of the index-addressed synthetic stream, every device
 //       launched then synchronised, throughput = samples / slowest device's time; `sweep` = config 5 with the spp range
@@ -71,6 +72,20 @@ rls_shading_soa make_shading(Arena &arena, size_t n, uint64_t seed, float backfa
     }
     rls_shading_soa sg = { as_const(U), as_const(Vv), as_const(N), as_const(W), bf };
     return sg;
+}
+
+// The same batch with compact frames: q per sample (rls_host.hpp quaternion_from_frame), wo and backfacing shared.
+rls_shading_quat_soa to_quat(Arena &arena, size_t n, const rls_shading_soa &sg)
+{
+    float *q[4] = { arena.floats(n), arena.floats(n), arena.floats(n), arena.floats(n) };
+    for (size_t i = 0; i < n; i++) {
+        const float U[3] = { sg.U.x[i], sg.U.y[i], sg.U.z[i] }, V[3] = { sg.V.x[i], sg.V.y[i], sg.V.z[i] }, N[3] = { sg.N.x[i], sg.N.y[i], sg.N.z[i] };
+        float o[4];
+        quaternion_from_frame(U, V, N, o);
+        for (int k = 0; k < 4; k++) q[k][i] = o[k];
+    }
+    rls_shading_quat_soa sq = { q[0], q[1], q[2], q[3], sg.wo, sg.backfacing };
+    return sq;
 }
 
 double seconds() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -248,6 +263,10 @@ int main(int argc, char **argv)
         return multi_main(gpus, policy, reps < 1 ? 1 : reps, w, i + 1 < argc ? atoi(argv[i + 1]) : 24);
     }
     std::string what = argc > 1 ? argv[1] : "dielectric";
+    // a trailing "_q" selects compact frames: unit quaternions uploaded, frames decoded on the device (rls_*_hostq)
+    const bool quat = what.size() > 2 && what.compare(what.size() - 2, 2, "_q") == 0;
+    const std::string label = what;
+    if (quat) what.resize(what.size() - 2);
     size_t n = (size_t)1 << (argc > 2 ? atoi(argv[2]) : 22);
     int device = argc > 3 ? atoi(argv[3]) : 0;
     try {
@@ -264,7 +283,7 @@ int main(int argc, char **argv)
             if (what == "ggx") {                       // gold fixture, testsuite/mtoa/0002
                 p.specularRoughness = uniform(0.3f); p.ior = uniform(0.47f);
                 rls_bsdf_out out = { arena.vec3(n), arena.vec3(n), arena.floats(n), nullptr, arena.words(n) };
-                GgxSampler s(ctx, n, sg, p);
+                GgxSampler s = quat ? GgxSampler(ctx, n, to_quat(arena, n, sg), p) : GgxSampler(ctx, n, sg, p);
                 for (int r = 0; r < reps; r++) { double t0 = seconds(); s.sampleEvalPdf(rx, ry, out); best = std::fmin(best, seconds() - t0); }
                 for (size_t i = 0; i < n; i++) if (!(out.flags[i] & (RLS_FLAG_ZERO_L | RLS_FLAG_BELOW_HORIZON))) { estimate += out.f.x[i] / out.pdf[i]; counted++; }
             } else {
@@ -273,7 +292,7 @@ int main(int argc, char **argv)
                 p.specularRoughness = varying(rough); p.ior = varying(ior);
                 rls_ggx_dielectric_out out = { arena.floats(n), arena.vec3(n), arena.floats(n), arena.floats(n),
                                                arena.vec3(n), arena.floats(n), arena.floats(n), arena.words(n) };
-                GgxSampler s(ctx, n, sg, p);
+                GgxSampler s = quat ? GgxSampler(ctx, n, to_quat(arena, n, sg), p) : GgxSampler(ctx, n, sg, p);
                 for (int r = 0; r < reps; r++) { double t0 = seconds(); s.dielectricSampleEvalPdf(rx, ry, out); best = std::fmin(best, seconds() - t0); }
                 for (size_t i = 0; i < n; i++) if (!(out.flags[i] & (RLS_FLAG_ZERO_L | RLS_FLAG_BELOW_HORIZON))) { estimate += out.f_r[i] / out.pdf_r[i]; counted++; }
             }
@@ -289,7 +308,7 @@ int main(int argc, char **argv)
             fill(base.x, n, 0x5EED0003, 30, 0, 1); fill(base.y, n, 0x5EED0003, 31, 0, 1); fill(base.z, n, 0x5EED0003, 32, 0, 1);
             p.base_color.array = as_const(base);
             rls_disney_out out = { arena.vec3(n), arena.vec3(n), arena.floats(n), arena.vec3(n), arena.vec3(n), arena.floats(n), arena.words(n) };
-            DisneySampler s(ctx, n, sg, p);
+            DisneySampler s = quat ? DisneySampler(ctx, n, to_quat(arena, n, sg), p) : DisneySampler(ctx, n, sg, p);
             for (int r = 0; r < reps; r++) { double t0 = seconds(); s.sampleEvalPdf(u[0], u[1], u[2], u[3], out); best = std::fmin(best, seconds() - t0); }
             for (size_t i = 0; i < n; i++) if (out.pdf_d[i] > 0) { estimate += out.f_d.x[i] / out.pdf_d[i]; counted++; }
         } else if (what == "skin") {
@@ -305,11 +324,11 @@ int main(int argc, char **argv)
             for (int r = 0; r < reps; r++) { double t0 = seconds(); s.sampleEvalPdf(rx, out); best = std::fmin(best, seconds() - t0); }
             for (size_t i = 0; i < n; i++) { estimate += out.Rd.x[i] / out.pdf[i]; counted++; }
         } else {
-            std::fprintf(stderr, "unknown workload '%s' (ggx | dielectric | disney | skin)\n", what.c_str());
+            std::fprintf(stderr, "unknown workload '%s' (ggx | dielectric | disney | skin, ggx_q | dielectric_q | disney_q)\n", what.c_str());
             return 2;
         }
         std::printf("{\"workload\": \"%s\", \"samples\": %zu, \"host_to_host_samples_per_s\": %.4g, \"mean_f_over_pdf\": %.6f, \"nodes\": [\"%s\", \"%s\", \"%s\"]}\n",
-                    what.c_str(), n, (double)n / best, counted ? estimate / (double)counted : 0.0,
+                    label.c_str(), n, (double)n / best, counted ? estimate / (double)counted : 0.0,
                     rls_node_name(0), rls_node_name(1), rls_node_name(2));
     } catch (const Error &e) {
         std::fprintf(stderr, "rls_driver: %s\n", e.what());

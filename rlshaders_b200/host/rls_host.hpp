@@ -9,6 +9,7 @@
 //
 // Header-only; link with librls_b200.so.  No CUDA headers are needed by the client.
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <stdexcept>
@@ -97,41 +98,71 @@ inline rls_skin_params skin_defaults()
     return p;
 }
 
-// Batched rls::GgxSampler.  `sg` and every array are pinned host memory of n entries.
+// Compact frames (include/rls_b200.h rls_shading_quat_soa): the unit quaternion of the rotation whose columns are
+// U, V, N, for hosts that hold their frames as vectors.  Computed in double (largest-component branch) and rounded once;
+// the library's decode of q DEFINES the frame the kernels see, so encode once and use q from then on.
+inline void quaternion_from_frame(const float U[3], const float V[3], const float N[3], float q[4])
+{
+    const double m00 = U[0], m10 = U[1], m20 = U[2], m01 = V[0], m11 = V[1], m21 = V[2], m02 = N[0], m12 = N[1], m22 = N[2];
+    double c[4][4] = { { 1 + m00 - m11 - m22, m01 + m10, m02 + m20, m21 - m12 },
+                       { m01 + m10, 1 - m00 + m11 - m22, m12 + m21, m02 - m20 },
+                       { m02 + m20, m12 + m21, 1 - m00 - m11 + m22, m10 - m01 },
+                       { m21 - m12, m02 - m20, m10 - m01, 1 + m00 + m11 + m22 } };
+    int best = 0;
+    for (int k = 1; k < 4; k++) if (c[k][k] > c[best][best]) best = k;
+    double s = 0.0;
+    for (int k = 0; k < 4; k++) s += c[best][k] * c[best][k];
+    s = 1.0 / std::sqrt(s);
+    for (int k = 0; k < 4; k++) q[k] = (float)(c[best][k] * s);
+}
+
+// Batched rls::GgxSampler.  `sg` and every array are pinned host memory of n entries; the second constructor takes the
+// compact shading batch (quaternion frames) and routes to the *_hostq forms.
 class GgxSampler {
 public:
     GgxSampler(const Context &ctx, size_t n, const rls_shading_soa &sg, const rls_ggx_params &params)
-        : mCtx(ctx), mN(n), mSg(sg), mParams(params) {}
+        : mCtx(ctx), mN(n), mSg(sg), mSq(), mQuat(false), mParams(params) {}
+    GgxSampler(const Context &ctx, size_t n, const rls_shading_quat_soa &sq, const rls_ggx_params &params)
+        : mCtx(ctx), mN(n), mSg(), mSq(sq), mQuat(true), mParams(params) {}
     // evalSample + evalBrdf + evalPdf for every sample (the fused unit of work).
     void sampleEvalPdf(const float *rx, const float *ry, const rls_bsdf_out &out, size_t chunk = 0) const
     {
-        mCtx.check(rls_ggx_sample_eval_pdf_host(mCtx.get(), mN, &mSg, &mParams, rx, ry, &out, chunk));
+        mCtx.check(mQuat ? rls_ggx_sample_eval_pdf_hostq(mCtx.get(), mN, &mSq, &mParams, rx, ry, &out, chunk)
+                         : rls_ggx_sample_eval_pdf_host(mCtx.get(), mN, &mSg, &mParams, rx, ry, &out, chunk));
     }
     // Rough dielectric: reflection and refraction branches (src/rlGgx.h:228-243).
     void dielectricSampleEvalPdf(const float *rx, const float *ry, const rls_ggx_dielectric_out &out, size_t chunk = 0) const
     {
-        mCtx.check(rls_ggx_dielectric_sample_eval_pdf_host(mCtx.get(), mN, &mSg, &mParams, rx, ry, &out, chunk));
+        mCtx.check(mQuat ? rls_ggx_dielectric_sample_eval_pdf_hostq(mCtx.get(), mN, &mSq, &mParams, rx, ry, &out, chunk)
+                         : rls_ggx_dielectric_sample_eval_pdf_host(mCtx.get(), mN, &mSg, &mParams, rx, ry, &out, chunk));
     }
 private:
     const Context &mCtx;
     size_t mN;
     rls_shading_soa mSg;
+    rls_shading_quat_soa mSq;
+    bool mQuat;
     rls_ggx_params mParams;
 };
 
 class DisneySampler {
 public:
     DisneySampler(const Context &ctx, size_t n, const rls_shading_soa &sg, const rls_disney_params &params)
-        : mCtx(ctx), mN(n), mSg(sg), mParams(params) {}
+        : mCtx(ctx), mN(n), mSg(sg), mSq(), mQuat(false), mParams(params) {}
+    DisneySampler(const Context &ctx, size_t n, const rls_shading_quat_soa &sq, const rls_disney_params &params)
+        : mCtx(ctx), mN(n), mSg(), mSq(sq), mQuat(true), mParams(params) {}
     void sampleEvalPdf(const float *rx_s, const float *ry_s, const float *rx_d, const float *ry_d,
                        const rls_disney_out &out, size_t chunk = 0) const
     {
-        mCtx.check(rls_disney_sample_eval_pdf_host(mCtx.get(), mN, &mSg, &mParams, rx_s, ry_s, rx_d, ry_d, &out, chunk));
+        mCtx.check(mQuat ? rls_disney_sample_eval_pdf_hostq(mCtx.get(), mN, &mSq, &mParams, rx_s, ry_s, rx_d, ry_d, &out, chunk)
+                         : rls_disney_sample_eval_pdf_host(mCtx.get(), mN, &mSg, &mParams, rx_s, ry_s, rx_d, ry_d, &out, chunk));
     }
 private:
     const Context &mCtx;
     size_t mN;
     rls_shading_soa mSg;
+    rls_shading_quat_soa mSq;
+    bool mQuat;
     rls_disney_params mParams;
 };
 

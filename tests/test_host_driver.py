@@ -37,3 +37,15 @@ def test_driver_runs_every_workload(driver, workload, lo, hi):
     assert d["host_to_host_samples_per_s"] > 1e7
     assert lo <= d["mean_f_over_pdf"] <= hi
     assert d["nodes"] == ["rlGgx", "rlDisney", "rlSkin"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("workload", ["ggx", "dielectric", "disney"])
+def test_driver_compact_frames_agree_with_full_frames(driver, workload):
+    """`<workload>_q`: the same batch with unit quaternions uploaded and the frames decoded on the device (rls_*_hostq,
+    rls_host.hpp quaternion_from_frame).  The decoded frames differ from U, V, N by one rounding (<= 4e-7), so the
+    white-furnace style estimate over 2^20 samples agrees to 1e-3 relative."""
+    a = json.loads(subprocess.run([driver, workload, "20"], capture_output=True, text=True, check=True).stdout)
+    b = json.loads(subprocess.run([driver, workload + "_q", "20"], capture_output=True, text=True, check=True).stdout)
+    assert b["workload"] == workload + "_q" and b["samples"] == a["samples"]
+    assert abs(a["mean_f_over_pdf"] - b["mean_f_over_pdf"]) <= 1e-3 * abs(a["mean_f_over_pdf"]) + 1e-6

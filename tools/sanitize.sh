@@ -19,7 +19,7 @@ if [ "$MODE" = gpu ]; then
     LOG=gpurun_out/${TAG}_sanitizer_${TOOL}.txt
     : > $LOG
     run() { echo "### $*" >> $LOG; timeout 900 $CS --tool $TOOL "$@" >> $LOG 2>&1; echo "rc=$?" >> $LOG; }
-    for W in ggx dielectric disney skin; do run $D $W 17; done                      # host-staged path, default policy
+    for W in ggx dielectric disney skin dielectric_q disney_q; do run $D $W 17; done                      # host-staged path, default policy
     for P in fast exact tolerant; do
       for W in dielectric disney skin; do run $D --gpus 1 --policy $P --reps 1 $W 17; done
       run $D --gpus 1 --policy $P --reps 1 sweep 6
