@@ -81,6 +81,25 @@ def test_bands_catch_adversarial_inputs(orc):
     assert int(bad.sum()) == 0, np.nonzero(bad)[0][:8]
 
 
+@pytest.mark.parametrize("ulp", [False, True])
+def test_band_regressions_found_by_the_ulp_hunt(orc, ulp):
+    """tests/golden/tol_band_regressions.npz (tests/golden/make_tol_regressions.py): rlDisney samples whose flags are
+    decided by the reference's own rounding noise in places the band tracker once had no estimate for.  Each must be
+    listed for the bit-exact re-run or agree with the reference on every flag, with and without the ulp perturbation."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tol_band_regressions.npz"))
+    sg = {k[3:]: np.ascontiguousarray(g[k]) for k in g.files if k.startswith("sg_")}
+    sg["backfacing"] = None
+    kw = {k[2:]: np.ascontiguousarray(g[k]) for k in g.files if k.startswith("p_") and not k.startswith("p_base_color")}
+    kw["base_color"] = tuple(np.ascontiguousarray(g[f"p_base_color_{j}"]) for j in range(3))
+    u = [np.ascontiguousarray(g[f"u_{j}"]) for j in range(4)]
+    p = abi.disney_params(**kw)
+    t, rerun = th.disney(th.load(ulp=ulp), sg, p, *u)
+    o = orc.disney_sample_eval_pdf(sg, p, *u)
+    bad = (t["flags"] != o["flags"]) & (rerun == 0)
+    assert not bad.any(), (np.nonzero(bad)[0], t["flags"], o["flags"], rerun)
+
+
 def test_policy_error_is_within_the_references_own_rounding_noise():
     """What "within tolerance of the reference" can mean here: against a binary64 evaluation of the SAME
     algorithm (oracle/rls_oracle_f64.c) the reference's binary32 results are themselves outside 1e-6 / 1e-5 for several
