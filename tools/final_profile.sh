@@ -3,7 +3,7 @@
 # line, ncu launch list, `ncu --set full` captures of every fused kernel under BOTH arithmetic policies.
 # Outputs under gpurun_out/<tag>_*; afterwards, in the build container:
 #   python tools/make_traffic.py <tag> gpurun_out/<tag>_prof_*.raw.csv      -> profiles/traffic.json (stamped with SASS hashes)
-#   python tools/ncu_summary.py gpurun_out/<tag>_prof_*.raw.csv             -> the table of profiles/<tag>_ncu_summary.md
+#   cp gpurun_out/<tag>_* profiles/ (what is to be judged); python tools/make_ncu_summary.py <tag>  -> profiles/<tag>_ncu_summary.md
 TAG=${1:-r02}
 STAGE=${2:-all}          # all | tests | bench | ncu
 mkdir -p gpurun_out
