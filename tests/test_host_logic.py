@@ -130,3 +130,36 @@ def test_api_rejects_wrong_lengths_dtypes_and_placement():
         sg.placed(FakeCtx, host=False)
     with pytest.raises(ValueError):
         api._params_placed(dict(ior=f(n + 1)), n, FakeCtx, True)                       # per-sample parameter of the wrong length
+
+
+def test_partition_is_the_librarys_and_survives_huge_totals():
+    """rls_multi_partition (rlshaders_b200/csrc/rls_multi.cu; shard.shard_range delegates to it): exact partition also where
+    total * k would overflow 64 bits."""
+    total = (1 << 64) - 3
+    ranges = [shard.shard_range(total, r, 7) for r in range(7)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == total
+    assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    assert max(e - b for b, e in ranges) - min(e - b for b, e in ranges) <= 1
+    assert [shard.shard_range(10, r, 4) for r in range(4)] == [(0, 2), (2, 5), (5, 7), (7, 10)]     # = r * 10 // 4
+
+
+def test_compact_frames_numpy_restatement_round_trips():
+    """oracle_lib.frame_from_quaternion restates the header's DEFINITION of the frame of a unit quaternion
+    (include/rls_b200.h rls_shading_quat_soa); quaternion_from_frame is how a host would encode its frames.  Encoding
+    random orthonormal frames and decoding them returns the frames to one rounding, orthonormal to 1e-6."""
+    import numpy as np
+    import oracle_lib as ol
+    sg = ol.make_shading(50000, 0xF7A3E)
+    q = ol.quaternion_from_frame(sg)
+    assert q.dtype == np.float32 and np.abs(np.sum(q.astype(np.float64) ** 2, axis=0) - 1.0).max() < 2e-7
+    d = ol.frame_from_quaternion(q)
+    assert max(np.abs(d[k] - sg[k]).max() for k in d) < 1e-6
+    U, V, N = (np.stack([d[a + c] for c in "xyz"]).astype(np.float64) for a in "UVN")
+    for a, b in ((U, V), (U, N), (V, N)):
+        assert np.abs((a * b).sum(0)).max() < 1e-6
+    for a in (U, V, N):
+        assert np.abs((a * a).sum(0) - 1.0).max() < 1e-6
+    assert np.abs(np.cross(U.T, V.T).T - N).max() < 1e-6          # right-handed
+    # the identity quaternion is the identity frame, exactly
+    e = ol.frame_from_quaternion(np.array([[0.0], [0.0], [0.0], [1.0]], np.float32))
+    assert [float(e[k][0]) for k in ("Ux", "Uy", "Uz", "Vx", "Vy", "Vz", "Nx", "Ny", "Nz")] == [1, 0, 0, 0, 1, 0, 0, 0, 1]
