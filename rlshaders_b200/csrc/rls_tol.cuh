@@ -240,6 +240,12 @@ RLT_HD v3 to_frame(float x, float y, float z, v3 u, v3 v, v3 w)      // AiV3Rota
 #ifndef RLS_TOL_U2_NOISE
 #define RLS_TOL_U2_NOISE 2.4e-7f
 #endif
+// The reference re-derives the half vector as normalize(V + L) with L = 2 |V.m| m - V stored in binary32: V + L cancels to
+// 2 |V.m| m plus ~1e-7 of rounding residue, so ITS V.h = V.m +- 1e-7 / (2 |V.m|) -- the sign test on V.h (the masking
+// terms, src/rlGgx.h:348) is decided by rounding once |V.m| falls below ~5e-4.  Half-width to add to a band on V.m.
+// (Found by tools/tol_stress_hunt.py with rx = 1 - 2^-24, which puts m in the tangent plane; the 1e-3 base width of
+// the round's first half had covered it by accident.)
+#define RLS_TOL_HALF_VECTOR_NOISE(vm) (4e-7f * rcp(fmaxf(fabsf(vm), 1e-4f)))
 // ------------------------------------------------------------------ the band tracker
 #if defined(RLS_TOL_BAND_STATS) && !defined(__CUDACC__)
 // Host-only diagnostics (tests/native/tol_host.cpp -DRLS_TOL_BAND_STATS): which band sends a sample to the re-run FIRST,
@@ -438,7 +444,7 @@ RLT_HD DielectricT dielectric_unit(Bands &bd, v3 U, v3 V, v3 N, v3 wo, bool back
     const float Vm = dot(wo, m), aVm = fabsf(Vm);
     const float mN = dot(m, N);
     const float band = RLS_TOL_BAND_BASE + noise;                           // on comparands that follow the sampled direction
-    bd.near(Vm, 0.0f, band);                                    // sign of V.m decides the masking terms
+    bd.near(Vm, 0.0f, band + RLS_TOL_HALF_VECTOR_NOISE(Vm));    // sign of V.m decides the masking terms
     // reflectDirection(V, m) = 2|V.m| m - V; its half vector with V is m, V.H = V.m, L.H = 2|V.m| - V.m
     r.wi_r = m * (2.0f * aVm) - wo;
     const float LH = 2.0f * aVm - Vm;
@@ -520,7 +526,7 @@ RLT_HD GgxBsdfT ggx_unit(Bands &bd, v3 U, v3 V, v3 N, v3 wo, bool backfacing, v3
     const v3 m = sample_visible_normal(bd, wo, U, V, N, g.vz, g.ax, g.ay, rx, ry, early, noise);   // requires V.N > eps
     const float Vm = dot(wo, m), aVm = fabsf(Vm);
     const float band = RLS_TOL_BAND_BASE + noise;
-    bd.near(Vm, 0.0f, band);
+    bd.near(Vm, 0.0f, band + RLS_TOL_HALF_VECTOR_NOISE(Vm));
     o.L = m * (2.0f * aVm) - wo;
     const float LH = 2.0f * aVm - Vm;
     o.fresnel = fresnel_c(ratio2, fabsf(LH));
@@ -618,7 +624,10 @@ RLT_HD DisneyT disney_unit(Bands &bd, v3 U, v3 V, v3 N, v3 wo, const DisneyIn &p
         const float rx = clampf(div(rx_s - gtr2Weight, 1.0f - gtr2Weight), 0.0f, 1.0f);
         float s, c;
         sincos_(kTwoPi * rx, &s, &c);
-        const float ct2 = (r2 == 1.0f) ? 1.0f - ry_s : div(1.0f - pow_(r2, 1.0f - ry_s), 1.0f - r2);
+        // a2 = 0 (roughness exactly 0 is a legal node value): powf(0, y > 0) = 0, cos(theta) = 1; log_ takes normal x only
+        bd.require(r2 == 0.0f || r2 >= 1.2e-38f);
+        const float pw = (r2 > 0.0f) ? pow_(r2, 1.0f - ry_s) : 0.0f;
+        const float ct2 = (r2 == 1.0f) ? 1.0f - ry_s : div(1.0f - pw, 1.0f - r2);
         bd.near(r2, 1.0f, 1e-3f);                                 // (1 - a2^(1-ry)) / (1 - a2) cancels as a2 -> 1
         const float ct = sqrt_(fmaxf(ct2, 0.0f)), st = sqrt_(fmaxf(1.0f - ct2, 0.0f));
         M = normalize(to_frame(st * c, st * s, ct, U, V, N));
@@ -634,7 +643,7 @@ RLT_HD DisneyT disney_unit(Bands &bd, v3 U, v3 V, v3 N, v3 wo, const DisneyIn &p
     bd.near(NM, 0.5f * kEps, 0.5f * kEps + band);                 // N.M < 0 and N.M < eps
     const bool zeroS = NM < 0.0f;
     const float VM = dot(wo, M), aVM = fabsf(VM);
-    bd.near(VM, 0.5f * kEps, 0.5f * kEps + band);   // L ~ -V: the reference's half vector normalize(L + V) is rounding noise; L.M < eps
+    bd.near(VM, 0.5f * kEps, 0.5f * kEps + band + RLS_TOL_HALF_VECTOR_NOISE(VM));   // L ~ -V: the reference's half vector normalize(L + V) is rounding noise; L.M < eps
     uint32_t fls = lobe << 8;
     if (early) fls |= kFlagSlopeEarlyOut;
     if (zeroS) {
