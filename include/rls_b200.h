@@ -263,18 +263,20 @@ uint64_t rls_kernel_launch_count(const rls_context *ctx);
  * re-run since creation / the last reset (synchronises the context's streams). */
 #define RLS_ARITH_FAST  0
 #define RLS_ARITH_EXACT 1
-/* RLS_ARITH_TOLERANT (opt-in): the four fused *_sample_eval_pdf units computed to a stated TOLERANCE instead of to the
- * bit (rlshaders_b200/csrc/rls_tol.cuh: fused multiply-adds, MUFU reciprocals / roots / exp2, polynomial log / sin /
- * cos, visible-normal sampling without its angle round trips) -- about 1/3 of the instructions of the bit-exact
- * kernels, which moves them from issue bound to HBM bound.  FLAGS, LOBE CHOICES AND DISCONTINUOUS BRANCHES STAY
- * BIT-EXACT: a sample whose deciding comparand lies within a band of its threshold is re-evaluated by the bit-exact
- * policy in a second kernel on the same stream (rls_fallback_count counts them, ~5e-4 of the samples).  Value
- * contract, measured against the reference compiled on the host (tests/test_tolerant_policy.py):
- * directions >= 95 % within 1e-6 absolute and >= 99.9 % within 1e-4; f / pdf / radii >= 90 % within 1e-5 relative and
- * >= 99.9 % within 1e-3 -- the spread is the reference's own rounding noise (its angle round trips and cancellations
- * amplify 1 ulp to more than 1e-6 in ~3 % of the samples), not an error of this policy: against an FP64
- * evaluation of the same formulas the tolerance results are closer than the reference's.  The entry points without a
- * tolerance form (triples with explicit wi, profiles, callers, sweep) run RLS_ARITH_FAST under this setting. */
+/* RLS_ARITH_TOLERANT (opt-in): the four fused *_sample_eval_pdf units and the albedo sweep computed to a stated
+ * TOLERANCE instead of to the bit (rlshaders_b200/csrc/rls_tol.cuh: fused multiply-adds, MUFU reciprocals / roots / exp2,
+ * polynomial log / sin / cos, visible-normal sampling without its angle round trips) -- about 40 % of the instructions
+ * of the bit-exact kernels, which moves them from issue bound to HBM bound (config 2: 0.94 of the measured HBM peak).
+ * FLAGS, LOBE CHOICES AND DISCONTINUOUS BRANCHES STAY BIT-EXACT: a sample whose deciding comparand lies within a band of
+ * its threshold -- the band includes the sample's own estimate of the REFERENCE's rounding noise where its algorithm is
+ * ill-conditioned -- is re-evaluated by the bit-exact policy in a second kernel on the same stream (rls_fallback_count
+ * counts them, ~3e-4 of the samples).  Inputs are assumed finite.  Value contract, measured against the reference
+ * compiled on the host (tests/test_tolerant_policy.py): directions >= 95 % within 1e-6 absolute and
+ * >= 99.9 % within 1e-4; f / pdf / radii >= 90 % within 1e-5 relative and >= 99.9 % within 1e-3 -- the spread is the
+ * reference's own rounding noise (its angle round trips and cancellations amplify 1 ulp to more than 1e-6 in several
+ * per cent of the samples), not an error of this policy: against a binary64 evaluation of the same algorithm the
+ * tolerance results are closer than the reference's own.  The entry points without a tolerance form (triples with
+ * explicit wi, profiles, callers) run RLS_ARITH_FAST under this setting. */
 #define RLS_ARITH_TOLERANT 2
 int rls_set_arith_policy(rls_context *ctx, int policy);
 int rls_get_arith_policy(const rls_context *ctx);
