@@ -673,6 +673,9 @@ RLT_HD DisneyT disney_unit(Bands &bd, v3 U, v3 V, v3 N, v3 wo, const DisneyIn &p
         if (LdotN < kEps || VdotN < kEps || NM < kEps || LdotM < kEps) {
             o.fs = zero;
         } else {
+            // L.h within an ulp or two of 1 (m along the view): the reference's (1 - L.h)^5 is exactly 0 or ~1e-36 by rounding
+            // alone, and with F0 = 0 and no clearcoat that alone decides whether f is black (tools/tol_stress_hunt.py --ulp)
+            bd.near(LdotM, 1.0f, 5e-7f);
             const float FH = pow5(clampf(1.0f - LdotM, 0.0f, 1.0f));
             const float Gs = smithG(LdotN, r2) * smithG(VdotN, r2);
             const float Gr = smithG(LdotN, 0.25f) * smithG(VdotN, 0.25f);
