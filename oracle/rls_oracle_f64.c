@@ -6,7 +6,7 @@
  * `float` spelled `double` and every libm call replaced by its binary64 form, so each arithmetic step of the
  * reference's algorithm (paths and lines as cited in rls_oracle.c) is carried with 29 more bits.  The float literals
  * keep their binary32 values (they are the reference's constants).  What it is for: tests/test_tolerant_policy.py and
- * tools/tol_vs_f64.py measure, sample by sample,
+ * tests/hunts/tol_vs_f64.py measure, sample by sample,
  *      |reference (binary32) - this|      the reference's own rounding noise, and
  *      |RLS_ARITH_TOLERANT   - this|      the tolerance policy's error,
  * which is how the repository states what "within tolerance of the reference" can mean for an ill-conditioned sampler.

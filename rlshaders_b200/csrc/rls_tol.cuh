@@ -243,7 +243,7 @@ RLT_HD v3 to_frame(float x, float y, float z, v3 u, v3 v, v3 w)      // AiV3Rota
 // The reference re-derives the half vector as normalize(V + L) with L = 2 |V.m| m - V stored in binary32: V + L cancels to
 // 2 |V.m| m plus ~1e-7 of rounding residue, so ITS V.h = V.m +- 1e-7 / (2 |V.m|) -- the sign test on V.h (the masking
 // terms, src/rlGgx.h:348) is decided by rounding once |V.m| falls below ~5e-4.  Half-width to add to a band on V.m.
-// (Found by tools/tol_stress_hunt.py with rx = 1 - 2^-24, which puts m in the tangent plane; the 1e-3 base width of
+// (Found by tests/hunts/tol_stress_hunt.py with rx = 1 - 2^-24, which puts m in the tangent plane; the 1e-3 base width of
 // the round's first half had covered it by accident.)
 #define RLS_TOL_HALF_VECTOR_NOISE(vm) (4e-7f * rcp(fmaxf(fabsf(vm), 1e-4f)))
 // ------------------------------------------------------------------ the band tracker
@@ -674,7 +674,7 @@ RLT_HD DisneyT disney_unit(Bands &bd, v3 U, v3 V, v3 N, v3 wo, const DisneyIn &p
             o.fs = zero;
         } else {
             // L.h within an ulp or two of 1 (m along the view): the reference's (1 - L.h)^5 is exactly 0 or ~1e-36 by rounding
-            // alone, and with F0 = 0 and no clearcoat that alone decides whether f is black (tools/tol_stress_hunt.py --ulp)
+            // alone, and with F0 = 0 and no clearcoat that alone decides whether f is black (tests/hunts/tol_stress_hunt.py --ulp)
             bd.near(LdotM, 1.0f, 5e-7f);
             const float FH = pow5(clampf(1.0f - LdotM, 0.0f, 1.0f));
             const float Gs = smithG(LdotN, r2) * smithG(VdotN, r2);

@@ -1,13 +1,13 @@
 #!/usr/bin/env python
-"""GPU: the stress distributions of tools/tol_stress_hunt.py through the CUDA library against the reference library.
+"""GPU: the stress distributions of tests/hunts/tol_stress_hunt.py through the CUDA library against the reference library.
   * default (bit-exact) policy: every output of every sample bit-identical (NaN = NaN), every flag equal;
   * tolerance policy: every flag equal (the device's real MUFU errors instead of the host build's emulation).
-    python tools/gpu_stress_parity.py [repetitions of 2^20 samples]"""
+    python tests/hunts/gpu_stress_parity.py [repetitions of 2^20 samples]"""
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "hunts")):
     sys.path.insert(0, p)
 
 import numpy as np

@@ -1,16 +1,16 @@
 #!/usr/bin/env python
 """CPU hunt for flag mismatches of the tolerance policy on the BENCH distributions (tests/native host build of
-csrc/rls_tol.cuh against the reference library; tools/tol_flag_hunt.py is the device version, tools/tol_stress_hunt.py the
+csrc/rls_tol.cuh against the reference library; tools/tol_flag_hunt.py is the device version, tests/hunts/tol_stress_hunt.py the
 one on stress distributions).  Each repetition draws 2^22 samples per unit from the recipes of BASELINE configs 2
 (isotropic and anisotropic alternating) and 3 with a new seed; a failure is a sample whose flags differ from the
 reference's without the band tracker having listed it for the bit-exact re-run.
 
-    python tools/tol_flag_hunt_host.py [repetitions] [--ulp] [--seed K]"""
+    python tests/hunts/tol_flag_hunt_host.py [repetitions] [--ulp] [--seed K]"""
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 

@@ -6,11 +6,11 @@ parameters exactly 0 and 1, clearcoat_gloss at both ends), views from grazing to
 uniforms at 2^-24, 1 - 2^-24, the lobe boundaries and the thirds.  A sample counts as a failure when its flags differ
 from the reference's AND the band tracker did not list it for the bit-exact re-run.
 
-    python tools/tol_stress_hunt.py [repetitions of 2^20 samples] [--ulp] [--quat] [--seed K]"""
+    python tests/hunts/tol_stress_hunt.py [repetitions of 2^20 samples] [--ulp] [--quat] [--seed K]"""
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 

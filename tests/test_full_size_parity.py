@@ -148,12 +148,12 @@ def test_config4_skin_profile_256M(orc):
 
 
 def test_stress_distributions_on_the_device():
-    """tools/gpu_stress_parity.py: the stress distributions (every end point and threshold of every parameter, degenerate
+    """tests/hunts/gpu_stress_parity.py: the stress distributions (every end point and threshold of every parameter, degenerate
     views, extreme uniforms) through the CUDA library.  Default policy: every output of every sample bit-identical to the
     reference, NaN for NaN; tolerance policy: every flag equal, with the device's real MUFU errors."""
     import os
     import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hunts"))
     import gpu_stress_parity
     status, why = parity.host_libm_status()
     if status != "ok":

@@ -102,14 +102,14 @@ def test_band_regressions_found_by_the_ulp_hunt(orc, ulp):
 
 @pytest.mark.parametrize("ulp", [False, True])
 def test_stress_distributions_keep_the_flag_contract(ulp):
-    """tools/tol_stress_hunt.py: parameters with mass on every end point and threshold (roughness 0 and 1, ior 1 +- 1e-4,
+    """tests/hunts/tol_stress_hunt.py: parameters with mass on every end point and threshold (roughness 0 and 1, ior 1 +- 1e-4,
     rlDisney parameters exactly 0 / 1, scatter distances at 1e-4), views along the normal, in the tangent plane and below
     the horizon, uniforms at 2^-24 / 1 - 2^-24 / the lobe boundaries: no sample may differ from the reference on a flag
     unless the band tracker listed it.  (This hunt found the roughness = 0 GTR1 case and the half-vector noise behind the
     V.m sign test; the long runs are in profiles/r02_tolerance_stress_hunt.txt.)"""
     import os
     import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hunts"))
     import tol_stress_hunt
     bad = tol_stress_hunt.run(2, ulp)
     assert not any(bad.values()), bad
@@ -123,7 +123,7 @@ def test_policy_error_is_within_the_references_own_rounding_noise():
     the threshold of the binary64 result at least as often as the reference is (margin 0.2 % of the samples)."""
     import os
     import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hunts"))
     import tol_vs_f64
     res = tol_vs_f64.run(1 << 18)
     tol_vs_f64.show(res)
