@@ -113,11 +113,14 @@ def test_no_cpu_fallback():
 
 
 def test_product_never_touches_the_oracle():
-    """The oracle is test infrastructure: nothing under rlshaders_b200/ may name it."""
-    pkg = os.path.join(ROOT, "rlshaders_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
-                text = open(os.path.join(dirpath, f), errors="ignore").read()
-                for needle in ("librls_oracle", "librls_ref", "oracle_lib", "oracle/", "oracle_api", "_ref/"):
-                    assert needle not in text, f"{f} mentions {needle}"
+    """The oracle is test infrastructure: nothing under rlshaders_b200/ may name it, and no tool under tools/ may load it
+    (the oracle-using hunts live in tests/hunts/; tools/sanitize.sh only hands its `host` leg over to them).  The header's
+    comments cite where the oracle restates a definition; it includes nothing from there."""
+    assert "#include \"../oracle" not in open(HEADER).read() and "#include \"oracle" not in open(HEADER).read()
+    for sub in ("rlshaders_b200", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                    text = open(os.path.join(dirpath, f), errors="ignore").read()
+                    for needle in ("librls_oracle", "librls_ref", "oracle_lib", "oracle/", "oracle_api", "_ref/"):
+                        assert needle not in text, f"{sub}/{f} mentions {needle}"

@@ -4,7 +4,7 @@
 #              driver (every fused kernel under the three arithmetic policies, the host-staged pipeline with its
 #              three copy streams, the compact-frame decode, the sweep + re-run lists) and over the experiments library's
 #              shared-memory kernels (TMA / mbarrier pipe, CTA-level lobe partition) through pytest at reduced sizes.
-#   anywhere:  tools/sanitize.sh host [tag]  -fsanitize=address,undefined builds of both oracles + the oracle pinning and
+#   anywhere:  tools/sanitize.sh host [tag]  = tests/hunts/sanitize_oracles.sh: ASan/UBSan builds of both oracles + the pinning and
 #              physics tests on them (CPU only).
 # Logs: gpurun_out/<tag>_sanitizer_*.txt (copy the summaries to profiles/).
 MODE=${1:-gpu}
@@ -46,21 +46,5 @@ if [ "$MODE" = gpu ]; then
   done
   echo "driver asan/ubsan: $(grep -c 'runtime error' $LOG) UBSan reports, $(grep -c 'ERROR: AddressSanitizer' $LOG) ASan reports, $(grep -c '^rc=0' $LOG) runs clean, $(grep -c '^rc=[1-9]' $LOG) failed"
 else
-  LOG=gpurun_out/${TAG}_sanitizer_host_asan_ubsan.txt
-  : > $LOG
-  SAN="-fsanitize=address,undefined -fno-omit-frame-pointer -g"
-  mkdir -p build/san
-  # same sources, same pinned FP flags (oracle/Makefile), into build/san/ (the normal libraries are left alone)
-  FP="-O1 -ffp-contract=off -fno-fast-math -fopenmp -fPIC -DNDEBUG"
-  gcc -std=c11 $FP $SAN -shared -o build/san/librls_oracle.so oracle/rls_oracle.c -lm >> $LOG 2>&1
-  if [ -f /root/reference/src/rlGgx.h ]; then
-    g++ -std=c++14 -D_LINUX $FP $SAN -Ioracle/shim -I/root/reference/src -Ioracle -w -shared -o build/san/librls_ref.so \
-        oracle/ref_driver.cpp oracle/shim/shim_stubs.cpp /root/reference/src/rlUtil.cpp /root/reference/src/rlGgx.cpp \
-        /root/reference/src/rlSss.cpp -lm >> $LOG 2>&1
-  fi
-  ASAN_LIB=$(gcc -print-file-name=libasan.so)
-  echo "### pytest tests/test_oracle_pinning.py tests/test_oracle_physics.py on the sanitized oracles" >> $LOG
-  RLS_ORACLE_DIR=$ROOT/build/san LD_PRELOAD=$ASAN_LIB ASAN_OPTIONS=detect_leaks=0:halt_on_error=0 UBSAN_OPTIONS=print_stacktrace=1 \
-      python -m pytest -q tests/test_oracle_pinning.py tests/test_oracle_physics.py >> $LOG 2>&1; echo "rc=$?" >> $LOG
-  echo "asan/ubsan: $(grep -c 'runtime error' $LOG) UBSan reports, $(grep -c 'ERROR: AddressSanitizer' $LOG) ASan reports; $(tail -3 $LOG | tr '\n' ' ')"
+  exec bash "$ROOT/tests/hunts/sanitize_oracles.sh" "$TAG"
 fi
