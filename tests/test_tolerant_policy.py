@@ -316,3 +316,22 @@ def test_gpu_disney_rerun_paths_give_the_bit_exact_result():
         assert int((a["flags"] != b["flags"]).sum()) == 0
     finally:
         t.close(); e.close()
+
+
+@pytest.mark.gpu
+def test_gpu_sweep_counts_equal_the_bit_exact_policy(tctx):
+    """Albedo sweep (config 5) under RLS_ARITH_TOLERANT: the two COUNT columns of the table (valid samples, total internal
+    reflections) are sums of flag bits and must equal the bit-exact policy's exactly, cell by cell; the three value
+    columns agree to 1e-5 relative (they are means over 1024 samples of quantities that agree to the policy's tolerance)."""
+    from rlshaders_b200 import api
+    e = api.Context(0)
+    try:
+        grid = abi.SweepGrid(16, 16, 8, 0.02, 1.0, 1.0, 2.5)
+        a = e.albedo_sweep(grid, 0x5EED0005, 0, 1024).cpu().numpy()
+        tctx.fallback_count(reset=True)
+        b = tctx.albedo_sweep(grid, 0x5EED0005, 0, 1024).cpu().numpy()
+        assert np.array_equal(a[:, 3:], b[:, 3:])
+        assert np.allclose(a[:, :3], b[:, :3], rtol=1e-5, atol=1e-9)
+        assert 0 < tctx.fallback_count() < 0.01 * 16 * 16 * 8 * 1024
+    finally:
+        e.close()
