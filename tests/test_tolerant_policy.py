@@ -322,7 +322,9 @@ def test_gpu_disney_rerun_paths_give_the_bit_exact_result():
 def test_gpu_sweep_counts_equal_the_bit_exact_policy(tctx):
     """Albedo sweep (config 5) under RLS_ARITH_TOLERANT: the two COUNT columns of the table (valid samples, total internal
     reflections) are sums of flag bits and must equal the bit-exact policy's exactly, cell by cell; the three value
-    columns agree to 1e-5 relative (they are means over 1024 samples of quantities that agree to the policy's tolerance)."""
+    columns (sums over 1024 samples of f / pdf, weight_t, F) agree per cell to 1e-4 relative + 5e-3 absolute -- the host
+    build of the same unit measures at most 2e-5 relative (sum F, cells with ior near 1) and 2e-2 absolute (sum weight_t
+    ~ 1e3) on this grid."""
     from rlshaders_b200 import api
     e = api.Context(0)
     try:
@@ -331,7 +333,7 @@ def test_gpu_sweep_counts_equal_the_bit_exact_policy(tctx):
         tctx.fallback_count(reset=True)
         b = tctx.albedo_sweep(grid, 0x5EED0005, 0, 1024).cpu().numpy()
         assert np.array_equal(a[:, 3:], b[:, 3:])
-        assert np.allclose(a[:, :3], b[:, :3], rtol=1e-5, atol=1e-9)
+        assert np.allclose(a[:, :3], b[:, :3], rtol=1e-4, atol=5e-3), float(np.abs(a[:, :3] - b[:, :3]).max())
         assert 0 < tctx.fallback_count() < 0.01 * 16 * 16 * 8 * 1024
     finally:
         e.close()
